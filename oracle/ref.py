@@ -1,0 +1,222 @@
+"""ctypes binding of oracle/_ref/libbiostrings_ref.so  (TEST INFRASTRUCTURE ONLY).
+
+The shared object is the *reference's own* hot-path C (match_pdict*.c & friends under
+/root/reference/src), compiled unmodified against the mini-R stand-in in oracle/shim/ by
+oracle/Makefile.  This module exposes the reference's ``.Call`` entry points at the level
+R calls them (src/R_init_Biostrings.c:27-147):
+
+    build_Twobit / ACtree2_build            -> RefPPTB(...)
+    match_PDict3Parts_XString               -> RefPPTB.match_xstring
+    match_PDict3Parts_XStringViews          -> RefPPTB.match_views
+    vmatch_PDict3Parts_XStringSet           -> RefPPTB.vmatch_set
+    ByPos_MIndex_combine / _endIndex        -> mindex_combine / mindex_endindex
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "libbiostrings_ref.so")
+
+NA_INTEGER = -2147483648
+MATCHES_AS_WHICH, MATCHES_AS_COUNTS, MATCHES_AS_ENDS = 1, 2, 4
+_INTSXP, _REALSXP, _VECSXP, _NILSXP = 13, 14, 19, 0
+
+_lib = None
+
+
+class RefError(RuntimeError):
+    """An Rf_error() raised inside the reference C code (message = R's error text)."""
+
+
+def available():
+    return os.path.exists(_SO)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise FileNotFoundError(
+                f"{_SO} not built: run `make -C oracle ref` where /root/reference exists")
+        L = C.CDLL(_SO)
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_last_warning.restype = C.c_char_p
+        L.ref_pptb_build.restype = C.c_void_p
+        L.ref_pptb_build.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
+        L.ref_pptb_blank_dups.argtypes = [C.c_void_p]
+        L.ref_pptb_free.argtypes = [C.c_void_p]
+        L.ref_actree2_nnodes.argtypes = [C.c_void_p]
+        L.ref_actree2_has_all_flinks.argtypes = [C.c_void_p]
+        L.ref_actree2_compute_all_flinks.argtypes = [C.c_void_p]
+        L.ref_match_xstring.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + \
+            [C.c_void_p, C.c_int] + [C.c_int] * 5
+        L.ref_match_views.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + \
+            [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_int] * 5
+        L.ref_vmatch_set.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + \
+            [C.c_void_p, C.c_void_p, C.c_int] + [C.c_int] * 4 + \
+            [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.ref_mindex_endindex.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_result_length.restype = C.c_long
+        L.ref_result_list_lengths.restype = C.c_long
+        L.ref_result_list_lengths.argtypes = [C.c_void_p]
+        L.ref_result_copy_int.argtypes = [C.c_void_p]
+        L.ref_result_copy_double.argtypes = [C.c_void_p]
+        L.ref_result_list_flat.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _check(rc):
+    if rc != 0:
+        msg = lib().ref_last_error().decode("latin1")
+        lib().ref_release()
+        raise RefError(msg)
+
+
+def last_warning():
+    return lib().ref_last_warning().decode("latin1")
+
+
+def _fetch_result(release=True):
+    """Current result -> numpy: int/double vector, or list of (int array | None)."""
+    L = lib()
+    t, n = L.ref_result_type(), L.ref_result_length()
+    if t == _INTSXP:
+        out = np.empty(n, dtype=np.int32)
+        L.ref_result_copy_int(_ptr(out))
+    elif t == _REALSXP:
+        out = np.empty(n, dtype=np.float64)
+        L.ref_result_copy_double(_ptr(out))
+    elif t == _VECSXP:
+        lens = np.empty(n, dtype=np.int32)
+        total = L.ref_result_list_lengths(_ptr(lens))
+        flat = np.empty(total, dtype=np.int32)
+        L.ref_result_list_flat(_ptr(flat))
+        out, off = [], 0
+        for k in lens.tolist():
+            if k < 0:
+                out.append(None)
+            else:
+                out.append(flat[off:off + k].copy())
+                off += k
+    elif t == _NILSXP:
+        out = None
+    else:
+        raise RuntimeError(f"unexpected result type {t}")
+    if release:
+        L.ref_release()
+    return out
+
+
+class RefPPTB:
+    """A PreprocessedTB ("Twobit" | "ACtree2") built by the reference C.
+
+    tb: (concat uint8 array, widths int32 array) of the Trusted Band (encoded bytes);
+    pp_exclude: None or int32[M] with NA_INTEGER for "keep" (R/PDict-class.R:229).
+    """
+
+    def __init__(self, algo, tb_concat, tb_widths, pp_exclude=None):
+        self.algo = algo
+        self._tb = _u8(tb_concat)          # must outlive the handle
+        self._tbw = _i32(tb_widths)
+        self.M = len(self._tbw)
+        excl = None if pp_exclude is None else _i32(pp_exclude)
+        self.high2low = np.empty(self.M, dtype=np.int32)
+        self._h = lib().ref_pptb_build(algo.encode(), self.M, _ptr(self._tb),
+                                       _ptr(self._tbw), _ptr(excl), _ptr(self.high2low))
+        if not self._h:
+            raise RefError(lib().ref_last_error().decode("latin1"))
+
+    def blank_dups(self):
+        _check(lib().ref_pptb_blank_dups(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ref_pptb_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def nnodes(self):
+        return lib().ref_actree2_nnodes(self._h)
+
+    def has_all_flinks(self):
+        return bool(lib().ref_actree2_has_all_flinks(self._h))
+
+    @staticmethod
+    def _flank(f):
+        if f is None:
+            return None, None
+        return _u8(f[0]), _i32(f[1])
+
+    def match_xstring(self, head, tail, subject, max_mismatch, min_mismatch, fixed,
+                      mode, keep=False):
+        hc, hw = self._flank(head)
+        tc, tw = self._flank(tail)
+        s = _u8(subject)
+        _check(lib().ref_match_xstring(self._h, self.M, _ptr(hc), _ptr(hw), _ptr(tc),
+                                       _ptr(tw), _ptr(s), len(s), max_mismatch,
+                                       min_mismatch, int(fixed[0]), int(fixed[1]), mode))
+        return _fetch_result(release=not keep)
+
+    def match_views(self, head, tail, subject, views_start, views_width, max_mismatch,
+                    min_mismatch, fixed, mode, keep=False):
+        hc, hw = self._flank(head)
+        tc, tw = self._flank(tail)
+        s, vs, vw = _u8(subject), _i32(views_start), _i32(views_width)
+        _check(lib().ref_match_views(self._h, self.M, _ptr(hc), _ptr(hw), _ptr(tc),
+                                     _ptr(tw), _ptr(s), len(s), _ptr(vs), _ptr(vw),
+                                     len(vs), max_mismatch, min_mismatch,
+                                     int(fixed[0]), int(fixed[1]), mode))
+        return _fetch_result(release=not keep)
+
+    def vmatch_set(self, head, tail, subj_concat, subj_widths, max_mismatch,
+                   min_mismatch, fixed, collapse, weight, mode):
+        hc, hw = self._flank(head)
+        tc, tw = self._flank(tail)
+        sc, sw = _u8(subj_concat), _i32(subj_widths)
+        w = np.asarray(weight)
+        is_double = w.dtype.kind == "f"
+        w = np.ascontiguousarray(w, dtype=np.float64 if is_double else np.int32)
+        _check(lib().ref_vmatch_set(self._h, self.M, _ptr(hc), _ptr(hw), _ptr(tc),
+                                    _ptr(tw), _ptr(sc), _ptr(sw), len(sw), max_mismatch,
+                                    min_mismatch, int(fixed[0]), int(fixed[1]),
+                                    collapse, int(is_double), _ptr(w), len(w), mode))
+        return _fetch_result()
+
+
+def stash_result():
+    """Keep the result of the last ``keep=True`` ENDS call for mindex_combine()."""
+    if lib().ref_result_stash() < 0:
+        raise RuntimeError("nothing to stash")
+
+
+def mindex_combine():
+    """ByPos_MIndex_combine over the stashed ENDS results (src/MIndex_class.c:230)."""
+    _check(lib().ref_mindex_combine())
+    return _fetch_result()
+
+
+def release():
+    lib().ref_release()
