@@ -1,0 +1,1333 @@
+// bsgpu.cu -- host side of libbsgpu.so: the C ABI declared in include/bsgpu.h.
+//
+// Plays the role of the reference's C layer under the .Call boundary
+// (src/match_pdict.c, src/match_pdict_Twobit.c, src/match_pdict_ACtree2.c,
+// src/match_pdict_utils.c, src/match_reporting.c, src/MIndex_class.c) with the per-base
+// work done by the kernels in bsgpu_kernels.cuh.  No CPU fallback: every compute entry
+// point needs a CUDA device.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+
+#include "../../include/bsgpu.h"
+#include "bsgpu_kernels.cuh"
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+
+static thread_local char g_err[1024] = "";
+static long long g_launches = 0;
+
+static int fail(int code, const char *fmt, ...)
+{
+	va_list ap;
+
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define CUDA_TRY(expr) do { \
+	cudaError_t e_ = (expr); \
+	if (e_ != cudaSuccess) \
+		return fail(e_ == cudaErrorMemoryAllocation ? BSGPU_ENOMEM : BSGPU_ECUDA, \
+			    "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, \
+			    __LINE__, cudaGetErrorString(e_)); \
+} while (0)
+
+#define TRY(expr) do { int rc_ = (expr); if (rc_ != BSGPU_OK) return rc_; } while (0)
+
+extern "C" const char *bsgpu_last_error(void) { return g_err; }
+extern "C" const char *bsgpu_version(void) { return "bsgpu 0.1 (sm_100a)"; }
+extern "C" int64_t bsgpu_launch_count(void) { return g_launches; }
+
+// ---------------------------------------------------------------------------------------
+// device selection
+// ---------------------------------------------------------------------------------------
+
+static int g_device = -1;
+static int g_num_sms = 148;
+
+extern "C" int bsgpu_device_count(void)
+{
+	int n = 0;
+
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+extern "C" int bsgpu_set_device(int device)
+{
+	int n = bsgpu_device_count();
+
+	if (n == 0)
+		return fail(BSGPU_ENODEVICE, "no CUDA device available: libbsgpu has no CPU fallback");
+	if (device < 0 || device >= n)
+		return fail(BSGPU_EINVAL, "invalid CUDA device %d (have %d)", device, n);
+	CUDA_TRY(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+	g_num_sms = prop.multiProcessorCount;
+	g_device = device;
+	return BSGPU_OK;
+}
+
+static int ensure_device(void)
+{
+	if (g_device >= 0) {
+		CUDA_TRY(cudaSetDevice(g_device));
+		return BSGPU_OK;
+	}
+	const char *env = getenv("BSGPU_DEVICE");
+	return bsgpu_set_device(env ? atoi(env) : 0);
+}
+
+static int grid_for(long long nthreads, int block, int per_sm)
+{
+	long long blocks = (nthreads + block - 1) / block;
+	long long cap = (long long) g_num_sms * per_sm;
+
+	if (blocks > cap)
+		blocks = cap;
+	if (blocks < 1)
+		blocks = 1;
+	return (int) blocks;
+}
+
+template <typename T>
+struct DevBuf {
+	T *p = nullptr;
+	size_t n = 0;
+
+	~DevBuf() { release(); }
+	void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+	int alloc(size_t count)
+	{
+		release();
+		if (count == 0)
+			count = 1;
+		cudaError_t e = cudaMalloc((void **) &p, count * sizeof(T));
+		if (e != cudaSuccess) {
+			p = nullptr;
+			cudaGetLastError();
+			return fail(BSGPU_ENOMEM, "cudaMalloc of %zu bytes failed: %s",
+				    count * sizeof(T), cudaGetErrorString(e));
+		}
+		n = count;
+		return BSGPU_OK;
+	}
+	int upload(const T *src, size_t count)
+	{
+		TRY(alloc(count));
+		if (count)
+			CUDA_TRY(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+		return BSGPU_OK;
+	}
+};
+
+// ---------------------------------------------------------------------------------------
+// PDict3Parts
+// ---------------------------------------------------------------------------------------
+
+struct bsgpu_pdict3parts {
+	int algo = 0, M = 0, w = 0, seed_w = 0;
+	bool has_head = false, has_tail = false;
+	int max_H = 0, max_T = 0;
+	std::vector<int32_t> high2low;          // NA or 1-based
+	std::vector<uint64_t> keys;             // seed key per pattern
+	std::vector<uint8_t> tb;                // M*w letters
+	std::vector<int32_t> tail_len;          // per pattern
+	uint32_t nbuckets = 0;
+	bool all_singletons = true;
+	DevBuf<uint4> d_table;
+	DevBuf<uint64_t> d_keys;
+	DevBuf<int32_t> d_seed_next;
+	DevBuf<int32_t> d_grp_off, d_grp_keys;
+	DevBuf<uint8_t> d_tb, d_head, d_tail;
+	DevBuf<int64_t> d_head_off, d_tail_off;
+
+	BsgpuIndexView view() const
+	{
+		BsgpuIndexView I;
+
+		I.table = d_table.p;
+		I.keys = d_keys.p;
+		I.seed_next = d_seed_next.p;
+		int lg = 0;
+		while ((1u << lg) < nbuckets)
+			lg++;
+		I.bucket_shift = 32 - lg;
+		I.bucket_mask = nbuckets - 1;
+		I.w = w;
+		I.seed_w = seed_w;
+		I.seed_mask = seed_w >= 32 ? ~0ull : ((1ull << (2 * seed_w)) - 1);
+		I.M = M;
+		I.grp_off = d_grp_off.p;
+		I.grp_keys = d_grp_keys.p;
+		I.tb_bytes = d_tb.p;
+		I.head = has_head ? d_head.p : nullptr;
+		I.head_off = d_head_off.p;
+		I.tail = has_tail ? d_tail.p : nullptr;
+		I.tail_off = d_tail_off.p;
+		I.all_singletons = all_singletons;
+		return I;
+	}
+};
+
+static int upload_groups(bsgpu_pdict3parts *p3, bool blank)
+{
+	int M = p3->M;
+	std::vector<int32_t> off(M + 1, 0), members;
+
+	// group of a leader = leader first, then low2high[leader] ascending
+	// (src/match_pdict_utils.c:153-181)
+	std::vector<int32_t> cnt(M, 0);
+	for (int i = 0; i < M; i++)
+		if (!blank && p3->high2low[i] != BSGPU_NA)
+			cnt[p3->high2low[i] - 1]++;
+	for (int i = 0; i < M; i++)
+		off[i + 1] = off[i] + 1 + cnt[i];       // every pattern gets a (maybe unused) slot
+	members.resize(off[M]);
+	std::vector<int32_t> cur(M);
+	for (int i = 0; i < M; i++) {
+		members[off[i]] = i;
+		cur[i] = off[i] + 1;
+	}
+	bool singles = true;
+	for (int i = 0; i < M; i++)
+		if (!blank && p3->high2low[i] != BSGPU_NA) {
+			int k = p3->high2low[i] - 1;
+
+			members[cur[k]++] = i;
+			singles = false;
+		}
+	p3->all_singletons = singles;
+	TRY(p3->d_grp_off.upload(off.data(), off.size()));
+	TRY(p3->d_grp_keys.upload(members.data(), members.size()));
+	return BSGPU_OK;
+}
+
+static int upload_flank(int M, const uint8_t *concat, const int32_t *widths, DevBuf<uint8_t> &d_bytes,
+			DevBuf<int64_t> &d_off, bool &present, int &maxw, std::vector<int32_t> *lens)
+{
+	std::vector<int64_t> off(M + 1, 0);
+
+	present = false;
+	maxw = 0;
+	if (widths != nullptr)
+		for (int i = 0; i < M; i++) {
+			if (widths[i] < 0)
+				return fail(BSGPU_EINVAL, "negative head/tail width for pattern %d", i + 1);
+			off[i + 1] = off[i] + widths[i];
+			maxw = std::max(maxw, (int) widths[i]);
+		}
+	if (lens) {
+		lens->assign(M, 0);
+		if (widths)
+			for (int i = 0; i < M; i++)
+				(*lens)[i] = widths[i];
+	}
+	present = maxw > 0;
+	TRY(d_off.upload(off.data(), off.size()));
+	TRY(d_bytes.upload(concat, present ? (size_t) off[M] : 0));
+	return BSGPU_OK;
+}
+
+extern "C" int bsgpu_pdict3parts_build(int algo, int32_t M,
+		const uint8_t *tb_concat, const int32_t *tb_widths,
+		const uint8_t *head_concat, const int32_t *head_widths,
+		const uint8_t *tail_concat, const int32_t *tail_widths,
+		const int32_t *pp_exclude, int32_t *high2low_out,
+		bsgpu_pdict3parts **out)
+{
+	if (out == nullptr || M < 0 || (M > 0 && (tb_concat == nullptr || tb_widths == nullptr)))
+		return fail(BSGPU_EINVAL, "bsgpu_pdict3parts_build(): bad arguments");
+	*out = nullptr;
+	if (algo != BSGPU_ALGO_ACTREE2 && algo != BSGPU_ALGO_TWOBIT)
+		return fail(BSGPU_EINVAL, "%d: unsupported Trusted Band type in 'pdict'", algo);
+	// --- validation, in the reference's order and with its messages -------------------
+	// src/match_pdict_ACtree2.c:801-824,761-763; src/match_pdict_Twobit.c:116-142
+	if (M == 0 && algo == BSGPU_ALGO_ACTREE2)
+		return fail(BSGPU_EINVAL, "Trusted Band is empty");
+	if (M > 0x3FFFFFFF)
+		return fail(BSGPU_EINVAL, "new_ACtree(): tb_length > MAX_P_ID");
+	int w = -1;
+	{
+		const uint8_t *p = tb_concat;
+
+		for (int i = 0; i < M; p += tb_widths[i], i++) {
+			if (pp_exclude != nullptr && pp_exclude[i] != BSGPU_NA)
+				continue;
+			if (algo == BSGPU_ALGO_TWOBIT && tb_widths[i] == 0)
+				return fail(BSGPU_EINVAL, "empty trusted region for pattern %d", i + 1);
+			if (w == -1) {
+				if (tb_widths[i] == 0)
+					return fail(BSGPU_EINVAL, "first element in Trusted Band is of length 0");
+				w = tb_widths[i];
+				if (algo == BSGPU_ALGO_TWOBIT && w > 14)
+					return fail(BSGPU_EINVAL, "the width of the Trusted Band must "
+						    "be <= 14 when 'type=\"Twobit\"'");
+			} else if (tb_widths[i] != w) {
+				if (algo == BSGPU_ALGO_TWOBIT)
+					return fail(BSGPU_EINVAL, "all the trusted regions must have the same length");
+				return fail(BSGPU_EINVAL, "element %d in Trusted Band has a different "
+					    "length than first element", i + 1);
+			}
+			for (int d = 0; d < w; d++)
+				if (!bsgpu_is_base(p[d]))
+					return fail(BSGPU_EINVAL, algo == BSGPU_ALGO_TWOBIT ?
+						    "non-base DNA letter found in Trusted Band for pattern %d" :
+						    "non base DNA letter found in Trusted Band for pattern %d",
+						    i + 1);
+		}
+	}
+	if (w > 64)
+		return fail(BSGPU_EUNSUPPORTED, "Trusted Band width %d > 64 is not supported by "
+			    "the GPU index yet", w);
+	TRY(ensure_device());
+
+	bsgpu_pdict3parts *p3 = new bsgpu_pdict3parts();
+	std::unique_ptr<bsgpu_pdict3parts> guard(p3);
+	p3->algo = algo;
+	p3->M = M;
+	p3->w = w < 0 ? 0 : w;
+	p3->seed_w = std::min(p3->w, 32);
+	p3->high2low.assign(M, BSGPU_NA);
+	p3->keys.assign(M, 0);
+	p3->tb.assign((size_t) M * p3->w, 0);
+
+	// --- TB keys, duplicates (high2low), leaders ------------------------------------------
+	std::vector<int32_t> leaders;
+	std::vector<int32_t> seed_next(M, -1);
+	{
+		std::unordered_map<uint64_t, int32_t> first32;          // w <= 32: full key
+		std::unordered_map<std::string, int32_t> firstlong;     // w > 32: all letters
+		std::unordered_map<uint64_t, int32_t> seed_tail;        // w > 32: last leader per seed
+		const uint8_t *p = tb_concat;
+
+		first32.reserve((size_t) M * 2);
+		for (int i = 0; i < M; p += tb_widths[i], i++) {
+			if (pp_exclude != nullptr && pp_exclude[i] != BSGPU_NA)
+				continue;
+			uint64_t key = 0;
+			for (int d = 0; d < p3->seed_w; d++)
+				key |= (uint64_t) bsgpu_base_code(p[d]) << (2 * d);
+			p3->keys[i] = key;
+			memcpy(p3->tb.data() + (size_t) i * w, p, w);
+			if (w <= 32) {
+				auto it = first32.find(key);
+				if (it != first32.end()) {
+					p3->high2low[i] = it->second + 1;
+					continue;
+				}
+				first32.emplace(key, i);
+			} else {
+				std::string s((const char *) p, w);
+				auto it = firstlong.find(s);
+				if (it != firstlong.end()) {
+					p3->high2low[i] = it->second + 1;
+					continue;
+				}
+				firstlong.emplace(std::move(s), i);
+				auto st = seed_tail.find(key);
+				if (st != seed_tail.end()) {
+					seed_next[st->second] = i;      // chain leaders sharing a seed
+					st->second = i;
+					continue;                       // only the first goes in the table
+				}
+				seed_tail.emplace(key, i);
+			}
+			leaders.push_back(i);
+		}
+	}
+	if (high2low_out != nullptr && M > 0)
+		memcpy(high2low_out, p3->high2low.data(), (size_t) M * sizeof(int32_t));
+
+	// --- hash table: 16-byte buckets of two {fp,id} slots, linear probing over buckets --------
+	uint32_t nb = 16;
+	while (nb < 2 * (uint64_t) leaders.size())
+		nb <<= 1;
+	p3->nbuckets = nb;
+	int lg = 0;
+	while ((1u << lg) < nb)
+		lg++;
+	std::vector<uint4> table(nb, make_uint4(0, BSGPU_EMPTY_ID, 0, BSGPU_EMPTY_ID));
+	for (int32_t id : leaders) {
+		uint32_t top, fp;
+
+		bsgpu_hash(p3->keys[id], top, fp);
+		uint32_t b = top >> (32 - lg);
+		for (;;) {
+			if (table[b].y == BSGPU_EMPTY_ID) {
+				table[b].x = fp;
+				table[b].y = (uint32_t) id;
+				break;
+			}
+			if (table[b].w == BSGPU_EMPTY_ID) {
+				table[b].z = fp;
+				table[b].w = (uint32_t) id;
+				break;
+			}
+			b = (b + 1) & (nb - 1);
+		}
+	}
+	TRY(p3->d_table.upload(table.data(), table.size()));
+	TRY(p3->d_keys.upload(p3->keys.data(), p3->keys.size()));
+	if (w > 32) {
+		TRY(p3->d_seed_next.upload(seed_next.data(), seed_next.size()));
+		TRY(p3->d_tb.upload(p3->tb.data(), p3->tb.size()));
+	}
+	TRY(upload_groups(p3, false));
+	TRY(upload_flank(M, head_concat, head_widths, p3->d_head, p3->d_head_off, p3->has_head,
+			 p3->max_H, nullptr));
+	TRY(upload_flank(M, tail_concat, tail_widths, p3->d_tail, p3->d_tail_off, p3->has_tail,
+			 p3->max_T, &p3->tail_len));
+	*out = guard.release();
+	return BSGPU_OK;
+}
+
+extern "C" int bsgpu_pdict3parts_blank_dups(bsgpu_pdict3parts *p3)
+{
+	if (p3 == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_pdict3parts_blank_dups(): NULL handle");
+	TRY(ensure_device());
+	TRY(upload_groups(p3, true));
+	std::fill(p3->high2low.begin(), p3->high2low.end(), BSGPU_NA);
+	return BSGPU_OK;
+}
+
+extern "C" void bsgpu_pdict3parts_free(bsgpu_pdict3parts *p3) { delete p3; }
+extern "C" int32_t bsgpu_pdict3parts_length(const bsgpu_pdict3parts *p3) { return p3 ? p3->M : 0; }
+extern "C" int32_t bsgpu_pdict3parts_tb_width(const bsgpu_pdict3parts *p3) { return p3 ? p3->w : 0; }
+
+// ---------------------------------------------------------------------------------------
+// Subjects
+// ---------------------------------------------------------------------------------------
+
+enum { SUBJ_XSTRING = 0, SUBJ_VIEWS = 1, SUBJ_SET = 2, SUBJ_CHUNK = 3 };
+
+struct bsgpu_subject {
+	int kind = SUBJ_XSTRING;
+	int32_t nseg = 0;
+	int64_t total = 0;              // letters of the concat buffer (multiple of 128)
+	int64_t nletters = 0;           // letters scanned
+	int64_t scan_lo = 0, scan_hi = 0;       // TB *ends* (concat index) in [scan_lo, scan_hi)
+	bool open_left = false, open_right = false;     // chunk edges that are not subject edges
+	int64_t halo_left = 0, halo_right = 0;  // letters available around the report range
+	std::vector<int64_t> seg_start, seg_coord;
+	std::vector<int32_t> seg_len;
+	DevBuf<uint8_t> d_bytes;
+	DevBuf<uint64_t> d_codes;
+	DevBuf<uint32_t> d_valid, d_iupac;
+	DevBuf<int64_t> d_seg_start, d_seg_coord;
+	DevBuf<int32_t> d_seg_len;
+
+	BsgpuSubjectView view() const
+	{
+		BsgpuSubjectView S;
+
+		S.bytes = d_bytes.p;
+		S.codes = d_codes.p;
+		S.valid = d_valid.p;
+		S.iupac = d_iupac.p;
+		S.seg_start = d_seg_start.p;
+		S.seg_len = d_seg_len.p;
+		S.seg_coord = d_seg_coord.p;
+		S.nseg = nseg;
+		S.total = total;
+		return S;
+	}
+};
+
+// Lays the segments out as [guard][seg0][sep][seg1]...[guard+pad], uploads, packs.
+// srcs[i] points at host letters of segment i (may alias one big buffer).
+static int subject_finish(bsgpu_subject *s, const uint8_t *const *srcs, const uint8_t *one_src)
+{
+	int64_t pos = BSGPU_GUARD;
+	int32_t n = s->nseg;
+
+	s->seg_start.resize(n);
+	for (int32_t i = 0; i < n; i++) {
+		s->seg_start[i] = pos;
+		pos += (int64_t) s->seg_len[i] + 1;     // one separator after every segment
+	}
+	s->total = ((pos + BSGPU_GUARD + 127) / 128) * 128;
+	if (s->total >= (1ll << BSGPU_POS_BITS))
+		return fail(BSGPU_EUNSUPPORTED, "subject too long for one device buffer (%lld letters)",
+			    (long long) s->total);
+	int64_t nwords = s->total / 32;
+	TRY(s->d_bytes.alloc((size_t) s->total + 64));
+	CUDA_TRY(cudaMemset(s->d_bytes.p, BSGPU_SEP_BYTE, (size_t) s->total + 64));
+	if (n == 1) {
+		if (s->seg_len[0] > 0)
+			CUDA_TRY(cudaMemcpy(s->d_bytes.p + s->seg_start[0], one_src ? one_src : srcs[0],
+					    (size_t) s->seg_len[0], cudaMemcpyHostToDevice));
+	} else if (n > 1) {
+		// assemble on the host in slabs to bound the staging memory
+		const int64_t SLAB = 256ll << 20;
+		std::vector<uint8_t> stage;
+		int32_t i = 0;
+
+		while (i < n) {
+			int64_t a = s->seg_start[i], b = a;
+			int32_t k = i;
+
+			while (k < n && (s->seg_start[k] + s->seg_len[k] + 1 - a <= SLAB || k == i)) {
+				b = s->seg_start[k] + s->seg_len[k] + 1;
+				k++;
+			}
+			stage.assign((size_t) (b - a), (uint8_t) BSGPU_SEP_BYTE);
+			for (int32_t q = i; q < k; q++)
+				if (s->seg_len[q] > 0)
+					memcpy(stage.data() + (s->seg_start[q] - a), srcs[q], (size_t) s->seg_len[q]);
+			CUDA_TRY(cudaMemcpy(s->d_bytes.p + a, stage.data(), (size_t) (b - a),
+					    cudaMemcpyHostToDevice));
+			i = k;
+		}
+	}
+	TRY(s->d_codes.alloc((size_t) nwords + 4));
+	TRY(s->d_valid.alloc((size_t) nwords + 4));
+	TRY(s->d_iupac.alloc((size_t) nwords + 4));
+	CUDA_TRY(cudaMemset(s->d_codes.p, 0, ((size_t) nwords + 4) * sizeof(uint64_t)));
+	CUDA_TRY(cudaMemset(s->d_valid.p, 0, ((size_t) nwords + 4) * sizeof(uint32_t)));
+	CUDA_TRY(cudaMemset(s->d_iupac.p, 0, ((size_t) nwords + 4) * sizeof(uint32_t)));
+	pack_subject_kernel<<<grid_for(nwords, 256, 8), 256>>>(s->d_bytes.p, nwords, s->d_codes.p,
+							      s->d_valid.p, s->d_iupac.p);
+	g_launches++;
+	CUDA_TRY(cudaGetLastError());
+	TRY(s->d_seg_start.upload(s->seg_start.data(), (size_t) n));
+	TRY(s->d_seg_len.upload(s->seg_len.data(), (size_t) n));
+	TRY(s->d_seg_coord.upload(s->seg_coord.data(), (size_t) n));
+	CUDA_TRY(cudaDeviceSynchronize());
+	if (s->kind != SUBJ_CHUNK) {
+		s->scan_lo = BSGPU_GUARD;
+		s->scan_hi = pos;
+	}
+	return BSGPU_OK;
+}
+
+extern "C" int bsgpu_subject_xstring(const uint8_t *sq, int64_t length, bsgpu_subject **out)
+{
+	if (out == nullptr || length < 0 || (length > 0 && sq == nullptr))
+		return fail(BSGPU_EINVAL, "bsgpu_subject_xstring(): bad arguments");
+	*out = nullptr;
+	if (length > INT32_MAX)
+		return fail(BSGPU_EINVAL, "subject longer than INT_MAX letters (use chunks or views)");
+	TRY(ensure_device());
+	std::unique_ptr<bsgpu_subject> s(new bsgpu_subject());
+	s->kind = SUBJ_XSTRING;
+	s->nseg = 1;
+	s->seg_len.assign(1, (int32_t) length);
+	s->seg_coord.assign(1, 0);
+	s->nletters = length;
+	TRY(subject_finish(s.get(), nullptr, sq));
+	*out = s.release();
+	return BSGPU_OK;
+}
+
+extern "C" int bsgpu_subject_views(const uint8_t *sq, int64_t length,
+		const int32_t *views_start, const int32_t *views_width, int32_t nviews,
+		bsgpu_subject **out)
+{
+	if (out == nullptr || length < 0 || nviews < 0 || (length > 0 && sq == nullptr) ||
+	    (nviews > 0 && (views_start == nullptr || views_width == nullptr)))
+		return fail(BSGPU_EINVAL, "bsgpu_subject_views(): bad arguments");
+	*out = nullptr;
+	std::vector<const uint8_t *> srcs(nviews);
+	std::unique_ptr<bsgpu_subject> s(new bsgpu_subject());
+	s->kind = SUBJ_VIEWS;
+	s->nseg = nviews;
+	s->seg_len.resize(nviews);
+	s->seg_coord.resize(nviews);
+	for (int32_t v = 0; v < nviews; v++) {
+		int64_t off = (int64_t) views_start[v] - 1;
+
+		// src/match_pdict.c:252-254
+		if (off < 0 || views_width[v] < 0 || off + views_width[v] > length)
+			return fail(BSGPU_EINVAL, "'subject' has \"out of limits\" views");
+		srcs[v] = sq + off;
+		s->seg_len[v] = views_width[v];
+		s->seg_coord[v] = off;
+		s->nletters += views_width[v];
+	}
+	TRY(ensure_device());
+	TRY(subject_finish(s.get(), srcs.data(), nullptr));
+	*out = s.release();
+	return BSGPU_OK;
+}
+
+extern "C" int bsgpu_subject_set(const uint8_t *concat, const int32_t *widths, int32_t n,
+		bsgpu_subject **out)
+{
+	if (out == nullptr || n < 0 || (n > 0 && widths == nullptr))
+		return fail(BSGPU_EINVAL, "bsgpu_subject_set(): bad arguments");
+	*out = nullptr;
+	std::vector<const uint8_t *> srcs(n);
+	std::unique_ptr<bsgpu_subject> s(new bsgpu_subject());
+	s->kind = SUBJ_SET;
+	s->nseg = n;
+	s->seg_len.resize(n);
+	s->seg_coord.assign(n, 0);
+	int64_t off = 0;
+	for (int32_t i = 0; i < n; i++) {
+		if (widths[i] < 0)
+			return fail(BSGPU_EINVAL, "negative width for subject element %d", i + 1);
+		srcs[i] = concat + off;
+		s->seg_len[i] = widths[i];
+		off += widths[i];
+	}
+	s->nletters = off;
+	TRY(ensure_device());
+	TRY(subject_finish(s.get(), srcs.data(), nullptr));
+	*out = s.release();
+	return BSGPU_OK;
+}
+
+extern "C" int bsgpu_subject_chunk(const uint8_t *chunk, int64_t chunk_len, int64_t chunk_start,
+		int64_t subject_len, int64_t report_lo, int64_t report_hi, bsgpu_subject **out)
+{
+	if (out == nullptr || chunk_len < 0 || chunk_start < 0 || chunk_start + chunk_len > subject_len ||
+	    (chunk_len > 0 && chunk == nullptr) || chunk_len > INT32_MAX)
+		return fail(BSGPU_EINVAL, "bsgpu_subject_chunk(): bad arguments");
+	*out = nullptr;
+	// clamp the report range (1-based TB ends n, lo < n <= hi) to the chunk
+	report_lo = std::max(report_lo, chunk_start);
+	report_hi = std::min(report_hi, chunk_start + chunk_len);
+	if (report_hi < report_lo)
+		report_hi = report_lo;
+	TRY(ensure_device());
+	std::unique_ptr<bsgpu_subject> s(new bsgpu_subject());
+	s->kind = SUBJ_CHUNK;
+	s->nseg = 1;
+	s->seg_len.assign(1, (int32_t) chunk_len);
+	s->seg_coord.assign(1, chunk_start);
+	s->nletters = report_hi - report_lo;
+	s->open_left = chunk_start > 0;
+	s->open_right = chunk_start + chunk_len < subject_len;
+	s->halo_left = report_lo - chunk_start;                 // letters before the first reported end
+	s->halo_right = chunk_start + chunk_len - report_hi;    // letters after the last reported end
+	TRY(subject_finish(s.get(), nullptr, chunk));
+	// TB end n (subject coords) <-> concat index seg_start + (n - chunk_start) - 1
+	s->scan_lo = s->seg_start[0] + (report_lo - chunk_start);
+	s->scan_hi = s->seg_start[0] + (report_hi - chunk_start);
+	*out = s.release();
+	return BSGPU_OK;
+}
+
+extern "C" void bsgpu_subject_free(bsgpu_subject *s) { delete s; }
+extern "C" int64_t bsgpu_subject_nletters(const bsgpu_subject *s) { return s ? s->nletters : 0; }
+
+// ---------------------------------------------------------------------------------------
+// Workspace: candidate / record buffers and counters (per process, grown on demand)
+// ---------------------------------------------------------------------------------------
+
+struct Workspace {
+	DevBuf<unsigned long long> cand, rec, rec2;
+	DevBuf<unsigned long long> counters;    // [0] = candidates, [1] = records
+	DevBuf<int> flags;                      // [0] = too many IUPAC expansions
+	DevBuf<uint8_t> cub_temp;
+	unsigned long long *h_counters = nullptr;       // pinned
+	int *h_flags = nullptr;
+};
+
+static Workspace *g_ws = nullptr;
+
+static int workspace(Workspace **out)
+{
+	if (g_ws == nullptr) {
+		Workspace *w = new Workspace();
+
+		if (w->counters.alloc(4) != BSGPU_OK || w->flags.alloc(4) != BSGPU_OK) {
+			delete w;
+			return BSGPU_ENOMEM;
+		}
+		CUDA_TRY(cudaMallocHost((void **) &w->h_counters, 4 * sizeof(unsigned long long)));
+		CUDA_TRY(cudaMallocHost((void **) &w->h_flags, 4 * sizeof(int)));
+		g_ws = w;
+	}
+	*out = g_ws;
+	return BSGPU_OK;
+}
+
+static const size_t CAND_MIN = 1u << 20;
+static const size_t CAND_MAX = 1ull << 30;      // records (8 GB)
+
+static int grow(DevBuf<unsigned long long> &buf, size_t need, size_t keep, cudaStream_t st)
+{
+	if (need <= buf.n)
+		return BSGPU_OK;
+	size_t cap = std::max(need + need / 8, CAND_MIN);
+	DevBuf<unsigned long long> nb;
+
+	TRY(nb.alloc(cap));
+	if (keep > 0) {
+		CUDA_TRY(cudaMemcpyAsync(nb.p, buf.p, keep * sizeof(unsigned long long),
+					 cudaMemcpyDeviceToDevice, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+	}
+	std::swap(buf.p, nb.p);
+	std::swap(buf.n, nb.n);
+	return BSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// The matching driver (match_pdict(), src/match_pdict.c:40-77, for one PDict3Parts)
+// ---------------------------------------------------------------------------------------
+
+struct MatchParams {
+	int max_nmis, min_nmis, fixedP, fixedS;
+};
+
+static unsigned int iupac_max_expansions(void)
+{
+	const char *env = getenv("BSGPU_MAX_IUPAC_EXPANSIONS");
+
+	return env ? (unsigned int) strtoul(env, nullptr, 10) : 4096u;
+}
+
+static int read_counter(Workspace *ws, int which, unsigned long long *out, cudaStream_t st)
+{
+	CUDA_TRY(cudaMemcpyAsync(ws->h_counters + which, ws->counters.p + which,
+				 sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	*out = ws->h_counters[which];
+	return BSGPU_OK;
+}
+
+static int write_counter(Workspace *ws, int which, unsigned long long v, cudaStream_t st)
+{
+	ws->h_counters[2] = v;
+	CUDA_TRY(cudaMemcpyAsync(ws->counters.p + which, ws->h_counters + 2,
+				 sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	return BSGPU_OK;
+}
+
+static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, const MatchParams &mp,
+			const BsgpuReport &R, const BsgpuReport &C, int direct,
+			int64_t end_lo, int64_t end_hi, Workspace *ws, cudaStream_t st)
+{
+	// window starts for TB ends in [end_lo, end_hi)
+	int64_t start_lo = end_lo - p3->w + 1, start_hi = end_hi - p3->w + 1;
+
+	if (start_lo < 0)
+		start_lo = 0;
+	if (start_hi <= start_lo)
+		return BSGPU_OK;
+	int64_t nwords = ((start_hi + 31) >> 5) - (start_lo >> 5);
+	BsgpuSubjectView S = subj->view();
+	BsgpuIndexView I = p3->view();
+
+	scan_tb_kernel<<<grid_for(nwords, 256, 8), 256, 0, st>>>(S, I, R, C, direct, start_lo, start_hi);
+	g_launches++;
+	CUDA_TRY(cudaGetLastError());
+	if (!mp.fixedS) {
+		scan_tb_iupac_kernel<<<grid_for(nwords, 128, 16), 128, 0, st>>>(
+			S, I, R, C, direct, start_lo, start_hi, iupac_max_expansions(), ws->flags.p);
+		g_launches++;
+		CUDA_TRY(cudaGetLastError());
+	}
+	return BSGPU_OK;
+}
+
+// Runs one part over the subject's scan range, reporting through R.  `rec_based` tells
+// whether R appends records (then the record buffer may have to grow and a slab rerun).
+static int run_part(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, const MatchParams &mp,
+		    BsgpuReport R, bool rec_based, Workspace *ws, cudaStream_t st, bool allow_sync)
+{
+	if (p3->M == 0 || p3->w == 0)
+		return BSGPU_OK;
+	if (p3->algo == BSGPU_ALGO_TWOBIT && !mp.fixedS)
+		return fail(BSGPU_EINVAL, "cannot treat IUPAC extended letters in the subject "
+			    "as ambiguities when 'pdict' is a PDict object of the \"Twobit\" type");
+	if (subj->kind == SUBJ_CHUNK) {
+		// the halo must cover every letter a reported match can touch
+		int64_t need_l = (int64_t) p3->w - 1 + p3->max_H, need_r = p3->max_T;
+
+		if ((subj->open_left && subj->halo_left < need_l) ||
+		    (subj->open_right && subj->halo_right < need_r))
+			return fail(BSGPU_EINVAL, "subject chunk has an insufficient halo: need %lld "
+				    "letters before and %lld after the report range",
+				    (long long) need_l, (long long) need_r);
+	}
+	bool direct = !p3->has_head && !p3->has_tail && p3->all_singletons;
+	BsgpuReport C = {};
+	int64_t lo = subj->scan_lo, hi = subj->scan_hi;
+
+	if (!mp.fixedS)
+		CUDA_TRY(cudaMemsetAsync(ws->flags.p, 0, sizeof(int), st));
+	if (direct && !rec_based) {
+		// fully asynchronous: counts straight from the scan
+		TRY(launch_scans(p3, subj, mp, R, C, 1, lo, hi, ws, st));
+	} else {
+		if (!allow_sync)
+			return fail(BSGPU_EUNSUPPORTED, "internal: this configuration needs host synchronisation");
+		int64_t a = lo;
+		int64_t slab = hi - lo;
+
+		while (a < hi) {
+			int64_t b = std::min(hi, a + slab);
+			unsigned long long rec_before = 0, ncand = 0, nrec = 0;
+
+			if (rec_based)
+				TRY(read_counter(ws, 1, &rec_before, st));
+			if (direct) {
+				TRY(launch_scans(p3, subj, mp, R, C, 1, a, b, ws, st));
+			} else {
+				TRY(grow(ws->cand, CAND_MIN, 0, st));
+				TRY(write_counter(ws, 0, 0, st));
+				C.mode = BSGPU_R_HIT_TBPOS;
+				C.records = ws->cand.p;
+				C.n_records = ws->counters.p + 0;
+				C.capacity = ws->cand.n;
+				TRY(launch_scans(p3, subj, mp, R, C, 0, a, b, ws, st));
+				TRY(read_counter(ws, 0, &ncand, st));
+				if (ncand > ws->cand.n) {
+					if (ncand <= CAND_MAX) {
+						TRY(grow(ws->cand, (size_t) ncand, 0, st));
+					} else {
+						// too many candidates for one pass: shrink the slab
+						slab = std::max<int64_t>(1024, (int64_t) ((double) (b - a) *
+							((double) CAND_MAX / (double) ncand) * 0.9));
+						TRY(grow(ws->cand, CAND_MAX, 0, st));
+					}
+					continue;       // rerun this slab
+				}
+				if (ncand > 0) {
+					verify_flanks_kernel<<<grid_for((long long) ncand, 256, 8), 256, 0, st>>>(
+						subj->view(), p3->view(), R, ws->cand.p, ncand,
+						mp.max_nmis, mp.min_nmis, mp.fixedP, mp.fixedS);
+					g_launches++;
+					CUDA_TRY(cudaGetLastError());
+				}
+			}
+			if (rec_based) {
+				TRY(read_counter(ws, 1, &nrec, st));
+				if (nrec > R.capacity) {
+					// grow the record buffer, keep what earlier slabs wrote, redo this slab
+					TRY(grow(ws->rec, (size_t) nrec, (size_t) rec_before, st));
+					R.records = ws->rec.p;
+					R.capacity = ws->rec.n;
+					TRY(write_counter(ws, 1, rec_before, st));
+					continue;
+				}
+			}
+			a = b;
+		}
+	}
+	if (!mp.fixedS && allow_sync) {
+		CUDA_TRY(cudaMemcpyAsync(ws->h_flags, ws->flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		if (ws->h_flags[0])
+			return fail(BSGPU_EINVAL, "too many IUPAC ambiguity letters in 'subject'");
+	}
+	return BSGPU_OK;
+}
+
+static int check_args(const bsgpu_pdict3parts *const *parts, int nparts, const bsgpu_subject *subj,
+		      int max_nmis, int min_nmis)
+{
+	if (parts == nullptr || nparts < 1 || subj == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_match(): bad arguments");
+	for (int p = 0; p < nparts; p++) {
+		if (parts[p] == nullptr)
+			return fail(BSGPU_EINVAL, "bsgpu_match(): NULL PDict3Parts handle");
+		if (parts[p]->M != parts[0]->M)
+			return fail(BSGPU_EINVAL, "cannot combine MIndex objects of different lengths");
+	}
+	if (max_nmis < 0 || min_nmis < 0)
+		return fail(BSGPU_EINVAL, "'max.mismatch' and 'min.mismatch' must be non-negative integers");
+	return BSGPU_OK;
+}
+
+// sorts ws->rec[0..n) (optionally uniq) -> result in ws->rec; returns new n
+static int sort_records(Workspace *ws, unsigned long long n, int end_bit, bool uniq,
+			unsigned long long *n_out, cudaStream_t st)
+{
+	*n_out = n;
+	if (n == 0)
+		return BSGPU_OK;
+	TRY(grow(ws->rec2, (size_t) n, 0, st));
+	size_t temp = 0;
+	cub::DoubleBuffer<unsigned long long> db(ws->rec.p, ws->rec2.p);
+	CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, temp, db, (long long) n, 0, end_bit, st));
+	if (temp > ws->cub_temp.n)
+		TRY(ws->cub_temp.alloc(temp));
+	CUDA_TRY(cub::DeviceRadixSort::SortKeys(ws->cub_temp.p, temp, db, (long long) n, 0, end_bit, st));
+	g_launches += 4;
+	if (db.Current() != ws->rec.p) {
+		std::swap(ws->rec.p, ws->rec2.p);
+		std::swap(ws->rec.n, ws->rec2.n);
+	}
+	if (uniq) {
+		TRY(grow(ws->rec2, (size_t) n, 0, st));
+		temp = 0;
+		unsigned long long *d_nsel = ws->counters.p + 3;
+		CUDA_TRY(cub::DeviceSelect::Unique(nullptr, temp, ws->rec.p, ws->rec2.p, d_nsel, (long long) n, st));
+		if (temp > ws->cub_temp.n)
+			TRY(ws->cub_temp.alloc(temp));
+		CUDA_TRY(cub::DeviceSelect::Unique(ws->cub_temp.p, temp, ws->rec.p, ws->rec2.p, d_nsel, (long long) n, st));
+		g_launches += 2;
+		std::swap(ws->rec.p, ws->rec2.p);
+		std::swap(ws->rec.n, ws->rec2.n);
+		TRY(read_counter(ws, 3, n_out, st));
+	}
+	return BSGPU_OK;
+}
+
+static int bits_for(unsigned long long v)
+{
+	int b = 1;
+
+	while (b < 64 && (v >> b) != 0)
+		b++;
+	return b;
+}
+
+extern "C" void bsgpu_result_free(bsgpu_result *res)
+{
+	if (res == nullptr)
+		return;
+	free(res->counts);
+	free(res->dcounts);
+	free(res->which);
+	free(res->ends_offsets);
+	free(res->ends);
+	memset(res, 0, sizeof(*res));
+}
+
+static void which_from_counts(bsgpu_result *res, const int32_t *counts, int32_t M)
+{
+	int64_t n = 0;
+
+	for (int32_t i = 0; i < M; i++)
+		n += counts[i] != 0;
+	res->which = (int32_t *) malloc((size_t) std::max<int64_t>(n, 1) * sizeof(int32_t));
+	res->n_which = n;
+	n = 0;
+	for (int32_t i = 0; i < M; i++)
+		if (counts[i] != 0)
+			res->which[n++] = i + 1;        // sort(ids)+1, src/match_reporting.c:150-161
+}
+
+extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
+		const bsgpu_subject *subj, int max_nmis, int min_nmis, int fixedP, int fixedS,
+		int matches_as, bsgpu_result *res)
+{
+	TRY(check_args(parts, nparts, subj, max_nmis, min_nmis));
+	if (res == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_match(): NULL result");
+	memset(res, 0, sizeof(*res));
+	if (subj->kind == SUBJ_SET)
+		return fail(BSGPU_EINVAL, "please use vmatchPDict() when 'subject' is an XStringSet "
+			    "object (multiple sequence)");
+	if (matches_as == BSGPU_MATCHES_AS_NULL)
+		return BSGPU_OK;
+	if (matches_as != BSGPU_MATCHES_AS_WHICH && matches_as != BSGPU_MATCHES_AS_COUNTS &&
+	    matches_as != BSGPU_MATCHES_AS_ENDS)
+		return fail(BSGPU_EINVAL, "\"%d\": unknown match storing mode", matches_as);
+	TRY(ensure_device());
+	Workspace *ws;
+	TRY(workspace(&ws));
+	cudaStream_t st = 0;
+	MatchParams mp = {max_nmis, min_nmis, fixedP != 0, fixedS != 0};
+	int32_t M = parts[0]->M;
+	res->M = M;
+	DevBuf<int32_t> d_counts;
+	TRY(d_counts.alloc((size_t) M));
+	CUDA_TRY(cudaMemsetAsync(d_counts.p, 0, (size_t) std::max(M, 1) * sizeof(int32_t), st));
+	std::vector<int32_t> counts((size_t) M, 0);
+
+	bool need_records = matches_as == BSGPU_MATCHES_AS_ENDS || nparts > 1;
+	if (!need_records) {
+		BsgpuReport R = {};
+		R.mode = BSGPU_R_COUNT;
+		R.M = M;
+		R.counts = d_counts.p;
+		TRY(run_part(parts[0], subj, mp, R, false, ws, st, true));
+		CUDA_TRY(cudaMemcpyAsync(counts.data(), d_counts.p, (size_t) M * sizeof(int32_t),
+					 cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+	} else {
+		// records: single part keeps the reference's per-view order (TB-end position);
+		// several parts are merged on the end coordinate (sort + uniq,
+		// src/MIndex_class.c:245-260)
+		bool tbpos = nparts == 1;
+		BsgpuReport R = {};
+		unsigned long long nrec = 0;
+
+		TRY(grow(ws->rec, CAND_MIN, 0, st));
+		TRY(write_counter(ws, 1, 0, st));
+		for (int p = 0; p < nparts; p++) {
+			R.mode = tbpos ? BSGPU_R_HIT_TBPOS : BSGPU_R_HIT_COORD;
+			R.M = M;
+			R.records = ws->rec.p;
+			R.n_records = ws->counters.p + 1;
+			R.capacity = ws->rec.n;
+			TRY(run_part(parts[p], subj, mp, R, true, ws, st, true));
+		}
+		TRY(read_counter(ws, 1, &nrec, st));
+		TRY(sort_records(ws, nrec, BSGPU_POS_BITS + bits_for((unsigned long long) std::max(M - 1, 1)),
+				 nparts > 1, &nrec, st));
+		DevBuf<int32_t> d_ends;
+		TRY(d_ends.alloc((size_t) nrec));
+		if (nrec > 0) {
+			finalize_ends_kernel<<<grid_for((long long) nrec, 256, 8), 256, 0, st>>>(
+				subj->view(), parts[0]->has_tail ? parts[0]->d_tail_off.p : nullptr,
+				tbpos ? 1 : 0, ws->rec.p, nrec, d_ends.p, d_counts.p);
+			g_launches++;
+			CUDA_TRY(cudaGetLastError());
+		}
+		CUDA_TRY(cudaMemcpyAsync(counts.data(), d_counts.p, (size_t) M * sizeof(int32_t),
+					 cudaMemcpyDeviceToHost, st));
+		if (matches_as == BSGPU_MATCHES_AS_ENDS) {
+			res->ends = (int32_t *) malloc((size_t) std::max<unsigned long long>(nrec, 1) * sizeof(int32_t));
+			if (res->ends == nullptr)
+				return fail(BSGPU_ENOMEM, "out of host memory");
+			if (nrec > 0)
+				CUDA_TRY(cudaMemcpyAsync(res->ends, d_ends.p, (size_t) nrec * sizeof(int32_t),
+							 cudaMemcpyDeviceToHost, st));
+		}
+		CUDA_TRY(cudaStreamSynchronize(st));
+		if (matches_as == BSGPU_MATCHES_AS_ENDS) {
+			res->n_rows = M;
+			res->ends_offsets = (int64_t *) malloc(((size_t) M + 1) * sizeof(int64_t));
+			res->ends_offsets[0] = 0;
+			for (int32_t i = 0; i < M; i++)
+				res->ends_offsets[i + 1] = res->ends_offsets[i] + counts[i];
+			return BSGPU_OK;
+		}
+	}
+	if (matches_as == BSGPU_MATCHES_AS_COUNTS) {
+		res->counts = (int32_t *) malloc((size_t) std::max(M, 1) * sizeof(int32_t));
+		res->n_counts = M;
+		memcpy(res->counts, counts.data(), (size_t) M * sizeof(int32_t));
+	} else {
+		which_from_counts(res, counts.data(), M);
+	}
+	return BSGPU_OK;
+}
+
+extern "C" int bsgpu_count_device(const bsgpu_pdict3parts *const *parts, int nparts,
+		const bsgpu_subject *subj, int max_nmis, int min_nmis, int fixedP, int fixedS,
+		int32_t *d_counts, void *stream, int *n_launches_out)
+{
+	TRY(check_args(parts, nparts, subj, max_nmis, min_nmis));
+	if (d_counts == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_count_device(): NULL d_counts");
+	TRY(ensure_device());
+	Workspace *ws;
+	TRY(workspace(&ws));
+	cudaStream_t st = (cudaStream_t) stream;
+	MatchParams mp = {max_nmis, min_nmis, fixedP != 0, fixedS != 0};
+	long long before = g_launches;
+	int32_t M = parts[0]->M;
+
+	if (nparts == 1) {
+		BsgpuReport R = {};
+		R.mode = subj->kind == SUBJ_SET ? BSGPU_R_COUNT : BSGPU_R_COUNT;
+		R.M = M;
+		R.counts = d_counts;
+		TRY(run_part(parts[0], subj, mp, R, false, ws, st, true));
+	} else {
+		BsgpuReport R = {};
+		unsigned long long nrec = 0;
+
+		TRY(grow(ws->rec, CAND_MIN, 0, st));
+		TRY(write_counter(ws, 1, 0, st));
+		for (int p = 0; p < nparts; p++) {
+			R.mode = BSGPU_R_HIT_COORD;
+			R.M = M;
+			R.records = ws->rec.p;
+			R.n_records = ws->counters.p + 1;
+			R.capacity = ws->rec.n;
+			TRY(run_part(parts[p], subj, mp, R, true, ws, st, true));
+		}
+		TRY(read_counter(ws, 1, &nrec, st));
+		TRY(sort_records(ws, nrec, BSGPU_POS_BITS + bits_for((unsigned long long) std::max(M - 1, 1)),
+				 true, &nrec, st));
+		if (nrec > 0) {
+			DevBuf<int32_t> d_ends;
+			TRY(d_ends.alloc((size_t) nrec));
+			finalize_ends_kernel<<<grid_for((long long) nrec, 256, 8), 256, 0, st>>>(
+				subj->view(), nullptr, 0, ws->rec.p, nrec, d_ends.p, d_counts);
+			g_launches++;
+			CUDA_TRY(cudaGetLastError());
+			CUDA_TRY(cudaStreamSynchronize(st));
+		}
+	}
+	if (n_launches_out)
+		*n_launches_out = (int) (g_launches - before);
+	return BSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// vmatch: vcountPDict / vwhichPDict on a set of subjects (src/match_pdict.c:320-346,386-432)
+// ---------------------------------------------------------------------------------------
+
+extern "C" int bsgpu_vmatch(const bsgpu_pdict3parts *const *parts, int nparts,
+		const bsgpu_subject *subj, int max_nmis, int min_nmis, int fixedP, int fixedS,
+		int collapse, int weight_is_double, const void *weight, int64_t weight_length,
+		int matches_as, bsgpu_result *res)
+{
+	TRY(check_args(parts, nparts, subj, max_nmis, min_nmis));
+	if (res == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_vmatch(): NULL result");
+	memset(res, 0, sizeof(*res));
+	if (subj->kind != SUBJ_SET)
+		return fail(BSGPU_EINVAL, "please use matchPDict() when 'subject' is an XString or "
+			    "MaskedXString object (single sequence)");
+	if (matches_as == BSGPU_MATCHES_AS_NULL)
+		return fail(BSGPU_EINVAL, "vmatch_PDict3Parts_XStringSet() does not support "
+			    "'matches_as=\"MATCHES_AS_NULL\"' yet, sorry");
+	if (matches_as != BSGPU_MATCHES_AS_WHICH && matches_as != BSGPU_MATCHES_AS_COUNTS)
+		return fail(BSGPU_EINVAL, "vmatchPDict() is not supported yet, sorry");
+	if (nparts > 1 && matches_as != BSGPU_MATCHES_AS_WHICH)
+		return fail(BSGPU_EINVAL, "MTB_PDict objects are not supported yet, sorry");
+	TRY(ensure_device());
+	Workspace *ws;
+	TRY(workspace(&ws));
+	cudaStream_t st = 0;
+	MatchParams mp = {max_nmis, min_nmis, fixedP != 0, fixedS != 0};
+	int32_t M = parts[0]->M;
+	int64_t N = subj->nseg;
+	res->M = M;
+
+	bool records = matches_as == BSGPU_MATCHES_AS_WHICH || (collapse != 0 && weight_is_double);
+	if (matches_as == BSGPU_MATCHES_AS_COUNTS) {
+		if (collapse < 0 || collapse > 2)
+			return fail(BSGPU_EINVAL, "'collapse' must be FALSE, 1 or 2");
+		if (collapse != 0) {
+			int64_t need = collapse == 1 ? N : M;
+
+			if (weight == nullptr || weight_length != need)
+				return fail(BSGPU_EINVAL, "'weight' must have length %lld", (long long) need);
+		}
+	}
+	if (!records) {
+		int64_t n_out = collapse == 0 ? (int64_t) M * N : (collapse == 1 ? M : N);
+		DevBuf<int32_t> d_out, d_w;
+		BsgpuReport R = {};
+
+		if (collapse == 0 && n_out > (int64_t) INT32_MAX)
+			return fail(BSGPU_EINVAL, "allocMatrix: too many elements specified");
+		TRY(d_out.alloc((size_t) n_out));
+		CUDA_TRY(cudaMemsetAsync(d_out.p, 0, (size_t) std::max<int64_t>(n_out, 1) * sizeof(int32_t), st));
+		R.M = M;
+		R.counts = d_out.p;
+		if (collapse == 0) {
+			R.mode = BSGPU_R_VMAT;
+		} else {
+			TRY(d_w.upload((const int32_t *) weight, (size_t) weight_length));
+			R.mode = collapse == 1 ? BSGPU_R_VC1 : BSGPU_R_VC2;
+			R.weight = d_w.p;
+		}
+		TRY(run_part(parts[0], subj, mp, R, false, ws, st, true));
+		res->counts = (int32_t *) malloc((size_t) std::max<int64_t>(n_out, 1) * sizeof(int32_t));
+		res->n_counts = n_out;
+		if (n_out > 0)
+			CUDA_TRY(cudaMemcpyAsync(res->counts, d_out.p, (size_t) n_out * sizeof(int32_t),
+						 cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		return BSGPU_OK;
+	}
+	// record-based: (segment << 30 | key), sorted
+	BsgpuReport R = {};
+	unsigned long long nrec = 0;
+	TRY(grow(ws->rec, CAND_MIN, 0, st));
+	TRY(write_counter(ws, 1, 0, st));
+	for (int p = 0; p < nparts; p++) {
+		R.mode = BSGPU_R_SEGKEY;
+		R.M = M;
+		R.records = ws->rec.p;
+		R.n_records = ws->counters.p + 1;
+		R.capacity = ws->rec.n;
+		TRY(run_part(parts[p], subj, mp, R, true, ws, st, true));
+	}
+	TRY(read_counter(ws, 1, &nrec, st));
+	bool uniq = matches_as == BSGPU_MATCHES_AS_WHICH;
+	TRY(sort_records(ws, nrec, BSGPU_SEGKEY_BITS + bits_for((unsigned long long) std::max<int64_t>(N - 1, 1)),
+			 uniq, &nrec, st));
+	std::vector<unsigned long long> h((size_t) nrec);
+	if (nrec > 0)
+		CUDA_TRY(cudaMemcpy(h.data(), ws->rec.p, (size_t) nrec * sizeof(unsigned long long),
+				    cudaMemcpyDeviceToHost));
+	const unsigned long long keymask = (1ull << BSGPU_SEGKEY_BITS) - 1;
+	if (matches_as == BSGPU_MATCHES_AS_WHICH) {
+		res->n_rows = N;
+		res->ends_offsets = (int64_t *) calloc((size_t) N + 1, sizeof(int64_t));
+		res->ends = (int32_t *) malloc((size_t) std::max<unsigned long long>(nrec, 1) * sizeof(int32_t));
+		for (size_t t = 0; t < h.size(); t++) {
+			res->ends_offsets[(h[t] >> BSGPU_SEGKEY_BITS) + 1]++;
+			res->ends[t] = (int32_t) (h[t] & keymask) + 1;
+		}
+		for (int64_t j = 0; j < N; j++)
+			res->ends_offsets[j + 1] += res->ends_offsets[j];
+		return BSGPU_OK;
+	}
+	// double weights: fold on the host in the reference's order (subject-major, pattern
+	// inner; src/match_pdict.c:409-427) from exact integer counts
+	const double *wd = (const double *) weight;
+	int64_t n_out = collapse == 1 ? M : N;
+	res->dcounts = (double *) calloc((size_t) std::max<int64_t>(n_out, 1), sizeof(double));
+	res->n_counts = n_out;
+	for (size_t t = 0; t < h.size();) {
+		size_t u = t;
+
+		while (u < h.size() && h[u] == h[t])
+			u++;
+		int64_t j = (int64_t) (h[t] >> BSGPU_SEGKEY_BITS), i = (int64_t) (h[t] & keymask);
+		int cnt = (int) (u - t);
+		if (collapse == 1)
+			res->dcounts[i] += cnt * wd[j];
+		else
+			res->dcounts[j] += cnt * wd[i];
+		t = u;
+	}
+	return BSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Host-buffer entry points with the reference's .Call shapes
+// ---------------------------------------------------------------------------------------
+
+extern "C" int bsgpu_match_PDict3Parts_XString(const bsgpu_pdict3parts *p3,
+		const uint8_t *subject, int64_t subject_length,
+		int max_nmis, int min_nmis, int fixedP, int fixedS, int matches_as, bsgpu_result *res)
+{
+	bsgpu_subject *s = nullptr;
+
+	TRY(bsgpu_subject_xstring(subject, subject_length, &s));
+	int rc = bsgpu_match(&p3, 1, s, max_nmis, min_nmis, fixedP, fixedS, matches_as, res);
+	bsgpu_subject_free(s);
+	return rc;
+}
+
+extern "C" int bsgpu_match_PDict3Parts_XStringViews(const bsgpu_pdict3parts *p3,
+		const uint8_t *subject, int64_t subject_length,
+		const int32_t *views_start, const int32_t *views_width, int32_t nviews,
+		int max_nmis, int min_nmis, int fixedP, int fixedS, int matches_as, bsgpu_result *res)
+{
+	bsgpu_subject *s = nullptr;
+
+	TRY(bsgpu_subject_views(subject, subject_length, views_start, views_width, nviews, &s));
+	int rc = bsgpu_match(&p3, 1, s, max_nmis, min_nmis, fixedP, fixedS, matches_as, res);
+	bsgpu_subject_free(s);
+	return rc;
+}
+
+extern "C" int bsgpu_vmatch_PDict3Parts_XStringSet(const bsgpu_pdict3parts *p3,
+		const uint8_t *subject_concat, const int32_t *subject_widths, int32_t nsubject,
+		int max_nmis, int min_nmis, int fixedP, int fixedS,
+		int collapse, int weight_is_double, const void *weight, int64_t weight_length,
+		int matches_as, bsgpu_result *res)
+{
+	bsgpu_subject *s = nullptr;
+
+	TRY(bsgpu_subject_set(subject_concat, subject_widths, nsubject, &s));
+	int rc = bsgpu_vmatch(&p3, 1, s, max_nmis, min_nmis, fixedP, fixedS, collapse,
+			      weight_is_double, weight, weight_length, matches_as, res);
+	bsgpu_subject_free(s);
+	return rc;
+}
+
+// ByPos_MIndex_combine (src/MIndex_class.c:230-263): per row, sorted distinct union.
+extern "C" int bsgpu_mindex_combine(const bsgpu_result *const *comps, int ncomps, bsgpu_result *res)
+{
+	if (comps == nullptr || ncomps < 1 || res == nullptr)
+		return fail(BSGPU_EINVAL, "nothing to combine");
+	memset(res, 0, sizeof(*res));
+	int64_t rows = comps[0]->n_rows;
+	for (int j = 1; j < ncomps; j++)
+		if (comps[j]->n_rows != rows)
+			return fail(BSGPU_EINVAL, "cannot combine MIndex objects of different lengths");
+	std::vector<int32_t> all, buf;
+	std::vector<int64_t> off((size_t) rows + 1, 0);
+	for (int64_t i = 0; i < rows; i++) {
+		buf.clear();
+		for (int j = 0; j < ncomps; j++)
+			buf.insert(buf.end(), comps[j]->ends + comps[j]->ends_offsets[i],
+				   comps[j]->ends + comps[j]->ends_offsets[i + 1]);
+		std::sort(buf.begin(), buf.end());
+		buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
+		all.insert(all.end(), buf.begin(), buf.end());
+		off[i + 1] = (int64_t) all.size();
+	}
+	res->M = comps[0]->M;
+	res->n_rows = rows;
+	res->ends_offsets = (int64_t *) malloc(((size_t) rows + 1) * sizeof(int64_t));
+	memcpy(res->ends_offsets, off.data(), ((size_t) rows + 1) * sizeof(int64_t));
+	res->ends = (int32_t *) malloc(std::max<size_t>(all.size(), 1) * sizeof(int32_t));
+	memcpy(res->ends, all.data(), all.size() * sizeof(int32_t));
+	return BSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Roofline probes
+// ---------------------------------------------------------------------------------------
+
+extern "C" int bsgpu_probe_peaks(double *copy_gbs, double *l2_gather_gsectors, int64_t table_bytes)
+{
+	TRY(ensure_device());
+	cudaEvent_t e0, e1;
+	CUDA_TRY(cudaEventCreate(&e0));
+	CUDA_TRY(cudaEventCreate(&e1));
+	float ms = 0;
+	if (copy_gbs) {
+		const int64_t n = (1ll << 30) / 16;     // 1 GiB
+		DevBuf<uint4> a, b;
+		TRY(a.alloc((size_t) n));
+		TRY(b.alloc((size_t) n));
+		CUDA_TRY(cudaMemset(a.p, 1, (size_t) n * 16));
+		double best = 0;
+		for (int it = 0; it < 6; it++) {
+			CUDA_TRY(cudaEventRecord(e0));
+			probe_copy_kernel<<<g_num_sms * 16, 256>>>(a.p, b.p, n);
+			g_launches++;
+			CUDA_TRY(cudaEventRecord(e1));
+			CUDA_TRY(cudaEventSynchronize(e1));
+			CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+			best = std::max(best, 2.0 * n * 16 / (ms * 1e-3) / 1e9);
+		}
+		*copy_gbs = best;
+	}
+	if (l2_gather_gsectors) {
+		int64_t nb = 16;
+		while (nb * 2 * 16 <= table_bytes)
+			nb *= 2;
+		DevBuf<uint4> t;
+		DevBuf<unsigned long long> sink;
+		TRY(t.alloc((size_t) nb));
+		TRY(sink.alloc(1));
+		CUDA_TRY(cudaMemset(t.p, 0, (size_t) nb * 16));
+		const int iters = 4096, blocks = g_num_sms * 8, threads = 256;
+		double best = 0;
+		for (int it = 0; it < 6; it++) {
+			CUDA_TRY(cudaEventRecord(e0));
+			probe_gather_kernel<<<blocks, threads>>>(t.p, (uint32_t) (nb - 1), iters, sink.p);
+			g_launches++;
+			CUDA_TRY(cudaEventRecord(e1));
+			CUDA_TRY(cudaEventSynchronize(e1));
+			CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+			best = std::max(best, (double) blocks * threads * iters / (ms * 1e-3) / 1e9);
+		}
+		*l2_gather_gsectors = best;
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	return BSGPU_OK;
+}

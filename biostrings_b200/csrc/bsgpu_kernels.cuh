@@ -1,0 +1,570 @@
+// bsgpu_kernels.cuh -- sm_100a kernels of the PDict matching path.
+//
+//   pack_subject_kernel   bytes -> 2-bit code plane + validity planes (HBM streaming)
+//   scan_tb_kernel        fixedS=TRUE Trusted-Band scan: one hash probe per window
+//                         (replaces walk_subject, src/match_pdict_Twobit.c:158-175 and
+//                          walk_tb_subject, src/match_pdict_ACtree2.c:1001-1021)
+//   scan_tb_iupac_kernel  fixedS=FALSE windows that hold an IUPAC ambiguity letter
+//                         (replaces walk_tb_nonfixed_subject, match_pdict_ACtree2.c:1124-1157)
+//   verify_flanks_kernel  head/tail mismatch counting + fan-out to TB duplicates
+//                         (replaces _match_pdict_all_flanks, src/match_pdict_utils.c:809-915)
+//   finalize_ends_kernel  sorted records -> end coordinates
+#pragma once
+#include <cooperative_groups.h>
+#include "bsgpu_common.cuh"
+
+namespace cg = cooperative_groups;
+
+// ------------------------------------------------------------------------------------
+// Packing: 32 letters per thread.
+// ------------------------------------------------------------------------------------
+
+// For a 32-bit word holding 4 letters: 8 code bits, 4 valid bits, 4 iupac bits.
+__device__ __forceinline__ void pack4(uint32_t x, uint32_t &code8, uint32_t &valid4, uint32_t &iupac4)
+{
+	// code = (b>>1) - (b>>3) restated with ORs: bit0 = b1|b3, bit1 = b2|b3
+	uint32_t c = ((x | (x >> 2)) & 0x02020202u) | ((x | (x >> 1)) & 0x04040404u);
+	code8 = ((c >> 1) * 0x01041040u) >> 24;
+	// byte != 0
+	uint32_t nz = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+	// byte >= 16
+	uint32_t hi = x & 0xF0F0F0F0u;
+	uint32_t ge16 = (((hi & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | hi) & 0x80808080u;
+	uint32_t iu = nz & ~ge16;
+	// b & (b-1) != 0  (not a power of two); bit 7 blocks the borrow between bytes
+	uint32_t z = x & ((x | 0x80808080u) - 0x01010101u) & 0x7F7F7F7Fu;
+	uint32_t np2 = (z + 0x7F7F7F7Fu) & 0x80808080u;
+	uint32_t va = iu & ~np2;
+	iupac4 = (((iu >> 7) * 0x00204081u) >> 21) & 0xFu;
+	valid4 = (((va >> 7) * 0x00204081u) >> 21) & 0xFu;
+	// non-base letters get code 0 so that equal keys imply equal letters only when valid
+	code8 &= (valid4 & 1u ? 0x03u : 0u) | (valid4 & 2u ? 0x0Cu : 0u)
+	       | (valid4 & 4u ? 0x30u : 0u) | (valid4 & 8u ? 0xC0u : 0u);
+}
+
+__global__ void __launch_bounds__(256)
+pack_subject_kernel(const uint8_t *__restrict__ bytes, int64_t nwords,
+		    uint64_t *__restrict__ codes, uint32_t *__restrict__ valid,
+		    uint32_t *__restrict__ iupac)
+{
+	int64_t j = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (; j < nwords; j += stride) {
+		const uint4 *src = reinterpret_cast<const uint4 *>(bytes + 32 * j);
+		uint4 a = __ldcs(src), b = __ldcs(src + 1);
+		uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+		uint64_t c = 0;
+		uint32_t v = 0, u = 0;
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			uint32_t c8, v4, u4;
+
+			pack4(w[k], c8, v4, u4);
+			c |= (uint64_t) c8 << (8 * k);
+			v |= v4 << (4 * k);
+			u |= u4 << (4 * k);
+		}
+		codes[j] = c;
+		valid[j] = v;
+		iupac[j] = u;
+	}
+}
+
+// ------------------------------------------------------------------------------------
+// Reporting a match (shared by the scan and verify kernels).
+// ------------------------------------------------------------------------------------
+
+__device__ __forceinline__ int find_segment(const BsgpuSubjectView &S, int64_t e)
+{
+	// last segment with seg_start <= e
+	int lo = 0, hi = S.nseg - 1;
+
+	while (lo < hi) {
+		int mid = (lo + hi + 1) >> 1;
+
+		if (__ldg(S.seg_start + mid) <= e)
+			lo = mid;
+		else
+			hi = mid - 1;
+	}
+	return lo;
+}
+
+__device__ __forceinline__ void append_record(const BsgpuReport &R, unsigned long long rec)
+{
+	cg::coalesced_group g = cg::coalesced_threads();
+	unsigned long long base = 0;
+
+	if (g.thread_rank() == 0)
+		base = atomicAdd(R.n_records, (unsigned long long) g.size());
+	base = g.shfl(base, 0);
+	unsigned long long idx = base + g.thread_rank();
+	if (idx < R.capacity)
+		R.records[idx] = rec;
+}
+
+// key: 0-based pattern id; seg: segment of the subject; n: 1-based local TB end;
+// e: concat index of the TB end; Tlen: tail width of 'key'.
+__device__ __forceinline__ void report_match(const BsgpuReport &R, const BsgpuSubjectView &S,
+		int key, int seg, int64_t n, int64_t e, int Tlen)
+{
+	switch (R.mode) {
+	case BSGPU_R_COUNT:
+		atomicAdd(R.counts + key, 1);
+		break;
+	case BSGPU_R_HIT_COORD: {
+		// end = tb_end + |tail|   (src/match_pdict_utils.c:99-106)
+		unsigned long long end = (unsigned long long) (n + Tlen + __ldg(S.seg_coord + seg));
+		append_record(R, ((unsigned long long) key << BSGPU_POS_BITS) | end);
+		break;
+	}
+	case BSGPU_R_HIT_TBPOS:
+		append_record(R, ((unsigned long long) key << BSGPU_POS_BITS) | (unsigned long long) e);
+		break;
+	case BSGPU_R_VMAT:
+		atomicAdd(R.counts + (int64_t) seg * R.M + key, 1);
+		break;
+	case BSGPU_R_VC1:
+		atomicAdd(R.counts + key, __ldg(R.weight + seg));
+		break;
+	case BSGPU_R_VC2:
+		atomicAdd(R.counts + seg, __ldg(R.weight + key));
+		break;
+	case BSGPU_R_SEGKEY:
+		append_record(R, ((unsigned long long) seg << BSGPU_SEGKEY_BITS) | (unsigned long long) key);
+		break;
+	}
+}
+
+// A confirmed Trusted-Band hit of TB id 'tb_id' ending at concat index e.
+// direct != 0: no head/tail and singleton TB groups -> report right away; otherwise the
+// hit becomes a candidate record (tb_id << 34 | e) for verify_flanks_kernel.
+__device__ __forceinline__ void tb_hit(const BsgpuIndexView &I, const BsgpuSubjectView &S,
+		const BsgpuReport &R, const BsgpuReport &C, int direct, int tb_id, int64_t e)
+{
+	if (!direct) {
+		append_record(C, ((unsigned long long) tb_id << BSGPU_POS_BITS) | (unsigned long long) e);
+		return;
+	}
+	if (R.mode == BSGPU_R_COUNT) {
+		atomicAdd(R.counts + tb_id, 1);
+		return;
+	}
+	int seg = S.nseg == 1 ? 0 : find_segment(S, e);
+	int64_t n = e - __ldg(S.seg_start + seg) + 1;
+	report_match(R, S, tb_id, seg, n, e, 0);
+}
+
+// ------------------------------------------------------------------------------------
+// Hash probe.
+// ------------------------------------------------------------------------------------
+
+// Slow path of a probe whose first bucket was full or held a fingerprint match.
+__device__ __noinline__ int probe_slow(const BsgpuIndexView &I, uint64_t key, uint32_t bucket,
+				       uint32_t fp, uint4 b)
+{
+	for (;;) {
+		if (b.x == fp && b.y != BSGPU_EMPTY_ID && __ldg(I.keys + b.y) == key)
+			return (int) b.y;
+		if (b.z == fp && b.w != BSGPU_EMPTY_ID && __ldg(I.keys + b.w) == key)
+			return (int) b.w;
+		if (b.w == BSGPU_EMPTY_ID)
+			return -1;      // bucket not full: the key would have been placed here
+		bucket = (bucket + 1) & I.bucket_mask;
+		b = __ldg(I.table + bucket);
+	}
+}
+
+__device__ __forceinline__ int probe(const BsgpuIndexView &I, uint64_t key)
+{
+	uint32_t top, fp;
+
+	bsgpu_hash(key, top, fp);
+	uint32_t bucket = top >> I.bucket_shift;
+	uint4 b = __ldg(I.table + bucket);
+	if (b.w == BSGPU_EMPTY_ID && b.x != fp && b.z != fp)
+		return -1;
+	return probe_slow(I, key, bucket, fp, b);
+}
+
+// For TB widths > 32 the hash covers the first 32 letters; the rest is compared here.
+// fixedS: s == t; otherwise s < 16 && (s & t) != 0  (TB letters t are base letters).
+__device__ __forceinline__ bool tb_rest_matches(const BsgpuIndexView &I, const BsgpuSubjectView &S,
+		int tb_id, int64_t e, int fixedS)
+{
+	const uint8_t *t = I.tb_bytes + (int64_t) tb_id * I.w;
+	const uint8_t *s = S.bytes + (e - I.w + 1);
+
+	for (int i = 32; i < I.w; i++) {
+		uint32_t sb = s[i], tb = t[i];
+
+		if (fixedS ? sb != tb : (sb >= 16 || (sb & tb) == 0))
+			return false;
+	}
+	return true;
+}
+
+// TB leaders sharing a 32-letter seed are chained; with fixedS at most one can match.
+__device__ __forceinline__ int resolve_long_tb(const BsgpuIndexView &I, const BsgpuSubjectView &S,
+		int id, int64_t e, int fixedS)
+{
+	for (; id >= 0; id = __ldg(I.seed_next + id))
+		if (tb_rest_matches(I, S, id, e, fixedS))
+			return id;
+	return -1;
+}
+
+// mask bit r set iff bits r..r+w-1 of v are all set (w in 1..64)
+__device__ __forceinline__ uint64_t all_set_run(uint64_t v, int w)
+{
+	uint64_t m = v;
+	int have = 1;           // m bit r <=> v[r .. r+have-1] all set
+
+	while (have * 2 <= w) {
+		m &= m >> have;
+		have *= 2;
+	}
+	if (have < w)
+		m &= m >> (w - have);
+	return m;
+}
+
+// ------------------------------------------------------------------------------------
+// Trusted-Band scan, fixedS = TRUE: every window of w base letters is looked up.
+// Thread t handles the 32 window starts of code word j; windows may extend into words
+// j+1 (and j+2 when w > 32: only the first 32 letters are hashed, the rest compared).
+// ------------------------------------------------------------------------------------
+
+#define SCAN_GROUP 8
+
+__global__ void __launch_bounds__(256)
+scan_tb_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R, BsgpuReport C,
+	       int direct, int64_t start_lo, int64_t start_hi)
+{
+	// window starts c0 in [start_lo, start_hi)
+	int64_t word_lo = start_lo >> 5, word_hi = (start_hi + 31) >> 5;
+	int64_t j = word_lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	const int w = I.w, sw = I.seed_w;
+
+	for (; j < word_hi; j += stride) {
+		uint64_t c0 = __ldcs(S.codes + j), c1 = __ldcs(S.codes + j + 1);
+		uint64_t v = (uint64_t) __ldcs(S.valid + j) | ((uint64_t) __ldcs(S.valid + j + 1) << 32);
+		uint32_t m;
+
+		if (w <= 32) {
+			m = (uint32_t) all_set_run(v, w);
+		} else {
+			// windows of 33..64 letters: need valid bits of a third word
+			uint64_t v2 = (uint64_t) __ldcs(S.valid + j + 1) |
+				      ((uint64_t) __ldcs(S.valid + j + 2) << 32);
+			// first 32 letters valid, then letters 32..w-1 valid
+			uint32_t m_lo = (uint32_t) all_set_run(v, 32);
+			uint32_t m_hi = (uint32_t) all_set_run(v2, w - 32);
+			m = m_lo & m_hi;
+		}
+		// clip to [start_lo, start_hi)
+		int64_t base = j << 5;
+		if (base < start_lo)
+			m &= 0xFFFFFFFFu << (int) (start_lo - base);
+		if (base + 32 > start_hi)
+			m &= (start_hi - base) <= 0 ? 0u : 0xFFFFFFFFu >> (int) (base + 32 - start_hi);
+		if (m == 0)
+			continue;
+#pragma unroll
+		for (int g = 0; g < 32; g += SCAN_GROUP) {
+			uint64_t key[SCAN_GROUP];
+			uint32_t fp[SCAN_GROUP], bucket[SCAN_GROUP];
+			uint4 b[SCAN_GROUP];
+
+			if (((m >> g) & ((1u << SCAN_GROUP) - 1)) == 0)
+				continue;
+#pragma unroll
+			for (int q = 0; q < SCAN_GROUP; q++) {
+				const int r = g + q;
+				uint64_t k = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
+				uint32_t top;
+
+				key[q] = k & I.seed_mask;
+				bsgpu_hash(key[q], top, fp[q]);
+				bucket[q] = top >> I.bucket_shift;
+			}
+#pragma unroll
+			for (int q = 0; q < SCAN_GROUP; q++) {
+				if ((m >> (g + q)) & 1u)
+					b[q] = __ldg(I.table + bucket[q]);
+				else
+					b[q] = make_uint4(0, BSGPU_EMPTY_ID, 0, BSGPU_EMPTY_ID);
+			}
+#pragma unroll
+			for (int q = 0; q < SCAN_GROUP; q++) {
+				// an empty, non-matching first bucket is the common case
+				bool rare = (m >> (g + q)) & 1u;
+
+				rare = rare && !(b[q].w == BSGPU_EMPTY_ID &&
+						 (b[q].y == BSGPU_EMPTY_ID || b[q].x != fp[q]));
+				if (rare) {
+					int id = probe_slow(I, key[q], bucket[q], fp[q], b[q]);
+					int64_t e = base + g + q + w - 1;
+
+					if (w > 32)
+						id = resolve_long_tb(I, S, id, e, 1);
+					if (id >= 0)
+						tb_hit(I, S, R, C, direct, id, e);
+				}
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------
+// Trusted-Band scan, fixedS = FALSE, windows holding at least one IUPAC ambiguity letter
+// (all-base windows are handled by scan_tb_kernel: for them (s & t) != 0 <=> s == t).
+// A window matches TB word t iff every letter is < 16 (and not 0) and shares a bit with
+// t[i]; all expansions of the ambiguity letters are looked up.  Windows whose number of
+// expansions exceeds max_expansions raise *too_many (the reference errors the same way
+// when its node set overflows, src/match_pdict_ACtree2.c:1051-1054).
+// ------------------------------------------------------------------------------------
+
+#define IUPAC_MAX_AMBIG 12
+
+__global__ void __launch_bounds__(128)
+scan_tb_iupac_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R, BsgpuReport C,
+		     int direct, int64_t start_lo, int64_t start_hi,
+		     unsigned int max_expansions, int *too_many)
+{
+	int64_t word_lo = start_lo >> 5, word_hi = (start_hi + 31) >> 5;
+	int64_t j = word_lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	const int w = I.w, sw = I.seed_w;
+
+	for (; j < word_hi; j += stride) {
+		uint64_t u0 = (uint64_t) __ldg(S.iupac + j) | ((uint64_t) __ldg(S.iupac + j + 1) << 32);
+		uint64_t v0 = (uint64_t) __ldg(S.valid + j) | ((uint64_t) __ldg(S.valid + j + 1) << 32);
+		uint32_t m_iu, m_va;
+
+		if (w <= 32) {
+			m_iu = (uint32_t) all_set_run(u0, w);
+			m_va = (uint32_t) all_set_run(v0, w);
+		} else {
+			uint64_t u1 = (uint64_t) __ldg(S.iupac + j + 1) | ((uint64_t) __ldg(S.iupac + j + 2) << 32);
+			uint64_t v1 = (uint64_t) __ldg(S.valid + j + 1) | ((uint64_t) __ldg(S.valid + j + 2) << 32);
+			m_iu = (uint32_t) all_set_run(u0, 32) & (uint32_t) all_set_run(u1, w - 32);
+			m_va = (uint32_t) all_set_run(v0, 32) & (uint32_t) all_set_run(v1, w - 32);
+		}
+		uint32_t m = m_iu & ~m_va;      // IUPAC-only windows that are not all-base
+		int64_t base = j << 5;
+		if (base < start_lo)
+			m &= 0xFFFFFFFFu << (int) (start_lo - base);
+		if (base + 32 > start_hi)
+			m &= (start_hi - base) <= 0 ? 0u : 0xFFFFFFFFu >> (int) (base + 32 - start_hi);
+		while (m) {
+			int r = __ffs(m) - 1;
+			m &= m - 1;
+			int64_t c0 = base + r, e = c0 + w - 1;
+			const uint8_t *s = S.bytes + c0;
+			// ambiguity letters inside the hashed seed (first sw letters)
+			uint64_t key0 = 0;
+			int apos[IUPAC_MAX_AMBIG], namb = 0;
+			uint32_t alet[IUPAC_MAX_AMBIG];
+			unsigned long long total = 1;
+			bool overflow = false;
+
+			for (int i = 0; i < sw; i++) {
+				uint32_t b = s[i];
+
+				if (bsgpu_is_base(b)) {
+					key0 |= (uint64_t) bsgpu_base_code(b) << (2 * i);
+				} else {
+					total *= __popc(b);
+					if (namb == IUPAC_MAX_AMBIG || total > max_expansions) {
+						overflow = true;
+						break;
+					}
+					apos[namb] = i;
+					alet[namb] = b;
+					namb++;
+				}
+			}
+			if (overflow) {
+				atomicExch(too_many, 1);
+				continue;
+			}
+			for (unsigned long long combo = 0; combo < total; combo++) {
+				uint64_t key = key0;
+				unsigned long long rem = combo;
+
+				for (int a = 0; a < namb; a++) {
+					uint32_t let = alet[a];
+					int nb = __popc(let), d = (int) (rem % nb);
+
+					rem /= nb;
+					// d-th set bit of the letter
+					for (int q = 0; q < d; q++)
+						let &= let - 1;
+					uint32_t bit = let & (0u - let);
+					key |= (uint64_t) bsgpu_base_code(bit) << (2 * apos[a]);
+				}
+				int id = probe(I, key);
+				if (w > 32) {
+					// several TB words may share the seed and match the
+					// (ambiguous) rest: report each of them
+					for (; id >= 0; id = __ldg(I.seed_next + id))
+						if (tb_rest_matches(I, S, id, e, 0))
+							tb_hit(I, S, R, C, direct, id, e);
+				} else if (id >= 0) {
+					tb_hit(I, S, R, C, direct, id, e);
+				}
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------
+// Flank verification.  One thread per candidate (tb_id, e); the thread walks the TB
+// duplicate group {key0} U low2high[key0] (src/match_pdict_utils.c:153-181) and counts
+// head-then-tail mismatches with the reference's early exit (:183-214); letters outside
+// the segment count as mismatches (src/lowlevel_matching.c:79-86).
+// ------------------------------------------------------------------------------------
+
+__device__ __forceinline__ bool letters_match(uint32_t p, uint32_t s, int fixedP, int fixedS)
+{
+	// src/lowlevel_matching.c:26-56, on the raw code bytes
+	if (fixedP)
+		return fixedS ? p == s : (p & ~s & 0xFFu) == 0;
+	return fixedS ? (~p & s & 0xFFu) == 0 : (p & s) != 0;
+}
+
+__device__ __forceinline__ int count_mismatches(const uint8_t *__restrict__ P, int Plen,
+		const uint8_t *__restrict__ seg, int64_t L, int64_t shift, int max_nmis,
+		int fixedP, int fixedS)
+{
+	// src/lowlevel_matching.c:66-89 (_nmismatch_at_Pshift)
+	int nmis = 0;
+
+	for (int i = 0; i < Plen; i++) {
+		int64_t jj = shift + i;
+
+		if (jj >= 0 && jj < L && letters_match(P[i], seg[jj], fixedP, fixedS))
+			continue;
+		if (nmis++ >= max_nmis)
+			break;
+	}
+	return nmis;
+}
+
+__global__ void __launch_bounds__(256)
+verify_flanks_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R,
+		     const unsigned long long *__restrict__ cand, unsigned long long ncand,
+		     int max_nmis, int min_nmis, int fixedP, int fixedS)
+{
+	unsigned long long t = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+
+	for (; t < ncand; t += stride) {
+		unsigned long long rec = cand[t];
+		int key0 = (int) (rec >> BSGPU_POS_BITS);
+		int64_t e = (int64_t) (rec & BSGPU_POS_MASK);
+		int seg = S.nseg == 1 ? 0 : find_segment(S, e);
+		int64_t lo = __ldg(S.seg_start + seg), L = __ldg(S.seg_len + seg);
+		int64_t n = e - lo + 1;                 // 1-based TB end inside the segment
+		const uint8_t *segp = S.bytes + lo;
+		int g0 = __ldg(I.grp_off + key0), g1 = __ldg(I.grp_off + key0 + 1);
+
+		for (int g = g0; g < g1; g++) {
+			int key = __ldg(I.grp_keys + g);
+			int64_t h0 = I.head ? __ldg(I.head_off + key) : 0;
+			int Hlen = I.head ? (int) (__ldg(I.head_off + key + 1) - h0) : 0;
+			int64_t t0 = I.tail ? __ldg(I.tail_off + key) : 0;
+			int Tlen = I.tail ? (int) (__ldg(I.tail_off + key + 1) - t0) : 0;
+			// src/match_pdict_utils.c:199-214: Hshift = tb_end - |H| - w, Tshift = tb_end
+			int nmis = count_mismatches(I.head + h0, Hlen, segp, L, n - Hlen - I.w,
+						    max_nmis, fixedP, fixedS);
+			if (nmis <= max_nmis)
+				nmis += count_mismatches(I.tail + t0, Tlen, segp, L, n,
+							 max_nmis - nmis, fixedP, fixedS);
+			if (nmis <= max_nmis && nmis >= min_nmis)
+				report_match(R, S, key, seg, n, e, Tlen);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------
+// Sorted records -> per-pattern counts and end coordinates.
+// ------------------------------------------------------------------------------------
+
+// mode HIT_COORD: low bits already are the end coordinate.
+// mode HIT_TBPOS: low bits = concat index of the TB end; end = local + |tail| + seg_coord.
+__global__ void __launch_bounds__(256)
+finalize_ends_kernel(BsgpuSubjectView S, const int64_t *__restrict__ tail_off, int tbpos_mode,
+		     const unsigned long long *__restrict__ rec, unsigned long long n,
+		     int32_t *__restrict__ ends, int32_t *__restrict__ counts)
+{
+	unsigned long long t = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+
+	for (; t < n; t += stride) {
+		unsigned long long r = rec[t];
+		int key = (int) (r >> BSGPU_POS_BITS);
+		int64_t v = (int64_t) (r & BSGPU_POS_MASK);
+
+		if (tbpos_mode) {
+			int seg = S.nseg == 1 ? 0 : find_segment(S, v);
+			int Tlen = tail_off ? (int) (__ldg(tail_off + key + 1) - __ldg(tail_off + key)) : 0;
+
+			v = v - __ldg(S.seg_start + seg) + 1 + Tlen + __ldg(S.seg_coord + seg);
+		}
+		ends[t] = (int32_t) v;
+		atomicAdd(counts + key, 1);
+	}
+}
+
+// flag[t] = 1 iff record t differs from record t-1 (input sorted)
+__global__ void __launch_bounds__(256)
+count_segkey_kernel(const unsigned long long *__restrict__ rec, unsigned long long n,
+		    int64_t *__restrict__ seg_counts)
+{
+	unsigned long long t = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+
+	for (; t < n; t += stride)
+		atomicAdd((unsigned long long *) (seg_counts + (rec[t] >> BSGPU_SEGKEY_BITS)), 1ull);
+}
+
+// ------------------------------------------------------------------------------------
+// Roofline probes.
+// ------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+probe_copy_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int64_t n)
+{
+	int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (; i < n; i += stride)
+		dst[i] = __ldcs(src + i);
+}
+
+// every lane reads one random 16-byte half of a random 32-byte sector
+__global__ void __launch_bounds__(256)
+probe_gather_kernel(const uint4 *__restrict__ table, uint32_t mask, int iters,
+		    unsigned long long *__restrict__ sink)
+{
+	uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+	uint32_t acc = 0;
+
+	for (int it = 0; it < iters; it += 8) {
+		uint4 b[8];
+#pragma unroll
+		for (int q = 0; q < 8; q++) {
+			x = x * 1664525u + 1013904223u;
+			b[q] = __ldg(table + ((x >> 4) & mask));
+		}
+#pragma unroll
+		for (int q = 0; q < 8; q++)
+			acc += b[q].x ^ b[q].w;
+	}
+	if (acc == 0x12345678u)
+		atomicAdd(sink, 1ull);
+}

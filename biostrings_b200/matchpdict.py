@@ -1,0 +1,385 @@
+"""matchPDict / countPDict / whichPDict / vcountPDict / vwhichPDict on the GPU.
+
+Mirror of R/matchPDict.R (argument normalisation, subject dispatch, duplicate
+bookkeeping) over the C ABI of libbsgpu.so.  What the reference does with one .Call per
+Trusted-Band component followed by ByPos_MIndex_combine (R/matchPDict.R:335-377) is one
+bsgpu_match() call here: the components are merged on the device.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MATCHES_AS_COUNTS, MATCHES_AS_ENDS, MATCHES_AS_WHICH, NA_INTEGER
+from .mindex import ByPos_MIndex
+from .pdict import MTB_PDict, PDict, TB_PDict
+from .xstring import DNAString, DNAStringSet, MaskedDNAString, XStringViews, encode_dna
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# ---- argument normalisation (R/lowlevel-matching.R:41-112) -----------------------------------
+
+def normarg_max_mismatch(v):
+    if isinstance(v, bool) or not isinstance(v, (int, float, np.integer, np.floating)):
+        raise ValueError("'max.mismatch' must be a single integer")
+    v = int(v)
+    if v < 0:
+        raise ValueError("'max.mismatch' must be a non-negative integer")
+    return v
+
+
+def normarg_min_mismatch(v, max_mismatch):
+    if isinstance(v, bool) or not isinstance(v, (int, float, np.integer, np.floating)):
+        raise ValueError("'min.mismatch' must be a single integer")
+    v = int(v)
+    if v < 0:
+        raise ValueError("'min.mismatch' must be a non-negative integer")
+    if v > max_mismatch:
+        raise ValueError("'min.mismatch' must be <= 'max.mismatch'")
+    return v
+
+
+def normarg_fixed(fixed):
+    """-> (fixedP, fixedS).  TRUE/FALSE, a pair, "pattern", "subject", or a dict with
+    keys pattern/subject (R's named logical vector)."""
+    if isinstance(fixed, (bool, np.bool_)):
+        return bool(fixed), bool(fixed)
+    if isinstance(fixed, dict):
+        if set(fixed) != {"pattern", "subject"}:
+            raise ValueError("'fixed' names must be \"pattern\" and \"subject\"")
+        return bool(fixed["pattern"]), bool(fixed["subject"])
+    if isinstance(fixed, str):
+        fixed = [fixed]
+    fixed = list(fixed)
+    if all(isinstance(f, (bool, np.bool_)) for f in fixed):
+        if len(fixed) not in (1, 2):
+            raise ValueError("when an unnamed logical vector, 'fixed' fixed must be of length 1 or 2")
+        return bool(fixed[0]), bool(fixed[-1])
+    if not all(isinstance(f, str) for f in fixed):
+        raise ValueError("'fixed' not a logical or character vector")
+    if len(set(fixed)) != len(fixed) or any(f not in ("pattern", "subject") for f in fixed):
+        raise ValueError("when a character vector, 'fixed' must be a subset of "
+                         "'c(\"pattern\", \"subject\")' with no duplicated")
+    return "pattern" in fixed, "subject" in fixed
+
+
+def normarg_collapse(collapse):
+    if collapse is False:
+        return 0
+    if isinstance(collapse, bool) or collapse not in (0, 1, 2):
+        raise ValueError("'collapse' must be FALSE, 1 or 2")
+    return int(collapse)
+
+
+# ---- device subjects ---------------------------------------------------------------------------
+
+class DeviceSubject:
+    """A subject resident on the GPU (bytes + packed planes); reusable across calls."""
+
+    def __init__(self, handle, kind, length):
+        self._h, self.kind, self.length = handle, kind, length
+
+    @classmethod
+    def from_xstring(cls, s):
+        codes = encode_dna(s)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().bsgpu_subject_xstring(_ptr(codes), codes.size, C.byref(h)))
+        return cls(h, "xstring", int(codes.size))
+
+    @classmethod
+    def from_views(cls, v):
+        codes = v.subject.codes
+        st = np.ascontiguousarray(v.start, dtype=np.int32)
+        wd = np.ascontiguousarray(v.width, dtype=np.int32)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().bsgpu_subject_views(_ptr(codes), codes.size, _ptr(st), _ptr(wd),
+                                                  st.size, C.byref(h)))
+        return cls(h, "views", int(st.size))
+
+    @classmethod
+    def from_set(cls, s):
+        h = C.c_void_p()
+        _lib.check(_lib.lib().bsgpu_subject_set(_ptr(s.concat), _ptr(s.widths), len(s), C.byref(h)))
+        return cls(h, "set", len(s))
+
+    @classmethod
+    def from_chunk(cls, chunk, chunk_start, subject_len, report_lo, report_hi):
+        codes = encode_dna(chunk)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().bsgpu_subject_chunk(_ptr(codes), codes.size, chunk_start,
+                                                  subject_len, report_lo, report_hi, C.byref(h)))
+        return cls(h, "chunk", int(codes.size))
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise RuntimeError("DeviceSubject has been freed")
+        return self._h
+
+    def nletters(self):
+        return int(_lib.lib().bsgpu_subject_nletters(self.handle))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().bsgpu_subject_free(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _parts_array(parts):
+    arr = (C.c_void_p * len(parts))(*[p.handle for p in parts])
+    return arr
+
+
+def _as_array(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+def _take_result(res, mode, vmatch_collapse=None, n_subjects=None):
+    try:
+        if mode == MATCHES_AS_COUNTS:
+            if res.dcounts:
+                return _as_array(res.dcounts, res.n_counts, np.float64)
+            return _as_array(res.counts, res.n_counts, np.int32)
+        if mode == MATCHES_AS_WHICH and n_subjects is None:
+            return _as_array(res.which, res.n_which, np.int32)
+        offsets = _as_array(res.ends_offsets, res.n_rows + 1, np.int64)
+        ends = _as_array(res.ends, int(offsets[-1]) if res.n_rows else 0, np.int32)
+        return offsets, ends
+    finally:
+        _lib.lib().bsgpu_result_free(C.byref(res))
+
+
+def match_parts(parts, dsubj, max_mismatch, min_mismatch, fixed, mode):
+    """bsgpu_match() on PDict3Parts objects and a DeviceSubject (the .Call level)."""
+    res = _lib.Result()
+    _lib.check(_lib.lib().bsgpu_match(_parts_array(parts), len(parts), dsubj.handle,
+                                      max_mismatch, min_mismatch, int(fixed[0]), int(fixed[1]),
+                                      mode, C.byref(res)))
+    return _take_result(res, mode)
+
+
+def vmatch_parts(parts, dsubj, max_mismatch, min_mismatch, fixed, collapse, weight, mode):
+    res = _lib.Result()
+    w = None
+    is_double = 0
+    if mode == MATCHES_AS_COUNTS and collapse != 0:
+        w = np.asarray(weight)
+        is_double = int(w.dtype.kind == "f")
+        w = np.ascontiguousarray(w, dtype=np.float64 if is_double else np.int32)
+    _lib.check(_lib.lib().bsgpu_vmatch(_parts_array(parts), len(parts), dsubj.handle,
+                                       max_mismatch, min_mismatch, int(fixed[0]), int(fixed[1]),
+                                       collapse, is_double, _ptr(w), 0 if w is None else w.size,
+                                       mode, C.byref(res)))
+    return _take_result(res, mode, n_subjects=dsubj.length)
+
+
+# ---- .checkUserArgsWhenTrustedBandIsFull / .checkMaxMismatch (R/matchPDict.R:118-141) --------
+
+def _check_args_full_tb(parts, max_mismatch, fixed):
+    import warnings
+    for p in parts:
+        if p.head_or_none() is None and p.tail_or_none() is None:
+            if max_mismatch != 0:
+                raise ValueError("'max.mismatch' must be 0 when there is no head and no tail")
+            if not fixed[0]:
+                warnings.warn("the value you specified for 'fixed' means that IUPAC\n"
+                              "extended letters in the patterns should be treated as\n"
+                              "ambiguities, but this has no effect because the patterns\n"
+                              "don't contain such letters")
+
+
+def _check_max_mismatch(max_mismatch, ntb):
+    if max_mismatch > ntb - 1:
+        raise ValueError("cannot use vmatchPDict()/vcountPDict()/vwhichPDict() with an "
+                         "MTB_PDict object that was preprocessed to be used with "
+                         f"'max.mismatch' <= {ntb - 1}")
+    if max_mismatch < ntb - 1:
+        print(f"WARNING: using 'max.mismatch={max_mismatch}' with an MTB_PDict object that "
+              f"was preprocessed for allowing up to {ntb - 1} mismatching letter(s) per "
+              "match is not optimal")
+
+
+# ---- .matchPDict (R/matchPDict.R:400-453) -------------------------------------------------------
+
+def _subject_to_device(subject):
+    """XString / XStringViews / MaskedXString dispatch of the generics
+    (R/matchPDict.R:612-760)."""
+    if isinstance(subject, DeviceSubject):
+        if subject.kind == "set":
+            raise ValueError("please use vmatchPDict() when 'subject' is an XStringSet object "
+                             "(multiple sequence)")
+        return subject, False
+    if isinstance(subject, (DNAStringSet, list, tuple)):
+        raise ValueError("please use vmatchPDict() when 'subject' is an XStringSet object "
+                         "(multiple sequence)")
+    if isinstance(subject, MaskedDNAString):
+        subject = subject.as_views()
+    if isinstance(subject, XStringViews):
+        return DeviceSubject.from_views(subject), True
+    return DeviceSubject.from_xstring(subject), True
+
+
+def _match_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, mode, what):
+    if not isinstance(pdict, PDict):
+        raise ValueError("'pdict' must be a PDict or XStringSet object")
+    try:
+        dsubj, owned = _subject_to_device(subject)
+    except ValueError as e:
+        raise ValueError(str(e).replace("vmatchPDict", "v" + what)) from None
+    try:
+        dups0 = pdict.dups()
+        max_mismatch = normarg_max_mismatch(max_mismatch)
+        min_mismatch = normarg_min_mismatch(min_mismatch, max_mismatch)
+        fixed = normarg_fixed(fixed)
+        parts = pdict.parts()
+        _check_args_full_tb(parts, max_mismatch, fixed)
+        if isinstance(pdict, MTB_PDict):
+            _check_max_mismatch(max_mismatch, len(parts))
+        ans = match_parts(parts, dsubj, max_mismatch, min_mismatch, fixed, mode)
+    finally:
+        if owned:
+            dsubj.close()
+    if mode == MATCHES_AS_ENDS:
+        offsets, ends = ans
+        return ByPos_MIndex(pdict.width(), offsets, ends, names=pdict.names(), dups0=dups0)
+    if dups0 is None:
+        return ans
+    which_pp_excluded = np.flatnonzero(dups0.duplicated()) + 1
+    if mode == MATCHES_AS_WHICH:
+        return dups0.members(ans)                     # members(dups0, ans)
+    ans[which_pp_excluded - 1] = ans[dups0.togroup(which_pp_excluded) - 1]
+    return ans
+
+
+def matchPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True):
+    """-> ByPos_MIndex (R/matchPDict.R:612-658)."""
+    return _match_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, MATCHES_AS_ENDS,
+                        "matchPDict")
+
+
+def countPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True):
+    """-> int32[length(pdict)] (R/matchPDict.R:664-709)."""
+    return _match_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, MATCHES_AS_COUNTS,
+                        "countPDict")
+
+
+def whichPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True):
+    """-> ascending 1-based indices of the patterns with a match (R/matchPDict.R:716-761)."""
+    return _match_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, MATCHES_AS_WHICH,
+                        "whichPDict")
+
+
+# ---- .vmatchPDict (R/matchPDict.R:514-605) ---------------------------------------------------------
+
+def _vsubject_to_device(subject, what):
+    if isinstance(subject, DeviceSubject):
+        if subject.kind != "set":
+            raise ValueError(f"please use {what}() when 'subject' is an XString or "
+                             "MaskedXString object (single sequence)")
+        return subject, False
+    if isinstance(subject, XStringViews):
+        subject = subject.to_set()
+    elif isinstance(subject, (list, tuple)):
+        subject = DNAStringSet(subject)
+    if not isinstance(subject, DNAStringSet):
+        raise ValueError(f"please use {what}() when 'subject' is an XString or "
+                         "MaskedXString object (single sequence)")
+    return DeviceSubject.from_set(subject), True
+
+
+def _vmatch_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, collapse, weight, mode, what):
+    if not isinstance(pdict, PDict):
+        raise ValueError("'pdict' must be a PDict or XStringSet object")
+    dsubj, owned = _vsubject_to_device(subject, what)
+    try:
+        N, M = dsubj.length, len(pdict)
+        dups0 = pdict.dups()
+        which_pp_excluded = None if dups0 is None else np.flatnonzero(dups0.duplicated()) + 1
+        max_mismatch = normarg_max_mismatch(max_mismatch)
+        min_mismatch = normarg_min_mismatch(min_mismatch, max_mismatch)
+        fixed = normarg_fixed(fixed)
+        if mode == MATCHES_AS_COUNTS:
+            collapse = normarg_collapse(collapse)
+            weight = np.atleast_1d(np.asarray(weight))
+            if collapse == 1:
+                weight = np.resize(weight, N)
+            elif collapse == 2:
+                weight = np.resize(weight, M).copy()
+                if which_pp_excluded is not None and which_pp_excluded.size:
+                    # R/matchPDict.R:547-558: duplicates' weights are folded into the
+                    # representative's before the C call
+                    w0 = weight.copy()
+                    for i in np.unique(dups0.togroup(which_pp_excluded)).tolist():
+                        # weight[i] + sum(weight[low2high[[i]]]); R's sum() accumulates
+                        # sequentially in long double
+                        acc = np.longdouble(0) if w0.dtype.kind == "f" else 0
+                        for h in dups0.low2high(i).tolist():
+                            acc = acc + (np.longdouble(w0[h - 1]) if w0.dtype.kind == "f"
+                                         else int(w0[h - 1]))
+                        weight[i - 1] = w0[i - 1] + (np.float64(acc) if w0.dtype.kind == "f"
+                                                     else acc)
+        else:
+            collapse = 0
+        parts = pdict.parts()
+        _check_args_full_tb(parts, max_mismatch, fixed)
+        if isinstance(pdict, MTB_PDict):
+            _check_max_mismatch(max_mismatch, len(parts))
+            if mode != MATCHES_AS_WHICH:
+                raise ValueError("MTB_PDict objects are not supported yet, sorry")
+        ans = vmatch_parts(parts, dsubj, max_mismatch, min_mismatch, fixed, collapse, weight, mode)
+    finally:
+        if owned:
+            dsubj.close()
+    if mode == MATCHES_AS_WHICH:
+        offsets, ids = ans
+        out = [ids[offsets[j]:offsets[j + 1]] for j in range(N)]
+        if dups0 is not None:
+            out = [dups0.members(o) for o in out]     # vmembers(dups0, ans)
+        return out
+    if collapse == 0:
+        ans = ans.reshape((M, N), order="F")
+        if which_pp_excluded is not None:
+            ans[which_pp_excluded - 1, :] = ans[dups0.togroup(which_pp_excluded) - 1, :]
+    elif collapse == 1 and which_pp_excluded is not None:
+        ans[which_pp_excluded - 1] = ans[dups0.togroup(which_pp_excluded) - 1]
+    return ans
+
+
+def vcountPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True,
+                collapse=False, weight=1):
+    """-> int matrix [length(pdict), length(subject)], or a collapsed vector
+    (R/matchPDict.R:819-861)."""
+    return _vmatch_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, collapse, weight,
+                         MATCHES_AS_COUNTS, "countPDict")
+
+
+def vwhichPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True):
+    """-> list (one per subject) of ascending 1-based pattern indices
+    (R/matchPDict.R:867-904)."""
+    return _vmatch_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, False, 1,
+                         MATCHES_AS_WHICH, "whichPDict")
+
+
+def vmatchPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True):
+    """R/matchPDict.R:778-809."""
+    if not isinstance(subject, (DNAStringSet, XStringViews, list, tuple)):
+        raise ValueError("please use matchPDict() when 'subject' is an XString or "
+                         "MaskedXString object (single sequence)")
+    raise NotImplementedError("vmatchPDict() is not ready yet, sorry")

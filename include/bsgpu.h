@@ -1,0 +1,227 @@
+/*
+ * bsgpu.h -- C ABI of the B200-native PDict matching path (libbsgpu.so).
+ *
+ * This is the drop-in boundary for ONE path of Bioconductor/Biostrings: PDict
+ * preprocessing + matchPDict / countPDict / whichPDict / vcountPDict / vwhichPDict.
+ * Each entry point names the reference interface it replaces (file:line under the
+ * Biostrings source tree).  Plain C: pointers and sizes only, no R types, no longjmp
+ * across the boundary, no torch types.  A C dispatch layer (the role src/match_pdict.c
+ * plays in the reference) turns return codes into R's error() with bsgpu_last_error(),
+ * whose text is the reference's own message for the same condition.
+ *
+ * Conventions
+ *   - Sequences are Biostrings-encoded bytes (A=1 C=2 G=4 T=8, IUPAC = OR of those,
+ *     '-'=16 '+'=32 '.'=64; R/XStringCodec-class.R:114,129-139), exactly what
+ *     Chars_holder.ptr points at in the reference (src/XStringSet_class.c:37-51).
+ *   - A set of sequences is (concat bytes, int32 widths[n]); a NULL widths pointer for
+ *     head/tail means "no head"/"no tail" (pdict_head == R_NilValue, src/match_pdict.c:28).
+ *   - NA is INT32_MIN (R's NA_INTEGER).  Pattern ids in results are 1-based where the
+ *     reference's are (which), 0-based array positions otherwise.
+ *   - Return value: 0 = OK, negative = error (BSGPU_E*); message in bsgpu_last_error().
+ *   - One caller thread at a time per process (the reference entry points are
+ *     non-reentrant too: static buffers in src/match_reporting.c:41,262).
+ *   - There is no CPU fallback: without a usable CUDA device every compute entry
+ *     point fails with BSGPU_ENODEVICE.
+ */
+#ifndef BSGPU_H
+#define BSGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSGPU_NA INT32_MIN
+
+enum {
+	BSGPU_OK = 0,
+	BSGPU_EINVAL = -1,	/* argument error; text mirrors the reference's error() */
+	BSGPU_ENODEVICE = -2,	/* no CUDA device / driver */
+	BSGPU_ECUDA = -3,	/* CUDA runtime failure */
+	BSGPU_ENOMEM = -4,
+	BSGPU_EUNSUPPORTED = -5
+};
+
+/* "matches_as" of the reference (src/match_reporting.c:10-31) */
+enum {
+	BSGPU_MATCHES_AS_NULL = 0,
+	BSGPU_MATCHES_AS_WHICH = 1,
+	BSGPU_MATCHES_AS_COUNTS = 2,
+	BSGPU_MATCHES_AS_ENDS = 4
+};
+
+enum { BSGPU_ALGO_ACTREE2 = 0, BSGPU_ALGO_TWOBIT = 1 };
+
+const char *bsgpu_last_error(void);
+const char *bsgpu_version(void);
+
+/* Number of CUDA devices (0 if none / no driver).  Never fails. */
+int bsgpu_device_count(void);
+/* Select the device used by this process (default: BSGPU_DEVICE env var, else 0). */
+int bsgpu_set_device(int device);
+
+/* ------------------------------------------------------------------------------------
+ * Preprocessing: one Trusted Band + its head and tail = the reference's PDict3Parts
+ * (R/PDict-class.R:174-233).  Replaces
+ *     build_Twobit(tb, pp_exclude, base_codes)            src/match_pdict_Twobit.c:104
+ *     ACtree2_build(tb, pp_exclude, base_codes, ...)      src/match_pdict_ACtree2.c:792
+ * and the per-call _new_HeadTail()                        src/match_pdict_utils.c:347.
+ * The result is a device-resident index (2-bit TB keys in a bucketed hash table, TB
+ * duplicate groups in CSR form = low2high, head/tail bytes) and `high2low_out[M]`, the
+ * same vector the reference returns (NA, or 1-based id of the first pattern with the
+ * same TB).  `pp_exclude` (may be NULL): patterns with a non-NA entry are skipped
+ * entirely, as in the reference.  Errors carry the reference's text: empty TB, TB
+ * width > 14 for Twobit, unequal TB widths, non-base letter in the TB.
+ * ------------------------------------------------------------------------------------ */
+typedef struct bsgpu_pdict3parts bsgpu_pdict3parts;
+
+int bsgpu_pdict3parts_build(int algo, int32_t M,
+		const uint8_t *tb_concat, const int32_t *tb_widths,
+		const uint8_t *head_concat, const int32_t *head_widths,
+		const uint8_t *tail_concat, const int32_t *tail_widths,
+		const int32_t *pp_exclude, int32_t *high2low_out,
+		bsgpu_pdict3parts **out);
+/* R/PDict-class.R:219-227: the whole-pattern index is reused with its dups blanked. */
+int bsgpu_pdict3parts_blank_dups(bsgpu_pdict3parts *p3);
+void bsgpu_pdict3parts_free(bsgpu_pdict3parts *p3);
+int32_t bsgpu_pdict3parts_length(const bsgpu_pdict3parts *p3);
+int32_t bsgpu_pdict3parts_tb_width(const bsgpu_pdict3parts *p3);
+
+/* ------------------------------------------------------------------------------------
+ * Subjects.  A device-resident subject holds the encoded bytes plus a 2-bit-packed
+ * code plane and 1-bit validity planes built on upload.  Replaces hold_XRaw(subject) /
+ * _hold_XStringSet(subject) / the views loop of src/match_pdict.c:164,240-262,330,399.
+ *   xstring: one sequence (DNAString)
+ *   views:   XStringViews / MaskedXString gaps: every view is an independent subject
+ *            (src/match_pdict.c:246-262); a view outside the subject is an error
+ *            ("'subject' has \"out of limits\" views", :253-254)
+ *   set:     DNAStringSet for vcountPDict / vwhichPDict
+ *   chunk:   bytes [chunk_start, chunk_start+chunk_len) of a longer sequence of
+ *            `subject_len` letters; only Trusted-Band ends n (1-based, subject
+ *            coordinates) with report_lo < n <= report_hi are reported, in subject
+ *            coordinates, and "out of limits" is judged against the whole subject.  This
+ *            is how one long subject is sharded over GPUs; the chunk must carry a halo of
+ *            width(pattern)-1 letters around the report range (checked at match time).
+ * ------------------------------------------------------------------------------------ */
+typedef struct bsgpu_subject bsgpu_subject;
+
+int bsgpu_subject_xstring(const uint8_t *s, int64_t length, bsgpu_subject **out);
+int bsgpu_subject_views(const uint8_t *s, int64_t length,
+		const int32_t *views_start, const int32_t *views_width, int32_t nviews,
+		bsgpu_subject **out);
+int bsgpu_subject_set(const uint8_t *concat, const int32_t *widths, int32_t n,
+		bsgpu_subject **out);
+int bsgpu_subject_chunk(const uint8_t *chunk, int64_t chunk_len, int64_t chunk_start,
+		int64_t subject_len, int64_t report_lo, int64_t report_hi,
+		bsgpu_subject **out);
+void bsgpu_subject_free(bsgpu_subject *subj);
+int64_t bsgpu_subject_nletters(const bsgpu_subject *subj);	/* letters that are scanned */
+
+/* ------------------------------------------------------------------------------------
+ * Results (library-allocated host memory; release with bsgpu_result_free()).
+ *   COUNTS: counts[M]                                   src/match_reporting.c:163-166
+ *   WHICH:  which[n_which], ascending 1-based ids        src/match_reporting.c:150-161
+ *   ENDS:   CSR ends_offsets[M+1], ends[]; an empty row is the reference's NULL list
+ *           element (src/match_reporting.c:192-201); per pattern the ends are in the
+ *           reference's order (ascending; view order for views)
+ * For vmatch (set subjects):
+ *   COUNTS, collapse=0: counts[M*N], column-major (column j = subject j)
+ *           collapse=1/2: counts[] (int weights) or dcounts[] (double weights), length
+ *           M (collapse=1) or N (collapse=2)             src/match_pdict.c:85-127,386-432
+ *   WHICH:  CSR ends_offsets[N+1], ends[] = ascending 1-based pattern ids per subject
+ *                                                        src/match_pdict.c:320-346
+ * ------------------------------------------------------------------------------------ */
+typedef struct bsgpu_result {
+	int32_t M;		/* number of patterns */
+	int64_t n_counts;
+	int32_t *counts;
+	double *dcounts;
+	int64_t n_which;
+	int32_t *which;
+	int64_t n_rows;		/* rows of the CSR (M, or N for vwhich) */
+	int64_t *ends_offsets;
+	int32_t *ends;
+} bsgpu_result;
+
+void bsgpu_result_free(bsgpu_result *res);
+
+/* ------------------------------------------------------------------------------------
+ * Matching against a device-resident subject.
+ *
+ * nparts == 1: one PDict3Parts = a TB_PDict; replaces the body of
+ *     match_PDict3Parts_XString()       src/match_pdict.c:153-171
+ *     match_PDict3Parts_XStringViews()  src/match_pdict.c:225-264
+ * i.e. TB scan (_match_Twobit / _match_tbACtree2, src/match_pdict_Twobit.c:177,
+ * src/match_pdict_ACtree2.c:1160), flank verification (_match_pdict_all_flanks,
+ * src/match_pdict_utils.c:809) and reporting (_MatchBuf_as_SEXP, src/match_reporting.c:232).
+ *
+ * nparts > 1: the components of an MTB_PDict; the per-component results are merged as
+ * .match.MTB_PDict + ByPos_MIndex_combine do (R/matchPDict.R:335-377,
+ * src/MIndex_class.c:230-263): per pattern the sorted distinct ends; counts = their
+ * number; which = the union.
+ * ------------------------------------------------------------------------------------ */
+int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
+		const bsgpu_subject *subject,
+		int max_mismatch, int min_mismatch, int fixedP, int fixedS,
+		int matches_as, bsgpu_result *res);
+
+/* Replaces vmatch_PDict3Parts_XStringSet(), src/match_pdict.c:484-516 (nparts > 1 only
+ * for WHICH, as in R/matchPDict.R:481-482).  weight: int32 or double vector of length
+ * N (collapse=1) or M (collapse=2); ignored when collapse=0. */
+int bsgpu_vmatch(const bsgpu_pdict3parts *const *parts, int nparts,
+		const bsgpu_subject *subject_set,
+		int max_mismatch, int min_mismatch, int fixedP, int fixedS,
+		int collapse, int weight_is_double, const void *weight, int64_t weight_length,
+		int matches_as, bsgpu_result *res);
+
+/*
+ * Device-side counting for callers that own the device (bench, multi-GPU sharding):
+ * adds the per-pattern match counts of `subject` into d_counts[M], a DEVICE pointer
+ * (e.g. a torch tensor's data_ptr, later all-reduced over NCCL), on CUDA stream
+ * `stream` (a cudaStream_t passed as void*; NULL = default stream).  Asynchronous
+ * when no candidate buffering is needed (full-width Trusted Band); otherwise it
+ * synchronises the stream internally.  n_launches_out (may be NULL) receives the number
+ * of kernels this call launched.
+ */
+int bsgpu_count_device(const bsgpu_pdict3parts *const *parts, int nparts,
+		const bsgpu_subject *subject,
+		int max_mismatch, int min_mismatch, int fixedP, int fixedS,
+		int32_t *d_counts, void *stream, int *n_launches_out);
+
+/* ------------------------------------------------------------------------------------
+ * Host-buffer entry points with the reference's .Call shapes (upload + match + free).
+ * ------------------------------------------------------------------------------------ */
+/* match_PDict3Parts_XString, src/match_pdict.c:153 */
+int bsgpu_match_PDict3Parts_XString(const bsgpu_pdict3parts *p3,
+		const uint8_t *subject, int64_t subject_length,
+		int max_mismatch, int min_mismatch, int fixedP, int fixedS,
+		int matches_as, bsgpu_result *res);
+/* match_PDict3Parts_XStringViews, src/match_pdict.c:225 */
+int bsgpu_match_PDict3Parts_XStringViews(const bsgpu_pdict3parts *p3,
+		const uint8_t *subject, int64_t subject_length,
+		const int32_t *views_start, const int32_t *views_width, int32_t nviews,
+		int max_mismatch, int min_mismatch, int fixedP, int fixedS,
+		int matches_as, bsgpu_result *res);
+/* vmatch_PDict3Parts_XStringSet, src/match_pdict.c:484 */
+int bsgpu_vmatch_PDict3Parts_XStringSet(const bsgpu_pdict3parts *p3,
+		const uint8_t *subject_concat, const int32_t *subject_widths, int32_t nsubject,
+		int max_mismatch, int min_mismatch, int fixedP, int fixedS,
+		int collapse, int weight_is_double, const void *weight, int64_t weight_length,
+		int matches_as, bsgpu_result *res);
+
+/* ByPos_MIndex_combine, src/MIndex_class.c:230: per-row sorted union of CSR results. */
+int bsgpu_mindex_combine(const bsgpu_result *const *components, int ncomponents,
+		bsgpu_result *res);
+
+/* Kernel launch counter (every kernel this library launched since process start). */
+int64_t bsgpu_launch_count(void);
+
+/* Micro-benchmarks used to establish the memory rooflines on this device (GB/s):
+ * a streaming copy and a random 32-byte-sector gather from an L2-resident buffer. */
+int bsgpu_probe_peaks(double *copy_gbs, double *l2_gather_gsectors, int64_t gather_table_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

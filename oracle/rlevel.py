@@ -558,6 +558,8 @@ def _vmatchPDict(pdict, subject, max_mismatch, min_mismatch, fixed, collapse, we
         ans = tp.pptb.vmatch_set(head, tail, subject.concat, subject.widths, max_mismatch,
                                  min_mismatch, fixed, collapse if mode == MATCHES_AS_COUNTS else 0,
                                  weight if mode == MATCHES_AS_COUNTS else np.array([1]), mode)
+        if mode == MATCHES_AS_COUNTS and collapse == 0 and getattr(ans, "ndim", 0) == 1:
+            ans = ans.reshape((len(pdict), len(subject)), order="F")   # allocMatrix(M, N)
     else:                               # .vmatch.MTB_PDict, R/matchPDict.R:472-504
         _check_max_mismatch(max_mismatch, len(pdict.threeparts_list))
         if mode != MATCHES_AS_WHICH:
