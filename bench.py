@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- countPDict subject Gbp/s (BASELINE.json metric) on N B200s of one box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mm 0|2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): countPDict of 1M 25-mers (C2 dictionary: random, 10 % cut from
+the subject, 1 % duplicates) against a synthetic chr1-shaped subject of 250 Mbp per GPU
+(i.i.d. letters, GC 0.41, ~7 % N in 40 runs).  With N GPUs the subject is N x 250 Mbp, split
+by Trusted-Band end with an overlap of width-1 (weak scaling); the per-pattern counts are
+all-reduced over NCCL inside the timed region.
+
+A step = one pass of the hot path over the rank's resident chunk: pack the encoded bytes
+(2-bit codes + validity planes), zero the counts, scan (one index probe per window),
+all-reduce.  `value` times K steps with CUDA events on the launching stream (L2 flushed
+between steps, outside the events), max over ranks.  `e2e` times the public host-buffer
+call (pinned host bytes -> H2D -> pack -> scan -> D2H counts).  `cpu_baseline` runs the
+reference's own C (oracle/_ref, else our C restatement) on one host core over a bounded
+sample of the same workload and doubles as a parity check of that sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WIDTH = 25
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mm", type=int, default=0, choices=[0, 2],
+                    help="max.mismatch of the headline metric (0 = exact, 2 = MTB_PDict)")
+    ap.add_argument("--subject-mbp", type=float, default=250.0, help="letters per GPU, in Mbp")
+    ap.add_argument("--patterns", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample-mbp", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.004)
+        except Exception as e:                      # noqa: BLE001
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def mark(self):
+        """Start of the timed region: only later samples count."""
+        deadline = time.time() + 3
+        while not self.samples and time.time() < deadline and self.is_alive():
+            time.sleep(0.005)
+        self.first = len(self.samples)
+        self.reasons.clear()
+
+    def summary(self):
+        s = sorted(self.samples[getattr(self, "first", 0):]) or sorted(self.samples[-1:])
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(s), "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm: the reference's own C (or our port) on host cores
+# ----------------------------------------------------------------------------------------
+
+def cpu_backend():
+    from oracle import ref
+    if ref.available():
+        return "reference", ref.RefPPTB, ref
+    from oracle import port
+    return "port", port.PortPPTB, port
+
+
+def cpu_count_exact(PPTB, mod, pats, sample):
+    """Build the whole-pattern ACtree2 index the way PDict() does and count one sample.
+    Returns (counts, build_seconds, match_seconds)."""
+    M = pats.shape[0]
+    t0 = time.perf_counter()
+    pptb = PPTB("ACtree2", pats.reshape(-1), np.full(M, WIDTH, np.int32), None)
+    h2l = pptb.high2low.copy()
+    pptb.blank_dups()
+    t1 = time.perf_counter()
+    c = pptb.match_xstring(None, None, sample, 0, 0, (True, True), mod.MATCHES_AS_COUNTS)
+    t2 = time.perf_counter()
+    dup = h2l != -2147483648
+    c = c.copy()
+    c[dup] = c[h2l[dup] - 1]
+    pptb.close()
+    return c, t1 - t0, t2 - t1
+
+
+def _cpu_worker(job):
+    kind, pats, lo, hi, chrom_len = job
+    from biostrings_b200 import synth
+    _, PPTB, mod = cpu_backend()
+    sample = synth.subject_region(lo, hi, chrom_len)
+    M = pats.shape[0]
+    pptb = PPTB("ACtree2", pats.reshape(-1), np.full(M, WIDTH, np.int32), None)
+    pptb.blank_dups()
+    t0 = time.perf_counter()
+    c = pptb.match_xstring(None, None, sample, 0, 0, (True, True), mod.MATCHES_AS_COUNTS)
+    return time.perf_counter() - t0, int(c.sum())
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the same workload on all
+    host cores (the reference is single-threaded: one process per core, each on its own
+    slice of the sample, index built per process outside the timed part)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mpc
+    from biostrings_b200 import synth
+    kind, _, _ = cpu_backend()
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    chrom_len = int(args.subject_mbp * 1e6)
+    pats = synth.dictionary(args.patterns, WIDTH, chrom_len, 1)
+    per_core = int(1e6)                             # 1 Mbp per core per step
+    times = []
+    ctx = mpc.get_context("fork")
+    for step in range(args.warmup + args.steps):
+        base = 20_000 + step * cores * per_core
+        jobs = [(kind, pats, base + i * per_core, base + (i + 1) * per_core + WIDTH - 1, chrom_len)
+                for i in range(cores)]
+        t0 = time.perf_counter()
+        with ctx.Pool(cores) as pool:
+            res = pool.map(_cpu_worker, jobs)
+        wall = time.perf_counter() - t0
+        match_t = max(r[0] for r in res)            # slowest core's matching time
+        if step >= args.warmup:
+            times.append(match_t)
+        del wall
+    ms = 1e3 * sum(times) / len(times)
+    value = cores * per_core / (ms * 1e-3) / 1e9
+    line = {"metric": "countPDict subject Gbp/s (1M 25-mers, max.mismatch 0)", "value": value,
+            "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "impl": "reference",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": value, "unit": "Gbp/s", "cores": cores, "kind": kind,
+                             "sample": f"{cores} x {per_core / 1e6:.0f} Mbp slices of the subject per step, "
+                                       "one single-threaded process per core, ACtree2 index built per "
+                                       "process outside the timed part (cold tree each step)"},
+            "e2e": {"value": value, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"countPDict, {args.patterns} x {WIDTH}-mers (Trusted Band = whole pattern, "
+                        f"max.mismatch={args.mm}), synthetic chr1-shaped subject of "
+                        f"{args.subject_mbp:g} Mbp per GPU ({args.subject_mbp * world:g} Mbp total)",
+            "patterns": args.patterns, "pattern_width": WIDTH, "max_mismatch": args.mm,
+            "subject_letters_per_gpu": int(args.subject_mbp * 1e6),
+            "sharding": f"{world} overlap chunk(s) by Trusted-Band end, halo = width-1",
+            "l2": "L2 flushed (256 MiB write) between timed steps, outside the CUDA events",
+            "step": "pack 1-byte codes -> 2-bit planes, zero counts, scan, all-reduce counts"}
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import biostrings_b200 as bs
+    from biostrings_b200 import _lib, matchpdict as mp, sharding, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the PDict path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    L = _lib.lib()
+    _lib.check(L.bsgpu_set_device(local))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    sptr = C.c_void_p(stream.cuda_stream)
+
+    chrom_len = int(args.subject_mbp * 1e6)
+    subject_len = chrom_len * world
+    M = args.patterns
+    pats = synth.dictionary(M, WIDTH, chrom_len, world)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pdict = bs.PDict(bs.DNAStringSet(concat=pats.reshape(-1), widths=np.full(M, WIDTH, np.int32)),
+                         max_mismatch=None if args.mm == 0 else args.mm)
+    parts = pdict.parts()
+    parr = mp._parts_array(parts)
+    halo = sharding.halo_of(pdict)
+    lo, hi = sharding.shard_bounds(subject_len, world, rank)
+    a, b = sharding.chunk_range(lo, hi, subject_len, halo[0], halo[1])
+    host = torch.empty(b - a, dtype=torch.uint8, pin_memory=True)
+    chunk = host.numpy()
+    synth.subject_region(a, b, chrom_len, out=chunk)
+    dsubj = mp.DeviceSubject.from_chunk(chunk, a, subject_len, lo, hi)
+    counts = torch.zeros(M, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    nl = C.c_int(0)
+
+    def step():
+        counts.zero_()
+        _lib.check(L.bsgpu_subject_repack(dsubj.handle, sptr))
+        _lib.check(L.bsgpu_count_device(parr, len(parts), dsubj.handle, args.mm, 0, 1, 1,
+                                        C.c_void_p(counts.data_ptr()), sptr, C.byref(nl)))
+        if world > 1:
+            dist.all_reduce(counts)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        step()
+    barrier()
+    sampler.mark()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    launches0 = L.bsgpu_launch_count()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                       # evict L2 between timed steps (untimed)
+        ev[k][0].record(stream)
+        counts.zero_()
+        _lib.check(L.bsgpu_subject_repack(dsubj.handle, sptr))
+        ev[k][1].record(stream)
+        _lib.check(L.bsgpu_count_device(parr, len(parts), dsubj.handle, args.mm, 0, 1, 1,
+                                        C.c_void_p(counts.data_ptr()), sptr, C.byref(nl)))
+        if world > 1:
+            dist.all_reduce(counts)
+        ev[k][2].record(stream)
+    barrier()
+    launches = int(L.bsgpu_launch_count() - launches0)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    pack_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    scan_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    total_ms = sum(e[0].elapsed_time(e[2]) for e in ev)
+    t = torch.tensor([total_ms, pack_ms, scan_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, pack_ms, scan_ms = t.tolist()
+    ms_per_step = total_ms / args.steps
+    letters_per_rank = hi - lo
+    value = world * letters_per_rank / (ms_per_step * 1e-3) / 1e9
+    total_hits = int(counts.sum().item())
+
+    # ---- end to end through the public host-buffer call -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        n_e2e = max(2, min(args.steps, 5))
+        times = []
+        for k in range(n_e2e + 1):
+            barrier()
+            t0 = time.perf_counter()
+            with mp.DeviceSubject.from_chunk(chunk, a, subject_len, lo, hi) as ds:      # H2D + pack
+                c = mp.match_parts(parts, ds, args.mm, 0, (True, True), _lib.MATCHES_AS_COUNTS)  # + D2H
+            if world > 1:
+                ct = torch.from_numpy(c).to(dev)
+                dist.all_reduce(ct)
+                c = ct.cpu().numpy()
+            torch.cuda.synchronize()
+            if k > 0:
+                times.append(time.perf_counter() - t0)
+            if os.environ.get("BENCH_DEBUG"):
+                print(f"[e2e {k}] {(time.perf_counter() - t0) * 1e3:.2f} ms", file=sys.stderr)
+        te = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * letters_per_rank / te.item() / 1e9, "unit": "Gbp/s",
+               "h2d_bytes_per_step": int(b - a), "d2h_bytes_per_step": int(4 * M),
+               "ms_per_step": 1e3 * te.item(),
+               "call": "DeviceSubject.from_chunk(pinned host bytes) + countPDict (bsgpu_subject_chunk + "
+                       "bsgpu_match through the C ABI), counts read back to the host"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peak, peak_src = peaks()
+    dominant = "scan_tb_kernel" if scan_ms >= pack_ms else "pack_subject_kernel"
+    dom_ms = max(scan_ms, pack_ms)
+    alg_bytes = float(letters_per_rank)            # 1.0 B per subject letter
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "kernel": dominant,
+            "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_bytes,
+            "kernel_ms": {"pack_subject_kernel": pack_ms, "scan_tb_kernel(+all-reduce)": scan_ms},
+            "note": "1.0 B per subject letter (reference's 1-byte encoding); the scan's own bound is "
+                    "the L2 random-sector gather (one 32 B sector per window), see l2_gather"}
+    probe = os.path.join(ROOT, "profiles", "r01_probe_peaks.json")
+    if os.path.exists(probe):
+        with open(probe) as f:
+            pk = json.load(f)
+        g = pk.get("gather_Gsectors_32MB")
+        if g:
+            rate = letters_per_rank / (scan_ms * 1e-3) / 1e9
+            roof["l2_gather"] = {"achieved_Gprobes_s": rate, "peak_Gsectors_s": g, "frac": rate / g,
+                                 "peak_source": "tools/probe_peaks.py on this pool (profiles/r01_probe_peaks.json)"}
+
+    # ---- CPU baseline on a bounded sample (also a parity check of that sample) --------------------
+    cpu = None
+    parity = None
+    if world == 1 and not args.no_cpu_baseline and args.mm == 0:
+        kind, PPTB, mod = cpu_backend()
+        n = int(min(args.cpu_sample_mbp * 1e6, chrom_len - 20_000))
+        s_lo = 20_000
+        sample = synth.subject_region(s_lo, s_lo + n, chrom_len)
+        want, t_build, t_match = cpu_count_exact(PPTB, mod, pats, sample)
+        got = bs.countPDict(pdict, sample)
+        parity = bool((got == want).all())
+        cpu = {"value": n / t_match / 1e9, "unit": "Gbp/s", "cores": 1, "kind": kind,
+               "sample": f"first {n / 1e6:g} Mbp after the telomere of the same subject, same 1M-pattern "
+                         f"dictionary; ACtree2 index build {t_build:.2f} s not included, cold tree; "
+                         f"{t_match:.2f} s of matching",
+               "parity_with_gpu_on_sample": parity, "sample_matches": int(want.sum())}
+
+    line = {"metric": f"countPDict subject Gbp/s (1M 25-mers, max.mismatch {args.mm})",
+            "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": sampler.summary(),
+            "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "matches_total": total_hits}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

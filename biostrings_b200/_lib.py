@@ -19,7 +19,7 @@ SYMBOLS = [
     "bsgpu_pdict3parts_build", "bsgpu_pdict3parts_blank_dups", "bsgpu_pdict3parts_free",
     "bsgpu_pdict3parts_length", "bsgpu_pdict3parts_tb_width",
     "bsgpu_subject_xstring", "bsgpu_subject_views", "bsgpu_subject_set",
-    "bsgpu_subject_chunk", "bsgpu_subject_free", "bsgpu_subject_nletters",
+    "bsgpu_subject_chunk", "bsgpu_subject_repack", "bsgpu_subject_free", "bsgpu_subject_nletters",
     "bsgpu_result_free", "bsgpu_match", "bsgpu_vmatch", "bsgpu_count_device",
     "bsgpu_match_PDict3Parts_XString", "bsgpu_match_PDict3Parts_XStringViews",
     "bsgpu_vmatch_PDict3Parts_XStringSet", "bsgpu_mindex_combine",
@@ -70,6 +70,7 @@ def lib():
     L.bsgpu_subject_views.argtypes = [vp, i64, vp, vp, i32, C.POINTER(vp)]
     L.bsgpu_subject_set.argtypes = [vp, vp, i32, C.POINTER(vp)]
     L.bsgpu_subject_chunk.argtypes = [vp, i64, i64, i64, i64, i64, C.POINTER(vp)]
+    L.bsgpu_subject_repack.argtypes = [vp, vp]
     L.bsgpu_subject_free.argtypes = [vp]
     L.bsgpu_subject_free.restype = None
     L.bsgpu_subject_nletters.argtypes = [vp]

@@ -108,24 +108,104 @@ static int grid_for(long long nthreads, int block, int per_sm)
 	return (int) blocks;
 }
 
+// Device memory pool: cudaMalloc/cudaFree cost milliseconds for the buffers of a 250 Mbp
+// subject, so freed blocks are kept (up to BSGPU_POOL_BYTES, default 8 GiB) and reused
+// by later calls of the same process.
+struct PoolBlock { void *p; size_t bytes; };
+static std::vector<PoolBlock> g_pool;
+static size_t g_pool_bytes = 0;
+
+static size_t pool_limit(void)
+{
+	static size_t lim = 0;
+
+	if (lim == 0) {
+		const char *env = getenv("BSGPU_POOL_BYTES");
+		lim = env ? (size_t) strtoull(env, nullptr, 10) : ((size_t) 8 << 30);
+		if (lim == 0)
+			lim = 1;
+	}
+	return lim;
+}
+
+static void pool_flush(void)
+{
+	for (auto &b : g_pool)
+		cudaFree(b.p);
+	g_pool.clear();
+	g_pool_bytes = 0;
+}
+
+static void *pool_alloc(size_t bytes, size_t *got)
+{
+	int best = -1;
+
+	bytes = (bytes + 511) & ~(size_t) 511;
+	for (int i = 0; i < (int) g_pool.size(); i++)
+		if (g_pool[i].bytes >= bytes && g_pool[i].bytes <= 2 * bytes + 4096 &&
+		    (best < 0 || g_pool[i].bytes < g_pool[best].bytes))
+			best = i;
+	if (best >= 0) {
+		void *p = g_pool[best].p;
+
+		*got = g_pool[best].bytes;
+		g_pool_bytes -= g_pool[best].bytes;
+		g_pool.erase(g_pool.begin() + best);
+		return p;
+	}
+	void *p = nullptr;
+	cudaError_t e = cudaMalloc(&p, bytes);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		pool_flush();
+		e = cudaMalloc(&p, bytes);
+		if (e != cudaSuccess) {
+			cudaGetLastError();
+			return nullptr;
+		}
+	}
+	*got = bytes;
+	return p;
+}
+
+static void pool_free(void *p, size_t bytes)
+{
+	if (p == nullptr)
+		return;
+	if (bytes > pool_limit() / 2 || g_pool.size() >= 256) {
+		cudaFree(p);
+		return;
+	}
+	while (g_pool_bytes + bytes > pool_limit() && !g_pool.empty()) {
+		cudaFree(g_pool.front().p);
+		g_pool_bytes -= g_pool.front().bytes;
+		g_pool.erase(g_pool.begin());
+	}
+	g_pool.push_back({p, bytes});
+	g_pool_bytes += bytes;
+}
+
 template <typename T>
 struct DevBuf {
 	T *p = nullptr;
-	size_t n = 0;
+	size_t n = 0;           // usable elements
+	size_t bytes = 0;       // size of the underlying block
 
+	DevBuf() {}
+	DevBuf(const DevBuf &) = delete;
+	DevBuf &operator=(const DevBuf &) = delete;
 	~DevBuf() { release(); }
-	void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+	void release() { pool_free(p, bytes); p = nullptr; n = 0; bytes = 0; }
+	void swap(DevBuf &o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(bytes, o.bytes); }
 	int alloc(size_t count)
 	{
 		release();
 		if (count == 0)
 			count = 1;
-		cudaError_t e = cudaMalloc((void **) &p, count * sizeof(T));
-		if (e != cudaSuccess) {
-			p = nullptr;
-			cudaGetLastError();
-			return fail(BSGPU_ENOMEM, "cudaMalloc of %zu bytes failed: %s",
-				    count * sizeof(T), cudaGetErrorString(e));
+		p = (T *) pool_alloc(count * sizeof(T), &bytes);
+		if (p == nullptr) {
+			bytes = 0;
+			return fail(BSGPU_ENOMEM, "cudaMalloc of %zu bytes failed", count * sizeof(T));
 		}
 		n = count;
 		return BSGPU_OK;
@@ -471,12 +551,20 @@ static int subject_finish(bsgpu_subject *s, const uint8_t *const *srcs, const ui
 			    (long long) s->total);
 	int64_t nwords = s->total / 32;
 	TRY(s->d_bytes.alloc((size_t) s->total + 64));
-	CUDA_TRY(cudaMemset(s->d_bytes.p, BSGPU_SEP_BYTE, (size_t) s->total + 64));
 	if (n == 1) {
+		// only the guards need the separator byte
+		int64_t seg_end = s->seg_start[0] + s->seg_len[0];
+
+		CUDA_TRY(cudaMemsetAsync(s->d_bytes.p, BSGPU_SEP_BYTE, (size_t) s->seg_start[0]));
+		CUDA_TRY(cudaMemsetAsync(s->d_bytes.p + seg_end, BSGPU_SEP_BYTE,
+					 (size_t) (s->total + 64 - seg_end)));
 		if (s->seg_len[0] > 0)
-			CUDA_TRY(cudaMemcpy(s->d_bytes.p + s->seg_start[0], one_src ? one_src : srcs[0],
-					    (size_t) s->seg_len[0], cudaMemcpyHostToDevice));
-	} else if (n > 1) {
+			CUDA_TRY(cudaMemcpyAsync(s->d_bytes.p + s->seg_start[0], one_src ? one_src : srcs[0],
+						 (size_t) s->seg_len[0], cudaMemcpyHostToDevice));
+	} else {
+		CUDA_TRY(cudaMemsetAsync(s->d_bytes.p, BSGPU_SEP_BYTE, (size_t) s->total + 64));
+	}
+	if (n > 1) {
 		// assemble on the host in slabs to bound the staging memory
 		const int64_t SLAB = 256ll << 20;
 		std::vector<uint8_t> stage;
@@ -502,9 +590,10 @@ static int subject_finish(bsgpu_subject *s, const uint8_t *const *srcs, const ui
 	TRY(s->d_codes.alloc((size_t) nwords + 4));
 	TRY(s->d_valid.alloc((size_t) nwords + 4));
 	TRY(s->d_iupac.alloc((size_t) nwords + 4));
-	CUDA_TRY(cudaMemset(s->d_codes.p, 0, ((size_t) nwords + 4) * sizeof(uint64_t)));
-	CUDA_TRY(cudaMemset(s->d_valid.p, 0, ((size_t) nwords + 4) * sizeof(uint32_t)));
-	CUDA_TRY(cudaMemset(s->d_iupac.p, 0, ((size_t) nwords + 4) * sizeof(uint32_t)));
+	// the pack kernel writes words [0, nwords); only the 4 spare words need zeroing
+	CUDA_TRY(cudaMemsetAsync(s->d_codes.p + nwords, 0, 4 * sizeof(uint64_t)));
+	CUDA_TRY(cudaMemsetAsync(s->d_valid.p + nwords, 0, 4 * sizeof(uint32_t)));
+	CUDA_TRY(cudaMemsetAsync(s->d_iupac.p + nwords, 0, 4 * sizeof(uint32_t)));
 	pack_subject_kernel<<<grid_for(nwords, 256, 8), 256>>>(s->d_bytes.p, nwords, s->d_codes.p,
 							      s->d_valid.p, s->d_iupac.p);
 	g_launches++;
@@ -628,6 +717,19 @@ extern "C" int bsgpu_subject_chunk(const uint8_t *chunk, int64_t chunk_len, int6
 	return BSGPU_OK;
 }
 
+extern "C" int bsgpu_subject_repack(bsgpu_subject *s, void *stream)
+{
+	if (s == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_subject_repack(): NULL handle");
+	TRY(ensure_device());
+	int64_t nwords = s->total / 32;
+	pack_subject_kernel<<<grid_for(nwords, 256, 8), 256, 0, (cudaStream_t) stream>>>(
+		s->d_bytes.p, nwords, s->d_codes.p, s->d_valid.p, s->d_iupac.p);
+	g_launches++;
+	CUDA_TRY(cudaGetLastError());
+	return BSGPU_OK;
+}
+
 extern "C" void bsgpu_subject_free(bsgpu_subject *s) { delete s; }
 extern "C" int64_t bsgpu_subject_nletters(const bsgpu_subject *s) { return s ? s->nletters : 0; }
 
@@ -679,8 +781,7 @@ static int grow(DevBuf<unsigned long long> &buf, size_t need, size_t keep, cudaS
 					 cudaMemcpyDeviceToDevice, st));
 		CUDA_TRY(cudaStreamSynchronize(st));
 	}
-	std::swap(buf.p, nb.p);
-	std::swap(buf.n, nb.n);
+	buf.swap(nb);
 	return BSGPU_OK;
 }
 
@@ -869,10 +970,8 @@ static int sort_records(Workspace *ws, unsigned long long n, int end_bit, bool u
 		TRY(ws->cub_temp.alloc(temp));
 	CUDA_TRY(cub::DeviceRadixSort::SortKeys(ws->cub_temp.p, temp, db, (long long) n, 0, end_bit, st));
 	g_launches += 4;
-	if (db.Current() != ws->rec.p) {
-		std::swap(ws->rec.p, ws->rec2.p);
-		std::swap(ws->rec.n, ws->rec2.n);
-	}
+	if (db.Current() != ws->rec.p)
+		ws->rec.swap(ws->rec2);
 	if (uniq) {
 		TRY(grow(ws->rec2, (size_t) n, 0, st));
 		temp = 0;
@@ -882,8 +981,7 @@ static int sort_records(Workspace *ws, unsigned long long n, int end_bit, bool u
 			TRY(ws->cub_temp.alloc(temp));
 		CUDA_TRY(cub::DeviceSelect::Unique(ws->cub_temp.p, temp, ws->rec.p, ws->rec2.p, d_nsel, (long long) n, st));
 		g_launches += 2;
-		std::swap(ws->rec.p, ws->rec2.p);
-		std::swap(ws->rec.n, ws->rec2.n);
+		ws->rec.swap(ws->rec2);
 		TRY(read_counter(ws, 3, n_out, st));
 	}
 	return BSGPU_OK;

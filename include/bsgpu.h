@@ -115,6 +115,10 @@ int bsgpu_subject_set(const uint8_t *concat, const int32_t *widths, int32_t n,
 int bsgpu_subject_chunk(const uint8_t *chunk, int64_t chunk_len, int64_t chunk_start,
 		int64_t subject_len, int64_t report_lo, int64_t report_hi,
 		bsgpu_subject **out);
+/* Re-derives the packed planes from the resident bytes on `stream` (asynchronous).  The
+ * upload functions already do this once; a caller that wants the packing inside its own
+ * timed region (bench.py does) calls it again. */
+int bsgpu_subject_repack(bsgpu_subject *subj, void *stream);
 void bsgpu_subject_free(bsgpu_subject *subj);
 int64_t bsgpu_subject_nletters(const bsgpu_subject *subj);	/* letters that are scanned */
 
