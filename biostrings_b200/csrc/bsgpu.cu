@@ -343,7 +343,7 @@ extern "C" int bsgpu_pdict3parts_build(int algo, int32_t M,
 	// src/match_pdict_ACtree2.c:801-824,761-763; src/match_pdict_Twobit.c:116-142
 	if (M == 0 && algo == BSGPU_ALGO_ACTREE2)
 		return fail(BSGPU_EINVAL, "Trusted Band is empty");
-	if (M > 0x3FFFFFFF)
+	if (M >= 0x3FFFFFFF)
 		return fail(BSGPU_EINVAL, "new_ACtree(): tb_length > MAX_P_ID");
 	int w = -1;
 	{
@@ -457,11 +457,12 @@ extern "C" int bsgpu_pdict3parts_build(int algo, int32_t M,
 				table[b].y = (uint32_t) id;
 				break;
 			}
-			if (table[b].w == BSGPU_EMPTY_ID) {
+			if ((table[b].w & BSGPU_ID_MASK) == BSGPU_EMPTY_ID) {
 				table[b].z = fp;
-				table[b].w = (uint32_t) id;
+				table[b].w = (table[b].w & BSGPU_OVERFLOW_FLAG) | (uint32_t) id;
 				break;
 			}
+			table[b].w |= BSGPU_OVERFLOW_FLAG;      // displaced: later buckets must be searched
 			b = (b + 1) & (nb - 1);
 		}
 	}

@@ -12,7 +12,9 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 
-#define BSGPU_EMPTY_ID 0xFFFFFFFFu
+#define BSGPU_EMPTY_ID 0x3FFFFFFFu       // id field of an empty slot (ids are < 2^30 - 1)
+#define BSGPU_ID_MASK 0x3FFFFFFFu
+#define BSGPU_OVERFLOW_FLAG 0x80000000u  // on slot 1: a key of this bucket lives further on
 #define BSGPU_SEP_BYTE 0x80u        // never matches anything in any of the 4 match tables
 #define BSGPU_GUARD 128             // guard letters in front of / behind the subject
 #define BSGPU_POS_BITS 34           // low bits of a 64-bit record = position / coordinate
@@ -72,7 +74,7 @@ struct BsgpuSubjectView {
 };
 
 struct BsgpuIndexView {
-	const uint4 *table;          // [nbuckets] {fp0,id0,fp1,id1}
+	const uint4 *table;          // [nbuckets] {fp0, id0, fp1, id1 | overflow flag}
 	const uint64_t *keys;        // [M] seed key of pattern id (valid for TB leaders)
 	const int32_t *seed_next;    // w > 32: next TB leader sharing the 32-letter seed, or -1
 	uint32_t bucket_shift;       // 32 - log2(nbuckets)

@@ -160,19 +160,22 @@ __device__ __forceinline__ void tb_hit(const BsgpuIndexView &I, const BsgpuSubje
 // Hash probe.
 // ------------------------------------------------------------------------------------
 
-// Slow path of a probe whose first bucket was full or held a fingerprint match.
-__device__ __noinline__ int probe_slow(const BsgpuIndexView &I, uint64_t key, uint32_t bucket,
-				       uint32_t fp, uint4 b)
+// Full probe: walks the buckets from the home bucket while the overflow flag says that
+// a key hashed here was displaced to a later bucket.  Returns the TB id or -1.
+__device__ __forceinline__ int probe_from(const BsgpuIndexView &I, uint64_t key, uint32_t bucket,
+					  uint32_t fp)
 {
 	for (;;) {
-		if (b.x == fp && b.y != BSGPU_EMPTY_ID && __ldg(I.keys + b.y) == key)
-			return (int) b.y;
-		if (b.z == fp && b.w != BSGPU_EMPTY_ID && __ldg(I.keys + b.w) == key)
-			return (int) b.w;
-		if (b.w == BSGPU_EMPTY_ID)
-			return -1;      // bucket not full: the key would have been placed here
+		uint4 b = __ldg(I.table + bucket);
+		uint32_t id0 = b.y & BSGPU_ID_MASK, id1 = b.w & BSGPU_ID_MASK;
+
+		if (b.x == fp && id0 != BSGPU_EMPTY_ID && __ldg(I.keys + id0) == key)
+			return (int) id0;
+		if (b.z == fp && id1 != BSGPU_EMPTY_ID && __ldg(I.keys + id1) == key)
+			return (int) id1;
+		if (!(b.w & BSGPU_OVERFLOW_FLAG))
+			return -1;
 		bucket = (bucket + 1) & I.bucket_mask;
-		b = __ldg(I.table + bucket);
 	}
 }
 
@@ -181,11 +184,7 @@ __device__ __forceinline__ int probe(const BsgpuIndexView &I, uint64_t key)
 	uint32_t top, fp;
 
 	bsgpu_hash(key, top, fp);
-	uint32_t bucket = top >> I.bucket_shift;
-	uint4 b = __ldg(I.table + bucket);
-	if (b.w == BSGPU_EMPTY_ID && b.x != fp && b.z != fp)
-		return -1;
-	return probe_slow(I, key, bucket, fp, b);
+	return probe_from(I, key, top >> I.bucket_shift, fp);
 }
 
 // For TB widths > 32 the hash covers the first 32 letters; the rest is compared here.
@@ -272,9 +271,12 @@ scan_tb_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R, BsgpuReport 
 			m &= (start_hi - base) <= 0 ? 0u : 0xFFFFFFFFu >> (int) (base + 32 - start_hi);
 		if (m == 0)
 			continue;
+		// Phase 1: one 16-byte bucket load per window, SCAN_GROUP loads in flight; a
+		// window needs a second look only if a fingerprint matches or the home bucket
+		// overflowed (about 1 % of the windows of a half-full table).
+		uint32_t rare = 0;
 #pragma unroll
 		for (int g = 0; g < 32; g += SCAN_GROUP) {
-			uint64_t key[SCAN_GROUP];
 			uint32_t fp[SCAN_GROUP], bucket[SCAN_GROUP];
 			uint4 b[SCAN_GROUP];
 
@@ -286,8 +288,7 @@ scan_tb_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R, BsgpuReport 
 				uint64_t k = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
 				uint32_t top;
 
-				key[q] = k & I.seed_mask;
-				bsgpu_hash(key[q], top, fp[q]);
+				bsgpu_hash(k & I.seed_mask, top, fp[q]);
 				bucket[q] = top >> I.bucket_shift;
 			}
 #pragma unroll
@@ -295,25 +296,28 @@ scan_tb_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R, BsgpuReport 
 				if ((m >> (g + q)) & 1u)
 					b[q] = __ldg(I.table + bucket[q]);
 				else
-					b[q] = make_uint4(0, BSGPU_EMPTY_ID, 0, BSGPU_EMPTY_ID);
+					b[q] = make_uint4(~fp[q], BSGPU_EMPTY_ID, ~fp[q], BSGPU_EMPTY_ID);
 			}
 #pragma unroll
 			for (int q = 0; q < SCAN_GROUP; q++) {
-				// an empty, non-matching first bucket is the common case
-				bool rare = (m >> (g + q)) & 1u;
-
-				rare = rare && !(b[q].w == BSGPU_EMPTY_ID &&
-						 (b[q].y == BSGPU_EMPTY_ID || b[q].x != fp[q]));
-				if (rare) {
-					int id = probe_slow(I, key[q], bucket[q], fp[q], b[q]);
-					int64_t e = base + g + q + w - 1;
-
-					if (w > 32)
-						id = resolve_long_tb(I, S, id, e, 1);
-					if (id >= 0)
-						tb_hit(I, S, R, C, direct, id, e);
-				}
+				bool look = b[q].x == fp[q] || b[q].z == fp[q] ||
+					    (b[q].w & BSGPU_OVERFLOW_FLAG);
+				rare |= (look ? 1u : 0u) << (g + q);
 			}
+		}
+		// Phase 2: the few windows that need the full probe, all lanes together.
+		while (rare) {
+			int r = __ffs(rare) - 1;
+			rare &= rare - 1;
+			uint64_t k = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
+			k &= I.seed_mask;
+			int id = probe(I, k);
+			int64_t e = base + r + w - 1;
+
+			if (id >= 0 && w > 32)
+				id = resolve_long_tb(I, S, id, e, 1);
+			if (id >= 0)
+				tb_hit(I, S, R, C, direct, id, e);
 		}
 	}
 }
