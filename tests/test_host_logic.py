@@ -1,0 +1,127 @@
+"""Host-side logic of the product (no GPU): containers, threebands, Dups, argument
+normalisation, MIndex CSR accessors, sharding arithmetic, synthetic inputs."""
+import numpy as np
+import pytest
+
+import biostrings_b200 as bs
+from biostrings_b200 import matchpdict as mp, pdict as pdm, sharding, synth
+from biostrings_b200._lib import NA_INTEGER
+from oracle import rlevel as R
+
+
+def test_encoding_roundtrip():
+    s = "ACGTMRWSYKVHDBN-+."
+    codes = bs.encode_dna(s)
+    assert codes.tolist() == [1, 2, 4, 8, 3, 5, 9, 6, 10, 12, 7, 11, 13, 14, 15, 16, 32, 64]
+    assert bs.decode_dna(codes) == s
+    assert bs.encode_dna("acgt").tolist() == [1, 2, 4, 8]
+    with pytest.raises(ValueError, match="not in lookup table"):
+        bs.encode_dna("ACGX")
+    assert (bs.encode_dna(s) == R.encode(s)).all()
+
+
+def test_threebands_matches_oracle_restatement():
+    g = np.random.Generator(np.random.PCG64(3))
+    seqs = ["".join("ACGT"[i] for i in g.integers(0, 4, int(n))) for n in g.integers(8, 20, 50)]
+    x, y = bs.DNAStringSet(seqs), R.SeqSet(seqs)
+    for kw in ({}, {"start": 2, "end": 6}, {"start": 1, "width": 8}, {"end": -1, "width": 3},
+               {"start": 3}, {"end": 5}, {"start": -6, "end": -2}):
+        a = pdm.threebands(x, **kw)
+        b = R.threebands(y, kw.get("start"), kw.get("end"), kw.get("width"))
+        for p, q in zip(a, b):
+            assert (p.widths == q.widths).all() and (p.concat == q.concat).all()
+    for kw in ({"start": 25}, {"start": 1, "end": 3, "width": 3}, {"width": 3}, {"width": -1, "start": 1}):
+        with pytest.raises(ValueError, match="solving row"):
+            pdm.threebands(x, **kw)
+
+
+def test_dups():
+    h2l = np.array([NA_INTEGER, NA_INTEGER, 1, NA_INTEGER, 2, 1], dtype=np.int32)
+    d, o = pdm.Dups(h2l), R.Dups(h2l)
+    assert d.duplicated().tolist() == [False, False, True, False, True, True]
+    assert d.togroup().tolist() == [1, 2, 1, 4, 2, 1]
+    assert d.togrouplength().tolist() == [3, 2, 3, 1, 2, 3] == o.togrouplength().tolist()
+    assert d.low2high(1).tolist() == [3, 6] and d.low2high(4) is None
+    assert d.members([1, 4]).tolist() == [1, 3, 4, 6] == o.members([1, 4]).tolist()
+    assert d.members([]).tolist() == []
+
+
+def test_normarg():
+    assert mp.normarg_fixed(True) == (True, True)
+    assert mp.normarg_fixed(False) == (False, False)
+    assert mp.normarg_fixed("pattern") == (True, False)
+    assert mp.normarg_fixed("subject") == (False, True)
+    assert mp.normarg_fixed(["pattern", "subject"]) == (True, True)
+    assert mp.normarg_fixed([True, False]) == (True, False)
+    assert mp.normarg_fixed({"subject": True, "pattern": False}) == (False, True)
+    for bad in (["pattern", "pattern"], "both", [True, True, True], 3):
+        with pytest.raises((ValueError, TypeError)):
+            mp.normarg_fixed(bad)
+    for f in (True, False, "pattern", "subject"):
+        assert mp.normarg_fixed(f) == tuple(R.normarg_fixed(f))
+    assert mp.normarg_max_mismatch(2.0) == 2
+    with pytest.raises(ValueError, match="non-negative"):
+        mp.normarg_max_mismatch(-1)
+    with pytest.raises(ValueError, match="must be <= 'max.mismatch'"):
+        mp.normarg_min_mismatch(2, 1)
+    assert mp.normarg_collapse(False) == 0 and mp.normarg_collapse(2) == 2
+    with pytest.raises(ValueError, match="FALSE, 1 or 2"):
+        mp.normarg_collapse(3)
+
+
+def test_mindex_csr_accessors():
+    # the example of R/MIndex-class.R:165-176
+    width0 = np.array([9, 10, 8, 4, 10], dtype=np.int32)
+    dups0 = pdm.Dups(np.array([NA_INTEGER] * 4 + [2], dtype=np.int32))
+    m = bs.ByPos_MIndex(width0, [0, 0, 2, 2, 2, 2], [199, 402], names=list("abcde"), dups0=dups0)
+    ends = m.endIndex()
+    assert ends[0] is None and ends[1].tolist() == [199, 402] and ends[4].tolist() == [199, 402]
+    st = m.startIndex()
+    assert st[1].tolist() == [190, 393] and st[4].tolist() == [190, 393] and st[2] is None
+    assert m.elementNROWS().tolist() == [0, 2, 0, 0, 2]
+    s, e, w = m[4]
+    assert s.tolist() == [190, 393] and w.tolist() == [10, 10]
+    with pytest.raises(IndexError):
+        m[5]
+    o = R.MIndex(width0, [None, np.array([199, 402]), None, None, None], dups0=R.Dups(dups0.high2low))
+    assert [None if x is None else x.tolist() for x in o.startIndex()] == \
+        [None if x is None else x.tolist() for x in st]
+
+
+def test_masked_views():
+    m = bs.MaskedDNAString("ATGGATACACAA", 4, 8).as_views()
+    assert m.start.tolist() == [1, 9] and m.width.tolist() == [3, 4]
+    m = bs.MaskedDNAString("ACGTACGTAC", [1, 3, 9], [2, 5, 20]).as_views()
+    assert m.start.tolist() == [6] and m.width.tolist() == [3]
+    o = R.Masked("ACGTACGTAC", [1, 3, 9], [2, 5, 20]).as_views()
+    assert o.start.tolist() == [6] and o.width.tolist() == [3]
+    v = bs.XStringViews("ACGTACGT", [0, 7, 3], [3, 5, 2]).to_set()     # trimmed, not an error
+    assert v.widths.tolist() == [2, 2, 2]
+
+
+def test_shard_bounds_and_chunks():
+    for n, world in ((10, 3), (250_000_000, 8), (7, 8), (0, 2)):
+        parts = [sharding.shard_bounds(n, world, r) for r in range(world)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        sizes = [b - a for a, b in parts]
+        assert max(sizes) - min(sizes) <= 1
+    assert sharding.chunk_range(100, 200, 1000, 24, 13) == (76, 213)
+    assert sharding.chunk_range(0, 200, 210, 24, 13) == (0, 210)
+    cuts = sharding.split_set_by_letters([5, 5, 5, 5, 100, 5, 5], 2)
+    assert cuts[0][0] == 0 and cuts[-1][1] == 7 and cuts[0][1] == cuts[1][0]
+
+
+def test_synth_is_block_deterministic():
+    a = synth.subject_region(0, 3_000_000, 250_000_000)
+    b = synth.subject_region(1_500_000, 2_500_000, 250_000_000)
+    assert (a[1_500_000:2_500_000] == b).all()
+    assert (a[:10_000] == 15).all() and set(np.unique(a[20_000:1_000_000]).tolist()) <= {1, 2, 4, 8, 15}
+    gc = np.isin(a[a != 15], [2, 4]).mean()
+    assert abs(gc - 0.41) < 0.01
+    whole = synth.subject_region(0, 250_000_000 // 50, 250_000_000 // 50)
+    assert 0.05 < (whole == 15).mean() < 0.09
+    p = synth.dictionary(20_000, 25, 250_000_000, 2)
+    q = synth.dictionary(20_000, 25, 250_000_000, 2)
+    assert p.shape == (20_000, 25) and (p == q).all() and np.isin(p, [1, 2, 4, 8]).all()
+    assert len(np.unique(p, axis=0)) < 20_000           # duplicates are present
