@@ -19,7 +19,7 @@
 #include <cub/device/device_select.cuh>
 
 #include "../../include/bsgpu.h"
-#include "bsgpu_kernels.cuh"
+#include "bsgpu_qindex.cuh"
 
 // ---------------------------------------------------------------------------------------
 // errors
@@ -231,6 +231,11 @@ struct bsgpu_pdict3parts {
 	std::vector<uint64_t> keys;             // seed key per pattern
 	std::vector<uint8_t> tb;                // M*w letters
 	std::vector<int32_t> tail_len;          // per pattern
+	std::vector<uint8_t> h_head, h_tail;    // host copies of the flank letters
+	std::vector<int64_t> h_head_off, h_tail_off;
+	std::vector<uint8_t> excluded;          // pp_exclude[i] != NA
+	std::vector<uint8_t> is_tb_dup;         // had a non-NA high2low at build time
+	mutable std::unique_ptr<struct QIndex> qcache;  // q-gram index built on first use
 	uint32_t nbuckets = 0;
 	bool all_singletons = true;
 	DevBuf<uint4> d_table;
@@ -268,6 +273,243 @@ struct bsgpu_pdict3parts {
 	}
 };
 
+// ---------------------------------------------------------------------------------------
+// q-gram seed index (bsgpu_qindex.cuh)
+// ---------------------------------------------------------------------------------------
+
+struct SeedShape { int m, k, q, span; unsigned long long mask, shifts; };
+static const SeedShape g_shapes[] = {
+#include "bsgpu_shapes.inc"
+};
+
+struct QIndex {
+	bool ok = false;        // false: this dictionary is not eligible (cached negative answer)
+	int nparts = 0;
+	BsgpuQIndexView v = {};
+	DevBuf<uint2> d_dir;
+	DevBuf<uint32_t> d_entries;
+	DevBuf<ulonglong2> d_pat;
+	DevBuf<uint8_t> d_len;
+	int max_len = 0;
+	int max_shift = 0;
+};
+
+static bool qindex_disabled(void)
+{
+	const char *env = getenv("BSGPU_NO_QINDEX");
+	return env != nullptr && env[0] == '1';
+}
+
+// Picks the seed family for a Hamming filter on windows of m letters with <= k mismatches.
+static bool pick_shape(int m, int k, SeedShape *out)
+{
+	if (m >= 12 * (k + 1)) {
+		out->m = m; out->k = k; out->q = 12; out->span = 12; out->mask = 0xFFFull;
+		out->shifts = 0;
+		for (int i = 0; i <= k; i++)
+			out->shifts |= 1ull << (12 * i);
+		return true;
+	}
+	for (const SeedShape &sh : g_shapes)
+		if (sh.m == m && sh.k == k) {
+			*out = sh;
+			return true;
+		}
+	return false;
+}
+
+// Builds (once) the q-gram index of the dictionary behind `parts`.
+//   nparts == 1: parts[0] must be a whole-pattern Trusted Band (no head, no tail)
+//   nparts  > 1: the components of an MTB_PDict (band b = letters [headw_b, headw_b+w_b))
+// Returns the cached index; ->ok tells whether the dictionary is eligible.
+static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const QIndex **out)
+{
+	const bsgpu_pdict3parts *p0 = parts[0];
+
+	*out = nullptr;
+	if (p0->qcache && p0->qcache->nparts == nparts) {
+		*out = p0->qcache.get();
+		return BSGPU_OK;
+	}
+	std::unique_ptr<QIndex> qi(new QIndex());
+	qi->nparts = nparts;
+	int M = p0->M;
+	auto done = [&]() {
+		p0->qcache = std::move(qi);
+		*out = p0->qcache.get();
+		return BSGPU_OK;
+	};
+	if (qindex_disabled() || M == 0 || M >= (1 << 27))
+		return done();
+	// --- reconstruct the full patterns: head0 + tb0 + tail0 ------------------------------
+	std::vector<int32_t> len(M);
+	std::vector<const uint8_t *> hp(M, nullptr), tp(M, nullptr);
+	std::vector<int32_t> hl(M, 0), tl(M, 0);
+	int min_w = 1 << 30, max_w = 0;
+	for (int i = 0; i < M; i++) {
+		if (p0->has_head) {
+			hp[i] = p0->h_head.data() + p0->h_head_off[i];
+			hl[i] = (int32_t) (p0->h_head_off[i + 1] - p0->h_head_off[i]);
+		}
+		if (p0->has_tail) {
+			tp[i] = p0->h_tail.data() + p0->h_tail_off[i];
+			tl[i] = (int32_t) (p0->h_tail_off[i + 1] - p0->h_tail_off[i]);
+		}
+		len[i] = hl[i] + p0->w + tl[i];
+		if (p0->excluded[i])
+			continue;
+		min_w = std::min(min_w, len[i]);
+		max_w = std::max(max_w, len[i]);
+	}
+	if (max_w == 0 || max_w > 64)
+		return done();
+	SeedShape sh;
+	if (nparts == 1) {
+		if (p0->has_head || p0->has_tail || !p0->all_singletons || p0->w < 20)
+			return done();
+		sh.m = p0->w; sh.k = 0; sh.q = 12; sh.span = 12; sh.mask = 0xFFFull; sh.shifts = 0;
+		int stride = std::min(p0->w - 12 + 1, BSGPU_Q_MAX_SHIFTS);
+		for (int t = 0; t < stride; t++)
+			sh.shifts |= 1ull << t;
+		qi->v.mode = 0;
+		qi->v.stride = stride;
+	} else {
+		// the parts must be the k+1 bands of one MTB_PDict: band b starts where band b-1
+		// ends, heads of band b = everything before it (R/PDict-class.R:476-484)
+		int at = 0;
+		for (int b = 0; b < nparts; b++) {
+			const bsgpu_pdict3parts *pb = parts[b];
+			if (pb->M != M || pb->excluded != p0->excluded)
+				return done();
+			if ((b == 0) != !pb->has_head)
+				return done();
+			if (b > 0)
+				for (int i = 0; i < M; i++)
+					if (pb->h_head_off[i + 1] - pb->h_head_off[i] != at)
+						return done();
+			at += pb->w;
+		}
+		if (at != min_w)
+			return done();
+		if (!pick_shape(min_w, nparts - 1, &sh))
+			return done();
+		qi->v.mode = 1;
+		qi->v.stride = 1;
+	}
+	if (sh.span > 32)
+		return done();
+	// --- all letters of the non-excluded patterns must be base letters ------------------------
+	std::vector<ulonglong2> pat(M, make_ulonglong2(0, 0));
+	std::vector<uint8_t> plen(M, 0);
+	std::vector<uint8_t> letters(64);
+	for (int i = 0; i < M; i++) {
+		if (p0->excluded[i])
+			continue;
+		int n = 0;
+		for (int d = 0; d < hl[i]; d++) letters[n++] = hp[i][d];
+		for (int d = 0; d < p0->w; d++) letters[n++] = p0->tb[(size_t) i * p0->w + d];
+		for (int d = 0; d < tl[i]; d++) letters[n++] = tp[i][d];
+		unsigned long long lo = 0, hi = 0;
+		for (int d = 0; d < n; d++) {
+			if (!bsgpu_is_base(letters[d]))
+				return done();
+			unsigned long long c = bsgpu_base_code(letters[d]);
+			if (d < 32) lo |= c << (2 * d); else hi |= c << (2 * (d - 32));
+		}
+		pat[i] = make_ulonglong2(lo, hi);
+		plen[i] = (uint8_t) n;
+	}
+	// --- seed family ---------------------------------------------------------------------------
+	BsgpuQIndexView &v = qi->v;
+	v.q = sh.q;
+	v.min_w = nparts == 1 ? p0->w : min_w;
+	v.shape1 = sh.mask;
+	v.shape2 = 0;
+	v.nruns = 0;
+	for (int i = 0; i < sh.span; i++)
+		if ((sh.mask >> i) & 1) {
+			v.shape2 |= 1ull << (2 * i);
+			if (i > 0 && ((sh.mask >> (i - 1)) & 1)) {
+				v.run_len[v.nruns - 1]++;
+			} else {
+				if (v.nruns == BSGPU_Q_MAX_RUNS)
+					return done();
+				v.run_src[v.nruns] = i;
+				v.run_len[v.nruns] = 1;
+				v.nruns++;
+			}
+		}
+	v.nshifts = 0;
+	for (int t = 0; t < 64; t++)
+		if ((sh.shifts >> t) & 1) {
+			if (v.nshifts == BSGPU_Q_MAX_SHIFTS || t + sh.span > v.min_w)
+				return done();
+			v.shift[v.nshifts++] = t;
+			qi->max_shift = t;
+		}
+	// --- entries, counting sort by seed key ---------------------------------------------------
+	size_t nkeys = (size_t) 1 << (2 * sh.q);
+	std::vector<uint32_t> cnt(nkeys + 1, 0);
+	auto seed_key = [&](int i, int t) {
+		uint32_t key = 0;
+		int out = 0;
+		for (int r = 0; r < v.nruns; r++)
+			for (int d = 0; d < v.run_len[r]; d++) {
+				int pos = t + v.run_src[r] + d;
+				unsigned long long c = pos < 32 ? (pat[i].x >> (2 * pos)) & 3 : (pat[i].y >> (2 * (pos - 32))) & 3;
+				key |= (uint32_t) c << out;
+				out += 2;
+			}
+		return key;
+	};
+	size_t nent = 0;
+	for (int i = 0; i < M; i++) {
+		if (p0->excluded[i])
+			continue;
+		if (nparts == 1 && p0->is_tb_dup[i])
+			continue;       // TB duplicates are never reported once dups are blanked
+		for (int s2 = 0; s2 < v.nshifts; s2++) {
+			cnt[seed_key(i, v.shift[s2])]++;
+			nent++;
+		}
+	}
+	for (size_t k2 = 0; k2 < nkeys; k2++)
+		if (cnt[k2] > 254)
+			return done();  // a very repetitive dictionary: keep the Trusted-Band engine
+	std::vector<uint2> dir(nkeys / 4);
+	std::vector<uint32_t> start(nkeys);
+	uint32_t run = 0;
+	for (size_t k2 = 0; k2 < nkeys; k2++) {
+		start[k2] = run;
+		if ((k2 & 3) == 0) {
+			dir[k2 >> 2].x = run;
+			dir[k2 >> 2].y = 0;
+		}
+		dir[k2 >> 2].y |= cnt[k2] << (8 * (k2 & 3));
+		run += cnt[k2];
+	}
+	std::vector<uint32_t> entries(nent ? nent : 1);
+	for (int i = 0; i < M; i++) {
+		if (p0->excluded[i])
+			continue;
+		if (nparts == 1 && p0->is_tb_dup[i])
+			continue;
+		for (int s2 = 0; s2 < v.nshifts; s2++)
+			entries[start[seed_key(i, v.shift[s2])]++] = ((uint32_t) i << 5) | (uint32_t) s2;
+	}
+	TRY(qi->d_dir.upload(dir.data(), dir.size()));
+	TRY(qi->d_entries.upload(entries.data(), entries.size()));
+	TRY(qi->d_pat.upload(pat.data(), pat.size()));
+	TRY(qi->d_len.upload(plen.data(), plen.size()));
+	v.dir = qi->d_dir.p;
+	v.entries = qi->d_entries.p;
+	v.pat = qi->d_pat.p;
+	v.pat_len = qi->d_len.p;
+	qi->max_len = max_w;
+	qi->ok = true;
+	return done();
+}
+
 static int upload_groups(bsgpu_pdict3parts *p3, bool blank)
 {
 	int M = p3->M;
@@ -302,9 +544,12 @@ static int upload_groups(bsgpu_pdict3parts *p3, bool blank)
 }
 
 static int upload_flank(int M, const uint8_t *concat, const int32_t *widths, DevBuf<uint8_t> &d_bytes,
-			DevBuf<int64_t> &d_off, bool &present, int &maxw, std::vector<int32_t> *lens)
+			DevBuf<int64_t> &d_off, bool &present, int &maxw, std::vector<int32_t> *lens,
+			std::vector<uint8_t> &h_bytes, std::vector<int64_t> &h_off)
 {
-	std::vector<int64_t> off(M + 1, 0);
+	std::vector<int64_t> &off = h_off;
+
+	off.assign(M + 1, 0);
 
 	present = false;
 	maxw = 0;
@@ -322,6 +567,8 @@ static int upload_flank(int M, const uint8_t *concat, const int32_t *widths, Dev
 				(*lens)[i] = widths[i];
 	}
 	present = maxw > 0;
+	if (present)
+		h_bytes.assign(concat, concat + off[M]);
 	TRY(d_off.upload(off.data(), off.size()));
 	TRY(d_bytes.upload(concat, present ? (size_t) off[M] : 0));
 	return BSGPU_OK;
@@ -474,9 +721,16 @@ extern "C" int bsgpu_pdict3parts_build(int algo, int32_t M,
 	}
 	TRY(upload_groups(p3, false));
 	TRY(upload_flank(M, head_concat, head_widths, p3->d_head, p3->d_head_off, p3->has_head,
-			 p3->max_H, nullptr));
+			 p3->max_H, nullptr, p3->h_head, p3->h_head_off));
 	TRY(upload_flank(M, tail_concat, tail_widths, p3->d_tail, p3->d_tail_off, p3->has_tail,
-			 p3->max_T, &p3->tail_len));
+			 p3->max_T, &p3->tail_len, p3->h_tail, p3->h_tail_off));
+	p3->is_tb_dup.assign(M, 0);
+	for (int i = 0; i < M; i++)
+		p3->is_tb_dup[i] = p3->high2low[i] != BSGPU_NA;
+	p3->excluded.assign(M, 0);
+	if (pp_exclude != nullptr)
+		for (int i = 0; i < M; i++)
+			p3->excluded[i] = pp_exclude[i] != BSGPU_NA;
 	*out = guard.release();
 	return BSGPU_OK;
 }
@@ -488,6 +742,7 @@ extern "C" int bsgpu_pdict3parts_blank_dups(bsgpu_pdict3parts *p3)
 	TRY(ensure_device());
 	TRY(upload_groups(p3, true));
 	std::fill(p3->high2low.begin(), p3->high2low.end(), BSGPU_NA);
+	p3->qcache.reset();
 	return BSGPU_OK;
 }
 
@@ -508,11 +763,12 @@ struct bsgpu_subject {
 	int64_t nletters = 0;           // letters scanned
 	int64_t scan_lo = 0, scan_hi = 0;       // TB *ends* (concat index) in [scan_lo, scan_hi)
 	bool open_left = false, open_right = false;     // chunk edges that are not subject edges
+	bool own_from_start = true, own_to_end = true;  // report range reaches the subject's edges
 	int64_t halo_left = 0, halo_right = 0;  // letters available around the report range
 	std::vector<int64_t> seg_start, seg_coord;
 	std::vector<int32_t> seg_len;
 	DevBuf<uint8_t> d_bytes;
-	DevBuf<uint64_t> d_codes;
+	DevBuf<uint64_t> d_codes, d_inv2;
 	DevBuf<uint32_t> d_valid, d_iupac;
 	DevBuf<int64_t> d_seg_start, d_seg_coord;
 	DevBuf<int32_t> d_seg_len;
@@ -525,6 +781,7 @@ struct bsgpu_subject {
 		S.codes = d_codes.p;
 		S.valid = d_valid.p;
 		S.iupac = d_iupac.p;
+		S.inv2 = d_inv2.p;
 		S.seg_start = d_seg_start.p;
 		S.seg_len = d_seg_len.p;
 		S.seg_coord = d_seg_coord.p;
@@ -591,12 +848,14 @@ static int subject_finish(bsgpu_subject *s, const uint8_t *const *srcs, const ui
 	TRY(s->d_codes.alloc((size_t) nwords + 4));
 	TRY(s->d_valid.alloc((size_t) nwords + 4));
 	TRY(s->d_iupac.alloc((size_t) nwords + 4));
+	TRY(s->d_inv2.alloc((size_t) nwords + 4));
 	// the pack kernel writes words [0, nwords); only the 4 spare words need zeroing
 	CUDA_TRY(cudaMemsetAsync(s->d_codes.p + nwords, 0, 4 * sizeof(uint64_t)));
 	CUDA_TRY(cudaMemsetAsync(s->d_valid.p + nwords, 0, 4 * sizeof(uint32_t)));
 	CUDA_TRY(cudaMemsetAsync(s->d_iupac.p + nwords, 0, 4 * sizeof(uint32_t)));
+	CUDA_TRY(cudaMemsetAsync(s->d_inv2.p + nwords, 0xFF, 4 * sizeof(uint64_t)));
 	pack_subject_kernel<<<grid_for(nwords, 256, 8), 256>>>(s->d_bytes.p, nwords, s->d_codes.p,
-							      s->d_valid.p, s->d_iupac.p);
+							      s->d_valid.p, s->d_iupac.p, s->d_inv2.p);
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
 	TRY(s->d_seg_start.upload(s->seg_start.data(), (size_t) n));
@@ -710,6 +969,8 @@ extern "C" int bsgpu_subject_chunk(const uint8_t *chunk, int64_t chunk_len, int6
 	s->open_right = chunk_start + chunk_len < subject_len;
 	s->halo_left = report_lo - chunk_start;                 // letters before the first reported end
 	s->halo_right = chunk_start + chunk_len - report_hi;    // letters after the last reported end
+	s->own_from_start = report_lo <= 0;
+	s->own_to_end = report_hi >= subject_len;
 	TRY(subject_finish(s.get(), nullptr, chunk));
 	// TB end n (subject coords) <-> concat index seg_start + (n - chunk_start) - 1
 	s->scan_lo = s->seg_start[0] + (report_lo - chunk_start);
@@ -725,7 +986,7 @@ extern "C" int bsgpu_subject_repack(bsgpu_subject *s, void *stream)
 	TRY(ensure_device());
 	int64_t nwords = s->total / 32;
 	pack_subject_kernel<<<grid_for(nwords, 256, 8), 256, 0, (cudaStream_t) stream>>>(
-		s->d_bytes.p, nwords, s->d_codes.p, s->d_valid.p, s->d_iupac.p);
+		s->d_bytes.p, nwords, s->d_codes.p, s->d_valid.p, s->d_iupac.p, s->d_inv2.p);
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
 	return BSGPU_OK;
@@ -848,8 +1109,11 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 
 // Runs one part over the subject's scan range, reporting through R.  `rec_based` tells
 // whether R appends records (then the record buffer may have to grow and a slab rerun).
+// own_shift: for band b of an MTB_PDict on a chunked subject the alignment is owned by the
+// end of its first min_w letters, which lies own_shift letters after the band's TB end.
 static int run_part(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, const MatchParams &mp,
-		    BsgpuReport R, bool rec_based, Workspace *ws, cudaStream_t st, bool allow_sync)
+		    BsgpuReport R, bool rec_based, Workspace *ws, cudaStream_t st, bool allow_sync,
+		    int64_t own_shift = 0)
 {
 	if (p3->M == 0 || p3->w == 0)
 		return BSGPU_OK;
@@ -858,7 +1122,7 @@ static int run_part(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, cons
 			    "as ambiguities when 'pdict' is a PDict object of the \"Twobit\" type");
 	if (subj->kind == SUBJ_CHUNK) {
 		// the halo must cover every letter a reported match can touch
-		int64_t need_l = (int64_t) p3->w - 1 + p3->max_H, need_r = p3->max_T;
+		int64_t need_l = (int64_t) p3->w - 1 + p3->max_H + own_shift, need_r = p3->max_T - own_shift;
 
 		if ((subj->open_left && subj->halo_left < need_l) ||
 		    (subj->open_right && subj->halo_right < need_r))
@@ -869,6 +1133,15 @@ static int run_part(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, cons
 	bool direct = !p3->has_head && !p3->has_tail && p3->all_singletons;
 	BsgpuReport C = {};
 	int64_t lo = subj->scan_lo, hi = subj->scan_hi;
+
+	if (subj->kind == SUBJ_CHUNK && own_shift != 0) {
+		if (!subj->own_from_start)
+			lo -= own_shift;
+		if (!subj->own_to_end)
+			hi -= own_shift;
+		if (hi < lo)
+			hi = lo;
+	}
 
 	if (!mp.fixedS)
 		CUDA_TRY(cudaMemsetAsync(ws->flags.p, 0, sizeof(int), st));
@@ -936,6 +1209,84 @@ static int run_part(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, cons
 		CUDA_TRY(cudaStreamSynchronize(st));
 		if (ws->h_flags[0])
 			return fail(BSGPU_EINVAL, "too many IUPAC ambiguity letters in 'subject'");
+	}
+	return BSGPU_OK;
+}
+
+// The q-gram engine over the subject's scan range (see bsgpu_qindex.cuh).
+static int run_q(const QIndex *qi, const bsgpu_subject *subj, const MatchParams &mp, BsgpuReport R,
+		 bool rec_based, Workspace *ws, cudaStream_t st)
+{
+	const BsgpuQIndexView &Q = qi->v;
+	int64_t own_lo = 0, own_hi = INT64_MAX;
+
+	if (subj->kind == SUBJ_CHUNK) {
+		int64_t need_l = (int64_t) Q.min_w - 1, need_r = (int64_t) qi->max_len - Q.min_w;
+
+		if (Q.mode == 0) {
+			need_l = qi->max_len - 1;
+			need_r = 0;
+		}
+		if ((subj->open_left && subj->halo_left < need_l) ||
+		    (subj->open_right && subj->halo_right < need_r))
+			return fail(BSGPU_EINVAL, "subject chunk has an insufficient halo: need %lld "
+				    "letters before and %lld after the report range",
+				    (long long) need_l, (long long) need_r);
+		if (!subj->own_from_start || Q.mode == 0)
+			own_lo = subj->scan_lo;
+		if (!subj->own_to_end || Q.mode == 0)
+			own_hi = subj->scan_hi;
+	}
+	// every probe position that can carry the seed of an owned alignment
+	int64_t probe_lo = std::max<int64_t>(0, subj->scan_lo - 64 - qi->max_shift);
+	int64_t probe_hi = std::min<int64_t>(subj->total, subj->scan_hi + 64 + qi->max_shift);
+	if (subj->kind != SUBJ_CHUNK) {
+		probe_lo = 0;
+		probe_hi = subj->total;
+	}
+	int64_t nwords = ((probe_hi + 31) >> 5) - (probe_lo >> 5);
+	if (nwords <= 0)
+		return BSGPU_OK;
+	for (;;) {
+		unsigned long long rec_before = 0, nrec = 0;
+
+		if (rec_based)
+			TRY(read_counter(ws, 1, &rec_before, st));
+		qscan_kernel<<<grid_for(nwords, 256, 8), 256, 0, st>>>(subj->view(), Q, R, mp.max_nmis,
+				mp.min_nmis, probe_lo, probe_hi, own_lo, own_hi);
+		g_launches++;
+		CUDA_TRY(cudaGetLastError());
+		if (!rec_based)
+			break;
+		TRY(read_counter(ws, 1, &nrec, st));
+		if (nrec <= R.capacity)
+			break;
+		TRY(grow(ws->rec, (size_t) nrec, (size_t) rec_before, st));
+		R.records = ws->rec.p;
+		R.capacity = ws->rec.n;
+		TRY(write_counter(ws, 1, rec_before, st));
+	}
+	return BSGPU_OK;
+}
+
+// Trusted-Band engine over all parts; for MTB bands on a chunk the report range of band b
+// is shifted so that an alignment is owned by the end of its first min_w letters.
+static int run_parts_tb(const bsgpu_pdict3parts *const *parts, int nparts, const bsgpu_subject *subj,
+			const MatchParams &mp, BsgpuReport R, bool rec_based, Workspace *ws,
+			cudaStream_t st)
+{
+	int64_t min_w = 0;
+
+	for (int p = 0; p < nparts; p++)
+		min_w += parts[p]->w;
+	int64_t at = 0;
+	for (int p = 0; p < nparts; p++) {
+		at += parts[p]->w;
+		if (rec_based) {
+			R.records = ws->rec.p;
+			R.capacity = ws->rec.n;
+		}
+		TRY(run_part(parts[p], subj, mp, R, rec_based, ws, st, true, nparts > 1 ? min_w - at : 0));
 	}
 	return BSGPU_OK;
 }
@@ -1051,13 +1402,25 @@ extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
 	CUDA_TRY(cudaMemsetAsync(d_counts.p, 0, (size_t) std::max(M, 1) * sizeof(int32_t), st));
 	std::vector<int32_t> counts((size_t) M, 0);
 
-	bool need_records = matches_as == BSGPU_MATCHES_AS_ENDS || nparts > 1;
+	// q-gram engine when the dictionary is eligible (whole-pattern TB or MTB bands, base-only
+	// patterns of <= 64 letters, fixedS): same results, far fewer index probes
+	const QIndex *qi = nullptr;
+	if (mp.fixedS)
+		TRY(get_qindex(parts, nparts, &qi));
+	bool useq = qi != nullptr && qi->ok;
+	// with the q-gram engine every alignment is reported exactly once, so MTB counts need no
+	// union -- except on views, where the reference's union also merges overlapping views
+	bool need_records = matches_as == BSGPU_MATCHES_AS_ENDS ||
+			    (nparts > 1 && !(useq && subj->kind != SUBJ_VIEWS));
 	if (!need_records) {
 		BsgpuReport R = {};
 		R.mode = BSGPU_R_COUNT;
 		R.M = M;
 		R.counts = d_counts.p;
-		TRY(run_part(parts[0], subj, mp, R, false, ws, st, true));
+		if (useq)
+			TRY(run_q(qi, subj, mp, R, false, ws, st));
+		else
+			TRY(run_parts_tb(parts, nparts, subj, mp, R, false, ws, st));
 		CUDA_TRY(cudaMemcpyAsync(counts.data(), d_counts.p, (size_t) M * sizeof(int32_t),
 					 cudaMemcpyDeviceToHost, st));
 		CUDA_TRY(cudaStreamSynchronize(st));
@@ -1071,14 +1434,15 @@ extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
 
 		TRY(grow(ws->rec, CAND_MIN, 0, st));
 		TRY(write_counter(ws, 1, 0, st));
-		for (int p = 0; p < nparts; p++) {
-			R.mode = tbpos ? BSGPU_R_HIT_TBPOS : BSGPU_R_HIT_COORD;
-			R.M = M;
-			R.records = ws->rec.p;
-			R.n_records = ws->counters.p + 1;
-			R.capacity = ws->rec.n;
-			TRY(run_part(parts[p], subj, mp, R, true, ws, st, true));
-		}
+		R.mode = tbpos ? BSGPU_R_HIT_TBPOS : BSGPU_R_HIT_COORD;
+		R.M = M;
+		R.records = ws->rec.p;
+		R.n_records = ws->counters.p + 1;
+		R.capacity = ws->rec.n;
+		if (useq)
+			TRY(run_q(qi, subj, mp, R, true, ws, st));
+		else
+			TRY(run_parts_tb(parts, nparts, subj, mp, R, true, ws, st));
 		TRY(read_counter(ws, 1, &nrec, st));
 		TRY(sort_records(ws, nrec, BSGPU_POS_BITS + bits_for((unsigned long long) std::max(M - 1, 1)),
 				 nparts > 1, &nrec, st));
@@ -1136,26 +1500,34 @@ extern "C" int bsgpu_count_device(const bsgpu_pdict3parts *const *parts, int npa
 	long long before = g_launches;
 	int32_t M = parts[0]->M;
 
-	if (nparts == 1) {
+	const QIndex *qi = nullptr;
+	if (mp.fixedS)
+		TRY(get_qindex(parts, nparts, &qi));
+	bool useq = qi != nullptr && qi->ok;
+	if (nparts == 1 || (useq && subj->kind != SUBJ_VIEWS)) {
 		BsgpuReport R = {};
-		R.mode = subj->kind == SUBJ_SET ? BSGPU_R_COUNT : BSGPU_R_COUNT;
+		R.mode = BSGPU_R_COUNT;
 		R.M = M;
 		R.counts = d_counts;
-		TRY(run_part(parts[0], subj, mp, R, false, ws, st, true));
+		if (useq)
+			TRY(run_q(qi, subj, mp, R, false, ws, st));
+		else
+			TRY(run_parts_tb(parts, nparts, subj, mp, R, false, ws, st));
 	} else {
 		BsgpuReport R = {};
 		unsigned long long nrec = 0;
 
 		TRY(grow(ws->rec, CAND_MIN, 0, st));
 		TRY(write_counter(ws, 1, 0, st));
-		for (int p = 0; p < nparts; p++) {
-			R.mode = BSGPU_R_HIT_COORD;
-			R.M = M;
-			R.records = ws->rec.p;
-			R.n_records = ws->counters.p + 1;
-			R.capacity = ws->rec.n;
-			TRY(run_part(parts[p], subj, mp, R, true, ws, st, true));
-		}
+		R.mode = BSGPU_R_HIT_COORD;
+		R.M = M;
+		R.records = ws->rec.p;
+		R.n_records = ws->counters.p + 1;
+		R.capacity = ws->rec.n;
+		if (useq)
+			TRY(run_q(qi, subj, mp, R, true, ws, st));
+		else
+			TRY(run_parts_tb(parts, nparts, subj, mp, R, true, ws, st));
 		TRY(read_counter(ws, 1, &nrec, st));
 		TRY(sort_records(ws, nrec, BSGPU_POS_BITS + bits_for((unsigned long long) std::max(M - 1, 1)),
 				 true, &nrec, st));
@@ -1205,6 +1577,10 @@ extern "C" int bsgpu_vmatch(const bsgpu_pdict3parts *const *parts, int nparts,
 	int32_t M = parts[0]->M;
 	int64_t N = subj->nseg;
 	res->M = M;
+	const QIndex *qi = nullptr;
+	if (mp.fixedS)
+		TRY(get_qindex(parts, nparts, &qi));
+	bool useq = qi != nullptr && qi->ok;
 
 	bool records = matches_as == BSGPU_MATCHES_AS_WHICH || (collapse != 0 && weight_is_double);
 	if (matches_as == BSGPU_MATCHES_AS_COUNTS) {
@@ -1235,7 +1611,10 @@ extern "C" int bsgpu_vmatch(const bsgpu_pdict3parts *const *parts, int nparts,
 			R.mode = collapse == 1 ? BSGPU_R_VC1 : BSGPU_R_VC2;
 			R.weight = d_w.p;
 		}
-		TRY(run_part(parts[0], subj, mp, R, false, ws, st, true));
+		if (useq)
+			TRY(run_q(qi, subj, mp, R, false, ws, st));
+		else
+			TRY(run_part(parts[0], subj, mp, R, false, ws, st, true));
 		res->counts = (int32_t *) malloc((size_t) std::max<int64_t>(n_out, 1) * sizeof(int32_t));
 		res->n_counts = n_out;
 		if (n_out > 0)
@@ -1249,14 +1628,15 @@ extern "C" int bsgpu_vmatch(const bsgpu_pdict3parts *const *parts, int nparts,
 	unsigned long long nrec = 0;
 	TRY(grow(ws->rec, CAND_MIN, 0, st));
 	TRY(write_counter(ws, 1, 0, st));
-	for (int p = 0; p < nparts; p++) {
-		R.mode = BSGPU_R_SEGKEY;
-		R.M = M;
-		R.records = ws->rec.p;
-		R.n_records = ws->counters.p + 1;
-		R.capacity = ws->rec.n;
-		TRY(run_part(parts[p], subj, mp, R, true, ws, st, true));
-	}
+	R.mode = BSGPU_R_SEGKEY;
+	R.M = M;
+	R.records = ws->rec.p;
+	R.n_records = ws->counters.p + 1;
+	R.capacity = ws->rec.n;
+	if (useq)
+		TRY(run_q(qi, subj, mp, R, true, ws, st));
+	else
+		TRY(run_parts_tb(parts, nparts, subj, mp, R, true, ws, st));
 	TRY(read_counter(ws, 1, &nrec, st));
 	bool uniq = matches_as == BSGPU_MATCHES_AS_WHICH;
 	TRY(sort_records(ws, nrec, BSGPU_SEGKEY_BITS + bits_for((unsigned long long) std::max<int64_t>(N - 1, 1)),

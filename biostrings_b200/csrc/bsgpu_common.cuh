@@ -5,7 +5,8 @@
 //              0x80 guards at both ends), codes[total/32] (uint64, 2 bits per letter,
 //              letter i of a word at bits 2i..2i+1, A=0 C=1 G=2 T=3, 0 for non-base),
 //              valid[total/32] (uint32, bit i = letter is A/C/G/T), iupac[total/32]
-//              (uint32, bit i = letter code in 1..15).
+//              (uint32, bit i = letter code in 1..15), inv2[total/32] (uint64, bit 2i =
+//              letter i is not a base letter).
 //   index    : bucketed hash table, 16 B per bucket = two {fingerprint, id} slots, keyed
 //              by the first min(w,32) letters of the Trusted Band packed the same way.
 #pragma once
@@ -66,6 +67,7 @@ struct BsgpuSubjectView {
 	const uint64_t *codes;
 	const uint32_t *valid;
 	const uint32_t *iupac;
+	const uint64_t *inv2;        // bit 2i = letter i is not A/C/G/T (2-bit layout)
 	const int64_t *seg_start;    // [nseg] concat index of the first letter
 	const int32_t *seg_len;      // [nseg]
 	const int64_t *seg_coord;    // [nseg] reported end = local end + seg_coord

@@ -20,7 +20,8 @@ namespace cg = cooperative_groups;
 // ------------------------------------------------------------------------------------
 
 // For a 32-bit word holding 4 letters: 8 code bits, 4 valid bits, 4 iupac bits.
-__device__ __forceinline__ void pack4(uint32_t x, uint32_t &code8, uint32_t &valid4, uint32_t &iupac4)
+__device__ __forceinline__ void pack4(uint32_t x, uint32_t &code8, uint32_t &valid4, uint32_t &iupac4,
+				      uint32_t &inv8)
 {
 	// code = (b>>1) - (b>>3) restated with ORs: bit0 = b1|b3, bit1 = b2|b3
 	uint32_t c = ((x | (x >> 2)) & 0x02020202u) | ((x | (x >> 1)) & 0x04040404u);
@@ -37,6 +38,8 @@ __device__ __forceinline__ void pack4(uint32_t x, uint32_t &code8, uint32_t &val
 	uint32_t va = iu & ~np2;
 	iupac4 = (((iu >> 7) * 0x00204081u) >> 21) & 0xFu;
 	valid4 = (((va >> 7) * 0x00204081u) >> 21) & 0xFu;
+	// "not a base letter" in the 2-bit layout (bit 2i), for XOR+popcount verification
+	inv8 = ((((~va) & 0x80808080u) >> 7) * 0x01041040u) >> 24;
 	// non-base letters get code 0 so that equal keys imply equal letters only when valid
 	code8 &= (valid4 & 1u ? 0x03u : 0u) | (valid4 & 2u ? 0x0Cu : 0u)
 	       | (valid4 & 4u ? 0x30u : 0u) | (valid4 & 8u ? 0xC0u : 0u);
@@ -45,7 +48,7 @@ __device__ __forceinline__ void pack4(uint32_t x, uint32_t &code8, uint32_t &val
 __global__ void __launch_bounds__(256)
 pack_subject_kernel(const uint8_t *__restrict__ bytes, int64_t nwords,
 		    uint64_t *__restrict__ codes, uint32_t *__restrict__ valid,
-		    uint32_t *__restrict__ iupac)
+		    uint32_t *__restrict__ iupac, uint64_t *__restrict__ inv2)
 {
 	int64_t j = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	int64_t stride = (int64_t) gridDim.x * blockDim.x;
@@ -54,20 +57,22 @@ pack_subject_kernel(const uint8_t *__restrict__ bytes, int64_t nwords,
 		const uint4 *src = reinterpret_cast<const uint4 *>(bytes + 32 * j);
 		uint4 a = __ldcs(src), b = __ldcs(src + 1);
 		uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-		uint64_t c = 0;
+		uint64_t c = 0, n2 = 0;
 		uint32_t v = 0, u = 0;
 #pragma unroll
 		for (int k = 0; k < 8; k++) {
-			uint32_t c8, v4, u4;
+			uint32_t c8, v4, u4, n8;
 
-			pack4(w[k], c8, v4, u4);
+			pack4(w[k], c8, v4, u4, n8);
 			c |= (uint64_t) c8 << (8 * k);
+			n2 |= (uint64_t) n8 << (8 * k);
 			v |= v4 << (4 * k);
 			u |= u4 << (4 * k);
 		}
 		codes[j] = c;
 		valid[j] = v;
 		iupac[j] = u;
+		inv2[j] = n2;
 	}
 }
 

@@ -1,0 +1,224 @@
+// bsgpu_qindex.cuh -- q-gram seed index + whole-pattern Hamming verification.
+//
+// Used where the reference's answer does not depend on HOW candidates are found:
+//   * a TB_PDict whose Trusted Band is the whole pattern (exact matching): contiguous
+//     q-mers of every pattern at offsets 0..s-1 are indexed and the subject is probed only
+//     at every s-th position (s = width-q+1): an occurrence starting at a is met exactly
+//     once, at the probe position p = a + ((-a) mod s).
+//   * an MTB_PDict (max.mismatch = k >= 1): the union over its k+1 Trusted Bands
+//     (R/matchPDict.R:335-377, src/MIndex_class.c:230-263) is exactly the set of alignments
+//     with min <= #mismatches <= max (pigeonhole), so any complete filter for Hamming
+//     distance <= k gives the same result.  One gapped shape of weight q applied at a small
+//     set of shifts (tools/find_seed_shapes.py) needs ONE directory probe per subject
+//     position and |shifts|*M/4^q candidates, instead of k+1 probes and
+//     sum_b M/4^w_b candidates for the reference's short bands.
+// Every candidate is verified against the whole pattern on the packed planes
+// (XOR + popcount), with letters outside the segment and non-base subject letters counted
+// as mismatches (src/lowlevel_matching.c:79-86), so the result is exact.
+#pragma once
+#include "bsgpu_kernels.cuh"
+
+#define BSGPU_Q_MAX_RUNS 8
+#define BSGPU_Q_MAX_SHIFTS 32
+
+struct BsgpuQIndexView {
+	const uint2 *dir;            // [4^q / 4] {base offset, 4 x u8 counts}
+	const uint32_t *entries;     // id << 5 | shift index, grouped by seed key
+	const ulonglong2 *pat;       // [M] 2-bit packed pattern letters (<= 64)
+	const uint8_t *pat_len;      // [M]
+	int32_t q;                   // seed weight (letters)
+	int32_t mode;                // 0 = exact, sampled; 1 = Hamming (gapped shape)
+	int32_t stride;              // probe every stride-th position (mode 0), else 1
+	int32_t min_w;               // window the shape lives in (mode 1)
+	int32_t nruns;               // runs of consecutive shape offsets
+	int32_t run_src[BSGPU_Q_MAX_RUNS];   // first offset of the run
+	int32_t run_len[BSGPU_Q_MAX_RUNS];
+	uint64_t shape1;             // 1 bit per letter
+	uint64_t shape2;             // the same, spread to the 2-bit layout (bit 2i)
+	int32_t nshifts;
+	int32_t shift[BSGPU_Q_MAX_SHIFTS];   // ascending
+};
+
+__device__ __forceinline__ uint32_t q_key(const BsgpuQIndexView &Q, uint64_t win)
+{
+	// compact the letters under the shape into 2q contiguous bits
+	uint32_t key = 0;
+	int out = 0;
+
+#pragma unroll
+	for (int i = 0; i < BSGPU_Q_MAX_RUNS; i++) {
+		if (i < Q.nruns) {
+			uint32_t part = (uint32_t) (win >> (2 * Q.run_src[i])) &
+					((1u << (2 * Q.run_len[i])) - 1u);
+			key |= part << out;
+			out += 2 * Q.run_len[i];
+		}
+	}
+	return key;
+}
+
+// 128-bit logical right shift by s (< 128) returning the low 64 bits
+__device__ __forceinline__ uint64_t shr128_lo(uint64_t lo, uint64_t hi, int s)
+{
+	if (s == 0)
+		return lo;
+	if (s < 64)
+		return (lo >> s) | (hi << (64 - s));
+	return s == 64 ? hi : hi >> (s - 64);
+}
+
+// bits [2*from, 2*to) at even positions, as a 128-bit (lo, hi) mask
+__device__ __forceinline__ void range_mask2(int from, int to, uint64_t &lo, uint64_t &hi)
+{
+	const uint64_t E = 0x5555555555555555ull;
+	auto below = [&](int n, uint64_t &l, uint64_t &h) {      // letters [0, n)
+		l = n >= 32 ? E : (n <= 0 ? 0ull : E & ((1ull << (2 * n)) - 1));
+		h = n <= 32 ? 0ull : (n >= 64 ? E : E & ((1ull << (2 * (n - 32))) - 1));
+	};
+	uint64_t al, ah, bl, bh;
+	below(to, al, ah);
+	below(from, bl, bh);
+	lo = al & ~bl;
+	hi = ah & ~bh;
+}
+
+__device__ __forceinline__ void q_verify(const BsgpuSubjectView &S, const BsgpuQIndexView &Q,
+		const BsgpuReport &R, uint32_t ent, int64_t p, int max_nmis, int min_nmis,
+		int64_t own_lo, int64_t own_hi)
+{
+	const uint64_t E = 0x5555555555555555ull;
+	int id = (int) (ent >> 5), ti = (int) (ent & 31u);
+	int t = Q.shift[ti];
+	int64_t a = p - t;
+	int len = __ldg(Q.pat_len + id);
+	int64_t own = Q.mode == 0 ? a + len - 1 : a + Q.min_w - 1;
+
+	if (own < own_lo || own >= own_hi)
+		return;
+	int seg = S.nseg == 1 ? 0 : find_segment(S, p);
+	int64_t lo = __ldg(S.seg_start + seg), L = __ldg(S.seg_len + seg);
+	int64_t wi = a >> 5;
+	int sh = 2 * (int) (a & 31);
+	uint64_t c0 = __ldg(S.codes + wi), c1 = __ldg(S.codes + wi + 1), c2 = __ldg(S.codes + wi + 2);
+	uint64_t i0 = __ldg(S.inv2 + wi), i1 = __ldg(S.inv2 + wi + 1), i2 = __ldg(S.inv2 + wi + 2);
+	uint64_t x_lo = sh ? (c0 >> sh) | (c1 << (64 - sh)) : c0;
+	uint64_t x_hi = sh ? (c1 >> sh) | (c2 << (64 - sh)) : c1;
+	uint64_t v_lo = sh ? (i0 >> sh) | (i1 << (64 - sh)) : i0;
+	uint64_t v_hi = sh ? (i1 >> sh) | (i2 << (64 - sh)) : i1;
+	ulonglong2 P = Q.pat[id];
+	uint64_t d_lo = x_lo ^ P.x, d_hi = x_hi ^ P.y;
+
+	d_lo = ((d_lo | (d_lo >> 1)) | v_lo) & E;
+	d_hi = ((d_hi | (d_hi >> 1)) | v_hi) & E;
+	// letters outside the segment are mismatches
+	int nbefore = (int) min((int64_t) len, max((int64_t) 0, lo - a));
+	int nafter = (int) min((int64_t) len, max((int64_t) 0, a + len - (lo + L)));
+	uint64_t m_lo, m_hi;
+	if (nbefore) {
+		range_mask2(0, nbefore, m_lo, m_hi);
+		d_lo |= m_lo;
+		d_hi |= m_hi;
+	}
+	if (nafter) {
+		range_mask2(len - nafter, len, m_lo, m_hi);
+		d_lo |= m_lo;
+		d_hi |= m_hi;
+	}
+	range_mask2(0, len, m_lo, m_hi);
+	d_lo &= m_lo;
+	d_hi &= m_hi;
+	int total = __popcll(d_lo) + __popcll(d_hi);
+	if (total > max_nmis || total < min_nmis)
+		return;
+	if (Q.mode == 1) {
+		// report from the first shift whose seed is clean, so that every alignment is
+		// reported exactly once
+		for (int k = 0; k < ti; k++)
+			if ((shr128_lo(d_lo, d_hi, 2 * Q.shift[k]) & Q.shape2) == 0)
+				return;
+	}
+	int64_t n = a - lo + len;               // 1-based local end of the match
+	report_match(R, S, id, seg, n, a + len - 1, 0);
+}
+
+__device__ __forceinline__ uint32_t q_prefix(uint32_t cnts, int i)
+{
+	// sum of the count bytes below byte i
+	uint32_t m = cnts & ((1u << (8 * i)) - 1u);     // i in 0..3
+	m = (m & 0x00FF00FFu) + ((m >> 8) & 0x00FF00FFu);
+	return (m & 0xFFFFu) + (m >> 16);
+}
+
+#define QSCAN_GROUP 8
+
+__global__ void __launch_bounds__(256)
+qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis, int min_nmis,
+	     int64_t probe_lo, int64_t probe_hi, int64_t own_lo, int64_t own_hi)
+{
+	int64_t word_lo = probe_lo >> 5, word_hi = (probe_hi + 31) >> 5;
+	int64_t j = word_lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (; j < word_hi; j += stride) {
+		int64_t base = j << 5;
+		uint64_t c0 = __ldcs(S.codes + j), c1 = __ldcs(S.codes + j + 1);
+		uint64_t v = (uint64_t) __ldcs(S.valid + j) | ((uint64_t) __ldcs(S.valid + j + 1) << 32);
+		uint32_t m = 0;
+
+		// positions whose seed letters are all base letters
+		if (Q.stride == 1) {
+#pragma unroll
+			for (int r = 0; r < 32; r++)
+				m |= (((v >> r) & Q.shape1) == Q.shape1 ? 1u : 0u) << r;
+		} else {
+			int r = (int) ((Q.stride - base % Q.stride) % Q.stride);
+			for (; r < 32; r += Q.stride)
+				m |= (((v >> r) & Q.shape1) == Q.shape1 ? 1u : 0u) << r;
+		}
+		if (base < probe_lo)
+			m &= 0xFFFFFFFFu << (int) (probe_lo - base);
+		if (base + 32 > probe_hi)
+			m &= (probe_hi - base) <= 0 ? 0u : 0xFFFFFFFFu >> (int) (base + 32 - probe_hi);
+		if (m == 0)
+			continue;
+		uint32_t have = 0;
+#pragma unroll
+		for (int g = 0; g < 32; g += QSCAN_GROUP) {
+			uint32_t key[QSCAN_GROUP];
+			uint2 G[QSCAN_GROUP];
+
+			if (((m >> g) & ((1u << QSCAN_GROUP) - 1)) == 0)
+				continue;
+#pragma unroll
+			for (int qq = 0; qq < QSCAN_GROUP; qq++) {
+				const int r = g + qq;
+				uint64_t win = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
+
+				key[qq] = q_key(Q, win);
+			}
+#pragma unroll
+			for (int qq = 0; qq < QSCAN_GROUP; qq++)
+				G[qq] = ((m >> (g + qq)) & 1u) ? __ldg(Q.dir + (key[qq] >> 2)) : make_uint2(0, 0);
+#pragma unroll
+			for (int qq = 0; qq < QSCAN_GROUP; qq++) {
+				uint32_t cnt = (G[qq].y >> (8 * (key[qq] & 3u))) & 0xFFu;
+
+				have |= (cnt ? 1u : 0u) << (g + qq);
+			}
+		}
+		// drain: all lanes verify their candidates together
+		while (have) {
+			int r = __ffs(have) - 1;
+			have &= have - 1;
+			uint64_t win = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
+			uint32_t key = q_key(Q, win);
+			uint2 G = __ldg(Q.dir + (key >> 2));
+			uint32_t cnt = (G.y >> (8 * (key & 3u))) & 0xFFu;
+			uint32_t off = G.x + q_prefix(G.y, (int) (key & 3u));
+
+			for (uint32_t e = 0; e < cnt; e++)
+				q_verify(S, Q, R, __ldg(Q.entries + off + e), base + r, max_nmis, min_nmis,
+					 own_lo, own_hi);
+		}
+	}
+}

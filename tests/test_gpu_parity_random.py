@@ -15,6 +15,17 @@ pytestmark = pytest.mark.gpu
 BACKEND = "ref" if ref.available() else "port"
 
 
+@pytest.fixture(autouse=True, params=["qgram", "tb_only"])
+def engine(request, monkeypatch):
+    """Every case runs twice: with the q-gram seed engine allowed (default) and with the
+    Trusted-Band engine forced (BSGPU_NO_QINDEX=1); both must equal the reference."""
+    if request.param == "tb_only":
+        monkeypatch.setenv("BSGPU_NO_QINDEX", "1")
+    else:
+        monkeypatch.delenv("BSGPU_NO_QINDEX", raising=False)
+    return request.param
+
+
 def make_dict(g, subject, M, width, frac_planted=0.3, frac_dup=0.05, nsub=0, sub_lo=0):
     """M patterns of `width` (int or (lo, hi)): random, planted windows of the subject
     (optionally with `nsub` substitutions at positions >= sub_lo), and exact duplicates."""
@@ -133,7 +144,8 @@ def test_out_of_limits_matches():
             check_all(prod, orac, s, s, max_mismatch=mm)
 
 
-@pytest.mark.parametrize("k,width", [(1, 25), (2, 25), (2, (20, 30)), (3, 36)])
+@pytest.mark.parametrize("k,width", [(1, 25), (2, 25), (2, (20, 30)), (3, 36), (1, 18), (1, (21, 40)),
+                                     (2, 30), (2, (36, 50)), (2, 64), (3, 50)])
 def test_mtb_pdict(k, width):
     g = rng(20 + k)
     s = subject_with_n_runs(g, 30_000)

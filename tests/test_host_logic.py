@@ -125,3 +125,25 @@ def test_synth_is_block_deterministic():
     q = synth.dictionary(20_000, 25, 250_000_000, 2)
     assert p.shape == (20_000, 25) and (p == q).all() and np.isin(p, [1, 2, 4, 8]).all()
     assert len(np.unique(p, axis=0)) < 20_000           # duplicates are present
+
+
+def test_seed_shape_table_is_complete():
+    """Every row of csrc/bsgpu_shapes.inc must be a complete Hamming filter: for every set
+    of k mismatch positions in a window of m letters some listed shift of the shape is
+    clean.  (A wrong row would silently lose matches of an MTB_PDict.)"""
+    import itertools
+    import os
+    import re
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                        "biostrings_b200", "csrc", "bsgpu_shapes.inc")
+    rows = re.findall(r"\{(\d+), (\d+), (\d+), (\d+), (0x[0-9a-f]+)ull, (0x[0-9a-f]+)ull\}", open(path).read())
+    assert len(rows) >= 15
+    for m, k, q, span, mask, shifts in rows:
+        m, k, q, span, mask, shifts = int(m), int(k), int(q), int(span), int(mask, 16), int(shifts, 16)
+        assert bin(mask).count("1") == q and mask.bit_length() == span and mask & 1 and span <= 32
+        ts = [t for t in range(64) if (shifts >> t) & 1]
+        assert ts and max(ts) + span <= m and len(ts) <= 32
+        placed = [mask << t for t in ts]
+        for mm in itertools.combinations(range(m), k):
+            bad = sum(1 << x for x in mm)
+            assert any((pl & bad) == 0 for pl in placed), (m, k, mm)

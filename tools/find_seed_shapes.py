@@ -1,82 +1,99 @@
-"""Offline search of gapped seed shapes for Hamming-distance filtering.
+"""Offline search of gapped seed shapes + shift sets for Hamming-distance filtering.
 
-A shape (set of offsets, weight q, span <= m) has threshold >= 1 for (m, k) when for every
-set of k mismatch positions inside a window of m letters at least one of the m-span+1
-shifts of the shape avoids all of them (Burkhardt & Karkkainen's gapped q-grams).  An index
-of the shape at every shift of every pattern then finds all occurrences with <= k
-mismatches with ONE probe per subject position.  Prints a C table for bsgpu_qindex.cuh.
+A seed family = one shape (q offsets inside a span) applied at a set T of shifts inside a
+window of m letters.  It is complete for (m, k) when for every set of k mismatch positions
+at least one t in T has shape+t free of mismatches (gapped q-grams with threshold >= 1,
+Burkhardt & Karkkainen).  Indexing every pattern at the shifts of T then finds all
+occurrences with <= k mismatches with ONE probe per subject position and |T|*M/4^q
+candidates per position.  We minimise |T| (index size, candidates), then maximise q.
+
+Prints rows {m, k, q, span, shape_mask, shifts_mask} for csrc/bsgpu_shapes.inc.
+
+    python tools/find_seed_shapes.py <seconds per (m,k,q)> <k list, e.g. 1,2> [m_lo m_hi]
 """
 import itertools
+import math
 import random
 import sys
 import time
 
 
-def covers(shape_mask, span, m, k):
+def greedy_cover(shape_mask, span, m, subsets, best_so_far):
+    """Greedy small set of shifts whose clean-sets cover all k-subsets; None if impossible
+    or not better than best_so_far."""
+    shifts = list(range(m - span + 1))
     full = (1 << m) - 1
-    U = [full & ~(shape_mask << t) for t in range(m - span + 1)]
-    if k == 1:
-        acc = 0
-        for u in U:
-            acc |= u
-        return acc == full
-    if k == 2:
-        for a in range(m):
-            acc = 0
-            for u in U:
-                if (u >> a) & 1:
-                    acc |= u
-            if acc != full:
-                return False
-        return True
-    if k == 3:
-        for a in range(m):
-            Ua = [u for u in U if (u >> a) & 1]
-            for b in range(a + 1, m):
-                acc = 0
-                for u in Ua:
-                    if (u >> b) & 1:
-                        acc |= u
-                if acc != full:
-                    return False
-        return True
-    raise ValueError(k)
+    cover = []
+    for t in shifts:
+        u = full & ~(shape_mask << t)
+        bits = 0
+        for i, s in enumerate(subsets):
+            if (u & s) == s:
+                bits |= 1 << i
+        cover.append(bits)
+    need = (1 << len(subsets)) - 1
+    allc = 0
+    for c in cover:
+        allc |= c
+    if allc != need:
+        return None
+    chosen, covered = [], 0
+    while covered != need:
+        if len(chosen) + 1 >= best_so_far:
+            return None
+        t = max(shifts, key=lambda x: bin(cover[x] & ~covered).count("1"))
+        chosen.append(t)
+        covered |= cover[t]
+    return chosen
 
 
-def search(m, k, q, budget_s):
-    """Smallest-span shape of weight q (most shifts), exhaustive when cheap else random."""
+def search(m, k, q, budget_s, rnd):
+    subsets = [sum(1 << x for x in c) for c in itertools.combinations(range(m), k)]
+    best = None
     t0 = time.time()
     for span in range(q, m + 1):
+        if time.time() - t0 > budget_s:
+            break
         n_inner = span - 2
-        import math
-        total = math.comb(n_inner, q - 2) if q >= 2 else 1
-        if total <= 300_000:
-            it = itertools.combinations(range(1, span - 1), q - 2)
+        if n_inner < q - 2:
+            continue
+        total = math.comb(n_inner, q - 2)
+        tries = min(total, 300)
+        if total <= tries:
+            cands = itertools.combinations(range(1, span - 1), q - 2)
         else:
-            rnd = random.Random(1234 + span)
-            it = (tuple(sorted(rnd.sample(range(1, span - 1), q - 2))) for _ in range(300_000))
-        for inner in it:
+            cands = (tuple(sorted(rnd.sample(range(1, span - 1), q - 2))) for _ in range(tries))
+        for inner in cands:
             mask = 1 | (1 << (span - 1))
             for i in inner:
                 mask |= 1 << i
-            if covers(mask, span, m, k):
-                return span, mask
+            r = greedy_cover(mask, span, m, subsets, best[0] if best else 99)
+            if r is not None and (best is None or len(r) < best[0]):
+                best = (len(r), span, mask, sorted(r))
             if time.time() - t0 > budget_s:
-                return None
-    return None
+                break
+    return best
 
 
 if __name__ == "__main__":
-    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 20.0
-    print("// {m, k, q, span, mask}")
-    for k in (1, 2, 3):
-        for m in range(14, 65):
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 10.0
+    ks = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 2, 3]
+    m_lo = int(sys.argv[3]) if len(sys.argv) > 3 else 14
+    m_hi = int(sys.argv[4]) if len(sys.argv) > 4 else 64
+    rnd = random.Random(12345)
+    print("// {m, k, q, span, shape_mask, shifts_mask}")
+    for k in ks:
+        for m in range(m_lo, m_hi + 1):
             best = None
             for q in (12, 11, 10):
-                r = search(m, k, q, budget)
+                r = search(m, k, q, budget, rnd)
                 if r:
                     best = (q,) + r
                     break
             if best:
-                q, span, mask = best
-                print(f"{{{m}, {k}, {q}, {span}, 0x{mask:x}ull}},", flush=True)
+                q, n, span, mask, shifts = best
+                sm = 0
+                for t in shifts:
+                    sm |= 1 << t
+                print(f"{{{m}, {k}, {q}, {span}, 0x{mask:x}ull, 0x{sm:x}ull}}, // {n} shifts {shifts}",
+                      flush=True)
