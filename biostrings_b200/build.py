@@ -15,7 +15,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libbsgpu.so")
 SOURCES = [os.path.join(CSRC, "bsgpu.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("bsgpu_kernels.cuh", "bsgpu_common.cuh")] + \
+DEPS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))
+        if f.endswith((".cu", ".cuh", ".inc", ".h"))] + \
     [os.path.join(os.path.dirname(HERE), "include", "bsgpu.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

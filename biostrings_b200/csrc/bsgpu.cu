@@ -236,6 +236,7 @@ struct bsgpu_pdict3parts {
 	std::vector<uint8_t> excluded;          // pp_exclude[i] != NA
 	std::vector<uint8_t> is_tb_dup;         // had a non-NA high2low at build time
 	mutable std::unique_ptr<struct QIndex> qcache;  // q-gram index built on first use
+	mutable std::unique_ptr<struct SampledIndex> scache;    // sampled-seed hash index (exact)
 	uint32_t nbuckets = 0;
 	bool all_singletons = true;
 	DevBuf<uint4> d_table;
@@ -287,7 +288,7 @@ struct QIndex {
 	int nparts = 0;
 	BsgpuQIndexView v = {};
 	DevBuf<uint2> d_dir;
-	DevBuf<uint32_t> d_entries;
+	DevBuf<uint32_t> d_entries, d_bitmap;
 	DevBuf<ulonglong2> d_pat;
 	DevBuf<uint8_t> d_len;
 	int max_len = 0;
@@ -365,10 +366,19 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 		return done();
 	SeedShape sh;
 	if (nparts == 1) {
+		// Exact dictionaries: the hash scan (one probe per window) is faster than sampled
+		// seeds at 1M patterns on B200 (0.95 vs 1.5 ms per 250 Mbp), so this mode is
+		// opt-in for experiments.
+		const char *env_x = getenv("BSGPU_Q_EXACT");
+		if (env_x == nullptr || env_x[0] != '1')
+			return done();
 		if (p0->has_head || p0->has_tail || !p0->all_singletons || p0->w < 20)
 			return done();
 		sh.m = p0->w; sh.k = 0; sh.q = 12; sh.span = 12; sh.mask = 0xFFFull; sh.shifts = 0;
 		int stride = std::min(p0->w - 12 + 1, BSGPU_Q_MAX_SHIFTS);
+		const char *env_s = getenv("BSGPU_Q_STRIDE");
+		if (env_s != nullptr && atoi(env_s) >= 1)
+			stride = std::min(stride, atoi(env_s));
 		for (int t = 0; t < stride; t++)
 			sh.shifts |= 1ull << t;
 		qi->v.mode = 0;
@@ -448,19 +458,16 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 			qi->max_shift = t;
 		}
 	// --- entries, counting sort by seed key ---------------------------------------------------
-	size_t nkeys = (size_t) 1 << (2 * sh.q);
+	v.key_bits = 24;
+	v.mask2 = v.shape2 | (v.shape2 << 1);
+	v.const_len = min_w == max_w ? max_w : 0;
+	size_t nkeys = (size_t) 1 << v.key_bits;
 	std::vector<uint32_t> cnt(nkeys + 1, 0);
 	auto seed_key = [&](int i, int t) {
-		uint32_t key = 0;
-		int out = 0;
-		for (int r = 0; r < v.nruns; r++)
-			for (int d = 0; d < v.run_len[r]; d++) {
-				int pos = t + v.run_src[r] + d;
-				unsigned long long c = pos < 32 ? (pat[i].x >> (2 * pos)) & 3 : (pat[i].y >> (2 * (pos - 32))) & 3;
-				key |= (uint32_t) c << out;
-				out += 2;
-			}
-		return key;
+		// the window of 32 letters starting at pattern offset t, in the subject's layout
+		unsigned long long win = t == 0 ? pat[i].x
+			: (t < 32 ? (pat[i].x >> (2 * t)) | (pat[i].y << (64 - 2 * t)) : pat[i].y >> (2 * (t - 32)));
+		return q_key_of(win & v.mask2, v.key_bits);
 	};
 	size_t nent = 0;
 	for (int i = 0; i < M; i++) {
@@ -477,10 +484,12 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 		if (cnt[k2] > 254)
 			return done();  // a very repetitive dictionary: keep the Trusted-Band engine
 	std::vector<uint2> dir(nkeys / 4);
-	std::vector<uint32_t> start(nkeys);
+	std::vector<uint32_t> start(nkeys), bitmap(nkeys / 32, 0);
 	uint32_t run = 0;
 	for (size_t k2 = 0; k2 < nkeys; k2++) {
 		start[k2] = run;
+		if (cnt[k2])
+			bitmap[k2 >> 5] |= 1u << (k2 & 31);
 		if ((k2 & 3) == 0) {
 			dir[k2 >> 2].x = run;
 			dir[k2 >> 2].y = 0;
@@ -497,6 +506,8 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 		for (int s2 = 0; s2 < v.nshifts; s2++)
 			entries[start[seed_key(i, v.shift[s2])]++] = ((uint32_t) i << 5) | (uint32_t) s2;
 	}
+	TRY(qi->d_bitmap.upload(bitmap.data(), bitmap.size()));
+	v.bitmap = qi->d_bitmap.p;
 	TRY(qi->d_dir.upload(dir.data(), dir.size()));
 	TRY(qi->d_entries.upload(entries.data(), entries.size()));
 	TRY(qi->d_pat.upload(pat.data(), pat.size()));
@@ -507,6 +518,109 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 	v.pat_len = qi->d_len.p;
 	qi->max_len = max_w;
 	qi->ok = true;
+	return done();
+}
+
+// Sampled-seed hash index for exact dictionaries (scan_tb_sampled_kernel).
+struct SampledIndex {
+	bool ok = false;
+	BsgpuSampledView t = {};
+	BsgpuQIndexView q = {};
+	DevBuf<uint4> d_table;
+	DevBuf<uint64_t> d_keys;
+	DevBuf<ulonglong2> d_pat;
+};
+
+static int sampled_stride(void)
+{
+	const char *env = getenv("BSGPU_SAMPLE_STRIDE");
+	int s2 = env ? atoi(env) : 4;
+
+	return s2 < 1 ? 1 : (s2 > 16 ? 16 : s2);
+}
+
+static int get_sampled(const bsgpu_pdict3parts *p3, const SampledIndex **out)
+{
+	*out = nullptr;
+	if (p3->scache) {
+		*out = p3->scache.get();
+		return BSGPU_OK;
+	}
+	std::unique_ptr<SampledIndex> si(new SampledIndex());
+	auto done = [&]() {
+		p3->scache = std::move(si);
+		*out = p3->scache.get();
+		return BSGPU_OK;
+	};
+	int M = p3->M, w = p3->w, s2 = sampled_stride();
+	if (s2 < 2 || w < 20 || w > 64 || p3->has_head || p3->has_tail || !p3->all_singletons ||
+	    (long long) M * s2 >= 0x3FFFFFFF || M >= (1 << 27))
+		return done();
+	int qw = std::min(32, w - s2 + 1);
+	uint64_t mask = qw >= 32 ? ~0ull : ((1ull << (2 * qw)) - 1);
+	std::vector<ulonglong2> pat(M, make_ulonglong2(0, 0));
+	std::vector<uint64_t> keys((size_t) M * s2, 0);
+	size_t nent = 0;
+	for (int i = 0; i < M; i++) {
+		if (p3->excluded[i] || p3->is_tb_dup[i])
+			continue;
+		unsigned long long lo = 0, hi = 0;
+		for (int d = 0; d < w; d++) {
+			unsigned long long c = bsgpu_base_code(p3->tb[(size_t) i * w + d]);
+			if (d < 32) lo |= c << (2 * d); else hi |= c << (2 * (d - 32));
+		}
+		pat[i] = make_ulonglong2(lo, hi);
+		nent += s2;
+	}
+	// buckets: about one entry per two-slot bucket, capped so that the table stays in L2
+	uint64_t nb = std::max<uint64_t>(16, nent);
+	std::vector<uint4> table(nb, make_uint4(0, BSGPU_EMPTY_ID, 0, BSGPU_EMPTY_ID));
+	for (int i = 0; i < M; i++) {
+		if (p3->excluded[i] || p3->is_tb_dup[i])
+			continue;
+		for (int t = 0; t < s2; t++) {
+			unsigned long long win = t == 0 ? pat[i].x
+				: (pat[i].x >> (2 * t)) | (pat[i].y << (64 - 2 * t));
+			uint64_t key = win & mask;
+			uint32_t e = (uint32_t) i * s2 + t, top, fp;
+
+			keys[e] = key;
+			bsgpu_hash(key, top, fp);
+			uint32_t b = (uint32_t) (((uint64_t) top * nb) >> 32);
+			for (;;) {
+				if (table[b].y == BSGPU_EMPTY_ID) {
+					table[b].x = fp;
+					table[b].y = e;
+					break;
+				}
+				if ((table[b].w & BSGPU_ID_MASK) == BSGPU_EMPTY_ID) {
+					table[b].z = fp;
+					table[b].w = (table[b].w & BSGPU_OVERFLOW_FLAG) | e;
+					break;
+				}
+				table[b].w |= BSGPU_OVERFLOW_FLAG;
+				b = b + 1 == nb ? 0 : b + 1;
+			}
+		}
+	}
+	TRY(si->d_table.upload(table.data(), table.size()));
+	TRY(si->d_keys.upload(keys.data(), keys.size()));
+	TRY(si->d_pat.upload(pat.data(), pat.size()));
+	si->t.table = si->d_table.p;
+	si->t.keys = si->d_keys.p;
+	si->t.nbuckets = (uint32_t) nb;
+	si->t.s = s2;
+	si->t.seed_w = qw;
+	si->t.seed_mask = mask;
+	si->q.pat = si->d_pat.p;
+	si->q.pat_len = nullptr;
+	si->q.const_len = w;
+	si->q.mode = 0;
+	si->q.min_w = w;
+	si->q.nshifts = s2;
+	for (int t = 0; t < s2; t++)
+		si->q.shift[t] = t;
+	si->ok = true;
 	return done();
 }
 
@@ -743,6 +857,7 @@ extern "C" int bsgpu_pdict3parts_blank_dups(bsgpu_pdict3parts *p3)
 	TRY(upload_groups(p3, true));
 	std::fill(p3->high2low.begin(), p3->high2low.end(), BSGPU_NA);
 	p3->qcache.reset();
+	p3->scache.reset();
 	return BSGPU_OK;
 }
 
@@ -854,7 +969,7 @@ static int subject_finish(bsgpu_subject *s, const uint8_t *const *srcs, const ui
 	CUDA_TRY(cudaMemsetAsync(s->d_valid.p + nwords, 0, 4 * sizeof(uint32_t)));
 	CUDA_TRY(cudaMemsetAsync(s->d_iupac.p + nwords, 0, 4 * sizeof(uint32_t)));
 	CUDA_TRY(cudaMemsetAsync(s->d_inv2.p + nwords, 0xFF, 4 * sizeof(uint64_t)));
-	pack_subject_kernel<<<grid_for(nwords, 256, 8), 256>>>(s->d_bytes.p, nwords, s->d_codes.p,
+	pack_subject_kernel<<<grid_for(2 * nwords, 256, 8), 256>>>(s->d_bytes.p, nwords, s->d_codes.p,
 							      s->d_valid.p, s->d_iupac.p, s->d_inv2.p);
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
@@ -985,7 +1100,7 @@ extern "C" int bsgpu_subject_repack(bsgpu_subject *s, void *stream)
 		return fail(BSGPU_EINVAL, "bsgpu_subject_repack(): NULL handle");
 	TRY(ensure_device());
 	int64_t nwords = s->total / 32;
-	pack_subject_kernel<<<grid_for(nwords, 256, 8), 256, 0, (cudaStream_t) stream>>>(
+	pack_subject_kernel<<<grid_for(2 * nwords, 256, 8), 256, 0, (cudaStream_t) stream>>>(
 		s->d_bytes.p, nwords, s->d_codes.p, s->d_valid.p, s->d_iupac.p, s->d_inv2.p);
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
@@ -1095,6 +1210,25 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 	BsgpuSubjectView S = subj->view();
 	BsgpuIndexView I = p3->view();
 
+	if (direct && mp.fixedS) {
+		// exact dictionary: sampled seeds, s times fewer index probes
+		const SampledIndex *si = nullptr;
+		TRY(get_sampled(p3, &si));
+		if (si != nullptr && si->ok) {
+			int64_t probe_hi = std::min<int64_t>(subj->total, start_hi + si->t.s);
+			int64_t nw = ((probe_hi + 31) >> 5) - (start_lo >> 5);
+
+			if (p3->w > 32)
+				scan_tb_sampled_kernel<true><<<grid_for(nw, 256, 8), 256, 0, st>>>(
+					S, si->t, si->q, R, start_lo, probe_hi, end_lo, end_hi);
+			else
+				scan_tb_sampled_kernel<false><<<grid_for(nw, 256, 8), 256, 0, st>>>(
+					S, si->t, si->q, R, start_lo, probe_hi, end_lo, end_hi);
+			g_launches++;
+			CUDA_TRY(cudaGetLastError());
+			return BSGPU_OK;
+		}
+	}
 	scan_tb_kernel<<<grid_for(nwords, 256, 8), 256, 0, st>>>(S, I, R, C, direct, start_lo, start_hi);
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
@@ -1252,8 +1386,12 @@ static int run_q(const QIndex *qi, const bsgpu_subject *subj, const MatchParams 
 
 		if (rec_based)
 			TRY(read_counter(ws, 1, &rec_before, st));
-		qscan_kernel<<<grid_for(nwords, 256, 8), 256, 0, st>>>(subj->view(), Q, R, mp.max_nmis,
-				mp.min_nmis, probe_lo, probe_hi, own_lo, own_hi);
+		if (qi->max_len > 32)
+			qscan_kernel<true><<<grid_for(nwords, 256, 8), 256, 0, st>>>(subj->view(), Q, R,
+					mp.max_nmis, mp.min_nmis, probe_lo, probe_hi, own_lo, own_hi);
+		else
+			qscan_kernel<false><<<grid_for(nwords, 256, 8), 256, 0, st>>>(subj->view(), Q, R,
+					mp.max_nmis, mp.min_nmis, probe_lo, probe_hi, own_lo, own_hi);
 		g_launches++;
 		CUDA_TRY(cudaGetLastError());
 		if (!rec_based)

@@ -45,34 +45,53 @@ __device__ __forceinline__ void pack4(uint32_t x, uint32_t &code8, uint32_t &val
 	       | (valid4 & 4u ? 0x30u : 0u) | (valid4 & 8u ? 0xC0u : 0u);
 }
 
+// One thread per 16 letters: every load (16 B per lane) and store (4/2/2/4 B per lane) of a
+// warp is contiguous.  The 64-bit code / inv2 words and the 32-bit flag words of the planes
+// are written as their 32-bit / 16-bit halves.
 __global__ void __launch_bounds__(256)
 pack_subject_kernel(const uint8_t *__restrict__ bytes, int64_t nwords,
 		    uint64_t *__restrict__ codes, uint32_t *__restrict__ valid,
 		    uint32_t *__restrict__ iupac, uint64_t *__restrict__ inv2)
 {
+	int64_t nhalf = 2 * nwords;
 	int64_t j = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	uint32_t *codes32 = reinterpret_cast<uint32_t *>(codes);
+	uint32_t *inv32 = reinterpret_cast<uint32_t *>(inv2);
+	uint16_t *valid16 = reinterpret_cast<uint16_t *>(valid);
+	uint16_t *iupac16 = reinterpret_cast<uint16_t *>(iupac);
 
-	for (; j < nwords; j += stride) {
-		const uint4 *src = reinterpret_cast<const uint4 *>(bytes + 32 * j);
-		uint4 a = __ldcs(src), b = __ldcs(src + 1);
-		uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-		uint64_t c = 0, n2 = 0;
-		uint32_t v = 0, u = 0;
+	// 4 independent 16-byte loads in flight per thread (HBM latency x bandwidth needs
+	// ~35 KB in flight per SM)
+	for (; j < nhalf; j += 4 * stride) {
+		uint4 a[4];
 #pragma unroll
-		for (int k = 0; k < 8; k++) {
-			uint32_t c8, v4, u4, n8;
+		for (int u = 0; u < 4; u++)
+			if (j + u * stride < nhalf)
+				a[u] = __ldcs(reinterpret_cast<const uint4 *>(bytes) + j + u * stride);
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			int64_t jj = j + u * stride;
 
-			pack4(w[k], c8, v4, u4, n8);
-			c |= (uint64_t) c8 << (8 * k);
-			n2 |= (uint64_t) n8 << (8 * k);
-			v |= v4 << (4 * k);
-			u |= u4 << (4 * k);
+			if (jj >= nhalf)
+				break;
+			uint32_t w[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+			uint32_t c = 0, n2 = 0, v = 0, f = 0;
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				uint32_t c8, v4, u4, n8;
+
+				pack4(w[k], c8, v4, u4, n8);
+				c |= c8 << (8 * k);
+				n2 |= n8 << (8 * k);
+				v |= v4 << (4 * k);
+				f |= u4 << (4 * k);
+			}
+			codes32[jj] = c;
+			inv32[jj] = n2;
+			valid16[jj] = (uint16_t) v;
+			iupac16[jj] = (uint16_t) f;
 		}
-		codes[j] = c;
-		valid[j] = v;
-		iupac[j] = u;
-		inv2[j] = n2;
 	}
 }
 

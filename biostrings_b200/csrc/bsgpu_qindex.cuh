@@ -21,8 +21,11 @@
 #define BSGPU_Q_MAX_RUNS 8
 #define BSGPU_Q_MAX_SHIFTS 32
 
+#define BSGPU_Q_HASH_C 0x9E3779B97F4A7C15ull
+
 struct BsgpuQIndexView {
-	const uint2 *dir;            // [4^q / 4] {base offset, 4 x u8 counts}
+	const uint32_t *bitmap;      // [2^key_bits / 32] bit = some entry has this directory key
+	const uint2 *dir;            // [2^key_bits / 4] {base offset, 4 x u8 counts}
 	const uint32_t *entries;     // id << 5 | shift index, grouped by seed key
 	const ulonglong2 *pat;       // [M] 2-bit packed pattern letters (<= 64)
 	const uint8_t *pat_len;      // [M]
@@ -35,26 +38,23 @@ struct BsgpuQIndexView {
 	int32_t run_len[BSGPU_Q_MAX_RUNS];
 	uint64_t shape1;             // 1 bit per letter
 	uint64_t shape2;             // the same, spread to the 2-bit layout (bit 2i)
+	uint64_t mask2;              // both bits of every shape letter in the 2-bit layout
+	int32_t key_bits;            // directory key = top key_bits of (window & mask2) * C
+	int32_t const_len;           // > 0: every pattern has this many letters
 	int32_t nshifts;
 	int32_t shift[BSGPU_Q_MAX_SHIFTS];   // ascending
 };
 
+// Directory key of a window: multiply-shift hash of the letters under the shape.  It does
+// not have to be injective -- every candidate is verified against the whole pattern.
+__host__ __device__ __forceinline__ uint32_t q_key_of(uint64_t masked, int key_bits)
+{
+	return (uint32_t) ((masked * BSGPU_Q_HASH_C) >> (64 - key_bits));
+}
+
 __device__ __forceinline__ uint32_t q_key(const BsgpuQIndexView &Q, uint64_t win)
 {
-	// compact the letters under the shape into 2q contiguous bits
-	uint32_t key = 0;
-	int out = 0;
-
-#pragma unroll
-	for (int i = 0; i < BSGPU_Q_MAX_RUNS; i++) {
-		if (i < Q.nruns) {
-			uint32_t part = (uint32_t) (win >> (2 * Q.run_src[i])) &
-					((1u << (2 * Q.run_len[i])) - 1u);
-			key |= part << out;
-			out += 2 * Q.run_len[i];
-		}
-	}
-	return key;
+	return q_key_of(win & Q.mask2, Q.key_bits);
 }
 
 // 128-bit logical right shift by s (< 128) returning the low 64 bits
@@ -82,6 +82,7 @@ __device__ __forceinline__ void range_mask2(int from, int to, uint64_t &lo, uint
 	hi = ah & ~bh;
 }
 
+template <bool LONG>
 __device__ __forceinline__ void q_verify(const BsgpuSubjectView &S, const BsgpuQIndexView &Q,
 		const BsgpuReport &R, uint32_t ent, int64_t p, int max_nmis, int min_nmis,
 		int64_t own_lo, int64_t own_hi)
@@ -90,7 +91,7 @@ __device__ __forceinline__ void q_verify(const BsgpuSubjectView &S, const BsgpuQ
 	int id = (int) (ent >> 5), ti = (int) (ent & 31u);
 	int t = Q.shift[ti];
 	int64_t a = p - t;
-	int len = __ldg(Q.pat_len + id);
+	int len = Q.const_len > 0 ? Q.const_len : (int) __ldg(Q.pat_len + id);
 	int64_t own = Q.mode == 0 ? a + len - 1 : a + Q.min_w - 1;
 
 	if (own < own_lo || own >= own_hi)
@@ -99,34 +100,54 @@ __device__ __forceinline__ void q_verify(const BsgpuSubjectView &S, const BsgpuQ
 	int64_t lo = __ldg(S.seg_start + seg), L = __ldg(S.seg_len + seg);
 	int64_t wi = a >> 5;
 	int sh = 2 * (int) (a & 31);
-	uint64_t c0 = __ldg(S.codes + wi), c1 = __ldg(S.codes + wi + 1), c2 = __ldg(S.codes + wi + 2);
-	uint64_t i0 = __ldg(S.inv2 + wi), i1 = __ldg(S.inv2 + wi + 1), i2 = __ldg(S.inv2 + wi + 2);
-	uint64_t x_lo = sh ? (c0 >> sh) | (c1 << (64 - sh)) : c0;
-	uint64_t x_hi = sh ? (c1 >> sh) | (c2 << (64 - sh)) : c1;
-	uint64_t v_lo = sh ? (i0 >> sh) | (i1 << (64 - sh)) : i0;
-	uint64_t v_hi = sh ? (i1 >> sh) | (i2 << (64 - sh)) : i1;
-	ulonglong2 P = Q.pat[id];
-	uint64_t d_lo = x_lo ^ P.x, d_hi = x_hi ^ P.y;
-
-	d_lo = ((d_lo | (d_lo >> 1)) | v_lo) & E;
-	d_hi = ((d_hi | (d_hi >> 1)) | v_hi) & E;
-	// letters outside the segment are mismatches
 	int nbefore = (int) min((int64_t) len, max((int64_t) 0, lo - a));
 	int nafter = (int) min((int64_t) len, max((int64_t) 0, a + len - (lo + L)));
-	uint64_t m_lo, m_hi;
-	if (nbefore) {
-		range_mask2(0, nbefore, m_lo, m_hi);
-		d_lo |= m_lo;
-		d_hi |= m_hi;
+	uint64_t d_lo, d_hi = 0;
+
+	if (!LONG) {
+		// patterns of <= 32 letters: one 64-bit lane
+		uint64_t c0 = __ldg(S.codes + wi), c1 = __ldg(S.codes + wi + 1);
+		uint64_t i0 = __ldg(S.inv2 + wi), i1 = __ldg(S.inv2 + wi + 1);
+		uint64_t x = sh ? (c0 >> sh) | (c1 << (64 - sh)) : c0;
+		uint64_t iv = sh ? (i0 >> sh) | (i1 << (64 - sh)) : i0;
+		uint64_t P = __ldg(reinterpret_cast<const unsigned long long *>(Q.pat) + 2 * (size_t) id);
+
+		d_lo = x ^ P;
+		d_lo = ((d_lo | (d_lo >> 1)) | iv) & E;
+		// letters outside the segment are mismatches
+		if (nbefore)
+			d_lo |= E & (nbefore >= 32 ? ~0ull : (1ull << (2 * nbefore)) - 1);
+		if (nafter)
+			d_lo |= E & ~((len - nafter) >= 32 ? ~0ull : (1ull << (2 * (len - nafter))) - 1);
+		d_lo &= len >= 32 ? E : E & ((1ull << (2 * len)) - 1);
+	} else {
+		uint64_t c0 = __ldg(S.codes + wi), c1 = __ldg(S.codes + wi + 1), c2 = __ldg(S.codes + wi + 2);
+		uint64_t i0 = __ldg(S.inv2 + wi), i1 = __ldg(S.inv2 + wi + 1), i2 = __ldg(S.inv2 + wi + 2);
+		uint64_t x_lo = sh ? (c0 >> sh) | (c1 << (64 - sh)) : c0;
+		uint64_t x_hi = sh ? (c1 >> sh) | (c2 << (64 - sh)) : c1;
+		uint64_t v_lo = sh ? (i0 >> sh) | (i1 << (64 - sh)) : i0;
+		uint64_t v_hi = sh ? (i1 >> sh) | (i2 << (64 - sh)) : i1;
+		ulonglong2 P = Q.pat[id];
+		uint64_t m_lo, m_hi;
+
+		d_lo = x_lo ^ P.x;
+		d_hi = x_hi ^ P.y;
+		d_lo = ((d_lo | (d_lo >> 1)) | v_lo) & E;
+		d_hi = ((d_hi | (d_hi >> 1)) | v_hi) & E;
+		if (nbefore) {
+			range_mask2(0, nbefore, m_lo, m_hi);
+			d_lo |= m_lo;
+			d_hi |= m_hi;
+		}
+		if (nafter) {
+			range_mask2(len - nafter, len, m_lo, m_hi);
+			d_lo |= m_lo;
+			d_hi |= m_hi;
+		}
+		range_mask2(0, len, m_lo, m_hi);
+		d_lo &= m_lo;
+		d_hi &= m_hi;
 	}
-	if (nafter) {
-		range_mask2(len - nafter, len, m_lo, m_hi);
-		d_lo |= m_lo;
-		d_hi |= m_hi;
-	}
-	range_mask2(0, len, m_lo, m_hi);
-	d_lo &= m_lo;
-	d_hi &= m_hi;
 	int total = __popcll(d_lo) + __popcll(d_hi);
 	if (total > max_nmis || total < min_nmis)
 		return;
@@ -151,6 +172,20 @@ __device__ __forceinline__ uint32_t q_prefix(uint32_t cnts, int i)
 
 #define QSCAN_GROUP 8
 
+// positions r (0..31) of a word whose seed letters (shape offsets) are all base letters;
+// v = valid bits of 64 letters starting at the word
+__device__ __forceinline__ uint32_t q_valid_positions(const BsgpuQIndexView &Q, uint64_t v)
+{
+	uint64_t m = ~0ull;
+
+#pragma unroll
+	for (int i = 0; i < BSGPU_Q_MAX_RUNS; i++)
+		if (i < Q.nruns)
+			m &= all_set_run(v, Q.run_len[i]) >> Q.run_src[i];
+	return (uint32_t) m;
+}
+
+template <bool LONG>
 __global__ void __launch_bounds__(256)
 qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis, int min_nmis,
 	     int64_t probe_lo, int64_t probe_hi, int64_t own_lo, int64_t own_hi)
@@ -163,17 +198,13 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 		int64_t base = j << 5;
 		uint64_t c0 = __ldcs(S.codes + j), c1 = __ldcs(S.codes + j + 1);
 		uint64_t v = (uint64_t) __ldcs(S.valid + j) | ((uint64_t) __ldcs(S.valid + j + 1) << 32);
-		uint32_t m = 0;
+		uint32_t m = q_valid_positions(Q, v);
 
-		// positions whose seed letters are all base letters
-		if (Q.stride == 1) {
-#pragma unroll
-			for (int r = 0; r < 32; r++)
-				m |= (((v >> r) & Q.shape1) == Q.shape1 ? 1u : 0u) << r;
-		} else {
-			int r = (int) ((Q.stride - base % Q.stride) % Q.stride);
-			for (; r < 32; r += Q.stride)
-				m |= (((v >> r) & Q.shape1) == Q.shape1 ? 1u : 0u) << r;
+		if (Q.stride > 1) {
+			uint32_t pm = 0;
+			for (int r = (int) ((Q.stride - base % Q.stride) % Q.stride); r < 32; r += Q.stride)
+				pm |= 1u << r;
+			m &= pm;
 		}
 		if (base < probe_lo)
 			m &= 0xFFFFFFFFu << (int) (probe_lo - base);
@@ -181,11 +212,12 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 			m &= (probe_hi - base) <= 0 ? 0u : 0xFFFFFFFFu >> (int) (base + 32 - probe_hi);
 		if (m == 0)
 			continue;
+		// Phase 1: one bitmap word per position (2 MiB for 24 key bits: stays in L1/L2);
+		// about a third of the positions have a non-empty directory slot
 		uint32_t have = 0;
 #pragma unroll
 		for (int g = 0; g < 32; g += QSCAN_GROUP) {
-			uint32_t key[QSCAN_GROUP];
-			uint2 G[QSCAN_GROUP];
+			uint32_t key[QSCAN_GROUP], bw[QSCAN_GROUP];
 
 			if (((m >> g) & ((1u << QSCAN_GROUP) - 1)) == 0)
 				continue;
@@ -198,15 +230,13 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 			}
 #pragma unroll
 			for (int qq = 0; qq < QSCAN_GROUP; qq++)
-				G[qq] = ((m >> (g + qq)) & 1u) ? __ldg(Q.dir + (key[qq] >> 2)) : make_uint2(0, 0);
+				bw[qq] = ((m >> (g + qq)) & 1u) ? __ldg(Q.bitmap + (key[qq] >> 5)) : 0u;
 #pragma unroll
-			for (int qq = 0; qq < QSCAN_GROUP; qq++) {
-				uint32_t cnt = (G[qq].y >> (8 * (key[qq] & 3u))) & 0xFFu;
-
-				have |= (cnt ? 1u : 0u) << (g + qq);
-			}
+			for (int qq = 0; qq < QSCAN_GROUP; qq++)
+				have |= ((bw[qq] >> (key[qq] & 31u)) & 1u) << (g + qq);
 		}
-		// drain: all lanes verify their candidates together
+		// Phase 2: all lanes walk their non-empty positions together: directory slot ->
+		// entries -> whole-pattern verification
 		while (have) {
 			int r = __ffs(have) - 1;
 			have &= have - 1;
@@ -217,8 +247,113 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 			uint32_t off = G.x + q_prefix(G.y, (int) (key & 3u));
 
 			for (uint32_t e = 0; e < cnt; e++)
-				q_verify(S, Q, R, __ldg(Q.entries + off + e), base + r, max_nmis, min_nmis,
-					 own_lo, own_hi);
+				q_verify<LONG>(S, Q, R, __ldg(Q.entries + off + e), base + r, max_nmis,
+					       min_nmis, own_lo, own_hi);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------
+// Exact dictionaries (Trusted Band = whole pattern), sampled seeds in the hash index.
+// Every pattern is indexed under its `s` seeds of q' = min(32, w-s+1) letters starting at
+// offsets 0..s-1, and the subject is probed only at positions p = 0 (mod s): an occurrence
+// starting at a meets exactly one of them (t = (-a) mod s), so the number of index probes
+// -- the L2 random-sector gathers that bound scan_tb_kernel -- drops by s.  A seed hit is
+// confirmed against the stored seed key and then against the whole pattern.
+// ------------------------------------------------------------------------------------
+
+struct BsgpuSampledView {
+	const uint4 *table;          // buckets {fp0, e0, fp1, e1 | overflow}; e = pattern * s + t
+	const uint64_t *keys;        // [M * s] seed key of every entry
+	uint32_t nbuckets;
+	int32_t s;                   // sampling stride
+	int32_t seed_w;              // q'
+	uint64_t seed_mask;
+};
+
+__device__ __forceinline__ uint32_t sampled_bucket(const BsgpuSampledView &T, uint32_t top)
+{
+	return (uint32_t) (((uint64_t) top * T.nbuckets) >> 32);
+}
+
+template <bool LONG>
+__global__ void __launch_bounds__(256)
+scan_tb_sampled_kernel(BsgpuSubjectView S, BsgpuSampledView T, BsgpuQIndexView Q, BsgpuReport R,
+		       int64_t probe_lo, int64_t probe_hi, int64_t own_lo, int64_t own_hi)
+{
+	int64_t word_lo = probe_lo >> 5, word_hi = (probe_hi + 31) >> 5;
+	int64_t j = word_lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (; j < word_hi; j += stride) {
+		int64_t base = j << 5;
+		uint64_t c0 = __ldcs(S.codes + j), c1 = __ldcs(S.codes + j + 1);
+		uint64_t v = (uint64_t) __ldcs(S.valid + j) | ((uint64_t) __ldcs(S.valid + j + 1) << 32);
+		uint32_t m = (uint32_t) all_set_run(v, T.seed_w), pm = 0;
+
+		for (int r = (int) ((T.s - base % T.s) % T.s); r < 32; r += T.s)
+			pm |= 1u << r;
+		m &= pm;
+		if (base < probe_lo)
+			m &= 0xFFFFFFFFu << (int) (probe_lo - base);
+		if (base + 32 > probe_hi)
+			m &= (probe_hi - base) <= 0 ? 0u : 0xFFFFFFFFu >> (int) (base + 32 - probe_hi);
+		// the probes of this word: at most ceil(32 / s), all loads issued before any is used
+		uint32_t rare = 0, todo = m;
+		while (todo) {
+			uint32_t fp[8], bucket[8];
+			uint4 b[8];
+			int rr[8], n = 0;
+
+#pragma unroll
+			for (int q = 0; q < 8; q++) {
+				rr[q] = todo ? __ffs(todo) - 1 : -1;
+				todo &= todo - 1;
+				n += rr[q] >= 0;
+			}
+#pragma unroll
+			for (int q = 0; q < 8; q++) {
+				int r = rr[q] < 0 ? 0 : rr[q];
+				uint64_t k = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
+				uint32_t top;
+
+				bsgpu_hash(k & T.seed_mask, top, fp[q]);
+				bucket[q] = sampled_bucket(T, top);
+			}
+#pragma unroll
+			for (int q = 0; q < 8; q++)
+				b[q] = rr[q] >= 0 ? __ldg(T.table + bucket[q])
+						  : make_uint4(~fp[q], BSGPU_EMPTY_ID, ~fp[q], BSGPU_EMPTY_ID);
+#pragma unroll
+			for (int q = 0; q < 8; q++)
+				if (rr[q] >= 0 && (b[q].x == fp[q] || b[q].z == fp[q] || (b[q].w & BSGPU_OVERFLOW_FLAG)))
+					rare |= 1u << rr[q];
+		}
+		while (rare) {
+			int r = __ffs(rare) - 1;
+			rare &= rare - 1;
+			uint64_t k = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
+			uint32_t top, fp;
+
+			k &= T.seed_mask;
+			bsgpu_hash(k, top, fp);
+			// Different patterns can share a seed (overlapping probes of one region), so
+			// every entry carrying this seed key is verified, along the whole bucket chain.
+			uint32_t bucket = sampled_bucket(T, top);
+			for (;;) {
+				uint4 b = __ldg(T.table + bucket);
+				uint32_t e0 = b.y & BSGPU_ID_MASK, e1 = b.w & BSGPU_ID_MASK;
+
+				if (b.x == fp && e0 != BSGPU_EMPTY_ID && __ldg(T.keys + e0) == k)
+					q_verify<LONG>(S, Q, R, ((e0 / T.s) << 5) | (e0 % T.s), base + r, 0, 0,
+						       own_lo, own_hi);
+				if (b.z == fp && e1 != BSGPU_EMPTY_ID && __ldg(T.keys + e1) == k)
+					q_verify<LONG>(S, Q, R, ((e1 / T.s) << 5) | (e1 % T.s), base + r, 0, 0,
+						       own_lo, own_hi);
+				if (!(b.w & BSGPU_OVERFLOW_FLAG))
+					break;
+				bucket = bucket + 1 == T.nbuckets ? 0 : bucket + 1;
+			}
 		}
 	}
 }
