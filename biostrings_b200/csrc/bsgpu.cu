@@ -884,7 +884,9 @@ struct bsgpu_subject {
 	std::vector<int32_t> seg_len;
 	DevBuf<uint8_t> d_bytes;
 	DevBuf<uint64_t> d_codes, d_inv2;
-	DevBuf<uint32_t> d_valid, d_iupac;
+	DevBuf<uint32_t> d_valid;
+	mutable DevBuf<uint32_t> d_iupac;       // built on first fixedS=FALSE use
+	mutable bool iupac_ready = false;
 	DevBuf<int64_t> d_seg_start, d_seg_coord;
 	DevBuf<int32_t> d_seg_len;
 
@@ -962,15 +964,14 @@ static int subject_finish(bsgpu_subject *s, const uint8_t *const *srcs, const ui
 	}
 	TRY(s->d_codes.alloc((size_t) nwords + 4));
 	TRY(s->d_valid.alloc((size_t) nwords + 4));
-	TRY(s->d_iupac.alloc((size_t) nwords + 4));
 	TRY(s->d_inv2.alloc((size_t) nwords + 4));
 	// the pack kernel writes words [0, nwords); only the 4 spare words need zeroing
 	CUDA_TRY(cudaMemsetAsync(s->d_codes.p + nwords, 0, 4 * sizeof(uint64_t)));
 	CUDA_TRY(cudaMemsetAsync(s->d_valid.p + nwords, 0, 4 * sizeof(uint32_t)));
-	CUDA_TRY(cudaMemsetAsync(s->d_iupac.p + nwords, 0, 4 * sizeof(uint32_t)));
 	CUDA_TRY(cudaMemsetAsync(s->d_inv2.p + nwords, 0xFF, 4 * sizeof(uint64_t)));
 	pack_subject_kernel<<<grid_for(2 * nwords, 256, 8), 256>>>(s->d_bytes.p, nwords, s->d_codes.p,
-							      s->d_valid.p, s->d_iupac.p, s->d_inv2.p);
+							      s->d_valid.p, s->d_inv2.p);
+	s->iupac_ready = false;
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
 	TRY(s->d_seg_start.upload(s->seg_start.data(), (size_t) n));
@@ -1101,7 +1102,8 @@ extern "C" int bsgpu_subject_repack(bsgpu_subject *s, void *stream)
 	TRY(ensure_device());
 	int64_t nwords = s->total / 32;
 	pack_subject_kernel<<<grid_for(2 * nwords, 256, 8), 256, 0, (cudaStream_t) stream>>>(
-		s->d_bytes.p, nwords, s->d_codes.p, s->d_valid.p, s->d_iupac.p, s->d_inv2.p);
+		s->d_bytes.p, nwords, s->d_codes.p, s->d_valid.p, s->d_inv2.p);
+	s->iupac_ready = false;
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
 	return BSGPU_OK;
@@ -1277,8 +1279,20 @@ static int run_part(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, cons
 			hi = lo;
 	}
 
-	if (!mp.fixedS)
+	if (!mp.fixedS) {
 		CUDA_TRY(cudaMemsetAsync(ws->flags.p, 0, sizeof(int), st));
+		if (!subj->iupac_ready) {
+			int64_t nwords = subj->total / 32;
+
+			TRY(subj->d_iupac.alloc((size_t) nwords + 4));
+			CUDA_TRY(cudaMemsetAsync(subj->d_iupac.p + nwords, 0, 4 * sizeof(uint32_t), st));
+			pack_iupac_kernel<<<grid_for(2 * nwords, 256, 8), 256, 0, st>>>(subj->d_bytes.p, nwords,
+											 subj->d_iupac.p);
+			g_launches++;
+			CUDA_TRY(cudaGetLastError());
+			subj->iupac_ready = true;
+		}
+	}
 	if (direct && !rec_based) {
 		// fully asynchronous: counts straight from the scan
 		TRY(launch_scans(p3, subj, mp, R, C, 1, lo, hi, ws, st));

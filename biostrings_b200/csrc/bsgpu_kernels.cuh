@@ -19,30 +19,33 @@ namespace cg = cooperative_groups;
 // Packing: 32 letters per thread.
 // ------------------------------------------------------------------------------------
 
-// For a 32-bit word holding 4 letters: 8 code bits, 4 valid bits, 4 iupac bits.
-__device__ __forceinline__ void pack4(uint32_t x, uint32_t &code8, uint32_t &valid4, uint32_t &iupac4,
-				      uint32_t &inv8)
+// For a 32-bit word holding 4 letters: 8 code bits, 4 valid bits, 8 "not a base" bits.
+// (Letters that are not A/C/G/T get an arbitrary code: every consumer also looks at the
+// valid / inv2 planes.)
+__device__ __forceinline__ void pack4(uint32_t x, uint32_t &code8, uint32_t &valid4, uint32_t &inv8)
 {
 	// code = (b>>1) - (b>>3) restated with ORs: bit0 = b1|b3, bit1 = b2|b3
 	uint32_t c = ((x | (x >> 2)) & 0x02020202u) | ((x | (x >> 1)) & 0x04040404u);
 	code8 = ((c >> 1) * 0x01041040u) >> 24;
-	// byte != 0
+	// valid <=> low nibble is a power of two and the high nibble is 0:
+	//   z = b & (b-1) (bit 7 blocks the borrow between bytes), plus the high nibble
+	uint32_t z = (x & ((x | 0x80808080u) - 0x01010101u) & 0x7F7F7F7Fu) | (x & 0x70707070u);
+	// byte == 0 is not a letter either: (b | 0x80) - 1 has bit 7 clear only for b == 0
+	uint32_t bad = (((z + 0x7F7F7F7Fu) | x) | ~((x | 0x80808080u) - 0x01010101u)) & 0x80808080u;
+	uint32_t b7 = bad >> 7;                 // 1 per invalid letter at bits 0, 8, 16, 24
+	inv8 = (b7 * 0x01041040u) >> 24;        // -> bits 0, 2, 4, 6
+	valid4 = (((b7 ^ 0x01010101u) * 0x00204081u) >> 21) & 0xFu;
+}
+
+// iupac plane (bit i = letter code in 1..15), only needed for fixedS = FALSE: 4 flag bits
+__device__ __forceinline__ uint32_t iupac4_of(uint32_t x)
+{
 	uint32_t nz = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
-	// byte >= 16
 	uint32_t hi = x & 0xF0F0F0F0u;
 	uint32_t ge16 = (((hi & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | hi) & 0x80808080u;
 	uint32_t iu = nz & ~ge16;
-	// b & (b-1) != 0  (not a power of two); bit 7 blocks the borrow between bytes
-	uint32_t z = x & ((x | 0x80808080u) - 0x01010101u) & 0x7F7F7F7Fu;
-	uint32_t np2 = (z + 0x7F7F7F7Fu) & 0x80808080u;
-	uint32_t va = iu & ~np2;
-	iupac4 = (((iu >> 7) * 0x00204081u) >> 21) & 0xFu;
-	valid4 = (((va >> 7) * 0x00204081u) >> 21) & 0xFu;
-	// "not a base letter" in the 2-bit layout (bit 2i), for XOR+popcount verification
-	inv8 = ((((~va) & 0x80808080u) >> 7) * 0x01041040u) >> 24;
-	// non-base letters get code 0 so that equal keys imply equal letters only when valid
-	code8 &= (valid4 & 1u ? 0x03u : 0u) | (valid4 & 2u ? 0x0Cu : 0u)
-	       | (valid4 & 4u ? 0x30u : 0u) | (valid4 & 8u ? 0xC0u : 0u);
+
+	return (((iu >> 7) * 0x00204081u) >> 21) & 0xFu;
 }
 
 // One thread per 16 letters: every load (16 B per lane) and store (4/2/2/4 B per lane) of a
@@ -51,7 +54,7 @@ __device__ __forceinline__ void pack4(uint32_t x, uint32_t &code8, uint32_t &val
 __global__ void __launch_bounds__(256)
 pack_subject_kernel(const uint8_t *__restrict__ bytes, int64_t nwords,
 		    uint64_t *__restrict__ codes, uint32_t *__restrict__ valid,
-		    uint32_t *__restrict__ iupac, uint64_t *__restrict__ inv2)
+		    uint64_t *__restrict__ inv2)
 {
 	int64_t nhalf = 2 * nwords;
 	int64_t j = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,10 +62,8 @@ pack_subject_kernel(const uint8_t *__restrict__ bytes, int64_t nwords,
 	uint32_t *codes32 = reinterpret_cast<uint32_t *>(codes);
 	uint32_t *inv32 = reinterpret_cast<uint32_t *>(inv2);
 	uint16_t *valid16 = reinterpret_cast<uint16_t *>(valid);
-	uint16_t *iupac16 = reinterpret_cast<uint16_t *>(iupac);
 
-	// 4 independent 16-byte loads in flight per thread (HBM latency x bandwidth needs
-	// ~35 KB in flight per SM)
+	// 4 independent 16-byte loads in flight per thread
 	for (; j < nhalf; j += 4 * stride) {
 		uint4 a[4];
 #pragma unroll
@@ -76,22 +77,37 @@ pack_subject_kernel(const uint8_t *__restrict__ bytes, int64_t nwords,
 			if (jj >= nhalf)
 				break;
 			uint32_t w[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
-			uint32_t c = 0, n2 = 0, v = 0, f = 0;
+			uint32_t c = 0, n2 = 0, v = 0;
 #pragma unroll
 			for (int k = 0; k < 4; k++) {
-				uint32_t c8, v4, u4, n8;
+				uint32_t c8, v4, n8;
 
-				pack4(w[k], c8, v4, u4, n8);
+				pack4(w[k], c8, v4, n8);
 				c |= c8 << (8 * k);
 				n2 |= n8 << (8 * k);
 				v |= v4 << (4 * k);
-				f |= u4 << (4 * k);
 			}
 			codes32[jj] = c;
 			inv32[jj] = n2;
 			valid16[jj] = (uint16_t) v;
-			iupac16[jj] = (uint16_t) f;
 		}
+	}
+}
+
+// The iupac plane is built on first use (fixedS = FALSE is the rare case).
+__global__ void __launch_bounds__(256)
+pack_iupac_kernel(const uint8_t *__restrict__ bytes, int64_t nwords, uint32_t *__restrict__ iupac)
+{
+	int64_t nhalf = 2 * nwords;
+	int64_t j = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	uint16_t *iupac16 = reinterpret_cast<uint16_t *>(iupac);
+
+	for (; j < nhalf; j += stride) {
+		uint4 a = __ldcs(reinterpret_cast<const uint4 *>(bytes) + j);
+
+		iupac16[j] = (uint16_t) (iupac4_of(a.x) | (iupac4_of(a.y) << 4) | (iupac4_of(a.z) << 8) |
+					 (iupac4_of(a.w) << 12));
 	}
 }
 
