@@ -531,12 +531,15 @@ struct SampledIndex {
 	DevBuf<ulonglong2> d_pat;
 };
 
-static int sampled_stride(void)
+static int sampled_stride(int w)
 {
+	// S in {1 (off), 2, 4, 8}; the seed keeps at least 16 letters
 	const char *env = getenv("BSGPU_SAMPLE_STRIDE");
-	int s2 = env ? atoi(env) : 4;
+	int s2 = env ? atoi(env) : 8;
 
-	return s2 < 1 ? 1 : (s2 > 16 ? 16 : s2);
+	while (s2 > 1 && w - s2 + 1 < 16)
+		s2 >>= 1;
+	return s2 >= 8 ? 8 : (s2 >= 4 ? 4 : (s2 >= 2 ? 2 : 1));
 }
 
 static int get_sampled(const bsgpu_pdict3parts *p3, const SampledIndex **out)
@@ -552,10 +555,15 @@ static int get_sampled(const bsgpu_pdict3parts *p3, const SampledIndex **out)
 		*out = p3->scache.get();
 		return BSGPU_OK;
 	};
-	int M = p3->M, w = p3->w, s2 = sampled_stride();
-	if (s2 < 2 || w < 20 || w > 64 || p3->has_head || p3->has_tail || !p3->all_singletons ||
-	    (long long) M * s2 >= 0x3FFFFFFF || M >= (1 << 27))
+	int M = p3->M, w = p3->w, s2 = sampled_stride(w);
+	if (s2 < 2 || w < 20 || w > 64 || p3->has_head || p3->has_tail || !p3->all_singletons)
 		return done();
+	uint32_t id_bits = 1;
+	while (((uint64_t) 1 << id_bits) < (uint64_t) M * s2 + 2)
+		id_bits++;
+	if (id_bits > 25)
+		return done();          // fewer than 6 fingerprint bits left: keep the plain scan
+	uint32_t idmask = (1u << id_bits) - 1u, fp_mask = 0x7FFFFFFFu & ~idmask;
 	int qw = std::min(32, w - s2 + 1);
 	uint64_t mask = qw >= 32 ? ~0ull : ((1ull << (2 * qw)) - 1);
 	std::vector<ulonglong2> pat(M, make_ulonglong2(0, 0));
@@ -572,9 +580,13 @@ static int get_sampled(const bsgpu_pdict3parts *p3, const SampledIndex **out)
 		pat[i] = make_ulonglong2(lo, hi);
 		nent += s2;
 	}
-	// buckets: about one entry per two-slot bucket, capped so that the table stays in L2
-	uint64_t nb = std::max<uint64_t>(16, nent);
-	std::vector<uint4> table(nb, make_uint4(0, BSGPU_EMPTY_ID, 0, BSGPU_EMPTY_ID));
+	// four entries per 16-byte bucket; BSGPU_SAMPLE_LOAD = entries per bucket x 100
+	const char *env_l = getenv("BSGPU_SAMPLE_LOAD");
+	double load = env_l ? atof(env_l) / 100.0 : 1.5;
+	if (load < 0.25) load = 0.25;
+	if (load > 3.0) load = 3.0;
+	uint64_t nb = std::max<uint64_t>(16, (uint64_t) ((double) nent / load));
+	std::vector<uint4> table(nb, make_uint4(BSGPU_S_EMPTY, BSGPU_S_EMPTY, BSGPU_S_EMPTY, BSGPU_S_EMPTY));
 	for (int i = 0; i < M; i++) {
 		if (p3->excluded[i] || p3->is_tb_dup[i])
 			continue;
@@ -586,19 +598,18 @@ static int get_sampled(const bsgpu_pdict3parts *p3, const SampledIndex **out)
 
 			keys[e] = key;
 			bsgpu_hash(key, top, fp);
-			uint32_t b = (uint32_t) (((uint64_t) top * nb) >> 32);
+			uint32_t word = sampled_fp_of(fp, id_bits, fp_mask) | e;
+			uint32_t b = sampled_bucket_of(top, (uint32_t) nb);
 			for (;;) {
-				if (table[b].y == BSGPU_EMPTY_ID) {
-					table[b].x = fp;
-					table[b].y = e;
+				uint32_t *slot = &table[b].x;
+				int z = 0;
+				while (z < 4 && (slot[z] & BSGPU_S_EMPTY) != BSGPU_S_EMPTY)
+					z++;
+				if (z < 4) {
+					slot[z] = (slot[z] & BSGPU_S_OVERFLOW) | word;
 					break;
 				}
-				if ((table[b].w & BSGPU_ID_MASK) == BSGPU_EMPTY_ID) {
-					table[b].z = fp;
-					table[b].w = (table[b].w & BSGPU_OVERFLOW_FLAG) | e;
-					break;
-				}
-				table[b].w |= BSGPU_OVERFLOW_FLAG;
+				table[b].w |= BSGPU_S_OVERFLOW;
 				b = b + 1 == nb ? 0 : b + 1;
 			}
 		}
@@ -609,6 +620,8 @@ static int get_sampled(const bsgpu_pdict3parts *p3, const SampledIndex **out)
 	si->t.table = si->d_table.p;
 	si->t.keys = si->d_keys.p;
 	si->t.nbuckets = (uint32_t) nb;
+	si->t.id_bits = id_bits;
+	si->t.fp_mask = fp_mask;
 	si->t.s = s2;
 	si->t.seed_w = qw;
 	si->t.seed_mask = mask;
@@ -1220,12 +1233,16 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 			int64_t probe_hi = std::min<int64_t>(subj->total, start_hi + si->t.s);
 			int64_t nw = ((probe_hi + 31) >> 5) - (start_lo >> 5);
 
-			if (p3->w > 32)
-				scan_tb_sampled_kernel<true><<<grid_for(nw, 256, 8), 256, 0, st>>>(
-					S, si->t, si->q, R, start_lo, probe_hi, end_lo, end_hi);
-			else
-				scan_tb_sampled_kernel<false><<<grid_for(nw, 256, 8), 256, 0, st>>>(
-					S, si->t, si->q, R, start_lo, probe_hi, end_lo, end_hi);
+#define LAUNCH_SAMPLED(LONG, SS) \
+	scan_tb_sampled_kernel<LONG, SS><<<grid_for(nw, 256, 8), 256, 0, st>>>( \
+		S, si->t, si->q, R, start_lo, probe_hi, end_lo, end_hi)
+			bool lng = p3->w > 32;
+			switch (si->t.s) {
+			case 2: if (lng) LAUNCH_SAMPLED(true, 2); else LAUNCH_SAMPLED(false, 2); break;
+			case 4: if (lng) LAUNCH_SAMPLED(true, 4); else LAUNCH_SAMPLED(false, 4); break;
+			default: if (lng) LAUNCH_SAMPLED(true, 8); else LAUNCH_SAMPLED(false, 8); break;
+			}
+#undef LAUNCH_SAMPLED
 			g_launches++;
 			CUDA_TRY(cudaGetLastError());
 			return BSGPU_OK;

@@ -254,81 +254,89 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 }
 
 // ------------------------------------------------------------------------------------
-// Exact dictionaries (Trusted Band = whole pattern), sampled seeds in the hash index.
-// Every pattern is indexed under its `s` seeds of q' = min(32, w-s+1) letters starting at
-// offsets 0..s-1, and the subject is probed only at positions p = 0 (mod s): an occurrence
-// starting at a meets exactly one of them (t = (-a) mod s), so the number of index probes
-// -- the L2 random-sector gathers that bound scan_tb_kernel -- drops by s.  A seed hit is
-// confirmed against the stored seed key and then against the whole pattern.
+// Exact dictionaries (Trusted Band = whole pattern), sampled seeds in a compact hash index.
+// Every pattern is indexed under its S seeds of q' = min(32, w-S+1) letters starting at
+// offsets 0..S-1, and the subject is probed only at positions p = 0 (mod S): an occurrence
+// starting at a meets exactly one of them (t = (-a) mod S), so the number of index probes
+// -- the L2 random-sector gathers that bound scan_tb_kernel -- drops by S.
+// Table: 16-byte buckets of four 4-byte entries {overflow:1 | fp | e}, e = pattern*S + t in
+// the low id_bits, fp = hash bits above them; 0x7FFFFFFF = empty.  The overflow bit (on
+// slot 3) says that an entry hashed here was placed further on.  A fingerprint hit is
+// confirmed against the stored seed key, then against the whole pattern (q_verify).
+// Different patterns may share a seed (overlapping probes), so every entry carrying the
+// seed is verified.
 // ------------------------------------------------------------------------------------
 
 struct BsgpuSampledView {
-	const uint4 *table;          // buckets {fp0, e0, fp1, e1 | overflow}; e = pattern * s + t
-	const uint64_t *keys;        // [M * s] seed key of every entry
+	const uint4 *table;
+	const uint64_t *keys;        // [M * S] seed key of every entry
 	uint32_t nbuckets;
-	int32_t s;                   // sampling stride
+	uint32_t id_bits;            // low bits of an entry = e
+	uint32_t fp_mask;            // fp occupies bits [id_bits, 31)
+	int32_t s;                   // sampling stride S
 	int32_t seed_w;              // q'
 	uint64_t seed_mask;
 };
 
-__device__ __forceinline__ uint32_t sampled_bucket(const BsgpuSampledView &T, uint32_t top)
+#define BSGPU_S_EMPTY 0x7FFFFFFFu       // all fp and id bits set, overflow bit clear
+#define BSGPU_S_OVERFLOW 0x80000000u
+
+__host__ __device__ __forceinline__ uint32_t sampled_bucket_of(uint32_t top, uint32_t nbuckets)
 {
-	return (uint32_t) (((uint64_t) top * T.nbuckets) >> 32);
+	return (uint32_t) (((uint64_t) top * nbuckets) >> 32);
 }
 
-template <bool LONG>
+// entry word without the id: fingerprint bits in place
+__host__ __device__ __forceinline__ uint32_t sampled_fp_of(uint32_t fp, uint32_t id_bits, uint32_t fp_mask)
+{
+	return (fp << id_bits) & fp_mask;
+}
+
+template <bool LONG, int SS>
 __global__ void __launch_bounds__(256)
 scan_tb_sampled_kernel(BsgpuSubjectView S, BsgpuSampledView T, BsgpuQIndexView Q, BsgpuReport R,
 		       int64_t probe_lo, int64_t probe_hi, int64_t own_lo, int64_t own_hi)
 {
+	constexpr int NP = 32 / SS;             // probes per 32-letter word (32 % SS == 0)
 	int64_t word_lo = probe_lo >> 5, word_hi = (probe_hi + 31) >> 5;
 	int64_t j = word_lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	const uint32_t idmask = (1u << T.id_bits) - 1u;
 
 	for (; j < word_hi; j += stride) {
 		int64_t base = j << 5;
 		uint64_t c0 = __ldcs(S.codes + j), c1 = __ldcs(S.codes + j + 1);
 		uint64_t v = (uint64_t) __ldcs(S.valid + j) | ((uint64_t) __ldcs(S.valid + j + 1) << 32);
-		uint32_t m = (uint32_t) all_set_run(v, T.seed_w), pm = 0;
+		uint32_t m = (uint32_t) all_set_run(v, T.seed_w);
 
-		for (int r = (int) ((T.s - base % T.s) % T.s); r < 32; r += T.s)
-			pm |= 1u << r;
-		m &= pm;
 		if (base < probe_lo)
 			m &= 0xFFFFFFFFu << (int) (probe_lo - base);
 		if (base + 32 > probe_hi)
 			m &= (probe_hi - base) <= 0 ? 0u : 0xFFFFFFFFu >> (int) (base + 32 - probe_hi);
-		// the probes of this word: at most ceil(32 / s), all loads issued before any is used
-		uint32_t rare = 0, todo = m;
-		while (todo) {
-			uint32_t fp[8], bucket[8];
-			uint4 b[8];
-			int rr[8], n = 0;
+		uint32_t fpw[NP], bucket[NP], rare = 0;
+		uint4 b[NP];
+#pragma unroll
+		for (int q = 0; q < NP; q++) {
+			const int r = q * SS;
+			uint64_t k = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
+			uint32_t top, fp;
 
-#pragma unroll
-			for (int q = 0; q < 8; q++) {
-				rr[q] = todo ? __ffs(todo) - 1 : -1;
-				todo &= todo - 1;
-				n += rr[q] >= 0;
-			}
-#pragma unroll
-			for (int q = 0; q < 8; q++) {
-				int r = rr[q] < 0 ? 0 : rr[q];
-				uint64_t k = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
-				uint32_t top;
-
-				bsgpu_hash(k & T.seed_mask, top, fp[q]);
-				bucket[q] = sampled_bucket(T, top);
-			}
-#pragma unroll
-			for (int q = 0; q < 8; q++)
-				b[q] = rr[q] >= 0 ? __ldg(T.table + bucket[q])
-						  : make_uint4(~fp[q], BSGPU_EMPTY_ID, ~fp[q], BSGPU_EMPTY_ID);
-#pragma unroll
-			for (int q = 0; q < 8; q++)
-				if (rr[q] >= 0 && (b[q].x == fp[q] || b[q].z == fp[q] || (b[q].w & BSGPU_OVERFLOW_FLAG)))
-					rare |= 1u << rr[q];
+			bsgpu_hash(k & T.seed_mask, top, fp);
+			bucket[q] = sampled_bucket_of(top, T.nbuckets);
+			fpw[q] = sampled_fp_of(fp, T.id_bits, T.fp_mask);
 		}
+#pragma unroll
+		for (int q = 0; q < NP; q++)
+			b[q] = ((m >> (q * SS)) & 1u) ? __ldg(T.table + bucket[q])
+						      : make_uint4(BSGPU_S_EMPTY, BSGPU_S_EMPTY, BSGPU_S_EMPTY, BSGPU_S_EMPTY);
+#pragma unroll
+		for (int q = 0; q < NP; q++) {
+			bool look = ((b[q].x ^ fpw[q]) & T.fp_mask) == 0 || ((b[q].y ^ fpw[q]) & T.fp_mask) == 0 ||
+				    ((b[q].z ^ fpw[q]) & T.fp_mask) == 0 || ((b[q].w ^ fpw[q]) & T.fp_mask) == 0 ||
+				    (b[q].w & BSGPU_S_OVERFLOW);
+			rare |= (look ? 1u : 0u) << (q * SS);
+		}
+		rare &= m;
 		while (rare) {
 			int r = __ffs(rare) - 1;
 			rare &= rare - 1;
@@ -337,22 +345,23 @@ scan_tb_sampled_kernel(BsgpuSubjectView S, BsgpuSampledView T, BsgpuQIndexView Q
 
 			k &= T.seed_mask;
 			bsgpu_hash(k, top, fp);
-			// Different patterns can share a seed (overlapping probes of one region), so
-			// every entry carrying this seed key is verified, along the whole bucket chain.
-			uint32_t bucket = sampled_bucket(T, top);
+			uint32_t fw = sampled_fp_of(fp, T.id_bits, T.fp_mask);
+			uint32_t bucket2 = sampled_bucket_of(top, T.nbuckets);
 			for (;;) {
-				uint4 b = __ldg(T.table + bucket);
-				uint32_t e0 = b.y & BSGPU_ID_MASK, e1 = b.w & BSGPU_ID_MASK;
+				uint4 bb = __ldg(T.table + bucket2);
+				uint32_t ent[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+				for (int z = 0; z < 4; z++) {
+					uint32_t e = ent[z] & idmask;
 
-				if (b.x == fp && e0 != BSGPU_EMPTY_ID && __ldg(T.keys + e0) == k)
-					q_verify<LONG>(S, Q, R, ((e0 / T.s) << 5) | (e0 % T.s), base + r, 0, 0,
-						       own_lo, own_hi);
-				if (b.z == fp && e1 != BSGPU_EMPTY_ID && __ldg(T.keys + e1) == k)
-					q_verify<LONG>(S, Q, R, ((e1 / T.s) << 5) | (e1 % T.s), base + r, 0, 0,
-						       own_lo, own_hi);
-				if (!(b.w & BSGPU_OVERFLOW_FLAG))
+					if (((ent[z] ^ fw) & T.fp_mask) == 0 && (ent[z] & BSGPU_S_EMPTY) != BSGPU_S_EMPTY &&
+					    __ldg(T.keys + e) == k)
+						q_verify<LONG>(S, Q, R, ((e / SS) << 5) | (e % SS), base + r, 0, 0,
+							       own_lo, own_hi);
+				}
+				if (!(bb.w & BSGPU_S_OVERFLOW))
 					break;
-				bucket = bucket + 1 == T.nbuckets ? 0 : bucket + 1;
+				bucket2 = bucket2 + 1 == T.nbuckets ? 0 : bucket2 + 1;
 			}
 		}
 	}
