@@ -23,7 +23,7 @@ SYMBOLS = [
     "bsgpu_result_free", "bsgpu_match", "bsgpu_vmatch", "bsgpu_count_device",
     "bsgpu_match_PDict3Parts_XString", "bsgpu_match_PDict3Parts_XStringViews",
     "bsgpu_vmatch_PDict3Parts_XStringSet", "bsgpu_mindex_combine",
-    "bsgpu_launch_count", "bsgpu_probe_peaks",
+    "bsgpu_last_plan", "bsgpu_launch_count", "bsgpu_probe_peaks",
 ]
 
 
@@ -88,6 +88,7 @@ def lib():
     L.bsgpu_vmatch_PDict3Parts_XStringSet.argtypes = [vp, vp, vp, i32] + [C.c_int] * 4 + \
         [C.c_int, C.c_int, vp, i64, C.c_int, C.POINTER(Result)]
     L.bsgpu_mindex_combine.argtypes = [C.POINTER(C.POINTER(Result)), C.c_int, C.POINTER(Result)]
+    L.bsgpu_last_plan.restype = C.c_char_p
     L.bsgpu_launch_count.restype = i64
     L.bsgpu_probe_peaks.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), i64]
     _lib = L

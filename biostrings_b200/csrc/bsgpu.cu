@@ -52,6 +52,17 @@ extern "C" const char *bsgpu_last_error(void) { return g_err; }
 extern "C" const char *bsgpu_version(void) { return "bsgpu 0.1 (sm_100a)"; }
 extern "C" int64_t bsgpu_launch_count(void) { return g_launches; }
 
+static char g_plan[512] = "";
+static void set_plan(const char *fmt, ...)
+{
+	va_list ap;
+
+	va_start(ap, fmt);
+	vsnprintf(g_plan, sizeof(g_plan), fmt, ap);
+	va_end(ap);
+}
+extern "C" const char *bsgpu_last_plan(void) { return g_plan; }
+
 // ---------------------------------------------------------------------------------------
 // device selection
 // ---------------------------------------------------------------------------------------
@@ -529,6 +540,7 @@ struct SampledIndex {
 	DevBuf<uint4> d_table;
 	DevBuf<uint64_t> d_keys;
 	DevBuf<ulonglong2> d_pat;
+	size_t nent = 0;
 };
 
 static int sampled_stride(int w)
@@ -617,6 +629,7 @@ static int get_sampled(const bsgpu_pdict3parts *p3, const SampledIndex **out)
 	TRY(si->d_table.upload(table.data(), table.size()));
 	TRY(si->d_keys.upload(keys.data(), keys.size()));
 	TRY(si->d_pat.upload(pat.data(), pat.size()));
+	si->nent = nent;
 	si->t.table = si->d_table.p;
 	si->t.keys = si->d_keys.p;
 	si->t.nbuckets = (uint32_t) nb;
@@ -1233,6 +1246,9 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 			int64_t probe_hi = std::min<int64_t>(subj->total, start_hi + si->t.s);
 			int64_t nw = ((probe_hi + 31) >> 5) - (start_lo >> 5);
 
+			set_plan("sampled_hash S=%d seed=%d buckets=%u table_bytes=%llu entries_per_bucket=%.2f",
+				 si->t.s, si->t.seed_w, si->t.nbuckets, (unsigned long long) si->t.nbuckets * 16,
+				 (double) si->nent / si->t.nbuckets);
 #define LAUNCH_SAMPLED(LONG, SS) \
 	scan_tb_sampled_kernel<LONG, SS><<<grid_for(nw, 256, 8), 256, 0, st>>>( \
 		S, si->t, si->q, R, start_lo, probe_hi, end_lo, end_hi)
@@ -1248,6 +1264,9 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 			return BSGPU_OK;
 		}
 	}
+	set_plan("tb_hash w=%d buckets=%u table_bytes=%llu%s%s", p3->w, p3->nbuckets,
+		 (unsigned long long) p3->nbuckets * 16, direct ? "" : " + verify_flanks",
+		 mp.fixedS ? "" : " + iupac_expansion");
 	scan_tb_kernel<<<grid_for(nwords, 256, 8), 256, 0, st>>>(S, I, R, C, direct, start_lo, start_hi);
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
@@ -1412,6 +1431,66 @@ static int run_q(const QIndex *qi, const bsgpu_subject *subj, const MatchParams 
 	int64_t nwords = ((probe_hi + 31) >> 5) - (probe_lo >> 5);
 	if (nwords <= 0)
 		return BSGPU_OK;
+	set_plan("qgram_%s q=%d shifts=%d stride=%d window=%d key_bits=%d entries=%zu", Q.mode ? "hamming" : "exact",
+		 Q.q, Q.nshifts, Q.stride, Q.min_w, Q.key_bits, qi->d_entries.n);
+	// The split form (emit candidates, verify one per thread) measured slower than the
+	// warp-synchronous fused kernel on B200 (6.4 vs 3.7 ms per 250 Mbp); kept for experiments.
+	const char *env_f = getenv("BSGPU_Q_SPLIT");
+	if (Q.mode == 1 && env_f != nullptr && env_f[0] == '1') {
+		// two kernels: emit candidates, then verify them one per thread
+		int64_t a = probe_lo, slab = std::min<int64_t>(probe_hi - probe_lo, (int64_t) 1 << 31);
+
+		TRY(grow(ws->cand, CAND_MIN, 0, st));
+		while (a < probe_hi) {
+			int64_t b = std::min(probe_hi, a + slab);
+			int64_t nw = ((b + 31) >> 5) - (a >> 5);
+			unsigned long long rec_before = 0, nrec = 0, ncand = 0;
+
+			if (rec_based)
+				TRY(read_counter(ws, 1, &rec_before, st));
+			TRY(write_counter(ws, 0, 0, st));
+			qprobe_kernel<<<grid_for(nw, 256, 8), 256, 0, st>>>(subj->view(), Q, a, b, ws->cand.p,
+					ws->counters.p + 0, ws->cand.n);
+			g_launches++;
+			CUDA_TRY(cudaGetLastError());
+			TRY(read_counter(ws, 0, &ncand, st));
+			if (ncand > ws->cand.n) {
+				if (ncand <= CAND_MAX) {
+					TRY(grow(ws->cand, (size_t) ncand, 0, st));
+				} else {
+					slab = std::max<int64_t>(4096, (int64_t) ((double) (b - a) *
+						((double) CAND_MAX / (double) ncand) * 0.9));
+					TRY(grow(ws->cand, CAND_MAX, 0, st));
+				}
+				continue;
+			}
+			for (;;) {
+				if (ncand > 0) {
+					if (qi->max_len > 32)
+						qverify_kernel<true><<<grid_for((long long) ncand, 256, 8), 256, 0, st>>>(
+							subj->view(), Q, R, mp.max_nmis, mp.min_nmis, a, own_lo, own_hi,
+							ws->cand.p, ncand);
+					else
+						qverify_kernel<false><<<grid_for((long long) ncand, 256, 8), 256, 0, st>>>(
+							subj->view(), Q, R, mp.max_nmis, mp.min_nmis, a, own_lo, own_hi,
+							ws->cand.p, ncand);
+					g_launches++;
+					CUDA_TRY(cudaGetLastError());
+				}
+				if (!rec_based)
+					break;
+				TRY(read_counter(ws, 1, &nrec, st));
+				if (nrec <= R.capacity)
+					break;
+				TRY(grow(ws->rec, (size_t) nrec, (size_t) rec_before, st));
+				R.records = ws->rec.p;
+				R.capacity = ws->rec.n;
+				TRY(write_counter(ws, 1, rec_before, st));
+			}
+			a = b;
+		}
+		return BSGPU_OK;
+	}
 	for (;;) {
 		unsigned long long rec_before = 0, nrec = 0;
 
@@ -1962,16 +2041,24 @@ extern "C" int bsgpu_probe_peaks(double *copy_gbs, double *l2_gather_gsectors, i
 		TRY(t.alloc((size_t) nb));
 		TRY(sink.alloc(1));
 		CUDA_TRY(cudaMemset(t.p, 0, (size_t) nb * 16));
-		const int iters = 4096, blocks = g_num_sms * 8, threads = 256;
+		const int iters = 4096, threads = 256;
 		double best = 0;
-		for (int it = 0; it < 6; it++) {
-			CUDA_TRY(cudaEventRecord(e0));
-			probe_gather_kernel<<<blocks, threads>>>(t.p, (uint32_t) (nb - 1), iters, sink.p);
-			g_launches++;
-			CUDA_TRY(cudaEventRecord(e1));
-			CUDA_TRY(cudaEventSynchronize(e1));
-			CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-			best = std::max(best, (double) blocks * threads * iters / (ms * 1e-3) / 1e9);
+		// best over a few launch shapes (loads in flight per thread x blocks per SM)
+		for (int cfg = 0; cfg < 6; cfg++) {
+			int blocks = g_num_sms * (cfg % 2 == 0 ? 8 : 4);
+			for (int it = 0; it < 4; it++) {
+				CUDA_TRY(cudaEventRecord(e0));
+				switch (cfg / 2) {
+				case 0: probe_gather_kernel<4><<<blocks, threads>>>(t.p, (uint32_t) (nb - 1), iters, sink.p); break;
+				case 1: probe_gather_kernel<8><<<blocks, threads>>>(t.p, (uint32_t) (nb - 1), iters, sink.p); break;
+				default: probe_gather_kernel<16><<<blocks, threads>>>(t.p, (uint32_t) (nb - 1), iters, sink.p); break;
+				}
+				g_launches++;
+				CUDA_TRY(cudaEventRecord(e1));
+				CUDA_TRY(cudaEventSynchronize(e1));
+				CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+				best = std::max(best, (double) blocks * threads * iters / (ms * 1e-3) / 1e9);
+			}
 		}
 		*l2_gather_gsectors = best;
 	}

@@ -590,7 +590,9 @@ probe_copy_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int64_
 		dst[i] = __ldcs(src + i);
 }
 
-// every lane reads one random 16-byte half of a random 32-byte sector
+// every lane reads one random 16-byte half of a random 32-byte sector, INFLIGHT loads per
+// thread issued before any is consumed (the access shape of the index probes)
+template <int INFLIGHT>
 __global__ void __launch_bounds__(256)
 probe_gather_kernel(const uint4 *__restrict__ table, uint32_t mask, int iters,
 		    unsigned long long *__restrict__ sink)
@@ -598,15 +600,15 @@ probe_gather_kernel(const uint4 *__restrict__ table, uint32_t mask, int iters,
 	uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
 	uint32_t acc = 0;
 
-	for (int it = 0; it < iters; it += 8) {
-		uint4 b[8];
+	for (int it = 0; it < iters; it += INFLIGHT) {
+		uint4 b[INFLIGHT];
 #pragma unroll
-		for (int q = 0; q < 8; q++) {
+		for (int q = 0; q < INFLIGHT; q++) {
 			x = x * 1664525u + 1013904223u;
 			b[q] = __ldg(table + ((x >> 4) & mask));
 		}
 #pragma unroll
-		for (int q = 0; q < 8; q++)
+		for (int q = 0; q < INFLIGHT; q++)
 			acc += b[q].x ^ b[q].w;
 	}
 	if (acc == 0x12345678u)

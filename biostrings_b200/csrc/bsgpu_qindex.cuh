@@ -185,42 +185,89 @@ __device__ __forceinline__ uint32_t q_valid_positions(const BsgpuQIndexView &Q, 
 	return (uint32_t) m;
 }
 
+// Cheap lower bound of the mismatch count of candidate `ent` at probe position p: letters
+// outside the segment are NOT forced to mismatch here, so the bound never exceeds the true
+// count and a candidate it rejects is certainly not a match.  ~5 loads + ~30 ALU ops.
+template <bool LONG>
+__device__ __forceinline__ int q_lower_bound(const BsgpuSubjectView &S, const BsgpuQIndexView &Q,
+					     uint32_t ent, int64_t p)
+{
+	const uint64_t E = 0x5555555555555555ull;
+	int id = (int) (ent >> 5);
+	int64_t a = p - Q.shift[ent & 31u];
+	int64_t wi = a >> 5;
+	int sh = 2 * (int) (a & 31);
+	int len = Q.const_len > 0 ? Q.const_len : (int) __ldg(Q.pat_len + id);
+
+	if (!LONG) {
+		uint64_t c0 = __ldg(S.codes + wi), c1 = __ldg(S.codes + wi + 1);
+		uint64_t i0 = __ldg(S.inv2 + wi), i1 = __ldg(S.inv2 + wi + 1);
+		uint64_t x = sh ? (c0 >> sh) | (c1 << (64 - sh)) : c0;
+		uint64_t iv = sh ? (i0 >> sh) | (i1 << (64 - sh)) : i0;
+		uint64_t P = __ldg(reinterpret_cast<const unsigned long long *>(Q.pat) + 2 * (size_t) id);
+		uint64_t d = x ^ P;
+
+		d = ((d | (d >> 1)) | iv) & (len >= 32 ? E : E & ((1ull << (2 * len)) - 1));
+		return __popcll(d);
+	} else {
+		uint64_t c0 = __ldg(S.codes + wi), c1 = __ldg(S.codes + wi + 1), c2 = __ldg(S.codes + wi + 2);
+		uint64_t i0 = __ldg(S.inv2 + wi), i1 = __ldg(S.inv2 + wi + 1), i2 = __ldg(S.inv2 + wi + 2);
+		uint64_t x_lo = sh ? (c0 >> sh) | (c1 << (64 - sh)) : c0;
+		uint64_t x_hi = sh ? (c1 >> sh) | (c2 << (64 - sh)) : c1;
+		uint64_t v_lo = sh ? (i0 >> sh) | (i1 << (64 - sh)) : i0;
+		uint64_t v_hi = sh ? (i1 >> sh) | (i2 << (64 - sh)) : i1;
+		ulonglong2 P = Q.pat[id];
+		uint64_t m_lo, m_hi, d_lo = x_lo ^ P.x, d_hi = x_hi ^ P.y;
+
+		range_mask2(0, len, m_lo, m_hi);
+		d_lo = ((d_lo | (d_lo >> 1)) | v_lo) & m_lo;
+		d_hi = ((d_hi | (d_hi >> 1)) | v_hi) & m_hi;
+		return __popcll(d_lo) + __popcll(d_hi);
+	}
+}
+
 template <bool LONG>
 __global__ void __launch_bounds__(256)
 qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis, int min_nmis,
 	     int64_t probe_lo, int64_t probe_hi, int64_t own_lo, int64_t own_hi)
 {
+	// Warp-synchronous: all 32 lanes of a warp stay in every loop (lanes without work are
+	// predicated off), so the candidate loop below reconverges every iteration.
+	const unsigned FULL = 0xFFFFFFFFu;
 	int64_t word_lo = probe_lo >> 5, word_hi = (probe_hi + 31) >> 5;
-	int64_t j = word_lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int lane = threadIdx.x & 31;
+	int64_t jb = word_lo + (int64_t) blockIdx.x * blockDim.x + (threadIdx.x & ~31);
 	int64_t stride = (int64_t) gridDim.x * blockDim.x;
 
-	for (; j < word_hi; j += stride) {
+	for (; jb < word_hi; jb += stride) {
+		int64_t j = jb + lane;
 		int64_t base = j << 5;
-		uint64_t c0 = __ldcs(S.codes + j), c1 = __ldcs(S.codes + j + 1);
-		uint64_t v = (uint64_t) __ldcs(S.valid + j) | ((uint64_t) __ldcs(S.valid + j + 1) << 32);
-		uint32_t m = q_valid_positions(Q, v);
+		uint64_t c0 = 0, c1 = 0;
+		uint32_t m = 0;
 
-		if (Q.stride > 1) {
-			uint32_t pm = 0;
-			for (int r = (int) ((Q.stride - base % Q.stride) % Q.stride); r < 32; r += Q.stride)
-				pm |= 1u << r;
-			m &= pm;
+		if (j < word_hi) {
+			c0 = __ldcs(S.codes + j);
+			c1 = __ldcs(S.codes + j + 1);
+			uint64_t v = (uint64_t) __ldcs(S.valid + j) | ((uint64_t) __ldcs(S.valid + j + 1) << 32);
+			m = q_valid_positions(Q, v);
+			if (Q.stride > 1) {
+				uint32_t pm = 0;
+				for (int r = (int) ((Q.stride - base % Q.stride) % Q.stride); r < 32; r += Q.stride)
+					pm |= 1u << r;
+				m &= pm;
+			}
+			if (base < probe_lo)
+				m &= 0xFFFFFFFFu << (int) (probe_lo - base);
+			if (base + 32 > probe_hi)
+				m &= (probe_hi - base) <= 0 ? 0u : 0xFFFFFFFFu >> (int) (base + 32 - probe_hi);
 		}
-		if (base < probe_lo)
-			m &= 0xFFFFFFFFu << (int) (probe_lo - base);
-		if (base + 32 > probe_hi)
-			m &= (probe_hi - base) <= 0 ? 0u : 0xFFFFFFFFu >> (int) (base + 32 - probe_hi);
-		if (m == 0)
-			continue;
-		// Phase 1: one bitmap word per position (2 MiB for 24 key bits: stays in L1/L2);
-		// about a third of the positions have a non-empty directory slot
+		// Phase 1: one bitmap word per position (2 MiB for 24 key bits); about a third of
+		// the positions have a non-empty directory slot
 		uint32_t have = 0;
 #pragma unroll
 		for (int g = 0; g < 32; g += QSCAN_GROUP) {
 			uint32_t key[QSCAN_GROUP], bw[QSCAN_GROUP];
 
-			if (((m >> g) & ((1u << QSCAN_GROUP) - 1)) == 0)
-				continue;
 #pragma unroll
 			for (int qq = 0; qq < QSCAN_GROUP; qq++) {
 				const int r = g + qq;
@@ -235,20 +282,31 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 			for (int qq = 0; qq < QSCAN_GROUP; qq++)
 				have |= ((bw[qq] >> (key[qq] & 31u)) & 1u) << (g + qq);
 		}
-		// Phase 2: all lanes walk their non-empty positions together: directory slot ->
-		// entries -> whole-pattern verification
-		while (have) {
-			int r = __ffs(have) - 1;
-			have &= have - 1;
-			uint64_t win = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
-			uint32_t key = q_key(Q, win);
-			uint2 G = __ldg(Q.dir + (key >> 2));
-			uint32_t cnt = (G.y >> (8 * (key & 3u))) & 0xFFu;
-			uint32_t off = G.x + q_prefix(G.y, (int) (key & 3u));
+		// Phase 2, flattened: every lane walks the concatenation of the entry lists of its
+		// non-empty positions, one candidate per lane and iteration.
+		uint32_t cur = 0, end = 0;
+		int64_t pos = 0;
+		for (;;) {
+			if (cur == end && have != 0) {
+				int r = __ffs(have) - 1;
+				have &= have - 1;
+				uint64_t win = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
+				uint32_t key = q_key(Q, win);
+				uint2 G = __ldg(Q.dir + (key >> 2));
 
-			for (uint32_t e = 0; e < cnt; e++)
-				q_verify<LONG>(S, Q, R, __ldg(Q.entries + off + e), base + r, max_nmis,
-					       min_nmis, own_lo, own_hi);
+				cur = G.x + q_prefix(G.y, (int) (key & 3u));
+				end = cur + ((G.y >> (8 * (key & 3u))) & 0xFFu);
+				pos = base + r;
+			}
+			bool busy = cur < end;
+			if (!__any_sync(FULL, busy || have != 0))
+				break;
+			if (busy) {
+				uint32_t ent = __ldg(Q.entries + cur++);
+
+				if (q_lower_bound<LONG>(S, Q, ent, pos) <= max_nmis)
+					q_verify<LONG>(S, Q, R, ent, pos, max_nmis, min_nmis, own_lo, own_hi);
+			}
 		}
 	}
 }
@@ -364,5 +422,100 @@ scan_tb_sampled_kernel(BsgpuSubjectView S, BsgpuSampledView T, BsgpuQIndexView Q
 				bucket2 = bucket2 + 1 == T.nbuckets ? 0 : bucket2 + 1;
 			}
 		}
+	}
+}
+
+// ------------------------------------------------------------------------------------
+// Two-kernel form of the q-gram engine (used for the Hamming mode, where a third of the
+// positions carry candidates): qprobe_kernel emits one record (entry, position) per
+// candidate with warp-aggregated appends, qverify_kernel checks one candidate per thread.
+// The fused qscan_kernel spends most of its issue slots in a divergent drain loop (ncu:
+// 17 of 32 lanes active, 57 % issue utilisation); split, both kernels run dense.
+// ------------------------------------------------------------------------------------
+
+#include <cooperative_groups/scan.h>
+
+__global__ void __launch_bounds__(256)
+qprobe_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, int64_t probe_lo, int64_t probe_hi,
+	      unsigned long long *__restrict__ records, unsigned long long *__restrict__ n_records,
+	      unsigned long long capacity)
+{
+	int64_t word_lo = probe_lo >> 5, word_hi = (probe_hi + 31) >> 5;
+	int64_t j = word_lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (; j < word_hi; j += stride) {
+		int64_t base = j << 5;
+		uint64_t c0 = __ldcs(S.codes + j), c1 = __ldcs(S.codes + j + 1);
+		uint64_t v = (uint64_t) __ldcs(S.valid + j) | ((uint64_t) __ldcs(S.valid + j + 1) << 32);
+		uint32_t m = q_valid_positions(Q, v);
+
+		if (base < probe_lo)
+			m &= 0xFFFFFFFFu << (int) (probe_lo - base);
+		if (base + 32 > probe_hi)
+			m &= (probe_hi - base) <= 0 ? 0u : 0xFFFFFFFFu >> (int) (base + 32 - probe_hi);
+		if (m == 0)
+			continue;
+		uint32_t have = 0;
+#pragma unroll
+		for (int g = 0; g < 32; g += QSCAN_GROUP) {
+			uint32_t key[QSCAN_GROUP], bw[QSCAN_GROUP];
+
+			if (((m >> g) & ((1u << QSCAN_GROUP) - 1)) == 0)
+				continue;
+#pragma unroll
+			for (int qq = 0; qq < QSCAN_GROUP; qq++) {
+				const int r = g + qq;
+				uint64_t win = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
+
+				key[qq] = q_key(Q, win);
+			}
+#pragma unroll
+			for (int qq = 0; qq < QSCAN_GROUP; qq++)
+				bw[qq] = ((m >> (g + qq)) & 1u) ? __ldg(Q.bitmap + (key[qq] >> 5)) : 0u;
+#pragma unroll
+			for (int qq = 0; qq < QSCAN_GROUP; qq++)
+				have |= ((bw[qq] >> (key[qq] & 31u)) & 1u) << (g + qq);
+		}
+		while (have) {
+			int r = __ffs(have) - 1;
+			have &= have - 1;
+			uint64_t win = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
+			uint32_t key = q_key(Q, win);
+			uint2 G = __ldg(Q.dir + (key >> 2));
+			uint32_t cnt = (G.y >> (8 * (key & 3u))) & 0xFFu;
+			uint32_t off = G.x + q_prefix(G.y, (int) (key & 3u));
+			// one append per warp and drain step
+			cg::coalesced_group grp = cg::coalesced_threads();
+			unsigned int before = cg::exclusive_scan(grp, cnt, cg::plus<unsigned int>());
+			unsigned long long wbase = 0;
+			if (grp.thread_rank() == grp.size() - 1)
+				wbase = atomicAdd(n_records, (unsigned long long) (before + cnt));
+			wbase = grp.shfl(wbase, grp.size() - 1);
+			unsigned long long hi = (unsigned long long) (base + r - probe_lo) << 32;
+			for (uint32_t e = 0; e < cnt; e++) {
+				unsigned long long idx = wbase + before + e;
+
+				if (idx < capacity)
+					records[idx] = hi | __ldg(Q.entries + off + e);
+			}
+		}
+	}
+}
+
+template <bool LONG>
+__global__ void __launch_bounds__(256)
+qverify_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis, int min_nmis,
+	       int64_t probe_lo, int64_t own_lo, int64_t own_hi,
+	       const unsigned long long *__restrict__ records, unsigned long long n)
+{
+	unsigned long long t = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+
+	for (; t < n; t += stride) {
+		unsigned long long rec = __ldcs(records + t);
+
+		q_verify<LONG>(S, Q, R, (uint32_t) rec, probe_lo + (int64_t) (rec >> 32), max_nmis, min_nmis,
+			       own_lo, own_hi);
 	}
 }

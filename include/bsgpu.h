@@ -218,6 +218,11 @@ int bsgpu_vmatch_PDict3Parts_XStringSet(const bsgpu_pdict3parts *p3,
 int bsgpu_mindex_combine(const bsgpu_result *const *components, int ncomponents,
 		bsgpu_result *res);
 
+/* Human-readable description of the engine the last match/count call used, e.g.
+ * "sampled_hash S=8 seed=18 buckets=5333333 table_bytes=85333328" or
+ * "qgram_hamming q=12 shifts=7 entries=6930000" or "tb_hash w=12 buckets=2097152 + verify". */
+const char *bsgpu_last_plan(void);
+
 /* Kernel launch counter (every kernel this library launched since process start). */
 int64_t bsgpu_launch_count(void);
 

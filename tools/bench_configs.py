@@ -1,0 +1,141 @@
+"""Times the other BASELINE.json configurations (C3, C3', C4, C5) on one
+GPU -- they are parity-test shapes, not the headline bench line, but their timings tell
+which kernel needs work next.  Prints one JSON line per configuration.
+
+    python tools/bench_configs.py [--scale 1.0] [--only C3,C4]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import biostrings_b200 as bs                                    # noqa: E402
+from biostrings_b200 import _lib, matchpdict as mp, synth       # noqa: E402
+
+L = _lib.lib()
+
+
+def timed(fn, reps=3):
+    import torch
+    best = None
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return out, best
+
+
+def dna_set(pats):
+    return bs.DNAStringSet(concat=pats.reshape(-1), widths=np.full(pats.shape[0], pats.shape[1], np.int32))
+
+
+def c3(scale):
+    """countPDict of 1M 36-mers, tb.start=1, tb.end=12, max.mismatch=2, 100 Mbp."""
+    n = int(100e6 * scale)
+    M = int(1e6 * scale) or 1000
+    subj = synth.subject_region(0, n, n, seed=5, with_n=False)
+    pats = synth.dictionary(M, 36, n, 1, seed=4, subject_seed=5, nsub=3, sub_lo=12)
+    t0 = time.perf_counter()
+    pd = bs.PDict(dna_set(pats), tb_start=1, tb_end=12)
+    t_build = time.perf_counter() - t0
+    ds = mp.DeviceSubject.from_xstring(subj)
+    out = {}
+    for mm in (0, 2):
+        c, dt = timed(lambda: mp.match_parts(pd.parts(), ds, mm, 0, (True, True), _lib.MATCHES_AS_COUNTS))
+        out[f"mm{mm}"] = {"seconds": dt, "Gbp_s": n / dt / 1e9, "matches": int(c.sum()),
+                          "plan": L.bsgpu_last_plan().decode()}
+    return {"config": "C3", "letters": n, "patterns": M, "pdict_build_s": t_build, **out}
+
+
+def c3prime(scale):
+    """countPDict of 1M 25-mers as PDict(max.mismatch=2) (bands 8/8/9), 250 Mbp."""
+    n = int(250e6 * scale)
+    M = int(1e6 * scale) or 1000
+    subj = synth.subject_region(0, n, n)
+    pats = synth.dictionary(M, 25, n, 1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        t0 = time.perf_counter()
+        pd = bs.PDict(dna_set(pats), max_mismatch=2)
+        t_build = time.perf_counter() - t0
+    ds = mp.DeviceSubject.from_xstring(subj)
+    c, dt = timed(lambda: mp.match_parts(pd.parts(), ds, 2, 0, (True, True), _lib.MATCHES_AS_COUNTS))
+    (_, e), dte = timed(lambda: mp.match_parts(pd.parts(), ds, 2, 0, (True, True), _lib.MATCHES_AS_ENDS), 1)
+    return {"config": "C3'", "letters": n, "patterns": M, "pdict_build_s": t_build,
+            "counts": {"seconds": dt, "Gbp_s": n / dt / 1e9, "matches": int(c.sum())},
+            "ends": {"seconds": dte, "hits": int(e.size)}, "plan": L.bsgpu_last_plan().decode()}
+
+
+def c4(scale):
+    """vcountPDict of 100k 25-mers against 10M x 150 bp reads, collapse=1 and 2."""
+    nreads = int(1e7 * scale)
+    M = int(1e5 * scale) or 1000
+    probes = synth.dictionary(M, 25, 10_000_000, 1, seed=6, frac_planted=0.0)
+    reads = synth.reads(nreads, 150, 0, seed=7, frac_planted=0.05, probes=probes)
+    t0 = time.perf_counter()
+    pd = bs.PDict(dna_set(probes))
+    t_build = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ds = mp.DeviceSubject.from_set(dna_set(reads))
+    t_up = time.perf_counter() - t0
+    out = {}
+    for coll in (1, 2):
+        w = np.ones(nreads if coll == 1 else M, dtype=np.int32)
+        c, dt = timed(lambda: mp.vmatch_parts(pd.parts(), ds, 0, 0, (True, True), coll, w,
+                                              _lib.MATCHES_AS_COUNTS))
+        out[f"collapse{coll}"] = {"seconds": dt, "Gbp_s": nreads * 150 / dt / 1e9,
+                                  "matches": int(c.sum())}
+    return {"config": "C4", "reads": nreads, "patterns": M, "pdict_build_s": t_build,
+            "upload_s": t_up, **out, "plan": L.bsgpu_last_plan().decode()}
+
+
+def c5(scale):
+    """2M patterns of 15-40 letters, tb.start=1, tb.width=15, fixed=FALSE, one 1/8 shard
+    (387.5 Mbp) of a 3.1 Gbp genome with isolated IUPAC letters at rate 1e-3."""
+    n = int(387.5e6 * scale)
+    M = int(2e6 * scale) or 1000
+    g = np.random.Generator(np.random.PCG64(8))
+    subj = synth.subject_region(0, n, n, seed=9, with_n=False)
+    amb_pos = np.flatnonzero(g.random(n) < 1e-3)
+    amb_pos = amb_pos[np.concatenate([[True], np.diff(amb_pos) > 15])]
+    amb = np.array([3, 5, 9, 6, 10, 12, 7, 11, 13, 14, 15], dtype=np.uint8)
+    subj[amb_pos] = amb[g.integers(0, len(amb), amb_pos.size)]
+    widths = g.integers(15, 41, M).astype(np.int32)
+    total = int(widths.sum())
+    concat = synth.BASES[g.integers(0, 4, total, dtype=np.uint8)]
+    offs = np.concatenate([[0], np.cumsum(widths)])
+    clean = synth.subject_region(0, min(n, 8_000_000), n, seed=9, with_n=False)
+    for i in g.choice(M, M // 10, replace=False).tolist():      # 10 % cut from the subject
+        st = int(g.integers(0, clean.size - 40))
+        concat[offs[i]:offs[i + 1]] = clean[st:st + widths[i]]
+    t0 = time.perf_counter()
+    pd = bs.PDict(bs.DNAStringSet(concat=concat, widths=widths), tb_start=1, tb_width=15)
+    t_build = time.perf_counter() - t0
+    ds = mp.DeviceSubject.from_xstring(subj)
+    out = {}
+    for fixed, name in (((True, True), "fixed_TRUE"), ((False, False), "fixed_FALSE")):
+        c, dt = timed(lambda: mp.match_parts(pd.parts(), ds, 0, 0, fixed, _lib.MATCHES_AS_COUNTS), 2)
+        out[name] = {"seconds": dt, "Gbp_s": n / dt / 1e9, "matches": int(c.sum()),
+                     "plan": L.bsgpu_last_plan().decode()}
+    return {"config": "C5 (one of 8 shards)", "letters": n, "patterns": M, "pdict_build_s": t_build, **out}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--only", default="C3,C3p,C4,C5")
+    a = ap.parse_args()
+    todo = {"C3": c3, "C3p": c3prime, "C4": c4, "C5": c5}
+    for name in a.only.split(","):
+        t0 = time.perf_counter()
+        res = todo[name](a.scale)
+        res["wall_s"] = time.perf_counter() - t0
+        print(json.dumps(res), flush=True)

@@ -11,7 +11,7 @@ from biostrings_b200 import _lib  # noqa: E402
 
 L = _lib.lib()
 out = {}
-for mb in (2, 8, 32, 64, 128, 256, 1024):
+for mb in (2, 8, 16, 32, 48, 64, 96, 128, 256, 1024):
     c, g = C.c_double(), C.c_double()
     _lib.check(L.bsgpu_probe_peaks(C.byref(c) if mb == 2 else None, C.byref(g), mb << 20))
     if mb == 2:
