@@ -537,7 +537,7 @@ struct SampledIndex {
 	bool ok = false;
 	BsgpuSampledView t = {};
 	BsgpuQIndexView q = {};
-	DevBuf<uint4> d_table;
+	DevBuf<uint4> d_table, d_filter;
 	DevBuf<uint64_t> d_keys;
 	DevBuf<ulonglong2> d_pat;
 	size_t nent = 0;
@@ -626,6 +626,30 @@ static int get_sampled(const bsgpu_pdict3parts *p3, const SampledIndex **out)
 			}
 		}
 	}
+	// first-level fingerprint filter: ~8 entries per 16-byte bucket
+	uint64_t nf = std::max<uint64_t>(16, nent / 8);
+	std::vector<uint4> filter(nf, make_uint4(0, 0, 0, 0));
+	for (int i = 0; i < M; i++) {
+		if (p3->excluded[i] || p3->is_tb_dup[i])
+			continue;
+		for (int t = 0; t < s2; t++) {
+			uint32_t top, fp, fb, fp8;
+
+			bsgpu_hash(keys[(size_t) i * s2 + t], top, fp);
+			sampled_filter_hash(top, fp, (uint32_t) nf, fb, fp8);
+			uint8_t *bytes = reinterpret_cast<uint8_t *>(&filter[fb]);
+			int z = 0;
+			while (z < 15 && bytes[z] != 0 && bytes[z] != fp8)
+				z++;
+			if (z < 15)
+				bytes[z] = (uint8_t) fp8;
+			else
+				bytes[15] = 1;          // overflow: everything is a "maybe" here
+		}
+	}
+	TRY(si->d_filter.upload(filter.data(), filter.size()));
+	si->t.filter = si->d_filter.p;
+	si->t.nfilter = (uint32_t) nf;
 	TRY(si->d_table.upload(table.data(), table.size()));
 	TRY(si->d_keys.upload(keys.data(), keys.size()));
 	TRY(si->d_pat.upload(pat.data(), pat.size()));
@@ -1246,9 +1270,9 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 			int64_t probe_hi = std::min<int64_t>(subj->total, start_hi + si->t.s);
 			int64_t nw = ((probe_hi + 31) >> 5) - (start_lo >> 5);
 
-			set_plan("sampled_hash S=%d seed=%d buckets=%u table_bytes=%llu entries_per_bucket=%.2f",
-				 si->t.s, si->t.seed_w, si->t.nbuckets, (unsigned long long) si->t.nbuckets * 16,
-				 (double) si->nent / si->t.nbuckets);
+			set_plan("sampled_hash S=%d seed=%d filter_bytes=%llu buckets=%u table_bytes=%llu entries_per_bucket=%.2f",
+				 si->t.s, si->t.seed_w, (unsigned long long) si->t.nfilter * 16, si->t.nbuckets,
+				 (unsigned long long) si->t.nbuckets * 16, (double) si->nent / si->t.nbuckets);
 #define LAUNCH_SAMPLED(LONG, SS) \
 	scan_tb_sampled_kernel<LONG, SS><<<grid_for(nw, 256, 8), 256, 0, st>>>( \
 		S, si->t, si->q, R, start_lo, probe_hi, end_lo, end_hi)

@@ -326,6 +326,8 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 // ------------------------------------------------------------------------------------
 
 struct BsgpuSampledView {
+	const uint4 *filter;         // first level: 15 one-byte fingerprints + 1 flag byte per bucket
+	uint32_t nfilter;            // number of filter buckets
 	const uint4 *table;
 	const uint64_t *keys;        // [M * S] seed key of every entry
 	uint32_t nbuckets;
@@ -350,6 +352,32 @@ __host__ __device__ __forceinline__ uint32_t sampled_fp_of(uint32_t fp, uint32_t
 	return (fp << id_bits) & fp_mask;
 }
 
+// First level of the sampled index: a 16-byte bucket holds the 8-bit fingerprints (1..255,
+// 0 = empty) of up to 15 entries and a flag byte (bit 0: more than 15 entries hashed here,
+// so the answer is "maybe" for everything).  ~8 entries per bucket on average: the whole
+// filter of 8M entries is 16 MiB and stays in L2, while the full table (fingerprint + entry
+// id, 85 MiB) is only touched by the ~4 % of the probes the filter lets through.
+__host__ __device__ __forceinline__ void sampled_filter_hash(uint32_t top, uint32_t fp, uint32_t nfilter,
+							      uint32_t &bucket, uint32_t &fp8)
+{
+	uint32_t h = top * 0xC2B2AE35u + fp;
+
+	h ^= h >> 15;
+	bucket = (uint32_t) (((uint64_t) h * nfilter) >> 32);
+	fp8 = 1u + (fp ^ (fp >> 16)) % 255u;
+}
+
+__device__ __forceinline__ bool filter_maybe(uint4 f, uint32_t fp8)
+{
+	uint32_t rep = fp8 * 0x01010101u;
+	uint32_t x0 = f.x ^ rep, x1 = f.y ^ rep, x2 = f.z ^ rep, x3 = (f.w ^ rep) | 0xFF000000u;
+	// any zero byte?  (exact zero-byte test on each word)
+	uint32_t z = ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) |
+		     ((x2 - 0x01010101u) & ~x2) | ((x3 - 0x01010101u) & ~x3);
+
+	return (z & 0x80808080u) != 0 || (f.w >> 24) != 0;
+}
+
 template <bool LONG, int SS>
 __global__ void __launch_bounds__(256)
 scan_tb_sampled_kernel(BsgpuSubjectView S, BsgpuSampledView T, BsgpuQIndexView Q, BsgpuReport R,
@@ -371,7 +399,7 @@ scan_tb_sampled_kernel(BsgpuSubjectView S, BsgpuSampledView T, BsgpuQIndexView Q
 			m &= 0xFFFFFFFFu << (int) (probe_lo - base);
 		if (base + 32 > probe_hi)
 			m &= (probe_hi - base) <= 0 ? 0u : 0xFFFFFFFFu >> (int) (base + 32 - probe_hi);
-		uint32_t fpw[NP], bucket[NP], rare = 0;
+		uint32_t fp8[NP], bucket[NP], rare = 0;
 		uint4 b[NP];
 #pragma unroll
 		for (int q = 0; q < NP; q++) {
@@ -380,20 +408,14 @@ scan_tb_sampled_kernel(BsgpuSubjectView S, BsgpuSampledView T, BsgpuQIndexView Q
 			uint32_t top, fp;
 
 			bsgpu_hash(k & T.seed_mask, top, fp);
-			bucket[q] = sampled_bucket_of(top, T.nbuckets);
-			fpw[q] = sampled_fp_of(fp, T.id_bits, T.fp_mask);
+			sampled_filter_hash(top, fp, T.nfilter, bucket[q], fp8[q]);
 		}
 #pragma unroll
 		for (int q = 0; q < NP; q++)
-			b[q] = ((m >> (q * SS)) & 1u) ? __ldg(T.table + bucket[q])
-						      : make_uint4(BSGPU_S_EMPTY, BSGPU_S_EMPTY, BSGPU_S_EMPTY, BSGPU_S_EMPTY);
+			b[q] = ((m >> (q * SS)) & 1u) ? __ldg(T.filter + bucket[q]) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-		for (int q = 0; q < NP; q++) {
-			bool look = ((b[q].x ^ fpw[q]) & T.fp_mask) == 0 || ((b[q].y ^ fpw[q]) & T.fp_mask) == 0 ||
-				    ((b[q].z ^ fpw[q]) & T.fp_mask) == 0 || ((b[q].w ^ fpw[q]) & T.fp_mask) == 0 ||
-				    (b[q].w & BSGPU_S_OVERFLOW);
-			rare |= (look ? 1u : 0u) << (q * SS);
-		}
+		for (int q = 0; q < NP; q++)
+			rare |= (filter_maybe(b[q], fp8[q]) ? 1u : 0u) << (q * SS);
 		rare &= m;
 		while (rare) {
 			int r = __ffs(rare) - 1;
