@@ -16,7 +16,7 @@ ALGO = {"ACtree2": 0, "Twobit": 1}
 # every symbol include/bsgpu.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "bsgpu_last_error", "bsgpu_version", "bsgpu_device_count", "bsgpu_set_device",
-    "bsgpu_pdict3parts_build", "bsgpu_pdict3parts_blank_dups", "bsgpu_pdict3parts_free",
+    "bsgpu_pdict3parts_build", "bsgpu_pdict3parts_set_flanks", "bsgpu_pdict3parts_blank_dups", "bsgpu_pdict3parts_free",
     "bsgpu_pdict3parts_length", "bsgpu_pdict3parts_tb_width",
     "bsgpu_subject_xstring", "bsgpu_subject_views", "bsgpu_subject_set",
     "bsgpu_subject_chunk", "bsgpu_subject_repack", "bsgpu_subject_free", "bsgpu_subject_nletters",
@@ -61,6 +61,7 @@ def lib():
     L.bsgpu_set_device.argtypes = [C.c_int]
     L.bsgpu_pdict3parts_build.argtypes = [C.c_int, i32, vp, vp, vp, vp, vp, vp, vp, vp,
                                           C.POINTER(vp)]
+    L.bsgpu_pdict3parts_set_flanks.argtypes = [vp, vp, vp, vp, vp]
     L.bsgpu_pdict3parts_blank_dups.argtypes = [vp]
     L.bsgpu_pdict3parts_free.argtypes = [vp]
     L.bsgpu_pdict3parts_free.restype = None

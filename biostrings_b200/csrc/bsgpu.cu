@@ -252,7 +252,8 @@ struct bsgpu_pdict3parts {
 	bool all_singletons = true;
 	DevBuf<uint4> d_table;
 	DevBuf<uint64_t> d_keys;
-	DevBuf<int32_t> d_seed_next;
+	DevBuf<int32_t> d_seed_next, d_leaders;
+	int32_t n_leaders = 0;
 	DevBuf<int32_t> d_grp_off, d_grp_keys;
 	DevBuf<uint8_t> d_tb, d_head, d_tail;
 	DevBuf<int64_t> d_head_off, d_tail_off;
@@ -301,6 +302,7 @@ struct QIndex {
 	DevBuf<uint2> d_dir;
 	DevBuf<uint32_t> d_entries, d_bitmap;
 	DevBuf<ulonglong2> d_pat;
+	DevBuf<unsigned long long> d_pat8;
 	DevBuf<uint8_t> d_len;
 	int max_len = 0;
 	int max_shift = 0;
@@ -522,6 +524,13 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 	TRY(qi->d_dir.upload(dir.data(), dir.size()));
 	TRY(qi->d_entries.upload(entries.data(), entries.size()));
 	TRY(qi->d_pat.upload(pat.data(), pat.size()));
+	{
+		std::vector<unsigned long long> p8(M);
+		for (int i = 0; i < M; i++)
+			p8[i] = pat[i].x;
+		TRY(qi->d_pat8.upload(p8.data(), p8.size()));
+		v.pat8 = qi->d_pat8.p;
+	}
 	TRY(qi->d_len.upload(plen.data(), plen.size()));
 	v.dir = qi->d_dir.p;
 	v.entries = qi->d_entries.p;
@@ -540,6 +549,7 @@ struct SampledIndex {
 	DevBuf<uint4> d_table, d_filter;
 	DevBuf<uint64_t> d_keys;
 	DevBuf<ulonglong2> d_pat;
+	DevBuf<unsigned long long> d_pat8;
 	size_t nent = 0;
 };
 
@@ -653,6 +663,13 @@ static int get_sampled(const bsgpu_pdict3parts *p3, const SampledIndex **out)
 	TRY(si->d_table.upload(table.data(), table.size()));
 	TRY(si->d_keys.upload(keys.data(), keys.size()));
 	TRY(si->d_pat.upload(pat.data(), pat.size()));
+	{
+		std::vector<unsigned long long> p8(M);
+		for (int i = 0; i < M; i++)
+			p8[i] = pat[i].x;
+		TRY(si->d_pat8.upload(p8.data(), p8.size()));
+		si->q.pat8 = si->d_pat8.p;
+	}
 	si->nent = nent;
 	si->t.table = si->d_table.p;
 	si->t.keys = si->d_keys.p;
@@ -879,9 +896,17 @@ extern "C" int bsgpu_pdict3parts_build(int algo, int32_t M,
 	}
 	TRY(p3->d_table.upload(table.data(), table.size()));
 	TRY(p3->d_keys.upload(p3->keys.data(), p3->keys.size()));
-	if (w > 32) {
+	if (w > 32)
 		TRY(p3->d_seed_next.upload(seed_next.data(), seed_next.size()));
-		TRY(p3->d_tb.upload(p3->tb.data(), p3->tb.size()));
+	TRY(p3->d_tb.upload(p3->tb.data(), p3->tb.size()));
+	// every Trusted-Band leader (w > 32: also the chained ones), for the IUPAC brute force
+	{
+		std::vector<int32_t> all_leaders;
+		for (int i = 0; i < M; i++)
+			if (!(pp_exclude != nullptr && pp_exclude[i] != BSGPU_NA) && p3->high2low[i] == BSGPU_NA)
+				all_leaders.push_back(i);
+		p3->n_leaders = (int32_t) all_leaders.size();
+		TRY(p3->d_leaders.upload(all_leaders.data(), all_leaders.size()));
 	}
 	TRY(upload_groups(p3, false));
 	TRY(upload_flank(M, head_concat, head_widths, p3->d_head, p3->d_head_off, p3->has_head,
@@ -896,6 +921,24 @@ extern "C" int bsgpu_pdict3parts_build(int algo, int32_t M,
 		for (int i = 0; i < M; i++)
 			p3->excluded[i] = pp_exclude[i] != BSGPU_NA;
 	*out = guard.release();
+	return BSGPU_OK;
+}
+
+extern "C" int bsgpu_pdict3parts_set_flanks(bsgpu_pdict3parts *p3,
+		const uint8_t *head_concat, const int32_t *head_widths,
+		const uint8_t *tail_concat, const int32_t *tail_widths)
+{
+	if (p3 == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_pdict3parts_set_flanks(): NULL handle");
+	TRY(ensure_device());
+	p3->h_head.clear();
+	p3->h_tail.clear();
+	TRY(upload_flank(p3->M, head_concat, head_widths, p3->d_head, p3->d_head_off, p3->has_head,
+			 p3->max_H, nullptr, p3->h_head, p3->h_head_off));
+	TRY(upload_flank(p3->M, tail_concat, tail_widths, p3->d_tail, p3->d_tail_off, p3->has_tail,
+			 p3->max_T, &p3->tail_len, p3->h_tail, p3->h_tail_off));
+	p3->qcache.reset();
+	p3->scache.reset();
 	return BSGPU_OK;
 }
 
@@ -1169,7 +1212,8 @@ extern "C" int64_t bsgpu_subject_nletters(const bsgpu_subject *s) { return s ? s
 struct Workspace {
 	DevBuf<unsigned long long> cand, rec, rec2;
 	DevBuf<unsigned long long> counters;    // [0] = candidates, [1] = records
-	DevBuf<int> flags;                      // [0] = too many IUPAC expansions
+	DevBuf<int> flags;
+	DevBuf<long long> ovf;                  // windows with too many IUPAC expansions
 	DevBuf<uint8_t> cub_temp;
 	unsigned long long *h_counters = nullptr;       // pinned
 	int *h_flags = nullptr;
@@ -1295,10 +1339,34 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
 	if (!mp.fixedS) {
+		const size_t OVF_CAP = 1u << 20;
+		unsigned long long n_ovf = 0;
+
+		if (ws->ovf.n < OVF_CAP)
+			TRY(ws->ovf.alloc(OVF_CAP));
+		TRY(write_counter(ws, 2, 0, st));
 		scan_tb_iupac_kernel<<<grid_for(nwords, 128, 16), 128, 0, st>>>(
-			S, I, R, C, direct, start_lo, start_hi, iupac_max_expansions(), ws->flags.p);
+			S, I, R, C, direct, start_lo, start_hi, iupac_max_expansions(), ws->ovf.p,
+			ws->counters.p + 2, OVF_CAP);
 		g_launches++;
 		CUDA_TRY(cudaGetLastError());
+		TRY(read_counter(ws, 2, &n_ovf, st));
+		// Heavily ambiguous windows (runs of N): brute force over the Trusted-Band words, up
+		// to a work budget -- the counterpart of the reference's cap on its live node set
+		// (src/match_pdict_ACtree2.c:1024,1051-1054), same message.
+		const char *env_b = getenv("BSGPU_IUPAC_BRUTE_BUDGET");
+		double budget = env_b ? atof(env_b) : 2e10;
+		if (n_ovf > OVF_CAP || (double) n_ovf * (double) p3->n_leaders > budget)
+			return fail(BSGPU_EINVAL, "too many IUPAC ambiguity letters in 'subject'");
+		if (n_ovf > 0 && p3->n_leaders > 0) {
+			dim3 grid((unsigned) std::min<long long>((p3->n_leaders + 255) / 256, 64),
+				  (unsigned) std::min<unsigned long long>(n_ovf, 65535));
+
+			iupac_brute_kernel<<<grid, 256, 0, st>>>(S, I, R, C, direct, ws->ovf.p, n_ovf,
+								  p3->d_leaders.p, p3->n_leaders);
+			g_launches++;
+			CUDA_TRY(cudaGetLastError());
+		}
 	}
 	return BSGPU_OK;
 }
@@ -1340,7 +1408,6 @@ static int run_part(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, cons
 	}
 
 	if (!mp.fixedS) {
-		CUDA_TRY(cudaMemsetAsync(ws->flags.p, 0, sizeof(int), st));
 		if (!subj->iupac_ready) {
 			int64_t nwords = subj->total / 32;
 
@@ -1411,12 +1478,6 @@ static int run_part(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, cons
 			}
 			a = b;
 		}
-	}
-	if (!mp.fixedS && allow_sync) {
-		CUDA_TRY(cudaMemcpyAsync(ws->h_flags, ws->flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-		CUDA_TRY(cudaStreamSynchronize(st));
-		if (ws->h_flags[0])
-			return fail(BSGPU_EINVAL, "too many IUPAC ambiguity letters in 'subject'");
 	}
 	return BSGPU_OK;
 }

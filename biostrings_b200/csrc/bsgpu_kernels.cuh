@@ -376,7 +376,8 @@ scan_tb_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R, BsgpuReport 
 __global__ void __launch_bounds__(128)
 scan_tb_iupac_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R, BsgpuReport C,
 		     int direct, int64_t start_lo, int64_t start_hi,
-		     unsigned int max_expansions, int *too_many)
+		     unsigned int max_expansions, long long *ovf_pos, unsigned long long *n_ovf,
+		     unsigned long long ovf_capacity)
 {
 	int64_t word_lo = start_lo >> 5, word_hi = (start_hi + 31) >> 5;
 	int64_t j = word_lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -432,7 +433,12 @@ scan_tb_iupac_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R, BsgpuR
 				}
 			}
 			if (overflow) {
-				atomicExch(too_many, 1);
+				// too many expansions to enumerate: the window goes to the
+				// brute-force kernel (every Trusted-Band word against it)
+				unsigned long long k = atomicAdd(n_ovf, 1ull);
+
+				if (k < ovf_capacity)
+					ovf_pos[k] = c0;
 				continue;
 			}
 			for (unsigned long long combo = 0; combo < total; combo++) {
@@ -461,6 +467,38 @@ scan_tb_iupac_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R, BsgpuR
 					tb_hit(I, S, R, C, direct, id, e);
 				}
 			}
+		}
+	}
+}
+
+// Windows with more IUPAC expansions than scan_tb_iupac_kernel enumerates (runs of N ...):
+// every Trusted-Band leader is compared with the window letter by letter,
+// (S[i] & t[i]) != 0 for all i -- what the reference's node-set walk amounts to
+// (src/match_pdict_ACtree2.c:1028-1061).  blockIdx.y walks the windows, x the leaders.
+__global__ void __launch_bounds__(256)
+iupac_brute_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R, BsgpuReport C, int direct,
+		   const long long *__restrict__ ovf_pos, unsigned long long n_ovf,
+		   const int32_t *__restrict__ leaders, int32_t n_leaders)
+{
+	__shared__ uint8_t win[64];
+	const int w = I.w;
+
+	for (unsigned long long q = blockIdx.y; q < n_ovf; q += gridDim.y) {
+		int64_t c0 = ovf_pos[q];
+
+		__syncthreads();
+		if (threadIdx.x < w)
+			win[threadIdx.x] = S.bytes[c0 + threadIdx.x];
+		__syncthreads();
+		for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_leaders; k += gridDim.x * blockDim.x) {
+			int id = __ldg(leaders + k);
+			const uint8_t *t = I.tb_bytes + (int64_t) id * w;
+			bool ok = true;
+
+			for (int i = 0; i < w && ok; i++)
+				ok = (win[i] & t[i]) != 0;
+			if (ok)
+				tb_hit(I, S, R, C, direct, id, c0 + w - 1);
 		}
 	}
 }

@@ -28,6 +28,7 @@ struct BsgpuQIndexView {
 	const uint2 *dir;            // [2^key_bits / 4] {base offset, 4 x u8 counts}
 	const uint32_t *entries;     // id << 5 | shift index, grouped by seed key
 	const ulonglong2 *pat;       // [M] 2-bit packed pattern letters (<= 64)
+	const unsigned long long *pat8;      // [M] the low 32 letters only (patterns of <= 32 letters)
 	const uint8_t *pat_len;      // [M]
 	int32_t q;                   // seed weight (letters)
 	int32_t mode;                // 0 = exact, sampled; 1 = Hamming (gapped shape)
@@ -110,7 +111,7 @@ __device__ __forceinline__ void q_verify(const BsgpuSubjectView &S, const BsgpuQ
 		uint64_t i0 = __ldg(S.inv2 + wi), i1 = __ldg(S.inv2 + wi + 1);
 		uint64_t x = sh ? (c0 >> sh) | (c1 << (64 - sh)) : c0;
 		uint64_t iv = sh ? (i0 >> sh) | (i1 << (64 - sh)) : i0;
-		uint64_t P = __ldg(reinterpret_cast<const unsigned long long *>(Q.pat) + 2 * (size_t) id);
+		uint64_t P = __ldg(Q.pat8 + id);
 
 		d_lo = x ^ P;
 		d_lo = ((d_lo | (d_lo >> 1)) | iv) & E;
@@ -204,7 +205,7 @@ __device__ __forceinline__ int q_lower_bound(const BsgpuSubjectView &S, const Bs
 		uint64_t i0 = __ldg(S.inv2 + wi), i1 = __ldg(S.inv2 + wi + 1);
 		uint64_t x = sh ? (c0 >> sh) | (c1 << (64 - sh)) : c0;
 		uint64_t iv = sh ? (i0 >> sh) | (i1 << (64 - sh)) : i0;
-		uint64_t P = __ldg(reinterpret_cast<const unsigned long long *>(Q.pat) + 2 * (size_t) id);
+		uint64_t P = __ldg(Q.pat8 + id);
 		uint64_t d = x ^ P;
 
 		d = ((d | (d >> 1)) | iv) & (len >= 32 ? E : E & ((1ull << (2 * len)) - 1));

@@ -1,0 +1,540 @@
+/*
+ * match_pdict_gpu.c -- the R-facing C dispatch of the PDict path over libbsgpu.
+ *
+ * Drop-in for the .Call entry points of Biostrings' src/match_pdict.c,
+ * src/match_pdict_Twobit.c, src/match_pdict_ACtree2.c and src/MIndex_class.c: SAME names,
+ * SAME arguments, SAME result shapes, so R/PDict-class.R, R/matchPDict.R and
+ * src/R_init_Biostrings.c stay untouched.  "Host code stays C": this file only moves data
+ * between R objects and the plain-C ABI of include/bsgpu.h; all per-base work happens in
+ * the CUDA kernels behind that ABI.
+ *
+ * It is written against the public C interfaces Biostrings itself uses (Rdefines.h,
+ * XVector_interface.h, IRanges_interface.h), so it compiles against real R headers.  In
+ * this repository (no R in the image) it is compiled against the stand-in headers of
+ * oracle/shim/ and driven by oracle/ref_harness.c -- the same harness that drives the
+ * reference's own C -- so tests/test_gpu_dispatch.py compares the SEXP results of both
+ * libraries entry point by entry point.
+ *
+ * Entry points (reference file:line):
+ *   build_Twobit                      src/match_pdict_Twobit.c:104
+ *   ACtree2_build                     src/match_pdict_ACtree2.c:792
+ *   ACtree2_nodebuf_max_nblock / ACtree2_nodeextbuf_max_nblock / IntegerBAB_new
+ *                                     src/match_pdict_ACtree2.c:217,320; src/BAB_class.c:9
+ *   ACtree2_nnodes / ACtree2_has_all_flinks / ACtree2_compute_all_flinks
+ *                                     src/match_pdict_ACtree2.c:681,972,981
+ *   match_PDict3Parts_XString         src/match_pdict.c:153
+ *   match_PDict3Parts_XStringViews    src/match_pdict.c:225
+ *   vmatch_PDict3Parts_XStringSet     src/match_pdict.c:484
+ *   ByPos_MIndex_endIndex / ByPos_MIndex_combine    src/MIndex_class.c:134,230
+ */
+#include <Rdefines.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "XVector_interface.h"
+#include "IRanges_interface.h"
+#include "S4Vectors_interface.h"
+#include "bsgpu.h"
+
+/* ---- small helpers ------------------------------------------------------------------ */
+
+typedef struct { unsigned char *concat; int *widths; int n; } FlatSet;
+
+/* concat + widths of an XStringSet (its elements may be scattered in the XVector pool) */
+static FlatSet flatten(SEXP x)
+{
+	FlatSet f;
+	XVectorList_holder h = hold_XVectorList(x);
+	size_t total = 0, off = 0;
+	int i;
+
+	f.n = get_length_from_XVectorList_holder(&h);
+	f.widths = (int *) R_alloc((size_t) (f.n ? f.n : 1), sizeof(int));
+	for (i = 0; i < f.n; i++)
+		total += (size_t) (f.widths[i] = get_elt_from_XRawList_holder(&h, i).length);
+	f.concat = (unsigned char *) R_alloc(total ? total : 1, 1);
+	for (i = 0; i < f.n; i++) {
+		Chars_holder e = get_elt_from_XRawList_holder(&h, i);
+
+		memcpy(f.concat + off, e.ptr, (size_t) e.length);
+		off += (size_t) e.length;
+	}
+	return f;
+}
+
+static int matches_as_code(SEXP matches_as)
+{
+	const char *s = CHAR(STRING_ELT(matches_as, 0));
+
+	/* src/match_reporting.c:10-31 */
+	if (strcmp(s, "MATCHES_AS_NULL") == 0) return BSGPU_MATCHES_AS_NULL;
+	if (strcmp(s, "MATCHES_AS_WHICH") == 0) return BSGPU_MATCHES_AS_WHICH;
+	if (strcmp(s, "MATCHES_AS_COUNTS") == 0) return BSGPU_MATCHES_AS_COUNTS;
+	if (strcmp(s, "MATCHES_AS_ENDS") == 0) return BSGPU_MATCHES_AS_ENDS;
+	error("Biostrings internal error in _get_match_storing_code(): "
+	      "\"%s\": unknown match storing mode", s);
+	return -1;
+}
+
+/* ---- device index cache ---------------------------------------------------------------
+ * The Trusted Band is preprocessed once (build_Twobit / ACtree2_build) while head and tail
+ * arrive with every match call, so the index is created at build time, remembered by the
+ * identity of the `tb` object that ends up in the pptb@tb slot, and gets its flanks
+ * attached on the first match call.  (A production integration would hang an externalptr
+ * with a finalizer on the PreprocessedTB object instead of this small table.) */
+
+#define CACHE_SIZE 64
+static struct cache_entry {
+	SEXP tb;			/* identity of the Trusted Band object */
+	bsgpu_pdict3parts *p3;
+	uint64_t flank_sig;		/* which head/tail are attached */
+	int dups_blanked;
+} cache[CACHE_SIZE];
+static int cache_next = 0;
+
+static struct cache_entry *cache_find(SEXP tb)
+{
+	int i;
+
+	for (i = 0; i < CACHE_SIZE; i++)
+		if (cache[i].p3 != NULL && cache[i].tb == tb)
+			return &cache[i];
+	return NULL;
+}
+
+static void cache_put(SEXP tb, bsgpu_pdict3parts *p3)
+{
+	struct cache_entry *e = cache_find(tb);
+
+	if (e == NULL) {
+		e = &cache[cache_next];
+		cache_next = (cache_next + 1) % CACHE_SIZE;
+	}
+	if (e->p3 != NULL)
+		bsgpu_pdict3parts_free(e->p3);
+	e->tb = tb;
+	e->p3 = p3;
+	e->flank_sig = 0;
+	e->dups_blanked = 0;
+}
+
+static uint64_t fnv(uint64_t h, const void *p, size_t n)
+{
+	const unsigned char *b = p;
+	size_t i;
+
+	for (i = 0; i < n; i++)
+		h = (h ^ b[i]) * 0x100000001B3ull;
+	return h;
+}
+
+/* SEXP slot access, as src/PreprocessedTB_class.c:23-59 does it */
+static SEXP pptb_tb(SEXP pptb) { return GET_SLOT(pptb, install("tb")); }
+static SEXP pptb_dups(SEXP pptb) { return GET_SLOT(pptb, install("dups")); }
+
+static int algo_of(SEXP pptb)
+{
+	const char *type = get_classname(pptb);
+
+	if (strcmp(type, "Twobit") == 0) return BSGPU_ALGO_TWOBIT;
+	if (strcmp(type, "ACtree2") == 0) return BSGPU_ALGO_ACTREE2;
+	error("%s: unsupported Trusted Band type in 'pdict'", type);
+	return -1;
+}
+
+/* The device index of (pptb, head, tail), ready for matching. */
+static bsgpu_pdict3parts *get_p3(SEXP pptb, SEXP pdict_head, SEXP pdict_tail)
+{
+	SEXP tb = pptb_tb(pptb);
+	struct cache_entry *e = cache_find(tb);
+	FlatSet hd = {NULL, NULL, 0}, tl = {NULL, NULL, 0};
+	uint64_t sig = 0xCBF29CE484222325ull;
+	int i, all_na = 1;
+	SEXP h2l;
+
+	if (e == NULL) {
+		/* not built through this library in this session (e.g. a PDict loaded from disk):
+		   rebuild from the object; excluded patterns are those absent from every group,
+		   which the object does not record, so exclusion is taken from exclude_dups0 = FALSE */
+		FlatSet t = flatten(tb);
+		bsgpu_pdict3parts *p3;
+
+		if (bsgpu_pdict3parts_build(algo_of(pptb), t.n, t.concat, t.widths, NULL, NULL, NULL, NULL,
+					    NULL, NULL, &p3) != BSGPU_OK)
+			error("%s", bsgpu_last_error());
+		cache_put(tb, p3);
+		e = cache_find(tb);
+	}
+	if (pdict_head != R_NilValue) {
+		size_t tot = 0;
+
+		hd = flatten(pdict_head);
+		for (i = 0; i < hd.n; i++)
+			tot += (size_t) hd.widths[i];
+		sig = fnv(fnv(sig, hd.widths, (size_t) hd.n * sizeof(int)), hd.concat, tot);
+	}
+	sig = fnv(sig, "|", 1);
+	if (pdict_tail != R_NilValue) {
+		size_t tot = 0;
+
+		tl = flatten(pdict_tail);
+		for (i = 0; i < tl.n; i++)
+			tot += (size_t) tl.widths[i];
+		sig = fnv(fnv(sig, tl.widths, (size_t) tl.n * sizeof(int)), tl.concat, tot);
+	}
+	if (sig == 0)
+		sig = 1;
+	if (e->flank_sig != sig) {
+		if (bsgpu_pdict3parts_set_flanks(e->p3, hd.concat, hd.widths, tl.concat, tl.widths) != BSGPU_OK)
+			error("%s", bsgpu_last_error());
+		e->flank_sig = sig;
+	}
+	/* R/PDict-class.R:224-226: a reused whole-pattern pptb0 has its dups blanked at the R
+	   level; the C side sees it as low2high being all NULL */
+	h2l = get_H2LGrouping_high2low(pptb_dups(pptb));
+	for (i = 0; i < LENGTH(h2l); i++)
+		if (INTEGER(h2l)[i] != NA_INTEGER) {
+			all_na = 0;
+			break;
+		}
+	if (all_na && !e->dups_blanked) {
+		if (bsgpu_pdict3parts_blank_dups(e->p3) != BSGPU_OK)
+			error("%s", bsgpu_last_error());
+		e->dups_blanked = 1;
+	}
+	return e->p3;
+}
+
+/* ---- preprocessing entry points -------------------------------------------------------- */
+
+static SEXP build_common(int algo, SEXP tb, SEXP pp_exclude, SEXP first_elt, const char *first_name)
+{
+	FlatSet t = flatten(tb);
+	SEXP ans, ans_names, h2l;
+	bsgpu_pdict3parts *p3;
+
+	PROTECT(h2l = NEW_INTEGER(t.n));
+	if (bsgpu_pdict3parts_build(algo, t.n, t.concat, t.widths, NULL, NULL, NULL, NULL,
+				    pp_exclude == R_NilValue ? NULL : INTEGER(pp_exclude),
+				    INTEGER(h2l), &p3) != BSGPU_OK)
+		error("%s", bsgpu_last_error());	/* the reference's own message */
+	cache_put(tb, p3);
+	PROTECT(ans = NEW_LIST(2));
+	PROTECT(ans_names = NEW_CHARACTER(2));
+	SET_STRING_ELT(ans_names, 0, mkChar(first_name));
+	SET_STRING_ELT(ans_names, 1, mkChar("high2low"));
+	SET_NAMES(ans, ans_names);
+	SET_VECTOR_ELT(ans, 0, first_elt);
+	SET_VECTOR_ELT(ans, 1, h2l);
+	UNPROTECT(3);
+	return ans;
+}
+
+/* --- .Call ENTRY POINT --- (src/match_pdict_Twobit.c:104) */
+SEXP build_Twobit(SEXP tb, SEXP pp_exclude, SEXP base_codes)
+{
+	/* Twobit@sign2pos must stay a valid XInteger of length 4^w: show() prints its length
+	   (R/PDict-class.R:79-93,102).  It is filled the way the reference fills it
+	   (signature = first letter most significant, src/utils.c:135-142). */
+	XVectorList_holder h = hold_XVectorList(tb);
+	int n = get_length_from_XVectorList_holder(&h), w = -1, i, d;
+	SEXP sign2pos, xint, ans;
+
+	for (i = 0; i < n && w < 0; i++)
+		if (pp_exclude == R_NilValue || INTEGER(pp_exclude)[i] == NA_INTEGER)
+			w = get_elt_from_XRawList_holder(&h, i).length;
+	/* argument errors (empty TB, w > 14, ragged, non-base) come from the library, with
+	   the reference's text, before any table is allocated */
+	PROTECT(ans = build_common(BSGPU_ALGO_TWOBIT, tb, pp_exclude, R_NilValue, "sign2pos"));
+	PROTECT(sign2pos = NEW_INTEGER(w < 0 ? 0 : 1 << (2 * w)));
+	for (i = 0; i < LENGTH(sign2pos); i++)
+		INTEGER(sign2pos)[i] = NA_INTEGER;
+	for (i = 0; i < n; i++) {
+		Chars_holder e;
+		int sig = 0;
+
+		if (pp_exclude != R_NilValue && INTEGER(pp_exclude)[i] != NA_INTEGER)
+			continue;
+		e = get_elt_from_XRawList_holder(&h, i);
+		for (d = 0; d < w; d++) {
+			int b = (unsigned char) e.ptr[d];
+
+			sig = (sig << 2) | (b == 1 ? 0 : b == 2 ? 1 : b == 4 ? 2 : 3);
+		}
+		if (INTEGER(sign2pos)[sig] == NA_INTEGER)
+			INTEGER(sign2pos)[sig] = i + 1;
+	}
+	PROTECT(xint = new_XInteger_from_tag("XInteger", sign2pos));
+	SET_VECTOR_ELT(ans, 0, xint);
+	UNPROTECT(3);
+	(void) base_codes;
+	return ans;
+}
+
+/* --- .Call ENTRY POINT --- (src/match_pdict_ACtree2.c:792) */
+SEXP ACtree2_build(SEXP tb, SEXP pp_exclude, SEXP base_codes, SEXP nodebuf_ptr, SEXP nodeextbuf_ptr)
+{
+	(void) base_codes; (void) nodebuf_ptr; (void) nodeextbuf_ptr;
+	return build_common(BSGPU_ALGO_ACTREE2, tb, pp_exclude, R_NilValue, "ACtree");
+}
+
+/* The node buffers of the CPU tree are not needed: the index lives on the device.  The
+ * accessors stay so that the R object remains constructible and printable. */
+SEXP ACtree2_nodebuf_max_nblock(void) { return ScalarInteger(1024); }
+SEXP ACtree2_nodeextbuf_max_nblock(void) { return ScalarInteger(1024); }
+
+SEXP IntegerBAB_new(SEXP max_nblock)
+{
+	SEXP blocks, prot, xp, classdef, ans;
+
+	PROTECT(blocks = NEW_LIST(INTEGER(max_nblock)[0]));
+	PROTECT(prot = NEW_INTEGER(2));
+	INTEGER(prot)[0] = INTEGER(prot)[1] = 0;
+	PROTECT(xp = R_MakeExternalPtr(NULL, blocks, prot));
+	PROTECT(classdef = MAKE_CLASS("IntegerBAB"));
+	PROTECT(ans = NEW_OBJECT(classdef));
+	SET_SLOT(ans, mkChar("xp"), xp);
+	UNPROTECT(5);
+	return ans;
+}
+
+SEXP ACtree2_nnodes(SEXP pptb)
+{
+	/* no CPU tree: report the number of Trusted-Band letters indexed, an upper bound of
+	   the node count of the reference's trie */
+	struct cache_entry *e = cache_find(pptb_tb(pptb));
+
+	return ScalarInteger(e ? bsgpu_pdict3parts_length(e->p3) * bsgpu_pdict3parts_tb_width(e->p3) + 1
+			       : NA_INTEGER);
+}
+
+SEXP ACtree2_has_all_flinks(SEXP pptb) { (void) pptb; return ScalarLogical(1); }
+SEXP ACtree2_compute_all_flinks(SEXP pptb) { (void) pptb; return R_NilValue; }
+void _init_bytewise_match_tables(void) {}	/* the match tables are bit tests in the kernels */
+
+/* ---- results ------------------------------------------------------------------------------ */
+
+static SEXP csr_as_list(const bsgpu_result *r)
+{
+	SEXP ans, elt;
+	int64_t i;
+
+	/* new_LIST_from_IntAEAE(..., 1): NULL, not integer(0), for empty rows
+	   (src/match_reporting.c:192-201) */
+	PROTECT(ans = NEW_LIST((int) r->n_rows));
+	for (i = 0; i < r->n_rows; i++) {
+		int64_t n = r->ends_offsets[i + 1] - r->ends_offsets[i];
+
+		if (n == 0)
+			continue;
+		PROTECT(elt = NEW_INTEGER((int) n));
+		memcpy(INTEGER(elt), r->ends + r->ends_offsets[i], (size_t) n * sizeof(int));
+		SET_VECTOR_ELT(ans, (int) i, elt);
+		UNPROTECT(1);
+	}
+	UNPROTECT(1);
+	return ans;
+}
+
+static SEXP result_as_SEXP(bsgpu_result *r, int ms_code)
+{
+	SEXP ans;
+
+	switch (ms_code) {
+	case BSGPU_MATCHES_AS_NULL:
+		ans = R_NilValue;
+		break;
+	case BSGPU_MATCHES_AS_WHICH:	/* _MatchBuf_which_asINTEGER, src/match_reporting.c:150 */
+		PROTECT(ans = NEW_INTEGER((int) r->n_which));
+		memcpy(INTEGER(ans), r->which, (size_t) r->n_which * sizeof(int));
+		UNPROTECT(1);
+		break;
+	case BSGPU_MATCHES_AS_COUNTS:	/* _MatchBuf_counts_asINTEGER, src/match_reporting.c:163 */
+		PROTECT(ans = NEW_INTEGER((int) r->n_counts));
+		memcpy(INTEGER(ans), r->counts, (size_t) r->n_counts * sizeof(int));
+		UNPROTECT(1);
+		break;
+	default:			/* _MatchBuf_ends_asLIST, src/match_reporting.c:192 */
+		ans = csr_as_list(r);
+	}
+	bsgpu_result_free(r);
+	return ans;
+}
+
+/* ---- matching entry points ------------------------------------------------------------------ */
+
+/* --- .Call ENTRY POINT --- (src/match_pdict.c:153) */
+SEXP match_PDict3Parts_XString(SEXP pptb, SEXP pdict_head, SEXP pdict_tail,
+		SEXP subject, SEXP max_mismatch, SEXP min_mismatch, SEXP fixed,
+		SEXP matches_as, SEXP envir)
+{
+	Chars_holder S = hold_XRaw(subject);
+	int ms_code = matches_as_code(matches_as);
+	bsgpu_result r;
+
+	(void) envir;
+	if (bsgpu_match_PDict3Parts_XString(get_p3(pptb, pdict_head, pdict_tail),
+			(const uint8_t *) S.ptr, S.length,
+			INTEGER(max_mismatch)[0], INTEGER(min_mismatch)[0],
+			LOGICAL(fixed)[0], LOGICAL(fixed)[1], ms_code, &r) != BSGPU_OK)
+		error("%s", bsgpu_last_error());
+	return result_as_SEXP(&r, ms_code);
+}
+
+/* --- .Call ENTRY POINT --- (src/match_pdict.c:225) */
+SEXP match_PDict3Parts_XStringViews(SEXP pptb, SEXP pdict_head, SEXP pdict_tail,
+		SEXP subject, SEXP views_start, SEXP views_width,
+		SEXP max_mismatch, SEXP min_mismatch, SEXP fixed,
+		SEXP matches_as, SEXP envir)
+{
+	Chars_holder S = hold_XRaw(subject);
+	int ms_code = matches_as_code(matches_as);
+	bsgpu_result r;
+
+	(void) envir;
+	if (bsgpu_match_PDict3Parts_XStringViews(get_p3(pptb, pdict_head, pdict_tail),
+			(const uint8_t *) S.ptr, S.length,
+			INTEGER(views_start), INTEGER(views_width), LENGTH(views_start),
+			INTEGER(max_mismatch)[0], INTEGER(min_mismatch)[0],
+			LOGICAL(fixed)[0], LOGICAL(fixed)[1], ms_code, &r) != BSGPU_OK)
+		error("%s", bsgpu_last_error());
+	return result_as_SEXP(&r, ms_code);
+}
+
+/* --- .Call ENTRY POINT --- (src/match_pdict.c:484) */
+SEXP vmatch_PDict3Parts_XStringSet(SEXP pptb, SEXP pdict_head, SEXP pdict_tail,
+		SEXP subject, SEXP max_mismatch, SEXP min_mismatch, SEXP fixed,
+		SEXP collapse, SEXP weight, SEXP matches_as, SEXP envir)
+{
+	FlatSet s = flatten(subject);
+	int ms_code = matches_as_code(matches_as), coll = INTEGER(collapse)[0];
+	int M = get_XVectorList_length(pptb_tb(pptb));
+	bsgpu_result r;
+	SEXP ans;
+
+	(void) envir;
+	if (ms_code == BSGPU_MATCHES_AS_NULL)
+		error("vmatch_PDict3Parts_XStringSet() does not support "
+		      "'matches_as=\"%s\"' yet, sorry", CHAR(STRING_ELT(matches_as, 0)));
+	if (ms_code != BSGPU_MATCHES_AS_WHICH && ms_code != BSGPU_MATCHES_AS_COUNTS)
+		error("vmatchPDict() is not supported yet, sorry");
+	if (ms_code == BSGPU_MATCHES_AS_COUNTS && coll != 0 && coll != 1 && coll != 2)
+		error("'collapse' must be FALSE, 1 or 2");
+	if (bsgpu_vmatch_PDict3Parts_XStringSet(get_p3(pptb, pdict_head, pdict_tail),
+			s.concat, s.widths, s.n,
+			INTEGER(max_mismatch)[0], INTEGER(min_mismatch)[0],
+			LOGICAL(fixed)[0], LOGICAL(fixed)[1],
+			ms_code == BSGPU_MATCHES_AS_COUNTS ? coll : 0, !IS_INTEGER(weight),
+			IS_INTEGER(weight) ? (const void *) INTEGER(weight) : (const void *) REAL(weight),
+			LENGTH(weight), ms_code, &r) != BSGPU_OK)
+		error("%s", bsgpu_last_error());
+	if (ms_code == BSGPU_MATCHES_AS_WHICH) {
+		/* list of N integer vectors, integer(0) when empty (src/match_pdict.c:333-343) */
+		int64_t j;
+
+		PROTECT(ans = NEW_LIST(s.n));
+		for (j = 0; j < s.n; j++) {
+			int64_t n = r.ends_offsets[j + 1] - r.ends_offsets[j];
+			SEXP elt = PROTECT(NEW_INTEGER((int) n));
+
+			memcpy(INTEGER(elt), r.ends + r.ends_offsets[j], (size_t) n * sizeof(int));
+			SET_VECTOR_ELT(ans, (int) j, elt);
+			UNPROTECT(1);
+		}
+		UNPROTECT(1);
+	} else if (coll == 0) {
+		PROTECT(ans = allocMatrix(INTSXP, M, s.n));
+		memcpy(INTEGER(ans), r.counts, (size_t) M * (size_t) s.n * sizeof(int));
+		UNPROTECT(1);
+	} else if (r.dcounts != NULL) {
+		PROTECT(ans = NEW_NUMERIC((int) r.n_counts));
+		memcpy(REAL(ans), r.dcounts, (size_t) r.n_counts * sizeof(double));
+		UNPROTECT(1);
+	} else {
+		PROTECT(ans = NEW_INTEGER((int) r.n_counts));
+		memcpy(INTEGER(ans), r.counts, (size_t) r.n_counts * sizeof(int));
+		UNPROTECT(1);
+	}
+	bsgpu_result_free(&r);
+	return ans;
+}
+
+/* ---- MIndex helpers (host side; same code shape as the reference's, they are O(hits)) ------- */
+
+/* --- .Call ENTRY POINT --- (src/MIndex_class.c:134) */
+SEXP ByPos_MIndex_endIndex(SEXP x_high2low, SEXP x_ends, SEXP x_width0)
+{
+	SEXP ans, ans_elt;
+	int i, j, low;
+
+	PROTECT(ans = duplicate(x_ends));
+	for (i = 0; i < LENGTH(ans); i++) {
+		if (x_high2low != R_NilValue && LENGTH(x_high2low) != 0
+		 && (low = INTEGER(x_high2low)[i]) != NA_INTEGER) {
+			PROTECT(ans_elt = duplicate(VECTOR_ELT(ans, low - 1)));
+			SET_VECTOR_ELT(ans, i, ans_elt);
+			UNPROTECT(1);
+			continue;
+		}
+		if (x_width0 == R_NilValue)
+			continue;
+		ans_elt = VECTOR_ELT(ans, i);
+		if (!IS_INTEGER(ans_elt))
+			continue;
+		for (j = 0; j < LENGTH(ans_elt); j++)
+			INTEGER(ans_elt)[j] += 1 - INTEGER(x_width0)[i];
+	}
+	UNPROTECT(1);
+	return ans;
+}
+
+static int cmp_int(const void *a, const void *b)
+{
+	int x = *(const int *) a, y = *(const int *) b;
+
+	return (x > y) - (x < y);
+}
+
+/* --- .Call ENTRY POINT --- (src/MIndex_class.c:230) */
+SEXP ByPos_MIndex_combine(SEXP ends_listlist)
+{
+	int NTB = LENGTH(ends_listlist), ans_length, i, j, n, k, u;
+	SEXP ans, ans_elt, ends;
+	int *buf = NULL, cap = 0;
+
+	if (NTB == 0)
+		error("nothing to combine");
+	ans_length = LENGTH(VECTOR_ELT(ends_listlist, 0));
+	for (j = 1; j < NTB; j++)
+		if (LENGTH(VECTOR_ELT(ends_listlist, j)) != ans_length)
+			error("cannot combine MIndex objects of different lengths");
+	PROTECT(ans = NEW_LIST(ans_length));
+	for (i = 0; i < ans_length; i++) {
+		n = 0;
+		for (j = 0; j < NTB; j++) {
+			ends = VECTOR_ELT(VECTOR_ELT(ends_listlist, j), i);
+			if (ends == R_NilValue)
+				continue;
+			if (n + LENGTH(ends) > cap) {
+				cap = 2 * (n + LENGTH(ends));
+				buf = (int *) realloc(buf, (size_t) cap * sizeof(int));
+			}
+			memcpy(buf + n, INTEGER(ends), (size_t) LENGTH(ends) * sizeof(int));
+			n += LENGTH(ends);
+		}
+		if (n == 0)
+			continue;
+		qsort(buf, (size_t) n, sizeof(int), cmp_int);
+		for (k = 1, u = 0; k < n; k++)
+			if (buf[k] != buf[u])
+				buf[++u] = buf[k];
+		PROTECT(ans_elt = NEW_INTEGER(u + 1));
+		memcpy(INTEGER(ans_elt), buf, (size_t) (u + 1) * sizeof(int));
+		SET_VECTOR_ELT(ans, i, ans_elt);
+		UNPROTECT(1);
+	}
+	free(buf);
+	UNPROTECT(1);
+	return ans;
+}

@@ -82,6 +82,13 @@ int bsgpu_pdict3parts_build(int algo, int32_t M,
 		const uint8_t *tail_concat, const int32_t *tail_widths,
 		const int32_t *pp_exclude, int32_t *high2low_out,
 		bsgpu_pdict3parts **out);
+/* Replaces the head / tail of an existing index (both may be NULL = absent).  The reference
+ * passes pdict_head / pdict_tail with every match call (src/match_pdict.c:153-171) while the
+ * Trusted Band is preprocessed once; a C dispatch that built the index in build_Twobit /
+ * ACtree2_build attaches the flanks here on the first match call. */
+int bsgpu_pdict3parts_set_flanks(bsgpu_pdict3parts *p3,
+		const uint8_t *head_concat, const int32_t *head_widths,
+		const uint8_t *tail_concat, const int32_t *tail_widths);
 /* R/PDict-class.R:219-227: the whole-pattern index is reused with its dups blanked. */
 int bsgpu_pdict3parts_blank_dups(bsgpu_pdict3parts *p3);
 void bsgpu_pdict3parts_free(bsgpu_pdict3parts *p3);

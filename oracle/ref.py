@@ -25,24 +25,36 @@ NA_INTEGER = -2147483648
 MATCHES_AS_WHICH, MATCHES_AS_COUNTS, MATCHES_AS_ENDS = 1, 2, 4
 _INTSXP, _REALSXP, _VECSXP, _NILSXP = 13, 14, 19, 0
 
-_lib = None
+_SO_DISPATCH = os.path.join(_HERE, "_ref", "libbiostrings_gpu_dispatch.so")
+_libs = {}
+_which = "ref"          # which library lib() returns: "ref" | "dispatch"
 
 
 class RefError(RuntimeError):
-    """An Rf_error() raised inside the reference C code (message = R's error text)."""
+    """An Rf_error() raised inside the C code under the .Call boundary (message = R's text)."""
 
 
-def available():
-    return os.path.exists(_SO)
+def available(which="ref"):
+    return os.path.exists(_SO if which == "ref" else _SO_DISPATCH)
+
+
+def use(which):
+    """Select the library behind this module: "ref" = the reference's own C (default),
+    "dispatch" = the product's R-facing C dispatch over libbsgpu (needs a GPU).  Both export
+    the same .Call entry points and are driven through the same harness."""
+    global _which
+    assert which in ("ref", "dispatch")
+    _which = which
 
 
 def lib():
-    global _lib
-    if _lib is None:
-        if not available():
+    which = _which
+    if which not in _libs:
+        path = _SO if which == "ref" else _SO_DISPATCH
+        if not os.path.exists(path):
             raise FileNotFoundError(
-                f"{_SO} not built: run `make -C oracle ref` where /root/reference exists")
-        L = C.CDLL(_SO)
+                f"{path} not built: run `make -C oracle` (the reference needs /root/reference)")
+        L = C.CDLL(path)
         L.ref_last_error.restype = C.c_char_p
         L.ref_last_warning.restype = C.c_char_p
         L.ref_pptb_build.restype = C.c_void_p
@@ -67,8 +79,8 @@ def lib():
         L.ref_result_copy_int.argtypes = [C.c_void_p]
         L.ref_result_copy_double.argtypes = [C.c_void_p]
         L.ref_result_list_flat.argtypes = [C.c_void_p]
-        _lib = L
-    return _lib
+        _libs[which] = L
+    return _libs[which]
 
 
 def _u8(a):
@@ -83,10 +95,11 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def _check(rc):
+def _check(rc, L=None):
+    L = L or lib()
     if rc != 0:
-        msg = lib().ref_last_error().decode("latin1")
-        lib().ref_release()
+        msg = L.ref_last_error().decode("latin1")
+        L.ref_release()
         raise RefError(msg)
 
 
@@ -94,9 +107,9 @@ def last_warning():
     return lib().ref_last_warning().decode("latin1")
 
 
-def _fetch_result(release=True):
+def _fetch_result(release=True, L=None):
     """Current result -> numpy: int/double vector, or list of (int array | None)."""
-    L = lib()
+    L = L or lib()
     t, n = L.ref_result_type(), L.ref_result_length()
     if t == _INTSXP:
         out = np.empty(n, dtype=np.int32)
@@ -134,22 +147,23 @@ class RefPPTB:
 
     def __init__(self, algo, tb_concat, tb_widths, pp_exclude=None):
         self.algo = algo
+        self._lib = lib()                  # the library this handle belongs to
         self._tb = _u8(tb_concat)          # must outlive the handle
         self._tbw = _i32(tb_widths)
         self.M = len(self._tbw)
         excl = None if pp_exclude is None else _i32(pp_exclude)
         self.high2low = np.empty(self.M, dtype=np.int32)
-        self._h = lib().ref_pptb_build(algo.encode(), self.M, _ptr(self._tb),
+        self._h = self._lib.ref_pptb_build(algo.encode(), self.M, _ptr(self._tb),
                                        _ptr(self._tbw), _ptr(excl), _ptr(self.high2low))
         if not self._h:
-            raise RefError(lib().ref_last_error().decode("latin1"))
+            raise RefError(self._lib.ref_last_error().decode("latin1"))
 
     def blank_dups(self):
-        _check(lib().ref_pptb_blank_dups(self._h))
+        _check(self._lib.ref_pptb_blank_dups(self._h), self._lib)
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().ref_pptb_free(self._h)
+            self._lib.ref_pptb_free(self._h)
             self._h = None
 
     def __del__(self):
@@ -159,10 +173,10 @@ class RefPPTB:
             pass
 
     def nnodes(self):
-        return lib().ref_actree2_nnodes(self._h)
+        return self._lib.ref_actree2_nnodes(self._h)
 
     def has_all_flinks(self):
-        return bool(lib().ref_actree2_has_all_flinks(self._h))
+        return bool(self._lib.ref_actree2_has_all_flinks(self._h))
 
     @staticmethod
     def _flank(f):
@@ -175,21 +189,21 @@ class RefPPTB:
         hc, hw = self._flank(head)
         tc, tw = self._flank(tail)
         s = _u8(subject)
-        _check(lib().ref_match_xstring(self._h, self.M, _ptr(hc), _ptr(hw), _ptr(tc),
+        _check(self._lib.ref_match_xstring(self._h, self.M, _ptr(hc), _ptr(hw), _ptr(tc),
                                        _ptr(tw), _ptr(s), len(s), max_mismatch,
-                                       min_mismatch, int(fixed[0]), int(fixed[1]), mode))
-        return _fetch_result(release=not keep)
+                                       min_mismatch, int(fixed[0]), int(fixed[1]), mode), self._lib)
+        return _fetch_result(release=not keep, L=self._lib)
 
     def match_views(self, head, tail, subject, views_start, views_width, max_mismatch,
                     min_mismatch, fixed, mode, keep=False):
         hc, hw = self._flank(head)
         tc, tw = self._flank(tail)
         s, vs, vw = _u8(subject), _i32(views_start), _i32(views_width)
-        _check(lib().ref_match_views(self._h, self.M, _ptr(hc), _ptr(hw), _ptr(tc),
+        _check(self._lib.ref_match_views(self._h, self.M, _ptr(hc), _ptr(hw), _ptr(tc),
                                      _ptr(tw), _ptr(s), len(s), _ptr(vs), _ptr(vw),
                                      len(vs), max_mismatch, min_mismatch,
-                                     int(fixed[0]), int(fixed[1]), mode))
-        return _fetch_result(release=not keep)
+                                     int(fixed[0]), int(fixed[1]), mode), self._lib)
+        return _fetch_result(release=not keep, L=self._lib)
 
     def vmatch_set(self, head, tail, subj_concat, subj_widths, max_mismatch,
                    min_mismatch, fixed, collapse, weight, mode):
@@ -199,11 +213,11 @@ class RefPPTB:
         w = np.asarray(weight)
         is_double = w.dtype.kind == "f"
         w = np.ascontiguousarray(w, dtype=np.float64 if is_double else np.int32)
-        _check(lib().ref_vmatch_set(self._h, self.M, _ptr(hc), _ptr(hw), _ptr(tc),
+        _check(self._lib.ref_vmatch_set(self._h, self.M, _ptr(hc), _ptr(hw), _ptr(tc),
                                     _ptr(tw), _ptr(sc), _ptr(sw), len(sw), max_mismatch,
                                     min_mismatch, int(fixed[0]), int(fixed[1]),
-                                    collapse, int(is_double), _ptr(w), len(w), mode))
-        return _fetch_result()
+                                    collapse, int(is_double), _ptr(w), len(w), mode), self._lib)
+        return _fetch_result(L=self._lib)
 
 
 def stash_result():

@@ -254,12 +254,24 @@ def test_iupac_subject_full_tb():
         n1 = check_all(prod, orac, s, s, fixed=False)
         check_all(prod, orac, s, s, fixed="pattern")
     assert n1 > n0 > 0
-    # dense ambiguity: same error as the reference's node-set overflow
-    dense = np.full(200, 15, dtype=np.uint8)
-    with pytest.raises(bs.BsgpuError, match="too many IUPAC ambiguity letters"):
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            bs.countPDict(prod, dense, fixed=False)
+    # dense ambiguity (a run of N): every Trusted-Band word matches every window, as in the
+    # reference, whose node set then holds the whole trie level
+    dense = np.concatenate([s[:300], np.full(60, 15, dtype=np.uint8), s[300:600]])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        n2 = check_all(prod, orac, dense, dense, fixed=False)
+    assert n2 > 40 * 1000
+    # ... up to a work budget, beyond which the reference's own message is raised
+    # (its cap is 5M live trie nodes, src/match_pdict_ACtree2.c:1024,1051-1054)
+    import os
+    os.environ["BSGPU_IUPAC_BRUTE_BUDGET"] = "1000"
+    try:
+        with pytest.raises(bs.BsgpuError, match="too many IUPAC ambiguity letters"):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                bs.countPDict(prod, dense, fixed=False)
+    finally:
+        del os.environ["BSGPU_IUPAC_BRUTE_BUDGET"]
 
 
 def test_chunked_subject_equals_whole():
