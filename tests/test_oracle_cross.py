@@ -104,3 +104,27 @@ def test_mtb():
     cmp_all(a, b, s, max_mismatch=2)
     cmp_all(a, b, s, max_mismatch=1)
     assert a.duplicated().tolist() == b.duplicated().tolist()
+
+
+YEAST = "/root/reference/data/yeastSEQCHR1.rda"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(YEAST), reason="reference data not mounted")
+def test_config1_yeast_chr1_twobit():
+    """BASELINE config 1: countPDict + matchPDict of 10k random 25-mers (+1k cut from the
+    subject) against yeastSEQCHR1 with a Twobit PDict (tb.start=1, tb.end=12), reference C vs
+    our restatement.  The sequence is read from the gzip'd RDX2 file (string of 230,208 letters
+    at offset 63 of the stream)."""
+    import gzip
+    raw = gzip.open(YEAST).read()
+    seq = raw[63:63 + 230_208].decode("ascii")
+    assert set(seq) <= set("ACGT") and seq.count("A") == 69_830 and seq.count("C") == 44_643
+    s = R.encode(seq)
+    g = rng(1)
+    pats = [random_dna(g, 25) for _ in range(10_000)] + \
+           [s[i:i + 25].copy() for i in g.integers(0, len(s) - 25, 1000)]
+    a, b = both(pats, tb_start=1, tb_end=12, algorithm="Twobit")
+    ca, cb = R.countPDict(a, s), R.countPDict(b, s)
+    assert ca.tolist() == cb.tolist() and ca[10_000:].min() >= 1
+    assert_same_ends(R.matchPDict(a, s).endIndex(), R.matchPDict(b, s).endIndex())
+    cmp_all(a, b, s, max_mismatch=2)
