@@ -243,12 +243,21 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 	for (; jb < word_hi; jb += stride) {
 		int64_t j = jb + lane;
 		int64_t base = j << 5;
-		uint64_t c0 = 0, c1 = 0;
+		uint64_t cm = 0, c0 = 0, c1 = 0, im = 0, i0 = 0, i1 = 0;
 		uint32_t m = 0;
 
 		if (j < word_hi) {
 			c0 = __ldcs(S.codes + j);
 			c1 = __ldcs(S.codes + j + 1);
+			if (!LONG) {
+				// the 96 letters around this word stay in registers: candidate windows
+				// (start within 31 letters before the probe position, <= 32 letters long)
+				// are cut from them without touching memory again
+				cm = j > 0 ? __ldcs(S.codes + j - 1) : 0;
+				im = j > 0 ? __ldcs(S.inv2 + j - 1) : ~0ull;
+				i0 = __ldcs(S.inv2 + j);
+				i1 = __ldcs(S.inv2 + j + 1);
+			}
 			uint64_t v = (uint64_t) __ldcs(S.valid + j) | ((uint64_t) __ldcs(S.valid + j + 1) << 32);
 			m = q_valid_positions(Q, v);
 			if (Q.stride > 1) {
@@ -304,8 +313,26 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 				break;
 			if (busy) {
 				uint32_t ent = __ldg(Q.entries + cur++);
+				int lb;
 
-				if (q_lower_bound<LONG>(S, Q, ent, pos) <= max_nmis)
+				if (!LONG) {
+					const uint64_t E = 0x5555555555555555ull;
+					int id = (int) (ent >> 5);
+					int o = (int) (pos - base) - Q.shift[ent & 31u];   // window start, -31..31
+					int len = Q.const_len > 0 ? Q.const_len : (int) __ldg(Q.pat_len + id);
+					uint64_t lo_c = o >= 0 ? c0 : cm, hi_c = o >= 0 ? c1 : c0;
+					uint64_t lo_i = o >= 0 ? i0 : im, hi_i = o >= 0 ? i1 : i0;
+					int sh = 2 * (o & 31);
+					uint64_t x = sh ? (lo_c >> sh) | (hi_c << (64 - sh)) : lo_c;
+					uint64_t iv = sh ? (lo_i >> sh) | (hi_i << (64 - sh)) : lo_i;
+					uint64_t d = x ^ __ldg(Q.pat8 + id);
+
+					d = ((d | (d >> 1)) | iv) & (len >= 32 ? E : E & ((1ull << (2 * len)) - 1));
+					lb = __popcll(d);
+				} else {
+					lb = q_lower_bound<LONG>(S, Q, ent, pos);
+				}
+				if (lb <= max_nmis)
 					q_verify<LONG>(S, Q, R, ent, pos, max_nmis, min_nmis, own_lo, own_hi);
 			}
 		}
