@@ -1003,7 +1003,10 @@ struct bsgpu_subject {
 
 // Lays the segments out as [guard][seg0][sep][seg1]...[guard+pad], uploads, packs.
 // srcs[i] points at host letters of segment i (may alias one big buffer).
-static int subject_finish(bsgpu_subject *s, const uint8_t *const *srcs, const uint8_t *one_src)
+// set_concat != NULL: the segments are the consecutive pieces of one packed host buffer
+// (a DNAStringSet): it is uploaded as is and laid out by scatter_set_kernel on the device.
+static int subject_finish(bsgpu_subject *s, const uint8_t *const *srcs, const uint8_t *one_src,
+			  const uint8_t *set_concat = nullptr)
 {
 	int64_t pos = BSGPU_GUARD;
 	int32_t n = s->nseg;
@@ -1032,7 +1035,27 @@ static int subject_finish(bsgpu_subject *s, const uint8_t *const *srcs, const ui
 	} else {
 		CUDA_TRY(cudaMemsetAsync(s->d_bytes.p, BSGPU_SEP_BYTE, (size_t) s->total + 64));
 	}
-	if (n > 1) {
+	if (n > 1 && set_concat != nullptr) {
+		std::vector<int64_t> src_off((size_t) n);
+		int64_t tot = 0;
+		for (int32_t i = 0; i < n; i++) {
+			src_off[i] = tot;
+			tot += s->seg_len[i];
+		}
+		DevBuf<uint8_t> d_src;
+		DevBuf<int64_t> d_src_off;
+		TRY(d_src.alloc((size_t) tot));
+		if (tot > 0)
+			CUDA_TRY(cudaMemcpyAsync(d_src.p, set_concat, (size_t) tot, cudaMemcpyHostToDevice));
+		TRY(d_src_off.upload(src_off.data(), (size_t) n));
+		TRY(s->d_seg_start.upload(s->seg_start.data(), (size_t) n));
+		TRY(s->d_seg_len.upload(s->seg_len.data(), (size_t) n));
+		scatter_set_kernel<<<grid_for((long long) n * 32, 256, 8), 256>>>(d_src.p, d_src_off.p,
+				s->d_seg_start.p, s->d_seg_len.p, n, s->d_bytes.p);
+		g_launches++;
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaDeviceSynchronize());      // d_src goes back to the pool
+	} else if (n > 1) {
 		// assemble on the host in slabs to bound the staging memory
 		const int64_t SLAB = 256ll << 20;
 		std::vector<uint8_t> stage;
@@ -1150,7 +1173,7 @@ extern "C" int bsgpu_subject_set(const uint8_t *concat, const int32_t *widths, i
 	}
 	s->nletters = off;
 	TRY(ensure_device());
-	TRY(subject_finish(s.get(), srcs.data(), nullptr));
+	TRY(subject_finish(s.get(), srcs.data(), nullptr, concat));
 	*out = s.release();
 	return BSGPU_OK;
 }

@@ -111,6 +111,28 @@ pack_iupac_kernel(const uint8_t *__restrict__ bytes, int64_t nwords, uint32_t *_
 	}
 }
 
+// Lays a sequence set out in the concat buffer: one warp per sequence copies its letters
+// from the packed upload (src + src_off[i]) to dst + seg_start[i]; the separator bytes were
+// memset before.
+__global__ void __launch_bounds__(256)
+scatter_set_kernel(const uint8_t *__restrict__ src, const int64_t *__restrict__ src_off,
+		   const int64_t *__restrict__ seg_start, const int32_t *__restrict__ seg_len,
+		   int32_t nseg, uint8_t *__restrict__ dst)
+{
+	int lane = threadIdx.x & 31;
+	int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+
+	for (int64_t i = warp; i < nseg; i += nwarps) {
+		const uint8_t *s = src + src_off[i];
+		uint8_t *d = dst + seg_start[i];
+		int n = seg_len[i];
+
+		for (int k = lane; k < n; k += 32)
+			d[k] = s[k];
+	}
+}
+
 // ------------------------------------------------------------------------------------
 // Reporting a match (shared by the scan and verify kernels).
 // ------------------------------------------------------------------------------------
