@@ -315,7 +315,7 @@ static int cmp_pair(const void *pa, const void *pb)
  * One subject against one PDict3Parts (match_pdict(), src/match_pdict.c:40-77).
  * head/tail: concat + widths, or NULL widths when absent.
  * Outputs: counts[M] (always), and the hit list (0-based key, 1-based end) through
- * *hit_keys/*hit_ends/*nhits (malloc'ed; caller frees with oracle_free) if non-NULL.
+ * hit_keys / hit_ends / nhits (malloc'ed; caller frees with oracle_free) if non-NULL.
  * Per key the ends come out in ascending TB-end order.
  * Returns 0, or -1 with a message in err.
  */

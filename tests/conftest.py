@@ -10,6 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # build what is missing (nvcc cross-compiles without a GPU; prebuilt files are kept)
+    import subprocess
+    from biostrings_b200 import build as b
+    if not os.path.exists(b.SO):
+        b.build()
+    if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"])
 
 
 def _have_gpu():
