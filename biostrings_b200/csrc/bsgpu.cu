@@ -248,6 +248,7 @@ struct bsgpu_pdict3parts {
 	std::vector<uint8_t> is_tb_dup;         // had a non-NA high2low at build time
 	mutable std::unique_ptr<struct QIndex> qcache;  // q-gram index built on first use
 	mutable std::unique_ptr<struct SampledIndex> scache;    // sampled-seed hash index (exact)
+	mutable std::unique_ptr<struct ByteSeedIndex> bcache;   // byte-seed index (exact, no planes)
 	uint32_t nbuckets = 0;
 	bool all_singletons = true;
 	DevBuf<uint4> d_table;
@@ -691,6 +692,128 @@ static int get_sampled(const bsgpu_pdict3parts *p3, const SampledIndex **out)
 	return done();
 }
 
+// Byte-seed index for exact dictionaries (scan_byteseed_kernel): the seeds are 16 encoded
+// letters hashed as four raw words, so the scan needs the subject's letters only.
+struct ByteSeedIndex {
+	bool ok = false;
+	BsgpuByteSeedView t = {};
+	DevBuf<uint4> d_table, d_filter;
+	DevBuf<uint64_t> d_pat2;
+	size_t nent = 0;
+};
+
+static int get_byteseed(const bsgpu_pdict3parts *p3, const ByteSeedIndex **out)
+{
+	*out = nullptr;
+	if (p3->bcache) {
+		*out = p3->bcache.get();
+		return BSGPU_OK;
+	}
+	std::unique_ptr<ByteSeedIndex> bi(new ByteSeedIndex());
+	auto done = [&]() {
+		p3->bcache = std::move(bi);
+		*out = p3->bcache.get();
+		return BSGPU_OK;
+	};
+	const int SEED = BSGPU_BYTESEED_LETTERS;
+	const char *env = getenv("BSGPU_BYTESEED_STRIDE");
+	int M = p3->M, w = p3->w, s2 = std::min(w - SEED + 1, 32);
+
+	if (env != nullptr && atoi(env) >= 1)
+		s2 = std::min(s2, atoi(env));
+	if (getenv("BSGPU_NO_BYTESEED") != nullptr || p3->has_head || p3->has_tail ||
+	    !p3->all_singletons || M == 0)
+		return done();
+	// the entry id (pattern * S + offset) and >= 6 fingerprint bits share 31 bits
+	while (s2 >= 2 && (uint64_t) M * s2 + 2 > (1ull << 25))
+		s2--;
+	if (s2 < 2)
+		return done();
+	uint32_t id_bits = 1;
+	while (((uint64_t) 1 << id_bits) < (uint64_t) M * s2 + 2)
+		id_bits++;
+	uint32_t idmask = (1u << id_bits) - 1u, fp_mask = 0x7FFFFFFFu & ~idmask;
+	std::vector<uint32_t> digest((size_t) M * s2, 0);
+	std::vector<uint8_t> live((size_t) M, 0);
+	size_t nent = 0;
+	for (int i = 0; i < M; i++) {
+		if (p3->excluded[i] || p3->is_tb_dup[i])
+			continue;
+		live[i] = 1;
+		nent += s2;
+		const uint8_t *pat = p3->tb.data() + (size_t) i * w;
+		for (int t = 0; t < s2; t++) {
+			uint32_t wd[4];
+
+			memcpy(wd, pat + t, 16);         // little-endian host, as on the device
+			digest[(size_t) i * s2 + t] = byteseed_digest(wd[0], wd[1], wd[2], wd[3]);
+		}
+	}
+	if (nent == 0)
+		return done();
+	const char *env_l = getenv("BSGPU_SAMPLE_LOAD");
+	double load = env_l ? atof(env_l) / 100.0 : 1.5;
+	if (load < 0.25) load = 0.25;
+	if (load > 3.0) load = 3.0;
+	uint64_t nb = std::max<uint64_t>(16, (uint64_t) ((double) nent / load));
+	const char *env_f = getenv("BSGPU_BYTESEED_FILTER_LOAD");      // entries per 16-byte Bloom block
+	double fload = env_f ? atof(env_f) : 8.0;
+	if (fload < 1.0) fload = 1.0;
+	uint64_t nf = std::max<uint64_t>(16, (uint64_t) ((double) nent / fload));
+	std::vector<uint4> table(nb, make_uint4(BSGPU_S_EMPTY, BSGPU_S_EMPTY, BSGPU_S_EMPTY, BSGPU_S_EMPTY));
+	std::vector<uint4> filter(nf, make_uint4(0, 0, 0, 0));
+	for (int i = 0; i < M; i++) {
+		if (!live[i])
+			continue;
+		for (int t = 0; t < s2; t++) {
+			uint32_t e = (uint32_t) i * s2 + t, b, fp, fb, bits;
+
+			byteseed_table_slot(digest[e] >> 2, (uint32_t) nb, b, fp);
+			uint32_t word = sampled_fp_of(fp, id_bits, fp_mask) | e;
+			for (;;) {
+				uint32_t *slot = &table[b].x;
+				int z = 0;
+				while (z < 4 && (slot[z] & BSGPU_S_EMPTY) != BSGPU_S_EMPTY)
+					z++;
+				if (z < 4) {
+					slot[z] = (slot[z] & BSGPU_S_OVERFLOW) | word;
+					break;
+				}
+				table[b].w |= BSGPU_S_OVERFLOW;
+				b = b + 1 == nb ? 0 : b + 1;
+			}
+			byteseed_filter_slot(digest[e], (uint32_t) nf, fb, bits);
+			filter[fb].x |= 1u << byteseed_bit(bits, 0);
+			filter[fb].y |= 1u << byteseed_bit(bits, 1);
+			filter[fb].z |= 1u << byteseed_bit(bits, 2);
+			filter[fb].w |= 1u << byteseed_bit(bits, 3);
+		}
+	}
+	TRY(bi->d_filter.upload(filter.data(), filter.size()));
+	TRY(bi->d_table.upload(table.data(), table.size()));
+	{
+		int nw = (w + 31) / 32;
+		std::vector<uint64_t> pat2((size_t) M * nw, 0);
+		for (int i = 0; i < M; i++)
+			for (int d = 0; d < w; d++)
+				pat2[(size_t) i * nw + d / 32] |=
+					(uint64_t) bsgpu_base_code(p3->tb[(size_t) i * w + d]) << (2 * (d % 32));
+		TRY(bi->d_pat2.upload(pat2.data(), pat2.size()));
+	}
+	bi->nent = nent;
+	bi->t.filter = bi->d_filter.p;
+	bi->t.nfilter = (uint32_t) nf;
+	bi->t.table = bi->d_table.p;
+	bi->t.nbuckets = (uint32_t) nb;
+	bi->t.pat2 = bi->d_pat2.p;
+	bi->t.id_bits = id_bits;
+	bi->t.fp_mask = fp_mask;
+	bi->t.s = s2;
+	bi->t.w = w;
+	bi->ok = true;
+	return done();
+}
+
 static int upload_groups(bsgpu_pdict3parts *p3, bool blank)
 {
 	int M = p3->M;
@@ -939,6 +1062,7 @@ extern "C" int bsgpu_pdict3parts_set_flanks(bsgpu_pdict3parts *p3,
 			 p3->max_T, &p3->tail_len, p3->h_tail, p3->h_tail_off));
 	p3->qcache.reset();
 	p3->scache.reset();
+	p3->bcache.reset();
 	return BSGPU_OK;
 }
 
@@ -951,6 +1075,7 @@ extern "C" int bsgpu_pdict3parts_blank_dups(bsgpu_pdict3parts *p3)
 	std::fill(p3->high2low.begin(), p3->high2low.end(), BSGPU_NA);
 	p3->qcache.reset();
 	p3->scache.reset();
+	p3->bcache.reset();
 	return BSGPU_OK;
 }
 
@@ -976,8 +1101,11 @@ struct bsgpu_subject {
 	std::vector<int64_t> seg_start, seg_coord;
 	std::vector<int32_t> seg_len;
 	DevBuf<uint8_t> d_bytes;
-	DevBuf<uint64_t> d_codes, d_inv2;
-	DevBuf<uint32_t> d_valid;
+	// packed planes, built by ensure_packed() on the first scan that needs them (the exact
+	// byte-seed scan reads the letters directly)
+	mutable DevBuf<uint64_t> d_codes, d_inv2;
+	mutable DevBuf<uint32_t> d_valid;
+	mutable bool packed = false;
 	mutable DevBuf<uint32_t> d_iupac;       // built on first fixedS=FALSE use
 	mutable bool iupac_ready = false;
 	DevBuf<int64_t> d_seg_start, d_seg_coord;
@@ -1001,7 +1129,10 @@ struct bsgpu_subject {
 	}
 };
 
-// Lays the segments out as [guard][seg0][sep][seg1]...[guard+pad], uploads, packs.
+// 2-bit code / validity planes of the subject, derived from its letters on first use.
+static int ensure_packed(const bsgpu_subject *s, cudaStream_t st);
+
+// Lays the segments out as [guard][seg0][sep][seg1]...[guard+pad] and uploads them.
 // srcs[i] points at host letters of segment i (may alias one big buffer).
 // set_concat != NULL: the segments are the consecutive pieces of one packed host buffer
 // (a DNAStringSet): it is uploaded as is and laid out by scatter_set_kernel on the device.
@@ -1078,18 +1209,8 @@ static int subject_finish(bsgpu_subject *s, const uint8_t *const *srcs, const ui
 			i = k;
 		}
 	}
-	TRY(s->d_codes.alloc((size_t) nwords + 4));
-	TRY(s->d_valid.alloc((size_t) nwords + 4));
-	TRY(s->d_inv2.alloc((size_t) nwords + 4));
-	// the pack kernel writes words [0, nwords); only the 4 spare words need zeroing
-	CUDA_TRY(cudaMemsetAsync(s->d_codes.p + nwords, 0, 4 * sizeof(uint64_t)));
-	CUDA_TRY(cudaMemsetAsync(s->d_valid.p + nwords, 0, 4 * sizeof(uint32_t)));
-	CUDA_TRY(cudaMemsetAsync(s->d_inv2.p + nwords, 0xFF, 4 * sizeof(uint64_t)));
-	pack_subject_kernel<<<grid_for(2 * nwords, 256, 8), 256>>>(s->d_bytes.p, nwords, s->d_codes.p,
-							      s->d_valid.p, s->d_inv2.p);
+	s->packed = false;
 	s->iupac_ready = false;
-	g_launches++;
-	CUDA_TRY(cudaGetLastError());
 	TRY(s->d_seg_start.upload(s->seg_start.data(), (size_t) n));
 	TRY(s->d_seg_len.upload(s->seg_len.data(), (size_t) n));
 	TRY(s->d_seg_coord.upload(s->seg_coord.data(), (size_t) n));
@@ -1211,17 +1332,37 @@ extern "C" int bsgpu_subject_chunk(const uint8_t *chunk, int64_t chunk_len, int6
 	return BSGPU_OK;
 }
 
-extern "C" int bsgpu_subject_repack(bsgpu_subject *s, void *stream)
+static int ensure_packed(const bsgpu_subject *s, cudaStream_t st)
 {
-	if (s == nullptr)
-		return fail(BSGPU_EINVAL, "bsgpu_subject_repack(): NULL handle");
-	TRY(ensure_device());
+	if (s->packed)
+		return BSGPU_OK;
 	int64_t nwords = s->total / 32;
-	pack_subject_kernel<<<grid_for(2 * nwords, 256, 8), 256, 0, (cudaStream_t) stream>>>(
-		s->d_bytes.p, nwords, s->d_codes.p, s->d_valid.p, s->d_inv2.p);
-	s->iupac_ready = false;
+
+	if (s->d_codes.n < (size_t) nwords + 4) {
+		TRY(s->d_codes.alloc((size_t) nwords + 4));
+		TRY(s->d_valid.alloc((size_t) nwords + 4));
+		TRY(s->d_inv2.alloc((size_t) nwords + 4));
+		// the pack kernel writes words [0, nwords); only the 4 spare words need a value
+		CUDA_TRY(cudaMemsetAsync(s->d_codes.p + nwords, 0, 4 * sizeof(uint64_t), st));
+		CUDA_TRY(cudaMemsetAsync(s->d_valid.p + nwords, 0, 4 * sizeof(uint32_t), st));
+		CUDA_TRY(cudaMemsetAsync(s->d_inv2.p + nwords, 0xFF, 4 * sizeof(uint64_t), st));
+	}
+	pack_subject_kernel<<<grid_for(2 * nwords, 256, 8), 256, 0, st>>>(s->d_bytes.p, nwords, s->d_codes.p,
+									  s->d_valid.p, s->d_inv2.p);
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
+	s->packed = true;
+	return BSGPU_OK;
+}
+
+// The caller overwrote the letters in place (same layout): the derived planes are stale.
+extern "C" int bsgpu_subject_repack(bsgpu_subject *s, void *stream)
+{
+	(void) stream;
+	if (s == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_subject_repack(): NULL handle");
+	s->packed = false;
+	s->iupac_ready = false;
 	return BSGPU_OK;
 }
 
@@ -1237,6 +1378,8 @@ struct Workspace {
 	DevBuf<unsigned long long> counters;    // [0] = candidates, [1] = records
 	DevBuf<int> flags;
 	DevBuf<long long> ovf;                  // windows with too many IUPAC expansions
+	DevBuf<unsigned long long> bs_cand;     // byte-seed scan: candidate slices, one per block
+	DevBuf<int32_t> bs_ncand;
 	DevBuf<uint8_t> cub_temp;
 	unsigned long long *h_counters = nullptr;       // pinned
 	int *h_flags = nullptr;
@@ -1330,7 +1473,61 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 	BsgpuIndexView I = p3->view();
 
 	if (direct && mp.fixedS) {
-		// exact dictionary: sampled seeds, s times fewer index probes
+		// exact dictionary, letters only: one probe every S letters
+		const ByteSeedIndex *bi = nullptr;
+		TRY(get_byteseed(p3, &bi));
+		if (bi != nullptr && bi->ok) {
+			int64_t S_ = bi->t.s;
+			int64_t first = ((start_lo + S_ - 1) / S_) * S_;
+			int64_t probe_hi = start_hi + S_ - 1;           // exclusive
+			int64_t nprobes = probe_hi > first ? (probe_hi - first + S_ - 1) / S_ : 0;
+
+			set_plan("byteseed_hash S=%d seed=%d filter_bytes=%llu buckets=%u table_bytes=%llu entries_per_bucket=%.2f",
+				 bi->t.s, BSGPU_BYTESEED_LETTERS, (unsigned long long) bi->t.nfilter * 16,
+				 bi->t.nbuckets, (unsigned long long) bi->t.nbuckets * 16,
+				 (double) bi->nent / bi->t.nbuckets);
+			if (nprobes > 0) {
+				// tile = NP * 256 probes; two stages of it per block
+				const char *env_np = getenv("BSGPU_BYTESEED_NP");
+				int np = bi->t.s <= 11 ? 8 : (bi->t.s <= 23 ? 4 : 2);
+				if (env_np != nullptr && (atoi(env_np) == 4 || atoi(env_np) == 2) && atoi(env_np) < np)
+					np = atoi(env_np);
+				size_t smem = 2 * (size_t) byteseed_stage_bytes(np, bi->t.s);
+				int per_sm = 1;
+				if (np == 8)
+					CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_byteseed_kernel<8>, 256, smem));
+				else if (np == 4)
+					CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_byteseed_kernel<4>, 256, smem));
+				else
+					CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_byteseed_kernel<2>, 256, smem));
+				int grid = grid_for((nprobes + np - 1) / np, 256, std::max(per_sm, 1));
+				// candidate slices: 1/8 of the probes a block sees (typical: ~1 %)
+				int64_t tiles_per_block = ((nprobes + np * 256 - 1) / (np * 256) + grid - 1) / grid;
+				int32_t cap = (int32_t) std::max<int64_t>(1024, tiles_per_block * np * 256 / 8);
+
+				if (ws->bs_cand.n < (size_t) grid * cap)
+					TRY(ws->bs_cand.alloc((size_t) grid * cap));
+				if (ws->bs_ncand.n < (size_t) grid)
+					TRY(ws->bs_ncand.alloc((size_t) grid));
+#define LAUNCH_BYTESEED(NP) \
+	scan_byteseed_kernel<NP><<<grid, 256, smem, st>>>(S, bi->t, R, first, nprobes, end_lo, end_hi, \
+							  ws->bs_cand.p, ws->bs_ncand.p, cap)
+				if (np == 8) LAUNCH_BYTESEED(8); else if (np == 4) LAUNCH_BYTESEED(4); else LAUNCH_BYTESEED(2);
+#undef LAUNCH_BYTESEED
+				g_launches++;
+				CUDA_TRY(cudaGetLastError());
+				confirm_byteseed_kernel<<<dim3(grid, 4), 256, 0, st>>>(S, bi->t, R, end_lo, end_hi, ws->bs_cand.p,
+									       ws->bs_ncand.p, cap);
+				g_launches++;
+				CUDA_TRY(cudaGetLastError());
+			}
+			return BSGPU_OK;
+		}
+	}
+	TRY(ensure_packed(subj, st));
+	S = subj->view();
+	if (direct && mp.fixedS) {
+		// exact dictionary on the packed planes: sampled seeds, s times fewer index probes
 		const SampledIndex *si = nullptr;
 		TRY(get_sampled(p3, &si));
 		if (si != nullptr && si->ok) {
@@ -1512,6 +1709,7 @@ static int run_q(const QIndex *qi, const bsgpu_subject *subj, const MatchParams 
 	const BsgpuQIndexView &Q = qi->v;
 	int64_t own_lo = 0, own_hi = INT64_MAX;
 
+	TRY(ensure_packed(subj, st));
 	if (subj->kind == SUBJ_CHUNK) {
 		int64_t need_l = (int64_t) Q.min_w - 1, need_r = (int64_t) qi->max_len - Q.min_w;
 

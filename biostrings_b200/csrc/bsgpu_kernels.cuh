@@ -20,21 +20,25 @@ namespace cg = cooperative_groups;
 // ------------------------------------------------------------------------------------
 
 // For a 32-bit word holding 4 letters: 8 code bits, 4 valid bits, 8 "not a base" bits.
-// (Letters that are not A/C/G/T get an arbitrary code: every consumer also looks at the
-// valid / inv2 planes.)
+// One PRMT does the per-letter table lookup: the low nibbles of the 4 bytes become the 4
+// selector nibbles; selector 1/2/4 pick the table bytes for A/C/G, selector 8 (T) is
+// "sign-replicate byte 0" = 0xFF because table byte 0 has its top bit set, selectors 9..15
+// (IUPAC codes with bit 3) replicate the clear top bits of bytes 1..7 = 0x00, and every
+// code whose low nibble is 0 ('-' '+' '.', the 0x80 separator, 0) reads table byte 0 = 0x80.
+// Table value: bit 3 = valid, bits 1..2 = 2-bit code.  (Input domain: DNA codes only.)
 __device__ __forceinline__ void pack4(uint32_t x, uint32_t &code8, uint32_t &valid4, uint32_t &inv8)
 {
-	// code = (b>>1) - (b>>3) restated with ORs: bit0 = b1|b3, bit1 = b2|b3
-	uint32_t c = ((x | (x >> 2)) & 0x02020202u) | ((x | (x >> 1)) & 0x04040404u);
-	code8 = ((c >> 1) * 0x01041040u) >> 24;
-	// valid <=> low nibble is a power of two and the high nibble is 0:
-	//   z = b & (b-1) (bit 7 blocks the borrow between bytes), plus the high nibble
-	uint32_t z = (x & ((x | 0x80808080u) - 0x01010101u) & 0x7F7F7F7Fu) | (x & 0x70707070u);
-	// byte == 0 is not a letter either: (b | 0x80) - 1 has bit 7 clear only for b == 0
-	uint32_t bad = (((z + 0x7F7F7F7Fu) | x) | ~((x | 0x80808080u) - 0x01010101u)) & 0x80808080u;
-	uint32_t b7 = bad >> 7;                 // 1 per invalid letter at bits 0, 8, 16, 24
-	inv8 = (b7 * 0x01041040u) >> 24;        // -> bits 0, 2, 4, 6
-	valid4 = (((b7 ^ 0x01010101u) * 0x00204081u) >> 21) & 0xFu;
+	uint32_t n = x & 0x0F0F0F0Fu;
+	n = (n | (n >> 4)) & 0x00FF00FFu;
+	n = (n | (n >> 8)) & 0x0000FFFFu;
+	//                       byte3 byte2 byte1 byte0          byte7..byte4
+	uint32_t v;                                               // A 0x08, C 0x0A, G 0x0C, T 0xFF
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(v) : "r"(0x000A0880u), "r"(0x0000000Cu), "r"(n));
+	uint32_t va = (v >> 3) & 0x01010101u;                     // 1 per valid letter
+
+	code8 = (((v >> 1) & 0x03030303u) * 0x01041040u) >> 24;
+	valid4 = ((va * 0x00204081u) >> 21) & 0xFu;
+	inv8 = ((va ^ 0x01010101u) * 0x01041040u) >> 24;          // bits 0, 2, 4, 6
 }
 
 // iupac plane (bit i = letter code in 1..15), only needed for fixedS = FALSE: 4 flag bits

@@ -476,6 +476,354 @@ scan_tb_sampled_kernel(BsgpuSubjectView S, BsgpuSampledView T, BsgpuQIndexView Q
 }
 
 // ------------------------------------------------------------------------------------
+// Exact dictionaries straight from the subject's letters (no packed planes).
+// Same sampling argument as above with a fixed seed of 16 letters: every pattern of width
+// w >= 17 is indexed under its S = min(w - 15, 32) seeds at offsets 0..S-1 and the subject
+// is probed at the positions p = 0 (mod S) only.  The seed is hashed as the four raw 32-bit
+// words of its 16 encoded bytes (multilinear hash, 4 IMAD.WIDE), so a probe costs 5 shared
+// memory word loads, 4 funnel shifts, the hash and one gather of a 16-byte Bloom block -- no
+// 2-bit conversion and no validity bookkeeping: a window holding a non-base letter, a
+// separator or a guard byte simply hashes to something no dictionary seed has (and the exact
+// checks below reject it if the filter lets it through).  HBM traffic per letter: 1 byte.
+//   filter : blocked Bloom filter, one 16-byte block per ~8 entries, one bit in each of the
+//            4 words (false positives ~0.6 %); it stays in L2.
+//   table  : 16-byte buckets of four {overflow:1 | fp | e} entries, e = pattern * S + offset;
+//            a filter hit walks it and compares the whole pattern of every entry whose
+//            fingerprint fits (p == s, the fixed=TRUE table of
+//            src/match_pdict_utils.c:33-50).
+// ------------------------------------------------------------------------------------
+
+struct BsgpuByteSeedView {
+	const uint4 *filter;         // Bloom blocks
+	uint32_t nfilter;
+	const uint4 *table;          // four {overflow:1 | fp | e} entries per bucket
+	uint32_t nbuckets;
+	const uint64_t *pat2;        // [M * ceil(w / 32)] 2-bit pattern words
+	uint32_t id_bits;
+	uint32_t fp_mask;
+	int32_t s;                   // sampling stride S
+	int32_t w;                   // pattern width
+};
+
+#define BSGPU_BYTESEED_LETTERS 16
+
+// 32-bit digest of the 16 seed bytes.  The 64-bit sum of the four 32 x 32 -> 64 products is
+// (nearly) injective on the 2^32 possible base-letter seeds; folding its halves keeps the
+// well-mixed low word and the smooth high word.
+__host__ __device__ __forceinline__ uint32_t byteseed_digest(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3)
+{
+	uint64_t h = (uint64_t) w0 * 0x9E3779B1u + (uint64_t) w1 * 0x85EBCA77u +
+		     (uint64_t) w2 * 0xC2B2AE3Du + (uint64_t) w3 * 0x27D4EB2Fu;
+
+	return (uint32_t) h ^ (uint32_t) (h >> 32);
+}
+
+// filter block of a digest, and the word holding its 4 bit positions (5 bits each from bit 12)
+__host__ __device__ __forceinline__ void byteseed_filter_slot(uint32_t x, uint32_t nfilter,
+							       uint32_t &block, uint32_t &bits)
+{
+	block = (uint32_t) (((uint64_t) (x * 0x9E3779B1u) * nfilter) >> 32);
+	bits = x * 0x85EBCA6Bu;
+}
+
+__host__ __device__ __forceinline__ uint32_t byteseed_bit(uint32_t bits, int k)
+{
+	return (bits >> (12 + 5 * k)) & 31u;
+}
+
+// entry table: x = the top 30 bits of the digest (what a candidate record carries); bucket
+// from the top of the fully mixed value, fingerprint from its low bits
+__host__ __device__ __forceinline__ void byteseed_table_slot(uint32_t x, uint32_t nbuckets,
+							      uint32_t &bucket, uint32_t &fp)
+{
+	x ^= x >> 16;
+	x *= 0x7FEB352Du;
+	x ^= x >> 15;
+	x *= 0x846CA68Bu;
+	x ^= x >> 16;
+	bucket = (uint32_t) (((uint64_t) x * nbuckets) >> 32);
+	fp = x;
+}
+
+// the 16 letters at byte offset p of 'bytes' (global or shared) as four little-endian words
+__device__ __forceinline__ void byteseed_window(const uint8_t *bytes, int64_t p,
+		uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3)
+{
+	const uint32_t *a = reinterpret_cast<const uint32_t *>(bytes + (p & ~(int64_t) 3));
+	uint32_t sh = 8u * (uint32_t) (p & 3);
+	uint32_t x0 = a[0], x1 = a[1], x2 = a[2], x3 = a[3], x4 = a[4];
+
+	w0 = __funnelshift_r(x0, x1, sh);
+	w1 = __funnelshift_r(x1, x2, sh);
+	w2 = __funnelshift_r(x2, x3, sh);
+	w3 = __funnelshift_r(x3, x4, sh);
+}
+
+// 2-bit codes of the 32 letters at concat index a (bit 2i.. = letter i), and which of them
+// are base letters; 9 independent word loads.
+__device__ __forceinline__ void byteseed_codes32(const uint8_t *__restrict__ bytes, int64_t a,
+		uint64_t &codes, uint32_t &valid)
+{
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(bytes + (a & ~(int64_t) 3));
+	uint32_t sh = 8u * (uint32_t) (a & 3);
+	uint32_t x[9];
+#pragma unroll
+	for (int k = 0; k < 9; k++)
+		x[k] = __ldg(w + k);
+	codes = 0;
+	valid = 0;
+#pragma unroll
+	for (int k = 0; k < 8; k++) {
+		uint32_t c8, v4, n8;
+
+		pack4(__funnelshift_r(x[k], x[k + 1], sh), c8, v4, n8);
+		codes |= (uint64_t) c8 << (8 * k);
+		valid |= v4 << (4 * k);
+	}
+}
+
+// A probe the filter let through, as queued by the scan: concat index in the high 34 bits,
+// the top 30 bits of the seed digest below.
+__device__ __forceinline__ unsigned long long byteseed_candidate(int64_t p, uint32_t x)
+{
+	return ((unsigned long long) p << 30) | (x >> 2);
+}
+
+// Confirms a candidate: entry table (fingerprint), then the whole pattern, 32 letters at a
+// time against the 2-bit pattern words (p == s, fixed=TRUE).
+__device__ __forceinline__ void byteseed_confirm(const BsgpuSubjectView &S, const BsgpuByteSeedView &T,
+		const BsgpuReport &R, unsigned long long cand, int64_t own_lo, int64_t own_hi)
+{
+	const int64_t p = (int64_t) (cand >> 30);
+	const uint32_t idmask = (1u << T.id_bits) - 1u;
+	const int nw = (T.w + 31) >> 5;
+	uint32_t bucket, fp;
+
+	byteseed_table_slot((uint32_t) cand & 0x3FFFFFFFu, T.nbuckets, bucket, fp);
+	uint32_t fw = sampled_fp_of(fp, T.id_bits, T.fp_mask);
+
+	for (;;) {
+		uint4 bb = __ldg(T.table + bucket);
+		uint32_t ent[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll 1
+		for (int z = 0; z < 4; z++) {
+			uint32_t e = ent[z] & idmask;
+
+			if (((ent[z] ^ fw) & T.fp_mask) != 0 || (ent[z] & BSGPU_S_EMPTY) == BSGPU_S_EMPTY)
+				continue;
+			int id = (int) (e / (uint32_t) T.s);
+			int64_t a = p - (int64_t) (e - (uint32_t) id * (uint32_t) T.s);
+			int64_t end = a + T.w - 1;
+
+			if (a < 0 || end < own_lo || end >= own_hi)
+				continue;
+			bool same = true;
+			for (int k = 0; k < nw && same; k++) {
+				int len = min(32, T.w - 32 * k);
+				uint64_t codes, pat = __ldg(T.pat2 + (int64_t) id * nw + k);
+				uint64_t m = len >= 32 ? ~0ull : (1ull << (2 * len)) - 1;
+				uint32_t valid, vm = len >= 32 ? ~0u : (1u << len) - 1;
+
+				byteseed_codes32(S.bytes, a + 32 * k, codes, valid);
+				same = ((codes ^ pat) & m) == 0 && (valid & vm) == vm;
+			}
+			if (!same)
+				continue;
+			if (R.mode == BSGPU_R_COUNT) {
+				atomicAdd(R.counts + id, 1);
+			} else {
+				int seg = S.nseg == 1 ? 0 : find_segment(S, p);
+
+				report_match(R, S, id, seg, end - __ldg(S.seg_start + seg) + 1, end, 0);
+			}
+		}
+		if (!(bb.w & BSGPU_S_OVERFLOW))
+			break;
+		bucket = bucket + 1 == T.nbuckets ? 0 : bucket + 1;
+	}
+}
+
+// out-of-line copy for the scan kernel's "candidate slice full" path
+__device__ __noinline__ void byteseed_confirm_now(BsgpuSubjectView S, BsgpuByteSeedView T, BsgpuReport R,
+		unsigned long long cand, int64_t own_lo, int64_t own_hi)
+{
+	byteseed_confirm(S, T, R, cand, own_lo, own_hi);
+}
+
+// --- TMA bulk copy + mbarrier (sm_90+ PTX) ---
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+	return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile("{\n"
+		     ".reg .pred P1;\n"
+		     "BSGPU_WAIT:\n"
+		     "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+		     "@P1 bra BSGPU_DONE;\n"
+		     "bra BSGPU_WAIT;\n"
+		     "BSGPU_DONE:\n"
+		     "}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// global -> shared bulk copy of 'bytes' (multiple of 16, both sides 16-byte aligned) that
+// completes on 'bar'
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+		     :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		     :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Probe g of the launch sits at concat index first + g * S.  A block takes tiles of
+// NP * 256 consecutive probes.  The letters under a tile (NP * 256 * S + 20 bytes) are
+// brought into shared memory by one TMA bulk copy, two stages deep; every thread hashes NP
+// windows of tile i (thread t takes probes t, t + 256, ...) while its NP filter gathers of
+// tile i - 1 are in flight, so the HBM stream, the hashing and the L2 gathers overlap.
+// Probes the filter lets through (false positives, seed hits, matches: ~1 %) are appended
+// to the block's own slice of a candidate buffer and confirmed by confirm_byteseed_kernel,
+// one candidate per thread, so that the dependent table / key / pattern loads of the
+// confirmations never stall the scan.  A full slice falls back to confirming in place.
+// Dynamic shared memory: 2 * byteseed_stage_bytes(NP, S).
+__host__ __device__ __forceinline__ uint32_t byteseed_stage_bytes(int np, int s)
+{
+	return (uint32_t) ((np * 256 * s + 16 + 20 + 15 + 127) & ~127);
+}
+
+template <int NP>
+__global__ void __launch_bounds__(256, NP == 8 ? 2 : 4)
+scan_byteseed_kernel(BsgpuSubjectView S, BsgpuByteSeedView T, BsgpuReport R, int64_t first,
+		     int64_t nprobes, int64_t own_lo, int64_t own_hi,
+		     unsigned long long *__restrict__ cand, int32_t *__restrict__ ncand_out, int32_t cap)
+{
+	extern __shared__ __align__(128) uint8_t byteseed_smem[];
+	__shared__ __align__(8) uint64_t bar[2];
+	__shared__ int ncand;
+	const int64_t tile = (int64_t) NP * 256;
+	const int64_t ntiles = (nprobes + tile - 1) / tile;
+	const uint32_t stage_bytes = byteseed_stage_bytes(NP, T.s);
+	unsigned long long *my_cand = cand + (int64_t) blockIdx.x * cap;
+
+	// tile tl -> (first byte, 16-byte aligned source, bytes to copy)
+	auto issue = [&](int64_t tl, int stage) {
+		int64_t g_lo = tl * tile, b0 = first + g_lo * T.s, base16 = b0 & ~(int64_t) 15;
+		int np = (int) min(tile, nprobes - g_lo);
+		uint32_t nbytes = (uint32_t) (((int) (b0 - base16) + (np - 1) * T.s + 20 + 15) & ~15);
+
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		tma_load_1d(byteseed_smem + (size_t) stage * stage_bytes, S.bytes + base16, nbytes, &bar[stage]);
+	};
+	// filter verdicts of a tile -> candidate slice
+	auto emit = [&](const uint4 (&b)[NP], const uint32_t (&xs)[NP], uint32_t live, int64_t b0) {
+		uint32_t rare = 0;
+#pragma unroll
+		for (int q = 0; q < NP; q++) {
+			uint32_t bits = xs[q] * 0x85EBCA6Bu;
+			uint32_t hit = __funnelshift_r(b[q].x, 0, bits >> 12) & __funnelshift_r(b[q].y, 0, bits >> 17) &
+				       __funnelshift_r(b[q].z, 0, bits >> 22) & __funnelshift_r(b[q].w, 0, bits >> 27);
+
+			rare |= (hit & 1u) << q;
+		}
+		rare &= live;
+		while (rare) {
+			int q = __ffs(rare) - 1;
+			int64_t p = b0 + (int64_t) (q * 256 + (int) threadIdx.x) * T.s;
+			uint32_t x = xs[0];
+#pragma unroll
+			for (int k = 1; k < NP; k++)
+				x = q == k ? xs[k] : x;
+
+			rare &= rare - 1;
+			int slot = atomicAdd(&ncand, 1);
+			if (slot < cap)
+				my_cand[slot] = byteseed_candidate(p, x);
+			else            // slice full: right away
+				byteseed_confirm_now(S, T, R, byteseed_candidate(p, x), own_lo, own_hi);
+		}
+	};
+
+	if (threadIdx.x == 0) {
+		ncand = 0;
+		mbar_init(&bar[0], 1);
+		mbar_init(&bar[1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		if ((int64_t) blockIdx.x < ntiles)
+			issue(blockIdx.x, 0);
+		if ((int64_t) blockIdx.x + gridDim.x < ntiles)
+			issue((int64_t) blockIdx.x + gridDim.x, 1);
+	}
+	__syncthreads();
+
+	uint4 b[NP];
+	uint32_t bits[NP], live = 0;
+	int64_t prev_b0 = 0;
+	int it = 0;
+	for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x, it++) {
+		const int stage = it & 1;
+		int64_t g_lo = tl * tile, b0 = first + g_lo * T.s;
+		int np = (int) min(tile, nprobes - g_lo);
+		int off = (int) (b0 & 15);
+		const uint8_t *sm = byteseed_smem + (size_t) stage * stage_bytes;
+		uint32_t nbits[NP];
+		// probes of this thread in the tile: q * 256 + t < np
+		uint32_t nlive = (1u << min(NP, max(0, (np - (int) threadIdx.x + 255) >> 8))) - 1u;
+
+		mbar_wait(&bar[stage], (uint32_t) ((it >> 1) & 1));
+		{
+			const int step = 256 * T.s;
+			int o = off + (int) threadIdx.x * T.s, o_max = off + (np - 1) * T.s;
+#pragma unroll
+			for (int q = 0; q < NP; q++) {
+				uint32_t w0, w1, w2, w3;
+
+				// past the last probe of a short tile: rehash the last one (masked by nlive)
+				byteseed_window(sm, min(o, o_max), w0, w1, w2, w3);
+				nbits[q] = byteseed_digest(w0, w1, w2, w3);
+				o += step;
+			}
+		}
+		__syncthreads();        // this stage has been read by everyone: refill it
+		if (threadIdx.x == 0 && tl + 2 * (int64_t) gridDim.x < ntiles)
+			issue(tl + 2 * (int64_t) gridDim.x, stage);
+		if (it > 0)
+			emit(b, bits, live, prev_b0);
+#pragma unroll
+		for (int q = 0; q < NP; q++) {
+			b[q] = __ldg(T.filter + (uint32_t) (((uint64_t) (nbits[q] * 0x9E3779B1u) * T.nfilter) >> 32));
+			bits[q] = nbits[q];
+		}
+		live = nlive;
+		prev_b0 = b0;
+	}
+	if (it > 0)
+		emit(b, bits, live, prev_b0);
+	__syncthreads();
+	if (threadIdx.x == 0)
+		ncand_out[blockIdx.x] = min(ncand, cap);
+}
+
+// One candidate per thread; block k takes the slice scan block k filled.
+__global__ void __launch_bounds__(256)
+confirm_byteseed_kernel(BsgpuSubjectView S, BsgpuByteSeedView T, BsgpuReport R, int64_t own_lo,
+			int64_t own_hi, const unsigned long long *__restrict__ cand,
+			const int32_t *__restrict__ ncand, int32_t cap)
+{
+	const unsigned long long *my_cand = cand + (int64_t) blockIdx.x * cap;
+	int n = ncand[blockIdx.x];
+
+	for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x)
+		byteseed_confirm(S, T, R, my_cand[i], own_lo, own_hi);
+}
+
+// ------------------------------------------------------------------------------------
 // Two-kernel form of the q-gram engine (used for the Hamming mode, where a third of the
 // positions carry candidates): qprobe_kernel emits one record (entry, position) per
 // candidate with warp-aggregated appends, qverify_kernel checks one candidate per thread.
