@@ -698,7 +698,7 @@ struct ByteSeedIndex {
 	bool ok = false;
 	BsgpuByteSeedView t = {};
 	DevBuf<uint4> d_table, d_filter;
-	DevBuf<uint64_t> d_pat2;
+	DevBuf<uint8_t> d_tb;
 	size_t nent = 0;
 };
 
@@ -792,20 +792,16 @@ static int get_byteseed(const bsgpu_pdict3parts *p3, const ByteSeedIndex **out)
 	TRY(bi->d_filter.upload(filter.data(), filter.size()));
 	TRY(bi->d_table.upload(table.data(), table.size()));
 	{
-		int nw = (w + 31) / 32;
-		std::vector<uint64_t> pat2((size_t) M * nw, 0);
-		for (int i = 0; i < M; i++)
-			for (int d = 0; d < w; d++)
-				pat2[(size_t) i * nw + d / 32] |=
-					(uint64_t) bsgpu_base_code(p3->tb[(size_t) i * w + d]) << (2 * (d % 32));
-		TRY(bi->d_pat2.upload(pat2.data(), pat2.size()));
+		std::vector<uint8_t> tbp((size_t) M * w + 8, 0);        // word loads may run 7 bytes over
+		memcpy(tbp.data(), p3->tb.data(), (size_t) M * w);
+		TRY(bi->d_tb.upload(tbp.data(), tbp.size()));
 	}
 	bi->nent = nent;
 	bi->t.filter = bi->d_filter.p;
 	bi->t.nfilter = (uint32_t) nf;
 	bi->t.table = bi->d_table.p;
 	bi->t.nbuckets = (uint32_t) nb;
-	bi->t.pat2 = bi->d_pat2.p;
+	bi->t.tb = bi->d_tb.p;
 	bi->t.id_bits = id_bits;
 	bi->t.fp_mask = fp_mask;
 	bi->t.s = s2;
@@ -1487,22 +1483,27 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 				 bi->t.nbuckets, (unsigned long long) bi->t.nbuckets * 16,
 				 (double) bi->nent / bi->t.nbuckets);
 			if (nprobes > 0) {
-				// tile = NP * 256 probes; two stages of it per block
+				// a warp's tile = NP * 32 probes, BSGPU_BYTESEED_STAGES of them in its ring
 				const char *env_np = getenv("BSGPU_BYTESEED_NP");
 				int np = bi->t.s <= 11 ? 8 : (bi->t.s <= 23 ? 4 : 2);
 				if (env_np != nullptr && (atoi(env_np) == 4 || atoi(env_np) == 2) && atoi(env_np) < np)
 					np = atoi(env_np);
-				size_t smem = 2 * (size_t) byteseed_stage_bytes(np, bi->t.s);
+				size_t smem = 8 * (size_t) BSGPU_BYTESEED_STAGES * byteseed_stage_bytes(np, bi->t.s);
 				int per_sm = 1;
-				if (np == 8)
-					CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_byteseed_kernel<8>, 256, smem));
-				else if (np == 4)
-					CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_byteseed_kernel<4>, 256, smem));
-				else
-					CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_byteseed_kernel<2>, 256, smem));
+#define PREPARE_BYTESEED(NP) do { \
+	static bool attr_set = false; \
+	if (!attr_set) { \
+		CUDA_TRY(cudaFuncSetAttribute(scan_byteseed_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+			8 * BSGPU_BYTESEED_STAGES * (int) byteseed_stage_bytes(NP, NP == 8 ? 11 : (NP == 4 ? 23 : 32)))); \
+		attr_set = true; \
+	} \
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_byteseed_kernel<NP>, 256, smem)); \
+} while (0)
+				if (np == 8) PREPARE_BYTESEED(8); else if (np == 4) PREPARE_BYTESEED(4); else PREPARE_BYTESEED(2);
+#undef PREPARE_BYTESEED
 				int grid = grid_for((nprobes + np - 1) / np, 256, std::max(per_sm, 1));
+				int64_t tiles_per_block = ((nprobes + np * 256 - 1) / (np * 256) + grid - 1) / grid + 1;
 				// candidate slices: 1/8 of the probes a block sees (typical: ~1 %)
-				int64_t tiles_per_block = ((nprobes + np * 256 - 1) / (np * 256) + grid - 1) / grid;
 				int32_t cap = (int32_t) std::max<int64_t>(1024, tiles_per_block * np * 256 / 8);
 
 				if (ws->bs_cand.n < (size_t) grid * cap)

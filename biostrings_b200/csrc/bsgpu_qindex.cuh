@@ -498,7 +498,7 @@ struct BsgpuByteSeedView {
 	uint32_t nfilter;
 	const uint4 *table;          // four {overflow:1 | fp | e} entries per bucket
 	uint32_t nbuckets;
-	const uint64_t *pat2;        // [M * ceil(w / 32)] 2-bit pattern words
+	const uint8_t *tb;           // [M * w (+ 8)] pattern letters
 	uint32_t id_bits;
 	uint32_t fp_mask;
 	int32_t s;                   // sampling stride S
@@ -559,27 +559,28 @@ __device__ __forceinline__ void byteseed_window(const uint8_t *bytes, int64_t p,
 	w3 = __funnelshift_r(x3, x4, sh);
 }
 
-// 2-bit codes of the 32 letters at concat index a (bit 2i.. = letter i), and which of them
-// are base letters; 9 independent word loads.
-__device__ __forceinline__ void byteseed_codes32(const uint8_t *__restrict__ bytes, int64_t a,
-		uint64_t &codes, uint32_t &valid)
+// Are the n bytes at x and y the same?  Word loads from the 4-byte aligned addresses below
+// x and y, realigned with funnel shifts; both buffers are readable 7 bytes past the end.
+__device__ __forceinline__ bool byteseed_same_bytes(const uint8_t *__restrict__ x,
+		const uint8_t *__restrict__ y, int n)
 {
-	const uint32_t *w = reinterpret_cast<const uint32_t *>(bytes + (a & ~(int64_t) 3));
-	uint32_t sh = 8u * (uint32_t) (a & 3);
-	uint32_t x[9];
-#pragma unroll
-	for (int k = 0; k < 9; k++)
-		x[k] = __ldg(w + k);
-	codes = 0;
-	valid = 0;
-#pragma unroll
-	for (int k = 0; k < 8; k++) {
-		uint32_t c8, v4, n8;
+	const uint32_t *xw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(x) & ~(uintptr_t) 3);
+	const uint32_t *yw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(y) & ~(uintptr_t) 3);
+	uint32_t xs = 8u * (uint32_t) (reinterpret_cast<uintptr_t>(x) & 3);
+	uint32_t ys = 8u * (uint32_t) (reinterpret_cast<uintptr_t>(y) & 3);
+	uint32_t x0 = __ldg(xw), y0 = __ldg(yw), diff = 0;
+	int k = 0;
 
-		pack4(__funnelshift_r(x[k], x[k + 1], sh), c8, v4, n8);
-		codes |= (uint64_t) c8 << (8 * k);
-		valid |= v4 << (4 * k);
+	for (; 4 * k < n; k++) {
+		uint32_t x1 = __ldg(xw + k + 1), y1 = __ldg(yw + k + 1);
+		uint32_t d = __funnelshift_r(x0, x1, xs) ^ __funnelshift_r(y0, y1, ys);
+		int left = n - 4 * k;
+
+		diff |= left >= 4 ? d : d & ((1u << (8 * left)) - 1u);
+		x0 = x1;
+		y0 = y1;
 	}
+	return diff == 0;
 }
 
 // A probe the filter let through, as queued by the scan: concat index in the high 34 bits,
@@ -589,14 +590,13 @@ __device__ __forceinline__ unsigned long long byteseed_candidate(int64_t p, uint
 	return ((unsigned long long) p << 30) | (x >> 2);
 }
 
-// Confirms a candidate: entry table (fingerprint), then the whole pattern, 32 letters at a
-// time against the 2-bit pattern words (p == s, fixed=TRUE).
+// Confirms a candidate: entry table (fingerprint), then the whole pattern
+// byte for byte (p == s, fixed=TRUE).
 __device__ __forceinline__ void byteseed_confirm(const BsgpuSubjectView &S, const BsgpuByteSeedView &T,
 		const BsgpuReport &R, unsigned long long cand, int64_t own_lo, int64_t own_hi)
 {
 	const int64_t p = (int64_t) (cand >> 30);
 	const uint32_t idmask = (1u << T.id_bits) - 1u;
-	const int nw = (T.w + 31) >> 5;
 	uint32_t bucket, fp;
 
 	byteseed_table_slot((uint32_t) cand & 0x3FFFFFFFu, T.nbuckets, bucket, fp);
@@ -617,16 +617,8 @@ __device__ __forceinline__ void byteseed_confirm(const BsgpuSubjectView &S, cons
 
 			if (a < 0 || end < own_lo || end >= own_hi)
 				continue;
-			bool same = true;
-			for (int k = 0; k < nw && same; k++) {
-				int len = min(32, T.w - 32 * k);
-				uint64_t codes, pat = __ldg(T.pat2 + (int64_t) id * nw + k);
-				uint64_t m = len >= 32 ? ~0ull : (1ull << (2 * len)) - 1;
-				uint32_t valid, vm = len >= 32 ? ~0u : (1u << len) - 1;
-
-				byteseed_codes32(S.bytes, a + 32 * k, codes, valid);
-				same = ((codes ^ pat) & m) == 0 && (valid & vm) == vm;
-			}
+			// pattern letters are base letters, so equal bytes <=> p == s on valid letters
+			bool same = byteseed_same_bytes(S.bytes + a, T.tb + (int64_t) id * T.w, T.w);
 			if (!same)
 				continue;
 			if (R.mode == BSGPU_R_COUNT) {
@@ -683,19 +675,22 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 		     :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// Probe g of the launch sits at concat index first + g * S.  A block takes tiles of
-// NP * 256 consecutive probes.  The letters under a tile (NP * 256 * S + 20 bytes) are
-// brought into shared memory by one TMA bulk copy, two stages deep; every thread hashes NP
-// windows of tile i (thread t takes probes t, t + 256, ...) while its NP filter gathers of
-// tile i - 1 are in flight, so the HBM stream, the hashing and the L2 gathers overlap.
+// Probe g of the launch sits at concat index first + g * S.  Every warp runs its own
+// pipeline over tiles of NP * 32 consecutive probes: the letters under a tile
+// (NP * 32 * S + 20 bytes) are brought into the warp's shared-memory ring by one TMA bulk
+// copy, STAGES deep; lane l hashes the NP windows l, l + 32, ... of tile i while its NP
+// filter gathers of tile i - 1 are in flight, so the HBM stream, the hashing and the L2
+// gathers overlap and no block-wide barrier sits in the loop.
 // Probes the filter lets through (false positives, seed hits, matches: ~1 %) are appended
 // to the block's own slice of a candidate buffer and confirmed by confirm_byteseed_kernel,
-// one candidate per thread, so that the dependent table / key / pattern loads of the
+// one candidate per thread, so that the dependent table / pattern loads of the
 // confirmations never stall the scan.  A full slice falls back to confirming in place.
-// Dynamic shared memory: 2 * byteseed_stage_bytes(NP, S).
+// Dynamic shared memory: 8 warps * STAGES * byteseed_stage_bytes(NP, S).
+#define BSGPU_BYTESEED_STAGES 3
+
 __host__ __device__ __forceinline__ uint32_t byteseed_stage_bytes(int np, int s)
 {
-	return (uint32_t) ((np * 256 * s + 16 + 20 + 15 + 127) & ~127);
+	return (uint32_t) ((np * 32 * s + 16 + 20 + 15 + 127) & ~127);
 }
 
 template <int NP>
@@ -704,12 +699,17 @@ scan_byteseed_kernel(BsgpuSubjectView S, BsgpuByteSeedView T, BsgpuReport R, int
 		     int64_t nprobes, int64_t own_lo, int64_t own_hi,
 		     unsigned long long *__restrict__ cand, int32_t *__restrict__ ncand_out, int32_t cap)
 {
+	constexpr int STAGES = BSGPU_BYTESEED_STAGES;
 	extern __shared__ __align__(128) uint8_t byteseed_smem[];
-	__shared__ __align__(8) uint64_t bar[2];
+	__shared__ __align__(8) uint64_t bars[8][STAGES];
 	__shared__ int ncand;
-	const int64_t tile = (int64_t) NP * 256;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int64_t tile = (int64_t) NP * 32;
 	const int64_t ntiles = (nprobes + tile - 1) / tile;
+	const int64_t gw = (int64_t) blockIdx.x * 8 + warp, nwarps = (int64_t) gridDim.x * 8;
 	const uint32_t stage_bytes = byteseed_stage_bytes(NP, T.s);
+	uint8_t *ring = byteseed_smem + (size_t) warp * STAGES * stage_bytes;
+	uint64_t *bar = bars[warp];
 	unsigned long long *my_cand = cand + (int64_t) blockIdx.x * cap;
 
 	// tile tl -> (first byte, 16-byte aligned source, bytes to copy)
@@ -719,7 +719,7 @@ scan_byteseed_kernel(BsgpuSubjectView S, BsgpuByteSeedView T, BsgpuReport R, int
 		uint32_t nbytes = (uint32_t) (((int) (b0 - base16) + (np - 1) * T.s + 20 + 15) & ~15);
 
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-		tma_load_1d(byteseed_smem + (size_t) stage * stage_bytes, S.bytes + base16, nbytes, &bar[stage]);
+		tma_load_1d(ring + (size_t) stage * stage_bytes, S.bytes + base16, nbytes, &bar[stage]);
 	};
 	// filter verdicts of a tile -> candidate slice
 	auto emit = [&](const uint4 (&b)[NP], const uint32_t (&xs)[NP], uint32_t live, int64_t b0) {
@@ -735,7 +735,7 @@ scan_byteseed_kernel(BsgpuSubjectView S, BsgpuByteSeedView T, BsgpuReport R, int
 		rare &= live;
 		while (rare) {
 			int q = __ffs(rare) - 1;
-			int64_t p = b0 + (int64_t) (q * 256 + (int) threadIdx.x) * T.s;
+			int64_t p = b0 + (int64_t) (q * 32 + lane) * T.s;
 			uint32_t x = xs[0];
 #pragma unroll
 			for (int k = 1; k < NP; k++)
@@ -750,61 +750,66 @@ scan_byteseed_kernel(BsgpuSubjectView S, BsgpuByteSeedView T, BsgpuReport R, int
 		}
 	};
 
-	if (threadIdx.x == 0) {
+	if (threadIdx.x == 0)
 		ncand = 0;
-		mbar_init(&bar[0], 1);
-		mbar_init(&bar[1], 1);
+	if (lane == 0) {
+		for (int k = 0; k < STAGES; k++)
+			mbar_init(&bar[k], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-		if ((int64_t) blockIdx.x < ntiles)
-			issue(blockIdx.x, 0);
-		if ((int64_t) blockIdx.x + gridDim.x < ntiles)
-			issue((int64_t) blockIdx.x + gridDim.x, 1);
 	}
 	__syncthreads();
+	if (lane == 0)
+		for (int k = 0; k < STAGES; k++)
+			if (gw + k * nwarps < ntiles)
+				issue(gw + k * nwarps, k);
 
 	uint4 b[NP];
-	uint32_t bits[NP], live = 0;
+	uint32_t xs[NP], live = 0, phase = 0;
 	int64_t prev_b0 = 0;
-	int it = 0;
-	for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x, it++) {
-		const int stage = it & 1;
+	int stage = 0;
+	bool have_prev = false;
+	for (int64_t tl = gw; tl < ntiles; tl += nwarps) {
 		int64_t g_lo = tl * tile, b0 = first + g_lo * T.s;
 		int np = (int) min(tile, nprobes - g_lo);
-		int off = (int) (b0 & 15);
-		const uint8_t *sm = byteseed_smem + (size_t) stage * stage_bytes;
-		uint32_t nbits[NP];
-		// probes of this thread in the tile: q * 256 + t < np
-		uint32_t nlive = (1u << min(NP, max(0, (np - (int) threadIdx.x + 255) >> 8))) - 1u;
+		const uint8_t *sm = ring + (size_t) stage * stage_bytes;
+		uint32_t nxs[NP];
+		// probes of this lane in the tile: q * 32 + lane < np
+		uint32_t nlive = (1u << min(NP, max(0, (np - lane + 31) >> 5))) - 1u;
 
-		mbar_wait(&bar[stage], (uint32_t) ((it >> 1) & 1));
+		mbar_wait(&bar[stage], phase);
 		{
-			const int step = 256 * T.s;
-			int o = off + (int) threadIdx.x * T.s, o_max = off + (np - 1) * T.s;
+			const int off = (int) (b0 & 15), step = 32 * T.s;
+			int o = off + lane * T.s, o_max = off + (np - 1) * T.s;
 #pragma unroll
 			for (int q = 0; q < NP; q++) {
 				uint32_t w0, w1, w2, w3;
 
 				// past the last probe of a short tile: rehash the last one (masked by nlive)
 				byteseed_window(sm, min(o, o_max), w0, w1, w2, w3);
-				nbits[q] = byteseed_digest(w0, w1, w2, w3);
+				nxs[q] = byteseed_digest(w0, w1, w2, w3);
 				o += step;
 			}
 		}
-		__syncthreads();        // this stage has been read by everyone: refill it
-		if (threadIdx.x == 0 && tl + 2 * (int64_t) gridDim.x < ntiles)
-			issue(tl + 2 * (int64_t) gridDim.x, stage);
-		if (it > 0)
-			emit(b, bits, live, prev_b0);
+		__syncwarp();           // every lane has read this stage: refill it
+		if (lane == 0 && tl + STAGES * nwarps < ntiles)
+			issue(tl + STAGES * nwarps, stage);
+		if (++stage == STAGES) {
+			stage = 0;
+			phase ^= 1u;
+		}
+		if (have_prev)
+			emit(b, xs, live, prev_b0);
 #pragma unroll
 		for (int q = 0; q < NP; q++) {
-			b[q] = __ldg(T.filter + (uint32_t) (((uint64_t) (nbits[q] * 0x9E3779B1u) * T.nfilter) >> 32));
-			bits[q] = nbits[q];
+			b[q] = __ldg(T.filter + (uint32_t) (((uint64_t) (nxs[q] * 0x9E3779B1u) * T.nfilter) >> 32));
+			xs[q] = nxs[q];
 		}
 		live = nlive;
 		prev_b0 = b0;
+		have_prev = true;
 	}
-	if (it > 0)
-		emit(b, bits, live, prev_b0);
+	if (have_prev)
+		emit(b, xs, live, prev_b0);
 	__syncthreads();
 	if (threadIdx.x == 0)
 		ncand_out[blockIdx.x] = min(ncand, cap);
