@@ -561,6 +561,7 @@ __device__ __forceinline__ void byteseed_window(const uint8_t *bytes, int64_t p,
 
 // Are the n bytes at x and y the same?  Word loads from the 4-byte aligned addresses below
 // x and y, realigned with funnel shifts; both buffers are readable 7 bytes past the end.
+// The first 32 bytes are loaded in one batch (18 independent loads).
 __device__ __forceinline__ bool byteseed_same_bytes(const uint8_t *__restrict__ x,
 		const uint8_t *__restrict__ y, int n)
 {
@@ -568,10 +569,25 @@ __device__ __forceinline__ bool byteseed_same_bytes(const uint8_t *__restrict__ 
 	const uint32_t *yw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(y) & ~(uintptr_t) 3);
 	uint32_t xs = 8u * (uint32_t) (reinterpret_cast<uintptr_t>(x) & 3);
 	uint32_t ys = 8u * (uint32_t) (reinterpret_cast<uintptr_t>(y) & 3);
-	uint32_t x0 = __ldg(xw), y0 = __ldg(yw), diff = 0;
-	int k = 0;
+	const int nw = (n + 3) >> 2;            // words to compare; the last one may be partial
+	uint32_t xv[9], yv[9], diff = 0;
+#pragma unroll
+	for (int k = 0; k < 9; k++) {
+		bool need = k <= nw;
+		xv[k] = need ? __ldg(xw + k) : 0u;
+		yv[k] = need ? __ldg(yw + k) : 0u;
+	}
+#pragma unroll
+	for (int k = 0; k < 8; k++) {
+		uint32_t d = __funnelshift_r(xv[k], xv[k + 1], xs) ^ __funnelshift_r(yv[k], yv[k + 1], ys);
+		int left = n - 4 * k;
 
-	for (; 4 * k < n; k++) {
+		diff |= left >= 4 ? d : (left > 0 ? d & ((1u << (8 * left)) - 1u) : 0u);
+	}
+	if (diff != 0 || n <= 32)
+		return diff == 0;
+	uint32_t x0 = xv[8], y0 = yv[8];
+	for (int k = 8; 4 * k < n; k++) {
 		uint32_t x1 = __ldg(xw + k + 1), y1 = __ldg(yw + k + 1);
 		uint32_t d = __funnelshift_r(x0, x1, xs) ^ __funnelshift_r(y0, y1, ys);
 		int left = n - 4 * k;
@@ -604,13 +620,17 @@ __device__ __forceinline__ void byteseed_confirm(const BsgpuSubjectView &S, cons
 
 	for (;;) {
 		uint4 bb = __ldg(T.table + bucket);
-		uint32_t ent[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll 1
-		for (int z = 0; z < 4; z++) {
-			uint32_t e = ent[z] & idmask;
+		// slots whose fingerprint fits (usually none or one)
+		uint32_t fits = 0;
+		fits |= (((bb.x ^ fw) & T.fp_mask) == 0 && (bb.x & BSGPU_S_EMPTY) != BSGPU_S_EMPTY) ? 1u : 0u;
+		fits |= (((bb.y ^ fw) & T.fp_mask) == 0 && (bb.y & BSGPU_S_EMPTY) != BSGPU_S_EMPTY) ? 2u : 0u;
+		fits |= (((bb.z ^ fw) & T.fp_mask) == 0 && (bb.z & BSGPU_S_EMPTY) != BSGPU_S_EMPTY) ? 4u : 0u;
+		fits |= (((bb.w ^ fw) & T.fp_mask) == 0 && (bb.w & BSGPU_S_EMPTY) != BSGPU_S_EMPTY) ? 8u : 0u;
+		while (fits) {
+			uint32_t ent = (fits & 1u) ? bb.x : ((fits & 2u) ? bb.y : ((fits & 4u) ? bb.z : bb.w));
+			uint32_t e = ent & idmask;
 
-			if (((ent[z] ^ fw) & T.fp_mask) != 0 || (ent[z] & BSGPU_S_EMPTY) == BSGPU_S_EMPTY)
-				continue;
+			fits &= fits - 1;
 			int id = (int) (e / (uint32_t) T.s);
 			int64_t a = p - (int64_t) (e - (uint32_t) id * (uint32_t) T.s);
 			int64_t end = a + T.w - 1;
@@ -618,8 +638,7 @@ __device__ __forceinline__ void byteseed_confirm(const BsgpuSubjectView &S, cons
 			if (a < 0 || end < own_lo || end >= own_hi)
 				continue;
 			// pattern letters are base letters, so equal bytes <=> p == s on valid letters
-			bool same = byteseed_same_bytes(S.bytes + a, T.tb + (int64_t) id * T.w, T.w);
-			if (!same)
+			if (!byteseed_same_bytes(S.bytes + a, T.tb + (int64_t) id * T.w, T.w))
 				continue;
 			if (R.mode == BSGPU_R_COUNT) {
 				atomicAdd(R.counts + id, 1);

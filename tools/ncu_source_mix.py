@@ -11,7 +11,15 @@ import sys
 
 def main(rep, top=40):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
+    allrows = list(csv.reader(io.StringIO(raw)))
+    # one section per kernel: a "Kernel Name" row, a header row, then the SASS lines
+    starts = [i for i, r in enumerate(allrows) if r and r[0] == "Kernel Name"] + [len(allrows)]
+    for a, b in zip(starts[:-1], starts[1:]):
+        print("\n=====", allrows[a][1][:100])
+        section(allrows[a:b], top)
+
+
+def section(rows, top):
     h = rows[1]
     isrc, iex, ism = h.index("Source"), h.index("Instructions Executed"), h.index("# Samples")
     ithr = h.index("Avg. Threads Executed")
