@@ -24,6 +24,7 @@ SYMBOLS = [
     "bsgpu_match_PDict3Parts_XString", "bsgpu_match_PDict3Parts_XStringViews",
     "bsgpu_vmatch_PDict3Parts_XStringSet", "bsgpu_mindex_combine",
     "bsgpu_last_plan", "bsgpu_launch_count", "bsgpu_probe_peaks",
+    "bsgpu_kernel_timing", "bsgpu_kernel_times",
 ]
 
 
@@ -92,8 +93,20 @@ def lib():
     L.bsgpu_last_plan.restype = C.c_char_p
     L.bsgpu_launch_count.restype = i64
     L.bsgpu_probe_peaks.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), i64]
+    L.bsgpu_kernel_timing.argtypes = [C.c_int]
+    L.bsgpu_kernel_times.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     _lib = L
     return L
+
+
+def kernel_times():
+    """(name, ms) of the hot kernels launched since bsgpu_kernel_timing(1), in launch order."""
+    names = (C.c_char_p * 256)()
+    ms = (C.c_float * 256)()
+    n = lib().bsgpu_kernel_times(names, ms, 256)
+    if n < 0:
+        raise RuntimeError(lib().bsgpu_last_error().decode())
+    return [(names[i].decode(), float(ms[i])) for i in range(n)]
 
 
 def check(rc):

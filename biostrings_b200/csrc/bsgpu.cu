@@ -63,6 +63,69 @@ static void set_plan(const char *fmt, ...)
 }
 extern "C" const char *bsgpu_last_plan(void) { return g_plan; }
 
+// Opt-in timing of the hot kernels with CUDA events on the launching stream
+// (bsgpu_kernel_timing / bsgpu_kernel_times; bench.py uses it for the roofline).
+struct KernelTime {
+	const char *name;
+	cudaEvent_t start, stop;
+};
+static bool g_timing = false;
+static std::vector<KernelTime> g_times;
+
+struct KernelTimer {
+	cudaStream_t st;
+	cudaEvent_t stop = nullptr;
+
+	KernelTimer(const char *name, cudaStream_t st_) : st(st_)
+	{
+		if (!g_timing || g_times.size() >= 256)
+			return;
+		KernelTime kt = {name, nullptr, nullptr};
+		if (cudaEventCreate(&kt.start) != cudaSuccess || cudaEventCreate(&kt.stop) != cudaSuccess)
+			return;
+		cudaEventRecord(kt.start, st);
+		stop = kt.stop;
+		g_times.push_back(kt);
+	}
+	~KernelTimer()
+	{
+		if (stop != nullptr)
+			cudaEventRecord(stop, st);
+	}
+};
+
+static void clear_kernel_times(void)
+{
+	for (auto &kt : g_times) {
+		cudaEventDestroy(kt.start);
+		cudaEventDestroy(kt.stop);
+	}
+	g_times.clear();
+}
+
+extern "C" int bsgpu_kernel_timing(int enable)
+{
+	clear_kernel_times();
+	g_timing = enable != 0;
+	return BSGPU_OK;
+}
+
+extern "C" int bsgpu_kernel_times(const char **names, float *ms, int max_entries)
+{
+	int n = 0;
+
+	for (auto &kt : g_times) {
+		if (n >= max_entries)
+			break;
+		if (cudaEventSynchronize(kt.stop) != cudaSuccess ||
+		    cudaEventElapsedTime(&ms[n], kt.start, kt.stop) != cudaSuccess)
+			return fail(BSGPU_ECUDA, "bsgpu_kernel_times(): event query failed"), -1;
+		names[n++] = kt.name;
+	}
+	clear_kernel_times();
+	return n;
+}
+
 // ---------------------------------------------------------------------------------------
 // device selection
 // ---------------------------------------------------------------------------------------
@@ -247,7 +310,6 @@ struct bsgpu_pdict3parts {
 	std::vector<uint8_t> excluded;          // pp_exclude[i] != NA
 	std::vector<uint8_t> is_tb_dup;         // had a non-NA high2low at build time
 	mutable std::unique_ptr<struct QIndex> qcache;  // q-gram index built on first use
-	mutable std::unique_ptr<struct SampledIndex> scache;    // sampled-seed hash index (exact)
 	mutable std::unique_ptr<struct ByteSeedIndex> bcache;   // byte-seed index (exact, no planes)
 	uint32_t nbuckets = 0;
 	bool all_singletons = true;
@@ -539,156 +601,6 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 	v.pat_len = qi->d_len.p;
 	qi->max_len = max_w;
 	qi->ok = true;
-	return done();
-}
-
-// Sampled-seed hash index for exact dictionaries (scan_tb_sampled_kernel).
-struct SampledIndex {
-	bool ok = false;
-	BsgpuSampledView t = {};
-	BsgpuQIndexView q = {};
-	DevBuf<uint4> d_table, d_filter;
-	DevBuf<uint64_t> d_keys;
-	DevBuf<ulonglong2> d_pat;
-	DevBuf<unsigned long long> d_pat8;
-	size_t nent = 0;
-};
-
-static int sampled_stride(int w)
-{
-	// S in {1 (off), 2, 4, 8}; the seed keeps at least 16 letters
-	const char *env = getenv("BSGPU_SAMPLE_STRIDE");
-	int s2 = env ? atoi(env) : 8;
-
-	while (s2 > 1 && w - s2 + 1 < 16)
-		s2 >>= 1;
-	return s2 >= 8 ? 8 : (s2 >= 4 ? 4 : (s2 >= 2 ? 2 : 1));
-}
-
-static int get_sampled(const bsgpu_pdict3parts *p3, const SampledIndex **out)
-{
-	*out = nullptr;
-	if (p3->scache) {
-		*out = p3->scache.get();
-		return BSGPU_OK;
-	}
-	std::unique_ptr<SampledIndex> si(new SampledIndex());
-	auto done = [&]() {
-		p3->scache = std::move(si);
-		*out = p3->scache.get();
-		return BSGPU_OK;
-	};
-	int M = p3->M, w = p3->w, s2 = sampled_stride(w);
-	if (s2 < 2 || w < 20 || w > 64 || p3->has_head || p3->has_tail || !p3->all_singletons)
-		return done();
-	uint32_t id_bits = 1;
-	while (((uint64_t) 1 << id_bits) < (uint64_t) M * s2 + 2)
-		id_bits++;
-	if (id_bits > 25)
-		return done();          // fewer than 6 fingerprint bits left: keep the plain scan
-	uint32_t idmask = (1u << id_bits) - 1u, fp_mask = 0x7FFFFFFFu & ~idmask;
-	int qw = std::min(32, w - s2 + 1);
-	uint64_t mask = qw >= 32 ? ~0ull : ((1ull << (2 * qw)) - 1);
-	std::vector<ulonglong2> pat(M, make_ulonglong2(0, 0));
-	std::vector<uint64_t> keys((size_t) M * s2, 0);
-	size_t nent = 0;
-	for (int i = 0; i < M; i++) {
-		if (p3->excluded[i] || p3->is_tb_dup[i])
-			continue;
-		unsigned long long lo = 0, hi = 0;
-		for (int d = 0; d < w; d++) {
-			unsigned long long c = bsgpu_base_code(p3->tb[(size_t) i * w + d]);
-			if (d < 32) lo |= c << (2 * d); else hi |= c << (2 * (d - 32));
-		}
-		pat[i] = make_ulonglong2(lo, hi);
-		nent += s2;
-	}
-	// four entries per 16-byte bucket; BSGPU_SAMPLE_LOAD = entries per bucket x 100
-	const char *env_l = getenv("BSGPU_SAMPLE_LOAD");
-	double load = env_l ? atof(env_l) / 100.0 : 1.5;
-	if (load < 0.25) load = 0.25;
-	if (load > 3.0) load = 3.0;
-	uint64_t nb = std::max<uint64_t>(16, (uint64_t) ((double) nent / load));
-	std::vector<uint4> table(nb, make_uint4(BSGPU_S_EMPTY, BSGPU_S_EMPTY, BSGPU_S_EMPTY, BSGPU_S_EMPTY));
-	for (int i = 0; i < M; i++) {
-		if (p3->excluded[i] || p3->is_tb_dup[i])
-			continue;
-		for (int t = 0; t < s2; t++) {
-			unsigned long long win = t == 0 ? pat[i].x
-				: (pat[i].x >> (2 * t)) | (pat[i].y << (64 - 2 * t));
-			uint64_t key = win & mask;
-			uint32_t e = (uint32_t) i * s2 + t, top, fp;
-
-			keys[e] = key;
-			bsgpu_hash(key, top, fp);
-			uint32_t word = sampled_fp_of(fp, id_bits, fp_mask) | e;
-			uint32_t b = sampled_bucket_of(top, (uint32_t) nb);
-			for (;;) {
-				uint32_t *slot = &table[b].x;
-				int z = 0;
-				while (z < 4 && (slot[z] & BSGPU_S_EMPTY) != BSGPU_S_EMPTY)
-					z++;
-				if (z < 4) {
-					slot[z] = (slot[z] & BSGPU_S_OVERFLOW) | word;
-					break;
-				}
-				table[b].w |= BSGPU_S_OVERFLOW;
-				b = b + 1 == nb ? 0 : b + 1;
-			}
-		}
-	}
-	// first-level fingerprint filter: ~8 entries per 16-byte bucket
-	uint64_t nf = std::max<uint64_t>(16, nent / 8);
-	std::vector<uint4> filter(nf, make_uint4(0, 0, 0, 0));
-	for (int i = 0; i < M; i++) {
-		if (p3->excluded[i] || p3->is_tb_dup[i])
-			continue;
-		for (int t = 0; t < s2; t++) {
-			uint32_t top, fp, fb, fp8;
-
-			bsgpu_hash(keys[(size_t) i * s2 + t], top, fp);
-			sampled_filter_hash(top, fp, (uint32_t) nf, fb, fp8);
-			uint8_t *bytes = reinterpret_cast<uint8_t *>(&filter[fb]);
-			int z = 0;
-			while (z < 15 && bytes[z] != 0 && bytes[z] != fp8)
-				z++;
-			if (z < 15)
-				bytes[z] = (uint8_t) fp8;
-			else
-				bytes[15] = 1;          // overflow: everything is a "maybe" here
-		}
-	}
-	TRY(si->d_filter.upload(filter.data(), filter.size()));
-	si->t.filter = si->d_filter.p;
-	si->t.nfilter = (uint32_t) nf;
-	TRY(si->d_table.upload(table.data(), table.size()));
-	TRY(si->d_keys.upload(keys.data(), keys.size()));
-	TRY(si->d_pat.upload(pat.data(), pat.size()));
-	{
-		std::vector<unsigned long long> p8(M);
-		for (int i = 0; i < M; i++)
-			p8[i] = pat[i].x;
-		TRY(si->d_pat8.upload(p8.data(), p8.size()));
-		si->q.pat8 = si->d_pat8.p;
-	}
-	si->nent = nent;
-	si->t.table = si->d_table.p;
-	si->t.keys = si->d_keys.p;
-	si->t.nbuckets = (uint32_t) nb;
-	si->t.id_bits = id_bits;
-	si->t.fp_mask = fp_mask;
-	si->t.s = s2;
-	si->t.seed_w = qw;
-	si->t.seed_mask = mask;
-	si->q.pat = si->d_pat.p;
-	si->q.pat_len = nullptr;
-	si->q.const_len = w;
-	si->q.mode = 0;
-	si->q.min_w = w;
-	si->q.nshifts = s2;
-	for (int t = 0; t < s2; t++)
-		si->q.shift[t] = t;
-	si->ok = true;
 	return done();
 }
 
@@ -1057,7 +969,6 @@ extern "C" int bsgpu_pdict3parts_set_flanks(bsgpu_pdict3parts *p3,
 	TRY(upload_flank(p3->M, tail_concat, tail_widths, p3->d_tail, p3->d_tail_off, p3->has_tail,
 			 p3->max_T, &p3->tail_len, p3->h_tail, p3->h_tail_off));
 	p3->qcache.reset();
-	p3->scache.reset();
 	p3->bcache.reset();
 	return BSGPU_OK;
 }
@@ -1070,7 +981,6 @@ extern "C" int bsgpu_pdict3parts_blank_dups(bsgpu_pdict3parts *p3)
 	TRY(upload_groups(p3, true));
 	std::fill(p3->high2low.begin(), p3->high2low.end(), BSGPU_NA);
 	p3->qcache.reset();
-	p3->scache.reset();
 	p3->bcache.reset();
 	return BSGPU_OK;
 }
@@ -1343,8 +1253,11 @@ static int ensure_packed(const bsgpu_subject *s, cudaStream_t st)
 		CUDA_TRY(cudaMemsetAsync(s->d_valid.p + nwords, 0, 4 * sizeof(uint32_t), st));
 		CUDA_TRY(cudaMemsetAsync(s->d_inv2.p + nwords, 0xFF, 4 * sizeof(uint64_t), st));
 	}
-	pack_subject_kernel<<<grid_for(2 * nwords, 256, 8), 256, 0, st>>>(s->d_bytes.p, nwords, s->d_codes.p,
-									  s->d_valid.p, s->d_inv2.p);
+	{
+		KernelTimer kt("pack_subject_kernel", st);
+		pack_subject_kernel<<<grid_for(2 * nwords, 256, 8), 256, 0, st>>>(s->d_bytes.p, nwords, s->d_codes.p,
+										  s->d_valid.p, s->d_inv2.p);
+	}
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
 	s->packed = true;
@@ -1513,12 +1426,18 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 #define LAUNCH_BYTESEED(NP) \
 	scan_byteseed_kernel<NP><<<grid, 256, smem, st>>>(S, bi->t, R, first, nprobes, end_lo, end_hi, \
 							  ws->bs_cand.p, ws->bs_ncand.p, cap)
-				if (np == 8) LAUNCH_BYTESEED(8); else if (np == 4) LAUNCH_BYTESEED(4); else LAUNCH_BYTESEED(2);
+				{
+					KernelTimer kt("scan_byteseed_kernel", st);
+					if (np == 8) LAUNCH_BYTESEED(8); else if (np == 4) LAUNCH_BYTESEED(4); else LAUNCH_BYTESEED(2);
+				}
 #undef LAUNCH_BYTESEED
 				g_launches++;
 				CUDA_TRY(cudaGetLastError());
-				confirm_byteseed_kernel<<<dim3(grid, 4), 256, 0, st>>>(S, bi->t, R, end_lo, end_hi, ws->bs_cand.p,
-									       ws->bs_ncand.p, cap);
+				{
+					KernelTimer kt("confirm_byteseed_kernel", st);
+					confirm_byteseed_kernel<<<dim3(grid, 4), 256, 0, st>>>(S, bi->t, R, end_lo, end_hi,
+							ws->bs_cand.p, ws->bs_ncand.p, cap);
+				}
 				g_launches++;
 				CUDA_TRY(cudaGetLastError());
 			}
@@ -1527,36 +1446,13 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 	}
 	TRY(ensure_packed(subj, st));
 	S = subj->view();
-	if (direct && mp.fixedS) {
-		// exact dictionary on the packed planes: sampled seeds, s times fewer index probes
-		const SampledIndex *si = nullptr;
-		TRY(get_sampled(p3, &si));
-		if (si != nullptr && si->ok) {
-			int64_t probe_hi = std::min<int64_t>(subj->total, start_hi + si->t.s);
-			int64_t nw = ((probe_hi + 31) >> 5) - (start_lo >> 5);
-
-			set_plan("sampled_hash S=%d seed=%d filter_bytes=%llu buckets=%u table_bytes=%llu entries_per_bucket=%.2f",
-				 si->t.s, si->t.seed_w, (unsigned long long) si->t.nfilter * 16, si->t.nbuckets,
-				 (unsigned long long) si->t.nbuckets * 16, (double) si->nent / si->t.nbuckets);
-#define LAUNCH_SAMPLED(LONG, SS) \
-	scan_tb_sampled_kernel<LONG, SS><<<grid_for(nw, 256, 8), 256, 0, st>>>( \
-		S, si->t, si->q, R, start_lo, probe_hi, end_lo, end_hi)
-			bool lng = p3->w > 32;
-			switch (si->t.s) {
-			case 2: if (lng) LAUNCH_SAMPLED(true, 2); else LAUNCH_SAMPLED(false, 2); break;
-			case 4: if (lng) LAUNCH_SAMPLED(true, 4); else LAUNCH_SAMPLED(false, 4); break;
-			default: if (lng) LAUNCH_SAMPLED(true, 8); else LAUNCH_SAMPLED(false, 8); break;
-			}
-#undef LAUNCH_SAMPLED
-			g_launches++;
-			CUDA_TRY(cudaGetLastError());
-			return BSGPU_OK;
-		}
-	}
 	set_plan("tb_hash w=%d buckets=%u table_bytes=%llu%s%s", p3->w, p3->nbuckets,
 		 (unsigned long long) p3->nbuckets * 16, direct ? "" : " + verify_flanks",
 		 mp.fixedS ? "" : " + iupac_expansion");
-	scan_tb_kernel<<<grid_for(nwords, 256, 8), 256, 0, st>>>(S, I, R, C, direct, start_lo, start_hi);
+	{
+		KernelTimer kt("scan_tb_kernel", st);
+		scan_tb_kernel<<<grid_for(nwords, 256, 8), 256, 0, st>>>(S, I, R, C, direct, start_lo, start_hi);
+	}
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
 	if (!mp.fixedS) {
@@ -1803,12 +1699,15 @@ static int run_q(const QIndex *qi, const bsgpu_subject *subj, const MatchParams 
 
 		if (rec_based)
 			TRY(read_counter(ws, 1, &rec_before, st));
-		if (qi->max_len > 32)
-			qscan_kernel<true><<<grid_for(nwords, 256, 8), 256, 0, st>>>(subj->view(), Q, R,
-					mp.max_nmis, mp.min_nmis, probe_lo, probe_hi, own_lo, own_hi);
-		else
-			qscan_kernel<false><<<grid_for(nwords, 256, 8), 256, 0, st>>>(subj->view(), Q, R,
-					mp.max_nmis, mp.min_nmis, probe_lo, probe_hi, own_lo, own_hi);
+		{
+			KernelTimer kt("qscan_kernel", st);
+			if (qi->max_len > 32)
+				qscan_kernel<true><<<grid_for(nwords, 256, 8), 256, 0, st>>>(subj->view(), Q, R,
+						mp.max_nmis, mp.min_nmis, probe_lo, probe_hi, own_lo, own_hi);
+			else
+				qscan_kernel<false><<<grid_for(nwords, 256, 8), 256, 0, st>>>(subj->view(), Q, R,
+						mp.max_nmis, mp.min_nmis, probe_lo, probe_hi, own_lo, own_hi);
+		}
 		g_launches++;
 		CUDA_TRY(cudaGetLastError());
 		if (!rec_based)

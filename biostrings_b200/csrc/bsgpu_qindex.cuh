@@ -340,39 +340,15 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 }
 
 // ------------------------------------------------------------------------------------
-// Exact dictionaries (Trusted Band = whole pattern), sampled seeds in a compact hash index.
-// Every pattern is indexed under its S seeds of q' = min(32, w-S+1) letters starting at
-// offsets 0..S-1, and the subject is probed only at positions p = 0 (mod S): an occurrence
-// starting at a meets exactly one of them (t = (-a) mod S), so the number of index probes
-// -- the L2 random-sector gathers that bound scan_tb_kernel -- drops by S.
+// Entry-table helpers of the sampled-seed index (exact dictionaries).
 // Table: 16-byte buckets of four 4-byte entries {overflow:1 | fp | e}, e = pattern*S + t in
 // the low id_bits, fp = hash bits above them; 0x7FFFFFFF = empty.  The overflow bit (on
-// slot 3) says that an entry hashed here was placed further on.  A fingerprint hit is
-// confirmed against the stored seed key, then against the whole pattern (q_verify).
-// Different patterns may share a seed (overlapping probes), so every entry carrying the
-// seed is verified.
+// slot 3) says that an entry hashed here was placed further on.  Different patterns may
+// share a seed (overlapping probes), so every entry carrying the fingerprint is verified.
 // ------------------------------------------------------------------------------------
-
-struct BsgpuSampledView {
-	const uint4 *filter;         // first level: 15 one-byte fingerprints + 1 flag byte per bucket
-	uint32_t nfilter;            // number of filter buckets
-	const uint4 *table;
-	const uint64_t *keys;        // [M * S] seed key of every entry
-	uint32_t nbuckets;
-	uint32_t id_bits;            // low bits of an entry = e
-	uint32_t fp_mask;            // fp occupies bits [id_bits, 31)
-	int32_t s;                   // sampling stride S
-	int32_t seed_w;              // q'
-	uint64_t seed_mask;
-};
 
 #define BSGPU_S_EMPTY 0x7FFFFFFFu       // all fp and id bits set, overflow bit clear
 #define BSGPU_S_OVERFLOW 0x80000000u
-
-__host__ __device__ __forceinline__ uint32_t sampled_bucket_of(uint32_t top, uint32_t nbuckets)
-{
-	return (uint32_t) (((uint64_t) top * nbuckets) >> 32);
-}
 
 // entry word without the id: fingerprint bits in place
 __host__ __device__ __forceinline__ uint32_t sampled_fp_of(uint32_t fp, uint32_t id_bits, uint32_t fp_mask)
@@ -380,106 +356,12 @@ __host__ __device__ __forceinline__ uint32_t sampled_fp_of(uint32_t fp, uint32_t
 	return (fp << id_bits) & fp_mask;
 }
 
-// First level of the sampled index: a 16-byte bucket holds the 8-bit fingerprints (1..255,
-// 0 = empty) of up to 15 entries and a flag byte (bit 0: more than 15 entries hashed here,
-// so the answer is "maybe" for everything).  ~8 entries per bucket on average: the whole
-// filter of 8M entries is 16 MiB and stays in L2, while the full table (fingerprint + entry
-// id, 85 MiB) is only touched by the ~4 % of the probes the filter lets through.
-__host__ __device__ __forceinline__ void sampled_filter_hash(uint32_t top, uint32_t fp, uint32_t nfilter,
-							      uint32_t &bucket, uint32_t &fp8)
-{
-	uint32_t h = top * 0xC2B2AE35u + fp;
-
-	h ^= h >> 15;
-	bucket = (uint32_t) (((uint64_t) h * nfilter) >> 32);
-	fp8 = 1u + (fp ^ (fp >> 16)) % 255u;
-}
-
-__device__ __forceinline__ bool filter_maybe(uint4 f, uint32_t fp8)
-{
-	uint32_t rep = fp8 * 0x01010101u;
-	uint32_t x0 = f.x ^ rep, x1 = f.y ^ rep, x2 = f.z ^ rep, x3 = (f.w ^ rep) | 0xFF000000u;
-	// any zero byte?  (exact zero-byte test on each word)
-	uint32_t z = ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) |
-		     ((x2 - 0x01010101u) & ~x2) | ((x3 - 0x01010101u) & ~x3);
-
-	return (z & 0x80808080u) != 0 || (f.w >> 24) != 0;
-}
-
-template <bool LONG, int SS>
-__global__ void __launch_bounds__(256)
-scan_tb_sampled_kernel(BsgpuSubjectView S, BsgpuSampledView T, BsgpuQIndexView Q, BsgpuReport R,
-		       int64_t probe_lo, int64_t probe_hi, int64_t own_lo, int64_t own_hi)
-{
-	constexpr int NP = 32 / SS;             // probes per 32-letter word (32 % SS == 0)
-	int64_t word_lo = probe_lo >> 5, word_hi = (probe_hi + 31) >> 5;
-	int64_t j = word_lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-	int64_t stride = (int64_t) gridDim.x * blockDim.x;
-	const uint32_t idmask = (1u << T.id_bits) - 1u;
-
-	for (; j < word_hi; j += stride) {
-		int64_t base = j << 5;
-		uint64_t c0 = __ldcs(S.codes + j), c1 = __ldcs(S.codes + j + 1);
-		uint64_t v = (uint64_t) __ldcs(S.valid + j) | ((uint64_t) __ldcs(S.valid + j + 1) << 32);
-		uint32_t m = (uint32_t) all_set_run(v, T.seed_w);
-
-		if (base < probe_lo)
-			m &= 0xFFFFFFFFu << (int) (probe_lo - base);
-		if (base + 32 > probe_hi)
-			m &= (probe_hi - base) <= 0 ? 0u : 0xFFFFFFFFu >> (int) (base + 32 - probe_hi);
-		uint32_t fp8[NP], bucket[NP], rare = 0;
-		uint4 b[NP];
-#pragma unroll
-		for (int q = 0; q < NP; q++) {
-			const int r = q * SS;
-			uint64_t k = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
-			uint32_t top, fp;
-
-			bsgpu_hash(k & T.seed_mask, top, fp);
-			sampled_filter_hash(top, fp, T.nfilter, bucket[q], fp8[q]);
-		}
-#pragma unroll
-		for (int q = 0; q < NP; q++)
-			b[q] = ((m >> (q * SS)) & 1u) ? __ldg(T.filter + bucket[q]) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-		for (int q = 0; q < NP; q++)
-			rare |= (filter_maybe(b[q], fp8[q]) ? 1u : 0u) << (q * SS);
-		rare &= m;
-		while (rare) {
-			int r = __ffs(rare) - 1;
-			rare &= rare - 1;
-			uint64_t k = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
-			uint32_t top, fp;
-
-			k &= T.seed_mask;
-			bsgpu_hash(k, top, fp);
-			uint32_t fw = sampled_fp_of(fp, T.id_bits, T.fp_mask);
-			uint32_t bucket2 = sampled_bucket_of(top, T.nbuckets);
-			for (;;) {
-				uint4 bb = __ldg(T.table + bucket2);
-				uint32_t ent[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-				for (int z = 0; z < 4; z++) {
-					uint32_t e = ent[z] & idmask;
-
-					if (((ent[z] ^ fw) & T.fp_mask) == 0 && (ent[z] & BSGPU_S_EMPTY) != BSGPU_S_EMPTY &&
-					    __ldg(T.keys + e) == k)
-						q_verify<LONG>(S, Q, R, ((e / SS) << 5) | (e % SS), base + r, 0, 0,
-							       own_lo, own_hi);
-				}
-				if (!(bb.w & BSGPU_S_OVERFLOW))
-					break;
-				bucket2 = bucket2 + 1 == T.nbuckets ? 0 : bucket2 + 1;
-			}
-		}
-	}
-}
-
 // ------------------------------------------------------------------------------------
 // Exact dictionaries straight from the subject's letters (no packed planes).
-// Same sampling argument as above with a fixed seed of 16 letters: every pattern of width
-// w >= 17 is indexed under its S = min(w - 15, 32) seeds at offsets 0..S-1 and the subject
-// is probed at the positions p = 0 (mod S) only.  The seed is hashed as the four raw 32-bit
+// Sampled seeds of 16 letters: every pattern of width w >= 17 is indexed under its
+// S = min(w - 15, 32) seeds at offsets 0..S-1 and the subject is probed at the positions
+// p = 0 (mod S) only: an occurrence starting at a meets exactly one of them
+// (t = (-a) mod S), so the number of index probes -- L2 random-sector gathers -- drops by S.  The seed is hashed as the four raw 32-bit
 // words of its 16 encoded bytes (multilinear hash, 4 IMAD.WIDE), so a probe costs 5 shared
 // memory word loads, 4 funnel shifts, the hash and one gather of a 16-byte Bloom block -- no
 // 2-bit conversion and no validity bookkeeping: a window holding a non-base letter, a

@@ -122,9 +122,11 @@ int bsgpu_subject_set(const uint8_t *concat, const int32_t *widths, int32_t n,
 int bsgpu_subject_chunk(const uint8_t *chunk, int64_t chunk_len, int64_t chunk_start,
 		int64_t subject_len, int64_t report_lo, int64_t report_hi,
 		bsgpu_subject **out);
-/* Re-derives the packed planes from the resident bytes on `stream` (asynchronous).  The
- * upload functions already do this once; a caller that wants the packing inside its own
- * timed region (bench.py does) calls it again. */
+/* Tells the library that the resident letters are to be treated as new (e.g. the caller
+ * overwrote them in place through its own device pointer, or wants the derivation inside a
+ * timed region as bench.py does): the packed 2-bit / validity planes, which are derived
+ * lazily by the first scan that needs them, are dropped.  The exact-dictionary scan reads
+ * the letters directly and never builds them.  `stream` is unused (kept for ABI stability). */
 int bsgpu_subject_repack(bsgpu_subject *subj, void *stream);
 void bsgpu_subject_free(bsgpu_subject *subj);
 int64_t bsgpu_subject_nletters(const bsgpu_subject *subj);	/* letters that are scanned */
@@ -226,12 +228,20 @@ int bsgpu_mindex_combine(const bsgpu_result *const *components, int ncomponents,
 		bsgpu_result *res);
 
 /* Human-readable description of the engine the last match/count call used, e.g.
- * "sampled_hash S=8 seed=18 buckets=5333333 table_bytes=85333328" or
+ * "byteseed_hash S=10 seed=16 filter_bytes=19779008 buckets=6593006 ..." or
  * "qgram_hamming q=12 shifts=7 entries=6930000" or "tb_hash w=12 buckets=2097152 + verify". */
 const char *bsgpu_last_plan(void);
 
 /* Kernel launch counter (every kernel this library launched since process start). */
 int64_t bsgpu_launch_count(void);
+
+/* Opt-in timing of the hot kernels (pack_subject_kernel, scan_byteseed_kernel,
+ * confirm_byteseed_kernel, scan_tb_kernel, qscan_kernel) with CUDA events recorded on the
+ * launching stream.  bsgpu_kernel_timing(1) starts collecting (at most 256 launches),
+ * bsgpu_kernel_times() waits for them, writes up to max_entries (name, milliseconds) pairs in
+ * launch order, forgets them and returns how many it wrote (-1 on error). */
+int bsgpu_kernel_timing(int enable);
+int bsgpu_kernel_times(const char **names, float *ms, int max_entries);
 
 /* Micro-benchmarks used to establish the memory rooflines on this device (GB/s):
  * a streaming copy and a random 32-byte-sector gather from an L2-resident buffer. */

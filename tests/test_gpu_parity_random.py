@@ -21,10 +21,10 @@ def engine(request, monkeypatch):
     Trusted-Band engine forced (BSGPU_NO_QINDEX=1); both must equal the reference."""
     if request.param == "tb_only":
         monkeypatch.setenv("BSGPU_NO_QINDEX", "1")
-        monkeypatch.setenv("BSGPU_SAMPLE_STRIDE", "1")      # plain one-probe-per-window scan
+        monkeypatch.setenv("BSGPU_NO_BYTESEED", "1")        # plain one-probe-per-window scan
     else:
         monkeypatch.delenv("BSGPU_NO_QINDEX", raising=False)
-        monkeypatch.delenv("BSGPU_SAMPLE_STRIDE", raising=False)
+        monkeypatch.delenv("BSGPU_NO_BYTESEED", raising=False)
     return request.param
 
 
