@@ -834,9 +834,6 @@ extern "C" int bsgpu_pdict3parts_build(int algo, int32_t M,
 						    i + 1);
 		}
 	}
-	if (w > 64)
-		return fail(BSGPU_EUNSUPPORTED, "Trusted Band width %d > 64 is not supported by "
-			    "the GPU index yet", w);
 	TRY(ensure_device());
 
 	bsgpu_pdict3parts *p3 = new bsgpu_pdict3parts();
@@ -1292,9 +1289,26 @@ struct Workspace {
 	DevBuf<uint8_t> cub_temp;
 	unsigned long long *h_counters = nullptr;       // pinned
 	int *h_flags = nullptr;
+	int32_t *h_counts = nullptr;                    // pinned, grown on demand
+	size_t h_counts_n = 0;
 };
 
 static Workspace *g_ws = nullptr;
+
+static int host_counts(Workspace *ws, size_t n, int32_t **out)
+{
+	if (ws->h_counts_n < n || ws->h_counts == nullptr) {
+		if (ws->h_counts != nullptr)
+			cudaFreeHost(ws->h_counts);
+		ws->h_counts = nullptr;
+		ws->h_counts_n = 0;
+		size_t want = std::max<size_t>(n, 1024);
+		CUDA_TRY(cudaMallocHost((void **) &ws->h_counts, want * sizeof(int32_t)));
+		ws->h_counts_n = want;
+	}
+	*out = ws->h_counts;
+	return BSGPU_OK;
+}
 
 static int workspace(Workspace **out)
 {
@@ -1802,11 +1816,48 @@ static int bits_for(unsigned long long v)
 	return b;
 }
 
+// Count vectors of results are recycled: a fresh 4 MB malloc() is mmap-backed and costs a
+// page fault per page on first touch, which shows in the end-to-end time of a 5 ms call.
+static std::vector<std::pair<void *, size_t>> g_count_blocks;   // free blocks
+static std::vector<std::pair<void *, size_t>> g_count_live;     // handed out
+
+static void *count_block_alloc(size_t bytes)
+{
+	for (size_t i = 0; i < g_count_blocks.size(); i++)
+		if (g_count_blocks[i].second >= bytes && g_count_blocks[i].second <= 2 * bytes + 4096) {
+			auto blk = g_count_blocks[i];
+			g_count_blocks.erase(g_count_blocks.begin() + i);
+			g_count_live.push_back(blk);
+			return blk.first;
+		}
+	void *p = malloc(bytes);
+	if (p != nullptr && bytes >= (1u << 16) && bytes <= (64u << 20))
+		g_count_live.push_back(std::make_pair(p, bytes));
+	return p;
+}
+
+static void count_block_free(void *p)
+{
+	if (p == nullptr)
+		return;
+	for (size_t i = 0; i < g_count_live.size(); i++)
+		if (g_count_live[i].first == p) {
+			auto blk = g_count_live[i];
+			g_count_live.erase(g_count_live.begin() + i);
+			if (g_count_blocks.size() < 4) {
+				g_count_blocks.push_back(blk);
+				return;
+			}
+			break;
+		}
+	free(p);
+}
+
 extern "C" void bsgpu_result_free(bsgpu_result *res)
 {
 	if (res == nullptr)
 		return;
-	free(res->counts);
+	count_block_free(res->counts);
 	free(res->dcounts);
 	free(res->which);
 	free(res->ends_offsets);
@@ -1854,7 +1905,8 @@ extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
 	DevBuf<int32_t> d_counts;
 	TRY(d_counts.alloc((size_t) M));
 	CUDA_TRY(cudaMemsetAsync(d_counts.p, 0, (size_t) std::max(M, 1) * sizeof(int32_t), st));
-	std::vector<int32_t> counts((size_t) M, 0);
+	int32_t *counts = nullptr;              // pinned staging for the device -> host copy
+	TRY(host_counts(ws, (size_t) M, &counts));
 
 	// q-gram engine when the dictionary is eligible (whole-pattern TB or MTB bands, base-only
 	// patterns of <= 64 letters, fixedS): same results, far fewer index probes
@@ -1875,7 +1927,7 @@ extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
 			TRY(run_q(qi, subj, mp, R, false, ws, st));
 		else
 			TRY(run_parts_tb(parts, nparts, subj, mp, R, false, ws, st));
-		CUDA_TRY(cudaMemcpyAsync(counts.data(), d_counts.p, (size_t) M * sizeof(int32_t),
+		CUDA_TRY(cudaMemcpyAsync(counts, d_counts.p, (size_t) M * sizeof(int32_t),
 					 cudaMemcpyDeviceToHost, st));
 		CUDA_TRY(cudaStreamSynchronize(st));
 	} else {
@@ -1909,7 +1961,7 @@ extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
 			g_launches++;
 			CUDA_TRY(cudaGetLastError());
 		}
-		CUDA_TRY(cudaMemcpyAsync(counts.data(), d_counts.p, (size_t) M * sizeof(int32_t),
+		CUDA_TRY(cudaMemcpyAsync(counts, d_counts.p, (size_t) M * sizeof(int32_t),
 					 cudaMemcpyDeviceToHost, st));
 		if (matches_as == BSGPU_MATCHES_AS_ENDS) {
 			res->ends = (int32_t *) malloc((size_t) std::max<unsigned long long>(nrec, 1) * sizeof(int32_t));
@@ -1930,11 +1982,13 @@ extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
 		}
 	}
 	if (matches_as == BSGPU_MATCHES_AS_COUNTS) {
-		res->counts = (int32_t *) malloc((size_t) std::max(M, 1) * sizeof(int32_t));
+		res->counts = (int32_t *) count_block_alloc((size_t) std::max(M, 1) * sizeof(int32_t));
+		if (res->counts == nullptr)
+			return fail(BSGPU_ENOMEM, "out of host memory");
 		res->n_counts = M;
-		memcpy(res->counts, counts.data(), (size_t) M * sizeof(int32_t));
+		memcpy(res->counts, counts, (size_t) M * sizeof(int32_t));
 	} else {
-		which_from_counts(res, counts.data(), M);
+		which_from_counts(res, counts, M);
 	}
 	return BSGPU_OK;
 }

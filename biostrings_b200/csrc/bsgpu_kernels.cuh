@@ -295,6 +295,23 @@ __device__ __forceinline__ uint64_t all_set_run(uint64_t v, int w)
 	return m;
 }
 
+// mask bit r set iff the flag bits of the w letters starting at letter 32 * j + r are all
+// set; 'first' holds the flag words j and j + 1 (already loaded), further words are read
+// 32 letters at a time (w of any size)
+__device__ __forceinline__ uint32_t window_mask(const uint32_t *__restrict__ plane, int64_t j,
+						uint64_t first, int w)
+{
+	uint32_t m = (uint32_t) all_set_run(first, min(w, 32));
+
+	for (int k = 32; k < w && m != 0; k += 32) {
+		int64_t jj = j + (k >> 5);
+		uint64_t v = (uint64_t) __ldg(plane + jj) | ((uint64_t) __ldg(plane + jj + 1) << 32);
+
+		m &= (uint32_t) all_set_run(v, min(w - k, 32));
+	}
+	return m;
+}
+
 // ------------------------------------------------------------------------------------
 // Trusted-Band scan, fixedS = TRUE: every window of w base letters is looked up.
 // Thread t handles the 32 window starts of code word j; windows may extend into words
@@ -316,19 +333,8 @@ scan_tb_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R, BsgpuReport 
 	for (; j < word_hi; j += stride) {
 		uint64_t c0 = __ldcs(S.codes + j), c1 = __ldcs(S.codes + j + 1);
 		uint64_t v = (uint64_t) __ldcs(S.valid + j) | ((uint64_t) __ldcs(S.valid + j + 1) << 32);
-		uint32_t m;
+		uint32_t m = window_mask(S.valid, j, v, w);
 
-		if (w <= 32) {
-			m = (uint32_t) all_set_run(v, w);
-		} else {
-			// windows of 33..64 letters: need valid bits of a third word
-			uint64_t v2 = (uint64_t) __ldcs(S.valid + j + 1) |
-				      ((uint64_t) __ldcs(S.valid + j + 2) << 32);
-			// first 32 letters valid, then letters 32..w-1 valid
-			uint32_t m_lo = (uint32_t) all_set_run(v, 32);
-			uint32_t m_hi = (uint32_t) all_set_run(v2, w - 32);
-			m = m_lo & m_hi;
-		}
 		// clip to [start_lo, start_hi)
 		int64_t base = j << 5;
 		if (base < start_lo)
@@ -413,17 +419,7 @@ scan_tb_iupac_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R, BsgpuR
 	for (; j < word_hi; j += stride) {
 		uint64_t u0 = (uint64_t) __ldg(S.iupac + j) | ((uint64_t) __ldg(S.iupac + j + 1) << 32);
 		uint64_t v0 = (uint64_t) __ldg(S.valid + j) | ((uint64_t) __ldg(S.valid + j + 1) << 32);
-		uint32_t m_iu, m_va;
-
-		if (w <= 32) {
-			m_iu = (uint32_t) all_set_run(u0, w);
-			m_va = (uint32_t) all_set_run(v0, w);
-		} else {
-			uint64_t u1 = (uint64_t) __ldg(S.iupac + j + 1) | ((uint64_t) __ldg(S.iupac + j + 2) << 32);
-			uint64_t v1 = (uint64_t) __ldg(S.valid + j + 1) | ((uint64_t) __ldg(S.valid + j + 2) << 32);
-			m_iu = (uint32_t) all_set_run(u0, 32) & (uint32_t) all_set_run(u1, w - 32);
-			m_va = (uint32_t) all_set_run(v0, 32) & (uint32_t) all_set_run(v1, w - 32);
-		}
+		uint32_t m_iu = window_mask(S.iupac, j, u0, w), m_va = window_mask(S.valid, j, v0, w);
 		uint32_t m = m_iu & ~m_va;      // IUPAC-only windows that are not all-base
 		int64_t base = j << 5;
 		if (base < start_lo)
