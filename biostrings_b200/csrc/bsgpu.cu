@@ -78,7 +78,7 @@ struct KernelTimer {
 
 	KernelTimer(const char *name, cudaStream_t st_) : st(st_)
 	{
-		if (!g_timing || g_times.size() >= 256)
+		if (!g_timing || g_times.size() >= 8192)
 			return;
 		KernelTime kt = {name, nullptr, nullptr};
 		if (cudaEventCreate(&kt.start) != cudaSuccess || cudaEventCreate(&kt.stop) != cudaSuccess)
