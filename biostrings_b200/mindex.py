@@ -74,15 +74,61 @@ class ByPos_MIndex:
         w = int(self.width0[i])
         return e - w + 1, e.copy(), np.full(e.size, w, dtype=np.int32)
 
-    def unlist(self):
-        """start/end/width of all matches, pattern-major (unlist(MIndex))."""
-        ends = self.endIndex()
-        s, e = [], []
-        for i, x in enumerate(ends):
-            if x is not None:
-                e.append(x)
-                s.append(x - int(self.width0[i]) + 1)
-        if not e:
+    def _rows(self):
+        """Row of the CSR holding the ends of every pattern (duplicates -> their low)."""
+        rows = np.arange(len(self), dtype=np.int64)
+        if self.dups0 is not None:
+            h2l = np.asarray(self.dups0.high2low, dtype=np.int64)
+            dup = h2l != NA_INTEGER
+            rows[dup] = h2l[dup] - 1
+        return rows
+
+    def unlist(self, use_names=False):
+        """start / end of all matches, pattern-major (unlist(MIndex), R/MIndex-class.R:56-79),
+        computed on the CSR without building the per-pattern lists; with use_names also the
+        pattern name of every match."""
+        rows = self._rows()
+        n = (self.offsets[rows + 1] - self.offsets[rows]).astype(np.int64)
+        total = int(n.sum())
+        if total == 0:
             z = np.zeros(0, dtype=np.int32)
-            return z, z
-        return np.concatenate(s), np.concatenate(e)
+            return (z, z, None) if use_names else (z, z)
+        # gather the CSR rows in pattern order
+        first = np.repeat(self.offsets[rows] - np.concatenate([[0], np.cumsum(n)[:-1]]), n)
+        e = self.ends[first + np.arange(total, dtype=np.int64)]
+        s = e - np.repeat(self.width0.astype(np.int32), n) + 1
+        if not use_names:
+            return s, e
+        names = None if self.NAMES is None else np.repeat(np.asarray(self.NAMES, dtype=object), n)
+        return s, e, names
+
+    def coverage(self, width=None):
+        """coverage(MIndex): how many matches cover each subject position 1..width (the method
+        IRanges supplies for the IntegerRanges that unlist() returns); width defaults to the
+        largest end."""
+        s, e = self.unlist()
+        if width is None:
+            width = int(e.max()) if e.size else 0
+        d = np.zeros(width + 2, dtype=np.int64)
+        lo = np.clip(s.astype(np.int64), 1, width + 1)
+        hi = np.clip(e.astype(np.int64) + 1, 1, width + 1)
+        keep = hi > lo
+        np.add.at(d, lo[keep], 1)
+        np.add.at(d, hi[keep], -1)
+        return np.cumsum(d)[1:width + 1].astype(np.int32)
+
+
+def extractAllMatches(subject, mindex):
+    """XStringViews of all the matches on the (unmasked) subject, pattern-major, named after
+    the patterns (R/MIndex-class.R:91-103)."""
+    from .xstring import DNAString, MaskedDNAString, XStringViews
+    if isinstance(subject, MaskedDNAString):
+        subject = subject.unmasked()
+    elif not isinstance(subject, (DNAString, np.ndarray, str, bytes)):
+        raise ValueError("'subject' must be an XString or MaskedXString object")
+    if not isinstance(mindex, ByPos_MIndex):
+        raise ValueError("'mindex' must be an MIndex object")
+    s, e, names = mindex.unlist(use_names=True)
+    v = XStringViews(subject, s, e - s + 1)     # unsafe.newXStringViews: no limits check
+    v.names = names
+    return v

@@ -86,6 +86,31 @@ def test_mindex_csr_accessors():
     o = R.MIndex(width0, [None, np.array([199, 402]), None, None, None], dups0=R.Dups(dups0.high2low))
     assert [None if x is None else x.tolist() for x in o.startIndex()] == \
         [None if x is None else x.tolist() for x in st]
+    # unlist / coverage / extractAllMatches on the CSR (R/MIndex-class.R:56-103)
+    us, ue, un = m.unlist(use_names=True)
+    assert us.tolist() == [190, 393, 190, 393] and ue.tolist() == [199, 402, 199, 402]
+    assert un.tolist() == ["b", "b", "e", "e"]
+    cov = m.coverage(410)
+    assert cov.size == 410 and cov[188] == 0 and cov[189] == 2 and cov[198] == 2 and cov[199] == 0
+    assert int(cov.sum()) == 40
+    g = np.random.default_rng(5)
+    rows = [np.sort(g.integers(30, 900, int(g.integers(0, 6)))).astype(np.int32) for _ in range(50)]
+    offs = np.concatenate([[0], np.cumsum([r.size for r in rows])])
+    wid = g.integers(1, 30, 50).astype(np.int32)
+    mm = bs.ByPos_MIndex(wid, offs, np.concatenate(rows) if offs[-1] else np.zeros(0, np.int32))
+    s2, e2 = mm.unlist()
+    want_s = np.concatenate([r - w + 1 for r, w in zip(rows, wid)])
+    assert s2.tolist() == want_s.tolist() and e2.tolist() == np.concatenate(rows).tolist()
+    brute = np.zeros(1000, dtype=np.int32)
+    for r, w in zip(rows, wid):
+        for e_ in r:
+            brute[max(e_ - w, 0):e_] += 1
+    assert mm.coverage(1000).tolist() == brute.tolist()
+    subj = bs.DNAString("ACGT" * 250)
+    v = bs.extractAllMatches(subj, mm)
+    assert len(v) == s2.size and v.start.tolist() == s2.tolist() and v.width.tolist() == (e2 - s2 + 1).tolist()
+    with pytest.raises(ValueError, match="MIndex"):
+        bs.extractAllMatches(subj, [1, 2])
 
 
 def test_masked_views():
