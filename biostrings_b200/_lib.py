@@ -24,7 +24,7 @@ SYMBOLS = [
     "bsgpu_match_PDict3Parts_XString", "bsgpu_match_PDict3Parts_XStringViews",
     "bsgpu_vmatch_PDict3Parts_XStringSet", "bsgpu_mindex_combine",
     "bsgpu_last_plan", "bsgpu_launch_count", "bsgpu_probe_peaks",
-    "bsgpu_kernel_timing", "bsgpu_kernel_times",
+    "bsgpu_kernel_timing", "bsgpu_kernel_times", "bsgpu_patterns_build",
 ]
 
 
@@ -93,6 +93,7 @@ def lib():
     L.bsgpu_last_plan.restype = C.c_char_p
     L.bsgpu_launch_count.restype = i64
     L.bsgpu_probe_peaks.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), i64]
+    L.bsgpu_patterns_build.argtypes = [vp, vp, i32, C.POINTER(vp)]
     L.bsgpu_kernel_timing.argtypes = [C.c_int]
     L.bsgpu_kernel_times.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     _lib = L

@@ -311,6 +311,10 @@ struct bsgpu_pdict3parts {
 	std::vector<uint8_t> is_tb_dup;         // had a non-NA high2low at build time
 	mutable std::unique_ptr<struct QIndex> qcache;  // q-gram index built on first use
 	mutable std::unique_ptr<struct ByteSeedIndex> bcache;   // byte-seed index (exact, no planes)
+	// non-preprocessed dictionary (bsgpu_patterns_build): the letters only, no Trusted Band
+	bool plain = false;
+	DevBuf<uint8_t> d_pat;
+	DevBuf<int64_t> d_pat_off;
 	uint32_t nbuckets = 0;
 	bool all_singletons = true;
 	DevBuf<uint4> d_table;
@@ -416,7 +420,7 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 		*out = p0->qcache.get();
 		return BSGPU_OK;
 	};
-	if (qindex_disabled() || M == 0 || M >= (1 << 27))
+	if (qindex_disabled() || M == 0 || M >= (1 << 27) || p0->plain)
 		return done();
 	// --- reconstruct the full patterns: head0 + tb0 + tail0 ------------------------------
 	std::vector<int32_t> len(M);
@@ -952,12 +956,46 @@ extern "C" int bsgpu_pdict3parts_build(int algo, int32_t M,
 	return BSGPU_OK;
 }
 
+// A non-preprocessed dictionary: the handle carries the pattern letters only and is accepted
+// by bsgpu_match() / bsgpu_vmatch() like a PDict3Parts (match_XStringSet_XString & co).
+extern "C" int bsgpu_patterns_build(const uint8_t *concat, const int32_t *widths, int32_t M,
+		bsgpu_pdict3parts **out)
+{
+	if (out == nullptr || M < 0 || (M > 0 && widths == nullptr))
+		return fail(BSGPU_EINVAL, "bsgpu_patterns_build(): bad arguments");
+	*out = nullptr;
+	std::vector<int64_t> off((size_t) M + 1, 0);
+	for (int32_t i = 0; i < M; i++) {
+		if (widths[i] <= 0)
+			return fail(BSGPU_EINVAL, "empty patterns are not supported");
+		if (widths[i] > 20000)
+			return fail(BSGPU_EINVAL, "patterns with more than 20000 letters are not supported");
+		off[i + 1] = off[i] + widths[i];
+	}
+	if (off[M] > 0 && concat == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_patterns_build(): bad arguments");
+	TRY(ensure_device());
+	std::unique_ptr<bsgpu_pdict3parts> p3(new bsgpu_pdict3parts());
+	p3->plain = true;
+	p3->M = M;
+	p3->w = 0;
+	p3->high2low.assign(M, BSGPU_NA);
+	TRY(p3->d_pat.alloc((size_t) off[M] + 8));
+	if (off[M] > 0)
+		CUDA_TRY(cudaMemcpy(p3->d_pat.p, concat, (size_t) off[M], cudaMemcpyHostToDevice));
+	TRY(p3->d_pat_off.upload(off.data(), off.size()));
+	*out = p3.release();
+	return BSGPU_OK;
+}
+
 extern "C" int bsgpu_pdict3parts_set_flanks(bsgpu_pdict3parts *p3,
 		const uint8_t *head_concat, const int32_t *head_widths,
 		const uint8_t *tail_concat, const int32_t *tail_widths)
 {
 	if (p3 == nullptr)
 		return fail(BSGPU_EINVAL, "bsgpu_pdict3parts_set_flanks(): NULL handle");
+	if (p3->plain)
+		return fail(BSGPU_EINVAL, "a non-preprocessed dictionary has no head or tail");
 	TRY(ensure_device());
 	p3->h_head.clear();
 	p3->h_tail.clear();
@@ -1284,6 +1322,8 @@ struct Workspace {
 	DevBuf<unsigned long long> counters;    // [0] = candidates, [1] = records
 	DevBuf<int> flags;
 	DevBuf<long long> ovf;                  // windows with too many IUPAC expansions
+	DevBuf<int64_t> slot_off;               // plain dictionaries: first slot of every segment
+	BsgpuPlainView plain = {};              // view of the last plain scan (for finalize_ends_kernel)
 	DevBuf<unsigned long long> bs_cand;     // byte-seed scan: candidate slices, one per block
 	DevBuf<int32_t> bs_ncand;
 	DevBuf<uint8_t> cub_temp;
@@ -1502,6 +1542,60 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 	return BSGPU_OK;
 }
 
+// A non-preprocessed dictionary against the subject: every (segment, shift) slot x every
+// pattern, brute force as in the reference (which runs one matchPattern per pattern).
+static int run_plain(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, const MatchParams &mp,
+		     BsgpuReport R, bool rec_based, Workspace *ws, cudaStream_t st)
+{
+	if (subj->kind == SUBJ_CHUNK)
+		return fail(BSGPU_EUNSUPPORTED, "non-preprocessed dictionaries on subject chunks are "
+			    "not supported yet (use a PDict object or the whole subject)");
+	if (p3->M == 0)
+		return BSGPU_OK;
+	int32_t n = subj->nseg;
+	int ext = mp.max_nmis;
+	std::vector<int64_t> slot_off((size_t) n + 1, 0);
+
+	for (int32_t g = 0; g < n; g++)
+		slot_off[g + 1] = slot_off[g] + subj->seg_len[g] + 2 * (int64_t) ext + 1;
+	if (slot_off[n] >= (1ll << BSGPU_POS_BITS))
+		return fail(BSGPU_EUNSUPPORTED, "subject too long for one device buffer");
+	TRY(ws->slot_off.upload(slot_off.data(), slot_off.size()));
+	BsgpuPlainView P = {};
+	P.pat = p3->d_pat.p;
+	P.pat_off = p3->d_pat_off.p;
+	P.M = p3->M;
+	P.slot_off = ws->slot_off.p;
+	P.ext = ext;
+	P.nslots = slot_off[n];
+	ws->plain = P;
+	set_plan("plain_bruteforce patterns=%d slots=%lld", p3->M, (long long) P.nslots);
+	dim3 grid((unsigned) grid_for(P.nslots, 256, 8), (unsigned) std::min(p3->M, 1024));
+	for (;;) {
+		unsigned long long rec_before = 0, nrec = 0;
+
+		if (rec_based)
+			TRY(read_counter(ws, 1, &rec_before, st));
+		{
+			KernelTimer kt("match_plain_kernel", st);
+			match_plain_kernel<<<grid, 256, 0, st>>>(subj->view(), P, R, mp.max_nmis, mp.min_nmis,
+								  mp.fixedP, mp.fixedS);
+		}
+		g_launches++;
+		CUDA_TRY(cudaGetLastError());
+		if (!rec_based)
+			break;
+		TRY(read_counter(ws, 1, &nrec, st));
+		if (nrec <= R.capacity)
+			break;
+		TRY(grow(ws->rec, (size_t) nrec, (size_t) rec_before, st));
+		R.records = ws->rec.p;
+		R.capacity = ws->rec.n;
+		TRY(write_counter(ws, 1, rec_before, st));
+	}
+	return BSGPU_OK;
+}
+
 // Runs one part over the subject's scan range, reporting through R.  `rec_based` tells
 // whether R appends records (then the record buffer may have to grow and a slab rerun).
 // own_shift: for band b of an MTB_PDict on a chunked subject the alignment is owned by the
@@ -1510,6 +1604,8 @@ static int run_part(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, cons
 		    BsgpuReport R, bool rec_based, Workspace *ws, cudaStream_t st, bool allow_sync,
 		    int64_t own_shift = 0)
 {
+	if (p3->plain)
+		return run_plain(p3, subj, mp, R, rec_based, ws, st);
 	if (p3->M == 0 || p3->w == 0)
 		return BSGPU_OK;
 	if (p3->algo == BSGPU_ALGO_TWOBIT && !mp.fixedS)
@@ -1957,7 +2053,8 @@ extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
 		if (nrec > 0) {
 			finalize_ends_kernel<<<grid_for((long long) nrec, 256, 8), 256, 0, st>>>(
 				subj->view(), parts[0]->has_tail ? parts[0]->d_tail_off.p : nullptr,
-				tbpos ? 1 : 0, ws->rec.p, nrec, d_ends.p, d_counts.p);
+				tbpos ? 1 : 0, parts[0]->plain ? ws->plain : BsgpuPlainView{}, ws->rec.p, nrec,
+				d_ends.p, d_counts.p);
 			g_launches++;
 			CUDA_TRY(cudaGetLastError());
 		}
@@ -2043,7 +2140,7 @@ extern "C" int bsgpu_count_device(const bsgpu_pdict3parts *const *parts, int npa
 			DevBuf<int32_t> d_ends;
 			TRY(d_ends.alloc((size_t) nrec));
 			finalize_ends_kernel<<<grid_for((long long) nrec, 256, 8), 256, 0, st>>>(
-				subj->view(), nullptr, 0, ws->rec.p, nrec, d_ends.p, d_counts);
+				subj->view(), nullptr, 0, BsgpuPlainView{}, ws->rec.p, nrec, d_ends.p, d_counts);
 			g_launches++;
 			CUDA_TRY(cudaGetLastError());
 			CUDA_TRY(cudaStreamSynchronize(st));

@@ -598,11 +598,81 @@ verify_flanks_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R,
 // Sorted records -> per-pattern counts and end coordinates.
 // ------------------------------------------------------------------------------------
 
+// ------------------------------------------------------------------------------------
+// Non-preprocessed dictionaries (pattern = plain XStringSet: any letters, any widths;
+// match_XStringSet_XString and friends, src/match_pdict.c:174-199,267-293,348-384,434-481).
+// The reference runs one matchPattern() per pattern; all its algorithms report the same
+// matches as the naive inexact one (src/match_pattern.c:53-76): pattern shift Pshift (0-based
+// position of the pattern's first letter in the subject, may be out of limits) matches iff
+// min <= nmis <= max, letters outside the subject counting as mismatches, for
+//   minP <= Pshift <= L - plen - minP,  minP = plen <= max ? 1 - plen : -max.
+// A "slot" is one (segment, Pshift) pair: segment g owns the slots slot_off[g] ..
+// slot_off[g+1]-1, Pshift = slot - slot_off[g] - ext (ext = max.mismatch); slots are
+// monotone in (segment, Pshift), which is the order the reference reports matches in.
+// ------------------------------------------------------------------------------------
+
+struct BsgpuPlainView {
+	const uint8_t *pat;          // concatenated pattern letters
+	const int64_t *pat_off;      // [M+1]
+	int32_t M;
+	const int64_t *slot_off;     // [nseg+1]
+	int32_t ext;
+	int64_t nslots;
+};
+
+__device__ __forceinline__ int find_slot_segment(const BsgpuPlainView &P, int nseg, int64_t slot)
+{
+	int lo = 0, hi = nseg - 1;
+
+	while (lo < hi) {
+		int mid = (lo + hi + 1) >> 1;
+
+		if (__ldg(P.slot_off + mid) <= slot)
+			lo = mid;
+		else
+			hi = mid - 1;
+	}
+	return lo;
+}
+
+// blockIdx.x strides over the slots, blockIdx.y over the patterns
+__global__ void __launch_bounds__(256)
+match_plain_kernel(BsgpuSubjectView S, BsgpuPlainView P, BsgpuReport R, int max_nmis, int min_nmis,
+		   int fixedP, int fixedS)
+{
+	int64_t slot = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (; slot < P.nslots; slot += stride) {
+		int seg = S.nseg == 1 ? 0 : find_slot_segment(P, S.nseg, slot);
+		int64_t L = __ldg(S.seg_len + seg);
+		int64_t Pshift = slot - __ldg(P.slot_off + seg) - P.ext;
+		const uint8_t *s = S.bytes + __ldg(S.seg_start + seg);
+
+		for (int i = blockIdx.y; i < P.M; i += gridDim.y) {
+			int64_t po = __ldg(P.pat_off + i);
+			int plen = (int) (__ldg(P.pat_off + i + 1) - po);
+			int64_t minP = plen <= max_nmis ? 1 - plen : -max_nmis;
+
+			if (Pshift < minP || Pshift + plen > L - minP)
+				continue;
+			int nmis = count_mismatches(P.pat + po, plen, s, L, Pshift, max_nmis, fixedP, fixedS);
+			if (nmis > max_nmis || nmis < min_nmis)
+				continue;
+			if (R.mode == BSGPU_R_COUNT)
+				atomicAdd(R.counts + i, 1);
+			else            // n = 1-based local end; the record position is the slot
+				report_match(R, S, i, seg, Pshift + plen, slot, 0);
+		}
+	}
+}
+
 // mode HIT_COORD: low bits already are the end coordinate.
 // mode HIT_TBPOS: low bits = concat index of the TB end; end = local + |tail| + seg_coord.
+// plain dictionaries (P.slot_off != NULL): low bits = slot; end = Pshift + plen + seg_coord.
 __global__ void __launch_bounds__(256)
 finalize_ends_kernel(BsgpuSubjectView S, const int64_t *__restrict__ tail_off, int tbpos_mode,
-		     const unsigned long long *__restrict__ rec, unsigned long long n,
+		     BsgpuPlainView P, const unsigned long long *__restrict__ rec, unsigned long long n,
 		     int32_t *__restrict__ ends, int32_t *__restrict__ counts)
 {
 	unsigned long long t = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
@@ -613,7 +683,12 @@ finalize_ends_kernel(BsgpuSubjectView S, const int64_t *__restrict__ tail_off, i
 		int key = (int) (r >> BSGPU_POS_BITS);
 		int64_t v = (int64_t) (r & BSGPU_POS_MASK);
 
-		if (tbpos_mode) {
+		if (P.slot_off != nullptr) {
+			int seg = S.nseg == 1 ? 0 : find_slot_segment(P, S.nseg, v);
+			int plen = (int) (__ldg(P.pat_off + key + 1) - __ldg(P.pat_off + key));
+
+			v = v - __ldg(P.slot_off + seg) - P.ext + plen + __ldg(S.seg_coord + seg);
+		} else if (tbpos_mode) {
 			int seg = S.nseg == 1 ? 0 : find_segment(S, v);
 			int Tlen = tail_off ? (int) (__ldg(tail_off + key + 1) - __ldg(tail_off + key)) : 0;
 

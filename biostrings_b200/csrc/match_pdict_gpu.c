@@ -402,26 +402,24 @@ SEXP match_PDict3Parts_XStringViews(SEXP pptb, SEXP pdict_head, SEXP pdict_tail,
 	return result_as_SEXP(&r, ms_code);
 }
 
-/* --- .Call ENTRY POINT --- (src/match_pdict.c:484) */
-SEXP vmatch_PDict3Parts_XStringSet(SEXP pptb, SEXP pdict_head, SEXP pdict_tail,
-		SEXP subject, SEXP max_mismatch, SEXP min_mismatch, SEXP fixed,
-		SEXP collapse, SEXP weight, SEXP matches_as, SEXP envir)
+/* vmatch on a sequence set for either kind of dictionary handle */
+static SEXP vmatch_common(bsgpu_pdict3parts *p3, int M, const char *entry, SEXP subject,
+		SEXP max_mismatch, SEXP min_mismatch, SEXP fixed,
+		SEXP collapse, SEXP weight, SEXP matches_as)
 {
 	FlatSet s = flatten(subject);
 	int ms_code = matches_as_code(matches_as), coll = INTEGER(collapse)[0];
-	int M = get_XVectorList_length(pptb_tb(pptb));
 	bsgpu_result r;
 	SEXP ans;
 
-	(void) envir;
 	if (ms_code == BSGPU_MATCHES_AS_NULL)
-		error("vmatch_PDict3Parts_XStringSet() does not support "
-		      "'matches_as=\"%s\"' yet, sorry", CHAR(STRING_ELT(matches_as, 0)));
+		error("%s() does not support 'matches_as=\"%s\"' yet, sorry", entry,
+		      CHAR(STRING_ELT(matches_as, 0)));
 	if (ms_code != BSGPU_MATCHES_AS_WHICH && ms_code != BSGPU_MATCHES_AS_COUNTS)
 		error("vmatchPDict() is not supported yet, sorry");
 	if (ms_code == BSGPU_MATCHES_AS_COUNTS && coll != 0 && coll != 1 && coll != 2)
 		error("'collapse' must be FALSE, 1 or 2");
-	if (bsgpu_vmatch_PDict3Parts_XStringSet(get_p3(pptb, pdict_head, pdict_tail),
+	if (bsgpu_vmatch_PDict3Parts_XStringSet(p3,
 			s.concat, s.widths, s.n,
 			INTEGER(max_mismatch)[0], INTEGER(min_mismatch)[0],
 			LOGICAL(fixed)[0], LOGICAL(fixed)[1],
@@ -457,6 +455,99 @@ SEXP vmatch_PDict3Parts_XStringSet(SEXP pptb, SEXP pdict_head, SEXP pdict_tail,
 		UNPROTECT(1);
 	}
 	bsgpu_result_free(&r);
+	return ans;
+}
+
+/* --- .Call ENTRY POINT --- (src/match_pdict.c:484) */
+SEXP vmatch_PDict3Parts_XStringSet(SEXP pptb, SEXP pdict_head, SEXP pdict_tail,
+		SEXP subject, SEXP max_mismatch, SEXP min_mismatch, SEXP fixed,
+		SEXP collapse, SEXP weight, SEXP matches_as, SEXP envir)
+{
+	(void) envir;
+	return vmatch_common(get_p3(pptb, pdict_head, pdict_tail),
+			get_XVectorList_length(pptb_tb(pptb)), "vmatch_PDict3Parts_XStringSet",
+			subject, max_mismatch, min_mismatch, fixed, collapse, weight, matches_as);
+}
+
+/* ---- non-preprocessed dictionaries: 'pattern' is a plain XStringSet --------------------------
+ * The reference runs one matchPattern() per pattern with the algorithm R selected; all of them
+ * report the same matches, so 'algorithm' only needs to be a known name here.  with.indels is
+ * the one thing the device path does not do. */
+
+static bsgpu_pdict3parts *plain_handle(SEXP pattern, SEXP with_indels, SEXP algorithm)
+{
+	static const char *known[] = {"naive-exact", "naive-inexact", "boyer-moore", "shift-or", NULL};
+	const char *algo = CHAR(STRING_ELT(algorithm, 0));
+	FlatSet p = flatten(pattern);
+	bsgpu_pdict3parts *p3 = NULL;
+	int k;
+
+	if (LOGICAL(with_indels)[0] || strcmp(algo, "indels") == 0)
+		error("with.indels=TRUE is not supported on the GPU path");
+	for (k = 0; known[k] != NULL && strcmp(known[k], algo) != 0; k++)
+		;
+	if (known[k] == NULL)
+		error("\"%s\": unknown algorithm", algo);
+	if (bsgpu_patterns_build(p.concat, p.widths, p.n, &p3) != BSGPU_OK)
+		error("%s", bsgpu_last_error());
+	return p3;
+}
+
+/* --- .Call ENTRY POINT --- (src/match_pdict.c:174) */
+SEXP match_XStringSet_XString(SEXP pattern, SEXP subject,
+		SEXP max_mismatch, SEXP min_mismatch, SEXP with_indels, SEXP fixed,
+		SEXP algorithm, SEXP matches_as, SEXP envir)
+{
+	Chars_holder S = hold_XRaw(subject);
+	int ms_code = matches_as_code(matches_as), rc;
+	bsgpu_pdict3parts *p3 = plain_handle(pattern, with_indels, algorithm);
+	bsgpu_result r;
+
+	(void) envir;
+	rc = bsgpu_match_PDict3Parts_XString(p3, (const uint8_t *) S.ptr, S.length,
+			INTEGER(max_mismatch)[0], INTEGER(min_mismatch)[0],
+			LOGICAL(fixed)[0], LOGICAL(fixed)[1], ms_code, &r);
+	bsgpu_pdict3parts_free(p3);
+	if (rc != BSGPU_OK)
+		error("%s", bsgpu_last_error());
+	return result_as_SEXP(&r, ms_code);
+}
+
+/* --- .Call ENTRY POINT --- (src/match_pdict.c:267) */
+SEXP match_XStringSet_XStringViews(SEXP pattern, SEXP subject, SEXP views_start, SEXP views_width,
+		SEXP max_mismatch, SEXP min_mismatch, SEXP with_indels, SEXP fixed,
+		SEXP algorithm, SEXP matches_as, SEXP envir)
+{
+	Chars_holder S = hold_XRaw(subject);
+	int ms_code = matches_as_code(matches_as), rc;
+	bsgpu_pdict3parts *p3 = plain_handle(pattern, with_indels, algorithm);
+	bsgpu_result r;
+
+	(void) envir;
+	rc = bsgpu_match_PDict3Parts_XStringViews(p3, (const uint8_t *) S.ptr, S.length,
+			INTEGER(views_start), INTEGER(views_width), LENGTH(views_start),
+			INTEGER(max_mismatch)[0], INTEGER(min_mismatch)[0],
+			LOGICAL(fixed)[0], LOGICAL(fixed)[1], ms_code, &r);
+	bsgpu_pdict3parts_free(p3);
+	if (rc != BSGPU_OK)
+		error("%s", bsgpu_last_error());
+	return result_as_SEXP(&r, ms_code);
+}
+
+/* --- .Call ENTRY POINT --- (src/match_pdict.c:519) */
+SEXP vmatch_XStringSet_XStringSet(SEXP pattern, SEXP subject,
+		SEXP max_mismatch, SEXP min_mismatch, SEXP with_indels, SEXP fixed,
+		SEXP algorithm, SEXP collapse, SEXP weight, SEXP matches_as, SEXP envir)
+{
+	bsgpu_pdict3parts *p3 = plain_handle(pattern, with_indels, algorithm);
+	SEXP ans;
+
+	(void) envir;
+	/* an error() inside vmatch_common() leaks p3 until the process ends (longjmp), as any C
+	 * allocation would in an R entry point that errors */
+	ans = vmatch_common(p3, get_XVectorList_length(pattern), "vmatch_XStringSet_XStringSet",
+			    subject, max_mismatch, min_mismatch, fixed, collapse, weight, matches_as);
+	bsgpu_pdict3parts_free(p3);
 	return ans;
 }
 

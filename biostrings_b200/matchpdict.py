@@ -190,6 +190,111 @@ def vmatch_parts(parts, dsubj, max_mismatch, min_mismatch, fixed, collapse, weig
     return _take_result(res, mode, n_subjects=dsubj.length)
 
 
+# ---- non-preprocessed dictionaries: 'pdict' is a plain DNAStringSet ------------------------------
+# (R/matchPDict.R:170-191,215-236,262-285,379-398,502-511; R/match-utils.R:21-85)
+
+ALL_ALGOS = ("auto", "naive-exact", "naive-inexact", "boyer-moore", "shift-or", "indels",
+             "gregexpr", "gregexpr2")
+CLONGINT_NBITS = 64
+
+
+def normarg_algorithm(algorithm):
+    if not isinstance(algorithm, str):
+        raise ValueError("'algorithm' must be a single string")
+    hits = [a for a in ALL_ALGOS if a.startswith(algorithm)]
+    if algorithm in ALL_ALGOS:
+        return algorithm
+    if len(hits) != 1:
+        raise ValueError("'arg' should be one of " + ", ".join(f"'{a}'" for a in ALL_ALGOS))
+    return hits[0]
+
+
+def normarg_with_indels(with_indels):
+    if not isinstance(with_indels, (bool, np.bool_)):
+        raise ValueError("'with.indels' must be TRUE or FALSE")
+    return bool(with_indels)
+
+
+def valid_algos(widths, max_mismatch, min_mismatch, with_indels, fixed):
+    """.valid.algos(): the algorithms the reference would accept, best suited first.  They all
+    report the same matches; the GPU path runs one kernel whatever the choice, but the choice
+    is validated as the reference validates it."""
+    if len(widths) and int(np.min(widths)) == 0:
+        raise ValueError("empty patterns are not supported")
+    if len(widths) and int(np.max(widths)) > 20000:
+        raise ValueError("patterns with more than 20000 letters are not supported")
+    if max_mismatch != 0 and with_indels:
+        if min_mismatch != 0:
+            raise ValueError("'min.mismatch' must be 0 when 'with.indels' is TRUE")
+        return ["indels"]
+    wmax = int(np.max(widths)) if len(widths) else 0
+    algos = []
+    if max_mismatch == 0 and all(fixed):
+        algos.append("boyer-moore")
+        if wmax <= CLONGINT_NBITS:
+            algos.append("shift-or")
+        algos.append("naive-exact")
+    elif min_mismatch == 0 and fixed[0] == fixed[1] and wmax <= CLONGINT_NBITS:
+        algos.append("shift-or")
+    return algos + ["naive-inexact"]
+
+
+def select_algo(algo, widths, max_mismatch, min_mismatch, with_indels, fixed):
+    algos = valid_algos(widths, max_mismatch, min_mismatch, with_indels, fixed)
+    if algo == "auto":
+        return algos[0]
+    if algo not in algos:
+        raise ValueError("valid algos for your string matching problem (best suited first): " +
+                         ", ".join(f'"{a}"' for a in algos))
+    return algo
+
+
+class PlainPatterns:
+    """Device handle of a non-preprocessed dictionary (bsgpu_patterns_build)."""
+
+    def __init__(self, dna_set):
+        self._h = C.c_void_p()
+        concat = np.ascontiguousarray(dna_set.concat, dtype=np.uint8)
+        widths = np.ascontiguousarray(dna_set.widths, dtype=np.int32)
+        _lib.check(_lib.lib().bsgpu_patterns_build(_ptr(concat), _ptr(widths), len(widths),
+                                                   C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().bsgpu_pdict3parts_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _as_plain_set(pdict):
+    if isinstance(pdict, DNAStringSet):
+        return pdict
+    if isinstance(pdict, (list, tuple)):
+        return DNAStringSet(pdict)
+    return None
+
+
+def _check_plain_args(pset, max_mismatch, min_mismatch, with_indels, fixed, algorithm, mode):
+    with_indels = normarg_with_indels(with_indels)
+    if with_indels and mode not in (MATCHES_AS_WHICH, MATCHES_AS_COUNTS):
+        raise ValueError("at the moment, within the matchPDict family, only countPDict(), "
+                         "whichPDict(), vcountPDict() and vwhichPDict() support indels")
+    algo = select_algo(normarg_algorithm(algorithm), np.asarray(pset.widths), max_mismatch,
+                       min_mismatch, with_indels, fixed)
+    if algo == "indels":
+        raise _lib.BsgpuError(-5, "with.indels=TRUE is not supported on the GPU path")
+    return algo
+
+
 # ---- .checkUserArgsWhenTrustedBandIsFull / .checkMaxMismatch (R/matchPDict.R:118-141) --------
 
 def _check_args_full_tb(parts, max_mismatch, fixed):
@@ -236,9 +341,41 @@ def _subject_to_device(subject):
     return DeviceSubject.from_xstring(subject), True
 
 
-def _match_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, mode, what):
+def _match_plain(pset, subject, max_mismatch, min_mismatch, with_indels, fixed, algorithm, mode,
+                 what):
+    """.match.XStringSet (R/matchPDict.R:380-398): no duplicates handling, no Trusted Band."""
+    try:
+        dsubj, owned = _subject_to_device(subject)
+    except ValueError as e:
+        raise ValueError(str(e).replace("vmatchPDict", "v" + what)) from None
+    pat = None
+    try:
+        max_mismatch = normarg_max_mismatch(max_mismatch)
+        min_mismatch = normarg_min_mismatch(min_mismatch, max_mismatch)
+        fixed = normarg_fixed(fixed)
+        _check_plain_args(pset, max_mismatch, min_mismatch, with_indels, fixed, algorithm, mode)
+        pat = PlainPatterns(pset)
+        ans = match_parts([pat], dsubj, max_mismatch, min_mismatch, fixed, mode)
+    finally:
+        if pat is not None:
+            pat.close()
+        if owned:
+            dsubj.close()
+    if mode == MATCHES_AS_ENDS:
+        offsets, ends = ans
+        return ByPos_MIndex(np.asarray(pset.widths, dtype=np.int32), offsets, ends,
+                            names=getattr(pset, "names", None))
+    return ans
+
+
+def _match_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, mode, what,
+                 with_indels=False, algorithm="auto"):
     if not isinstance(pdict, PDict):
-        raise ValueError("'pdict' must be a PDict or XStringSet object")
+        pset = _as_plain_set(pdict)
+        if pset is None:
+            raise ValueError("'pdict' must be a PDict or XStringSet object")
+        return _match_plain(pset, subject, max_mismatch, min_mismatch, with_indels, fixed,
+                            algorithm, mode, what)
     try:
         dsubj, owned = _subject_to_device(subject)
     except ValueError as e:
@@ -248,6 +385,12 @@ def _match_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, mode, what):
         max_mismatch = normarg_max_mismatch(max_mismatch)
         min_mismatch = normarg_min_mismatch(min_mismatch, max_mismatch)
         fixed = normarg_fixed(fixed)
+        if normarg_with_indels(with_indels):
+            raise ValueError("at the moment, matchPDict() and family only support indels "
+                             "on a non-preprocessed pattern dictionary, sorry")
+        if algorithm != "auto":
+            import warnings
+            warnings.warn("'algorithm' is ignored when 'pdict' is a PDict object")
         parts = pdict.parts()
         _check_args_full_tb(parts, max_mismatch, fixed)
         if isinstance(pdict, MTB_PDict):
@@ -268,22 +411,26 @@ def _match_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, mode, what):
     return ans
 
 
-def matchPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True):
-    """-> ByPos_MIndex (R/matchPDict.R:612-658)."""
+def matchPDict(pdict, subject, max_mismatch=0, min_mismatch=0, with_indels=False, fixed=True,
+               algorithm="auto"):
+    """-> ByPos_MIndex (R/matchPDict.R:612-658).  `pdict`: a PDict, or a plain DNAStringSet
+    (non-preprocessed dictionary: any letters, any widths, mismatches anywhere)."""
     return _match_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, MATCHES_AS_ENDS,
-                        "matchPDict")
+                        "matchPDict", with_indels, algorithm)
 
 
-def countPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True):
+def countPDict(pdict, subject, max_mismatch=0, min_mismatch=0, with_indels=False, fixed=True,
+               algorithm="auto"):
     """-> int32[length(pdict)] (R/matchPDict.R:664-709)."""
     return _match_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, MATCHES_AS_COUNTS,
-                        "countPDict")
+                        "countPDict", with_indels, algorithm)
 
 
-def whichPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True):
+def whichPDict(pdict, subject, max_mismatch=0, min_mismatch=0, with_indels=False, fixed=True,
+               algorithm="auto"):
     """-> ascending 1-based indices of the patterns with a match (R/matchPDict.R:716-761)."""
     return _match_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, MATCHES_AS_WHICH,
-                        "whichPDict")
+                        "whichPDict", with_indels, algorithm)
 
 
 # ---- .vmatchPDict (R/matchPDict.R:514-605) ---------------------------------------------------------
@@ -304,9 +451,52 @@ def _vsubject_to_device(subject, what):
     return DeviceSubject.from_set(subject), True
 
 
-def _vmatch_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, collapse, weight, mode, what):
+def _vmatch_plain(pset, subject, max_mismatch, min_mismatch, with_indels, fixed, algorithm,
+                  collapse, weight, mode, what):
+    """.vmatch.XStringSet (R/matchPDict.R:502-511) behind .vmatchPDict (:514-605)."""
+    dsubj, owned = _vsubject_to_device(subject, what)
+    pat = None
+    try:
+        N, M = dsubj.length, len(pset)
+        max_mismatch = normarg_max_mismatch(max_mismatch)
+        min_mismatch = normarg_min_mismatch(min_mismatch, max_mismatch)
+        fixed = normarg_fixed(fixed)
+        if mode == MATCHES_AS_COUNTS:
+            collapse = normarg_collapse(collapse)
+            weight = np.atleast_1d(np.asarray(weight))
+            if collapse == 1:
+                weight = np.resize(weight, N)
+            elif collapse == 2:
+                weight = np.resize(weight, M)
+        else:
+            collapse = 0
+        _check_plain_args(pset, max_mismatch, min_mismatch, with_indels, fixed, algorithm, mode)
+        pat = PlainPatterns(pset)
+        ans = vmatch_parts([pat], dsubj, max_mismatch, min_mismatch, fixed, collapse, weight, mode)
+    finally:
+        if pat is not None:
+            pat.close()
+        if owned:
+            dsubj.close()
+    if mode == MATCHES_AS_WHICH:
+        offsets, ids = ans
+        return [ids[offsets[j]:offsets[j + 1]] for j in range(N)]
+    if collapse == 0:
+        ans = ans.reshape((M, N), order="F")
+    return ans
+
+
+def _vmatch_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, collapse, weight, mode, what,
+                  with_indels=False, algorithm="auto"):
     if not isinstance(pdict, PDict):
-        raise ValueError("'pdict' must be a PDict or XStringSet object")
+        pset = _as_plain_set(pdict)
+        if pset is None:
+            raise ValueError("'pdict' must be a PDict or XStringSet object")
+        return _vmatch_plain(pset, subject, max_mismatch, min_mismatch, with_indels, fixed,
+                             algorithm, collapse, weight, mode, what)
+    if normarg_with_indels(with_indels):
+        raise ValueError("at the moment, matchPDict() and family only support indels "
+                         "on a non-preprocessed pattern dictionary, sorry")
     dsubj, owned = _vsubject_to_device(subject, what)
     try:
         N, M = dsubj.length, len(pdict)
@@ -362,19 +552,20 @@ def _vmatch_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, collapse, w
     return ans
 
 
-def vcountPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True,
-                collapse=False, weight=1):
+def vcountPDict(pdict, subject, max_mismatch=0, min_mismatch=0, with_indels=False, fixed=True,
+                algorithm="auto", collapse=False, weight=1):
     """-> int matrix [length(pdict), length(subject)], or a collapsed vector
     (R/matchPDict.R:819-861)."""
     return _vmatch_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, collapse, weight,
-                         MATCHES_AS_COUNTS, "countPDict")
+                         MATCHES_AS_COUNTS, "countPDict", with_indels, algorithm)
 
 
-def vwhichPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True):
+def vwhichPDict(pdict, subject, max_mismatch=0, min_mismatch=0, with_indels=False, fixed=True,
+                algorithm="auto"):
     """-> list (one per subject) of ascending 1-based pattern indices
     (R/matchPDict.R:867-904)."""
     return _vmatch_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, False, 1,
-                         MATCHES_AS_WHICH, "whichPDict")
+                         MATCHES_AS_WHICH, "whichPDict", with_indels, algorithm)
 
 
 def vmatchPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True):

@@ -82,6 +82,17 @@ int bsgpu_pdict3parts_build(int algo, int32_t M,
 		const uint8_t *tail_concat, const int32_t *tail_widths,
 		const int32_t *pp_exclude, int32_t *high2low_out,
 		bsgpu_pdict3parts **out);
+/* Non-preprocessed dictionary: `pattern` is a plain XStringSet (any letters, any widths, no
+ * Trusted Band).  Replaces the `pattern` argument of match_XStringSet_XString,
+ * match_XStringSet_XStringViews and vmatch_XStringSet_XStringSet (src/match_pdict.c:174,267,519),
+ * which run one matchPattern() per pattern; all of the reference's algorithms report what its
+ * naive inexact one does (src/match_pattern.c:53-76), and so does this.  The handle is passed to
+ * bsgpu_match() / bsgpu_vmatch() (nparts = 1) like a PDict3Parts; with.indels is not supported.
+ * Errors: "empty patterns are not supported", "patterns with more than 20000 letters are not
+ * supported" (R/match-utils.R:47-52). */
+int bsgpu_patterns_build(const uint8_t *concat, const int32_t *widths, int32_t M,
+		bsgpu_pdict3parts **out);
+
 /* Replaces the head / tail of an existing index (both may be NULL = absent).  The reference
  * passes pdict_head / pdict_tail with every match call (src/match_pdict.c:153-171) while the
  * Trusted Band is preprocessed once; a C dispatch that built the index in build_Twobit /

@@ -73,6 +73,15 @@ def lib():
             [C.c_void_p, C.c_void_p, C.c_int] + [C.c_int] * 4 + \
             [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
         L.ref_mindex_endindex.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        if hasattr(L, "ref_match_set_xstring"):
+            L.ref_match_set_xstring.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + \
+                [C.c_int] * 5 + [C.c_char_p, C.c_int]
+            L.ref_match_set_views.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                              C.c_void_p, C.c_void_p, C.c_int] + [C.c_int] * 5 + \
+                [C.c_char_p, C.c_int]
+            L.ref_vmatch_set_set.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_int] + [C.c_int] * 5 + \
+                [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
         L.ref_result_length.restype = C.c_long
         L.ref_result_list_lengths.restype = C.c_long
         L.ref_result_list_lengths.argtypes = [C.c_void_p]
@@ -218,6 +227,44 @@ class RefPPTB:
                                     min_mismatch, int(fixed[0]), int(fixed[1]),
                                     collapse, int(is_double), _ptr(w), len(w), mode), self._lib)
         return _fetch_result(L=self._lib)
+
+
+# ---- the non-preprocessed dictionary path (src/match_pdict.c:174,267,519) ---------------------
+
+def match_set_xstring(pat_concat, pat_widths, subject, max_mismatch, min_mismatch, with_indels,
+                      fixed, algo, mode):
+    """match_XStringSet_XString: `pattern` is a plain XStringSet, one matchPattern per element."""
+    L = lib()
+    pc, pw, s = _u8(pat_concat), _i32(pat_widths), _u8(subject)
+    _check(L.ref_match_set_xstring(_ptr(pc), _ptr(pw), len(pw), _ptr(s), len(s), max_mismatch,
+                                   min_mismatch, int(with_indels), int(fixed[0]), int(fixed[1]),
+                                   algo.encode(), mode), L)
+    return _fetch_result(L=L)
+
+
+def match_set_views(pat_concat, pat_widths, subject, views_start, views_width, max_mismatch,
+                    min_mismatch, with_indels, fixed, algo, mode):
+    L = lib()
+    pc, pw, s = _u8(pat_concat), _i32(pat_widths), _u8(subject)
+    vs, vw = _i32(views_start), _i32(views_width)
+    _check(L.ref_match_set_views(_ptr(pc), _ptr(pw), len(pw), _ptr(s), len(s), _ptr(vs), _ptr(vw),
+                                 len(vs), max_mismatch, min_mismatch, int(with_indels),
+                                 int(fixed[0]), int(fixed[1]), algo.encode(), mode), L)
+    return _fetch_result(L=L)
+
+
+def vmatch_set_set(pat_concat, pat_widths, subj_concat, subj_widths, max_mismatch, min_mismatch,
+                   with_indels, fixed, algo, collapse, weight, mode):
+    L = lib()
+    pc, pw, sc, sw = _u8(pat_concat), _i32(pat_widths), _u8(subj_concat), _i32(subj_widths)
+    w = np.asarray(weight)
+    is_double = w.dtype.kind == "f"
+    w = np.ascontiguousarray(w, dtype=np.float64 if is_double else np.int32)
+    _check(L.ref_vmatch_set_set(_ptr(pc), _ptr(pw), len(pw), _ptr(sc), _ptr(sw), len(sw),
+                                max_mismatch, min_mismatch, int(with_indels), int(fixed[0]),
+                                int(fixed[1]), algo.encode(), collapse, int(is_double), _ptr(w),
+                                len(w), mode), L)
+    return _fetch_result(L=L)
 
 
 def stash_result():

@@ -47,13 +47,19 @@ SEXP match_PDict3Parts_XStringViews(SEXP pptb, SEXP pdict_head, SEXP pdict_tail,
 SEXP vmatch_PDict3Parts_XStringSet(SEXP pptb, SEXP pdict_head, SEXP pdict_tail,
 		SEXP subject, SEXP max_mismatch, SEXP min_mismatch, SEXP fixed,
 		SEXP collapse, SEXP weight, SEXP matches_as, SEXP envir);
+SEXP match_XStringSet_XString(SEXP pattern, SEXP subject, SEXP max_mismatch, SEXP min_mismatch,
+		SEXP with_indels, SEXP fixed, SEXP algorithm, SEXP matches_as, SEXP envir);
+SEXP match_XStringSet_XStringViews(SEXP pattern, SEXP subject, SEXP views_start, SEXP views_width,
+		SEXP max_mismatch, SEXP min_mismatch, SEXP with_indels, SEXP fixed,
+		SEXP algorithm, SEXP matches_as, SEXP envir);
+SEXP vmatch_XStringSet_XStringSet(SEXP pattern, SEXP subject, SEXP max_mismatch, SEXP min_mismatch,
+		SEXP with_indels, SEXP fixed, SEXP algorithm, SEXP collapse, SEXP weight,
+		SEXP matches_as, SEXP envir);
 SEXP ByPos_MIndex_endIndex(SEXP x_high2low, SEXP x_ends, SEXP x_width0);
 SEXP ByPos_MIndex_combine(SEXP ends_listlist);
 
 /* Out-of-scope Biostrings internals referenced by the compiled files (the
  * non-preprocessed dictionary path and SparseMIndex); never reached here. */
-void _match_pattern_XString(void) { Rf_error("ref_harness: matchPattern path is out of scope"); }
-void _match_pattern_XStringViews(void) { Rf_error("ref_harness: matchPattern path is out of scope"); }
 void _copy_CHARSXP_to_Chars_holder(void) { Rf_error("ref_harness: out of scope"); }
 void _new_CHARSXP_from_Chars_holder(void) { Rf_error("ref_harness: out of scope"); }
 void _get_val_from_env(void) { Rf_error("ref_harness: out of scope"); }
@@ -337,6 +343,71 @@ int ref_vmatch_set(void *pptb, int M,
 			Rf_ScalarInteger(max_mismatch), Rf_ScalarInteger(min_mismatch),
 			new_fixed(fixedP, fixedS),
 			Rf_ScalarInteger(collapse), w,
+			Rf_mkString(mode_name(mode)), R_NilValue);
+	GUARD_END(0, -1)
+}
+
+/* ---- the non-preprocessed dictionary path (pattern = plain XStringSet) ----- */
+
+/* match_XStringSet_XString, src/match_pdict.c:174 */
+int ref_match_set_xstring(const unsigned char *pat_concat, const int *pat_widths, int M,
+		const unsigned char *subject, int subject_length,
+		int max_mismatch, int min_mismatch, int with_indels, int fixedP, int fixedS,
+		const char *algo, int mode)
+{
+	GUARD_BEGIN
+	minir_set_generation(2);
+	result = match_XStringSet_XString(
+			new_set("DNAStringSet", M, pat_concat, pat_widths),
+			minir_new_XString("DNAString", (const char *) subject, subject_length),
+			Rf_ScalarInteger(max_mismatch), Rf_ScalarInteger(min_mismatch),
+			Rf_ScalarLogical(with_indels), new_fixed(fixedP, fixedS),
+			Rf_mkString(algo), Rf_mkString(mode_name(mode)), R_NilValue);
+	GUARD_END(0, -1)
+}
+
+/* match_XStringSet_XStringViews, src/match_pdict.c:267 */
+int ref_match_set_views(const unsigned char *pat_concat, const int *pat_widths, int M,
+		const unsigned char *subject, int subject_length,
+		const int *views_start, const int *views_width, int nviews,
+		int max_mismatch, int min_mismatch, int with_indels, int fixedP, int fixedS,
+		const char *algo, int mode)
+{
+	GUARD_BEGIN
+	minir_set_generation(2);
+	result = match_XStringSet_XStringViews(
+			new_set("DNAStringSet", M, pat_concat, pat_widths),
+			minir_new_XString("DNAString", (const char *) subject, subject_length),
+			new_int(nviews, views_start), new_int(nviews, views_width),
+			Rf_ScalarInteger(max_mismatch), Rf_ScalarInteger(min_mismatch),
+			Rf_ScalarLogical(with_indels), new_fixed(fixedP, fixedS),
+			Rf_mkString(algo), Rf_mkString(mode_name(mode)), R_NilValue);
+	GUARD_END(0, -1)
+}
+
+/* vmatch_XStringSet_XStringSet, src/match_pdict.c:519 */
+int ref_vmatch_set_set(const unsigned char *pat_concat, const int *pat_widths, int M,
+		const unsigned char *subject_concat, const int *subject_widths, int nsubject,
+		int max_mismatch, int min_mismatch, int with_indels, int fixedP, int fixedS,
+		const char *algo, int collapse, int weight_is_double, const void *weight,
+		int weight_length, int mode)
+{
+	SEXP w;
+
+	GUARD_BEGIN
+	minir_set_generation(2);
+	if (weight_is_double) {
+		w = NEW_NUMERIC(weight_length);
+		memcpy(REAL(w), weight, (size_t) weight_length * sizeof(double));
+	} else {
+		w = new_int(weight_length, weight);
+	}
+	result = vmatch_XStringSet_XStringSet(
+			new_set("DNAStringSet", M, pat_concat, pat_widths),
+			new_set("DNAStringSet", nsubject, subject_concat, subject_widths),
+			Rf_ScalarInteger(max_mismatch), Rf_ScalarInteger(min_mismatch),
+			Rf_ScalarLogical(with_indels), new_fixed(fixedP, fixedS),
+			Rf_mkString(algo), Rf_ScalarInteger(collapse), w,
 			Rf_mkString(mode_name(mode)), R_NilValue);
 	GUARD_END(0, -1)
 }

@@ -480,29 +480,234 @@ def _matchPDict(pdict, subject, max_mismatch, min_mismatch, fixed, mode):
     return ans
 
 
+# ---- non-preprocessed dictionaries: 'pdict' is a plain SeqSet ------------------------------------
+# R/matchPDict.R:170-191,215-236,262-285,379-398,502-511 over src/match_pdict.c:174,267,519
+
+def _valid_algos(widths, max_mismatch, min_mismatch, with_indels, fixed):
+    """.valid.algos, R/match-utils.R:36-71."""
+    if len(widths) and int(np.min(widths)) == 0:
+        raise ValueError("empty patterns are not supported")
+    if len(widths) and int(np.max(widths)) > 20000:
+        raise ValueError("patterns with more than 20000 letters are not supported")
+    if max_mismatch != 0 and with_indels:
+        if min_mismatch != 0:
+            raise ValueError("'min.mismatch' must be 0 when 'with.indels' is TRUE")
+        return ["indels"]
+    wmax = int(np.max(widths)) if len(widths) else 0
+    algos = []
+    if max_mismatch == 0 and all(fixed):
+        algos.append("boyer-moore")
+        if wmax <= 64:
+            algos.append("shift-or")
+        algos.append("naive-exact")
+    elif min_mismatch == 0 and fixed[0] == fixed[1] and wmax <= 64:
+        algos.append("shift-or")
+    return algos + ["naive-inexact"]
+
+
+def select_algo(algo, widths, max_mismatch, min_mismatch, with_indels, fixed):
+    """selectAlgo, R/match-utils.R:73-85."""
+    algos = _valid_algos(widths, max_mismatch, min_mismatch, with_indels, fixed)
+    if algo == "auto":
+        return algos[0]
+    if algo not in algos:
+        raise ValueError("valid algos for your string matching problem (best suited first): " +
+                         ", ".join(f'"{a}"' for a in algos))
+    return algo
+
+
+def _letters_match(p, s, fixedP, fixedS):
+    """src/lowlevel_matching.c:26-56 on the raw code bytes."""
+    if fixedP:
+        return p == s if fixedS else (p & ~s & 0xFF) == 0
+    return (~p & s & 0xFF) == 0 if fixedS else (p & s) != 0
+
+
+def naive_match_ends(P, S, max_nmis, min_nmis, fixedP, fixedS):
+    """Independent restatement of match_naive_inexact (src/match_pattern.c:53-76) over
+    _nmismatch_at_Pshift (src/lowlevel_matching.c:66-89): 1-based ends of the matches of
+    pattern P in subject S, out-of-limits letters counting as mismatches.  Pure Python:
+    small cases only."""
+    plen, slen = len(P), len(S)
+    if plen <= 0:
+        raise ValueError("empty pattern")
+    if max_nmis < plen - slen or min_nmis > plen:
+        return []
+    min_pshift = 1 - plen if plen <= max_nmis else -max_nmis
+    out = []
+    for pshift in range(min_pshift, slen - plen - min_pshift + 1):
+        nmis = 0
+        for i in range(plen):
+            j = pshift + i
+            if 0 <= j < slen and _letters_match(int(P[i]), int(S[j]), fixedP, fixedS):
+                continue
+            nmis += 1
+            if nmis > max_nmis:
+                break
+        if min_nmis <= nmis <= max_nmis:
+            out.append(pshift + plen)
+    return out
+
+
+def _plain_match(pset, subject, max_mismatch, min_mismatch, with_indels, fixed, algo, mode, backend):
+    """One subject (encoded bytes) or Views against a plain SeqSet; returns what the .Call
+    returns: counts int32[M] / which int32[] / list of ends (None for no match)."""
+    if backend == "ref":
+        from . import ref
+        if isinstance(subject, Views):
+            return ref.match_set_views(pset.concat, pset.widths, subject.subject, subject.start,
+                                       subject.width, max_mismatch, min_mismatch, with_indels,
+                                       fixed, algo, mode)
+        return ref.match_set_xstring(pset.concat, pset.widths, subject, max_mismatch,
+                                     min_mismatch, with_indels, fixed, algo, mode)
+    if with_indels:
+        raise NotImplementedError("indels are not restated")
+    ends = []
+    for i in range(len(pset)):
+        if isinstance(subject, Views):
+            e = []
+            L = len(subject.subject)
+            for st, w in zip(subject.start.tolist(), subject.width.tolist()):
+                if st - 1 < 0 or st - 1 + w > L:
+                    raise ValueError("'subject' has \"out of limits\" views")
+                e += [x + st - 1 for x in naive_match_ends(pset[i], subject.subject[st - 1:st - 1 + w],
+                                                           max_mismatch, min_mismatch, *fixed)]
+        else:
+            e = naive_match_ends(pset[i], subject, max_mismatch, min_mismatch, *fixed)
+        ends.append(np.array(e, dtype=np.int32) if e else None)
+    if mode == MATCHES_AS_ENDS:
+        return ends
+    counts = np.array([0 if e is None else len(e) for e in ends], dtype=np.int32)
+    if mode == MATCHES_AS_COUNTS:
+        return counts
+    return (np.flatnonzero(counts) + 1).astype(np.int32)
+
+
+def _plain_matchPDict(pset, subject, max_mismatch, min_mismatch, with_indels, fixed, algorithm,
+                      mode, backend):
+    """.matchPDict -> .match.XStringSet, R/matchPDict.R:400-453,380-398."""
+    if min_mismatch > max_mismatch:
+        raise ValueError("'min.mismatch' must be <= 'max.mismatch'")
+    fixed = normarg_fixed(fixed)
+    if isinstance(subject, Masked):
+        subject = subject.as_views()
+    elif not isinstance(subject, Views):
+        subject = encode(subject)
+    if with_indels and mode not in (MATCHES_AS_WHICH, MATCHES_AS_COUNTS):
+        raise ValueError("at the moment, within the matchPDict family, only countPDict(), "
+                         "whichPDict(), vcountPDict() and vwhichPDict() support indels")
+    algo = select_algo(algorithm, pset.widths, max_mismatch, min_mismatch, with_indels, fixed)
+    ans = _plain_match(pset, subject, max_mismatch, min_mismatch, with_indels, fixed, algo, mode,
+                       backend)
+    if mode == MATCHES_AS_ENDS:
+        return MIndex(pset.widths, ans, pset.names)
+    return ans
+
+
+def _plain_vmatchPDict(pset, subject, max_mismatch, min_mismatch, with_indels, fixed, algorithm,
+                       collapse, weight, mode, backend):
+    """.vmatchPDict -> .vmatch.XStringSet, R/matchPDict.R:514-605,502-511."""
+    if isinstance(subject, Views):
+        subject = _views_to_set(subject)
+    elif not isinstance(subject, SeqSet):
+        if isinstance(subject, (list, tuple)):
+            subject = SeqSet(list(subject))
+        else:
+            what = {MATCHES_AS_WHICH: "whichPDict", MATCHES_AS_COUNTS: "countPDict"}[mode]
+            raise ValueError(f"please use {what}() when 'subject' is an XString or "
+                             "MaskedXString object (single sequence)")
+    if min_mismatch > max_mismatch:
+        raise ValueError("'min.mismatch' must be <= 'max.mismatch'")
+    fixed = normarg_fixed(fixed)
+    M, N = len(pset), len(subject)
+    if mode == MATCHES_AS_COUNTS:
+        collapse = 0 if collapse is False else int(collapse)
+        if collapse not in (0, 1, 2):
+            raise ValueError("'collapse' must be FALSE, 1 or 2")
+        weight = np.atleast_1d(np.asarray(weight))
+        if collapse == 1:
+            weight = np.resize(weight, N)
+        elif collapse == 2:
+            weight = np.resize(weight, M)
+    else:
+        collapse, weight = 0, np.array([1])
+    algo = select_algo(algorithm, pset.widths, max_mismatch, min_mismatch, with_indels, fixed)
+    if backend == "ref":
+        from . import ref
+        ans = ref.vmatch_set_set(pset.concat, pset.widths, subject.concat, subject.widths,
+                                 max_mismatch, min_mismatch, with_indels, fixed, algo, collapse,
+                                 weight, mode)
+        if mode == MATCHES_AS_COUNTS and collapse == 0 and getattr(ans, "ndim", 0) == 1:
+            ans = ans.reshape((M, N), order="F")
+        if mode == MATCHES_AS_WHICH:
+            ans = [np.zeros(0, np.int32) if a is None else a for a in ans]
+        return ans
+    cnt = np.zeros((M, N), dtype=np.int64)
+    for i in range(M):
+        for j in range(N):
+            cnt[i, j] = len(naive_match_ends(pset[i], subject[j], max_mismatch, min_mismatch, *fixed))
+    if mode == MATCHES_AS_WHICH:
+        return [(np.flatnonzero(cnt[:, j]) + 1).astype(np.int32) for j in range(N)]
+    if collapse == 0:
+        return cnt.astype(np.int32)
+    # update_vcount_collapsed_ans, src/match_pdict.c:85-127, i outer / j inner
+    out = np.zeros(M if collapse == 1 else N, dtype=weight.dtype if weight.dtype.kind == "f" else np.int32)
+    for i in range(M):
+        for j in range(N):
+            if collapse == 1:
+                out[i] += cnt[i, j] * weight[j]
+            else:
+                out[j] += cnt[i, j] * weight[i]
+    return out
+
+
+def _plain_backend(pdict, backend):
+    if backend is not None:
+        return backend
+    from . import ref
+    return "ref" if ref.available() else "port"
+
+
 def _is_set(subject):
     return isinstance(subject, (SeqSet, list, tuple))
 
 
-def matchPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True):
+def _dispatch(pdict, subject, max_mismatch, min_mismatch, with_indels, fixed, algorithm, mode,
+              backend):
+    if isinstance(pdict, SeqSet):
+        return _plain_matchPDict(pdict, subject, max_mismatch, min_mismatch, with_indels, fixed,
+                                 algorithm, mode, _plain_backend(pdict, backend))
+    if with_indels:
+        raise ValueError("at the moment, matchPDict() and family only support indels "
+                         "on a non-preprocessed pattern dictionary, sorry")
+    return _matchPDict(pdict, subject, max_mismatch, min_mismatch, fixed, mode)
+
+
+def matchPDict(pdict, subject, max_mismatch=0, min_mismatch=0, with_indels=False, fixed=True,
+               algorithm="auto", backend=None):
     if _is_set(subject):             # R/matchPDict.R:631-636
         raise ValueError("please use vmatchPDict() when 'subject' is an XStringSet object "
                          "(multiple sequence)")
-    return _matchPDict(pdict, subject, max_mismatch, min_mismatch, fixed, MATCHES_AS_ENDS)
+    return _dispatch(pdict, subject, max_mismatch, min_mismatch, with_indels, fixed, algorithm,
+                     MATCHES_AS_ENDS, backend)
 
 
-def countPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True):
+def countPDict(pdict, subject, max_mismatch=0, min_mismatch=0, with_indels=False, fixed=True,
+               algorithm="auto", backend=None):
     if _is_set(subject):
         raise ValueError("please use vcountPDict() when 'subject' is an XStringSet object "
                          "(multiple sequence)")
-    return _matchPDict(pdict, subject, max_mismatch, min_mismatch, fixed, MATCHES_AS_COUNTS)
+    return _dispatch(pdict, subject, max_mismatch, min_mismatch, with_indels, fixed, algorithm,
+                     MATCHES_AS_COUNTS, backend)
 
 
-def whichPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True):
+def whichPDict(pdict, subject, max_mismatch=0, min_mismatch=0, with_indels=False, fixed=True,
+               algorithm="auto", backend=None):
     if _is_set(subject):
         raise ValueError("please use vwhichPDict() when 'subject' is an XStringSet object "
                          "(multiple sequence)")
-    return _matchPDict(pdict, subject, max_mismatch, min_mismatch, fixed, MATCHES_AS_WHICH)
+    return _dispatch(pdict, subject, max_mismatch, min_mismatch, with_indels, fixed, algorithm,
+                     MATCHES_AS_WHICH, backend)
 
 
 def _views_to_set(v):
@@ -583,13 +788,22 @@ def _vmatchPDict(pdict, subject, max_mismatch, min_mismatch, fixed, collapse, we
     return ans
 
 
-def vcountPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True,
-                collapse=False, weight=1):
+def vcountPDict(pdict, subject, max_mismatch=0, min_mismatch=0, with_indels=False, fixed=True,
+                algorithm="auto", collapse=False, weight=1, backend=None):
+    if isinstance(pdict, SeqSet):
+        return _plain_vmatchPDict(pdict, subject, max_mismatch, min_mismatch, with_indels, fixed,
+                                  algorithm, collapse, weight, MATCHES_AS_COUNTS,
+                                  _plain_backend(pdict, backend))
     return _vmatchPDict(pdict, subject, max_mismatch, min_mismatch, fixed, collapse,
                         weight, MATCHES_AS_COUNTS)
 
 
-def vwhichPDict(pdict, subject, max_mismatch=0, min_mismatch=0, fixed=True):
+def vwhichPDict(pdict, subject, max_mismatch=0, min_mismatch=0, with_indels=False, fixed=True,
+                algorithm="auto", backend=None):
+    if isinstance(pdict, SeqSet):
+        return _plain_vmatchPDict(pdict, subject, max_mismatch, min_mismatch, with_indels, fixed,
+                                  algorithm, False, 1, MATCHES_AS_WHICH,
+                                  _plain_backend(pdict, backend))
     return _vmatchPDict(pdict, subject, max_mismatch, min_mismatch, fixed, False, 1,
                         MATCHES_AS_WHICH)
 

@@ -162,3 +162,36 @@ def test_known_answer_oligo_frequency(be):
                 idx = idx * 4 + code[b]
             want[idx] += 1
     assert R.countPDict(pd, x).tolist() == want.tolist()
+
+
+def test_plain_dictionary_known_answers(be):
+    """Non-preprocessed dictionaries (one matchPattern per pattern): the golden vectors of
+    tests/testthat/test-matchPattern.R:55-125 and test-matchPDict.R:15-17, through
+    matchPDict(DNAStringSet, ...)."""
+    dna = "ATGCATGCATGC"
+
+    def se(pat, subject, **kw):
+        m = R.matchPDict(R.SeqSet([pat]), subject, backend=be, **kw)
+        s, e = m.startIndex()[0], m.endIndex()[0]
+        return ([] if s is None else s.tolist(), [] if e is None else e.tolist())
+
+    algos = ["naive-exact", "naive-inexact", "boyer-moore", "shift-or"] if be == "ref" else ["auto"]
+    for algo in algos:
+        assert se("ATG", dna, algorithm=algo) == ([1, 5, 9], [3, 7, 11])
+        assert se("ATG", R.Masked(dna, [2, 9], [4, 11]), algorithm=algo) == ([5], [7])
+        assert se("ATG", R.Views(dna, [2, 9], [3, 3]), algorithm=algo) == ([9], [11])
+    assert se("ATC", dna, max_mismatch=2) == ([1, 2, 5, 6, 9, 10], [3, 4, 7, 8, 11, 12])
+    assert se("ATC", dna, max_mismatch=2, min_mismatch=2) == ([2, 6, 10], [4, 8, 12])
+    dna2 = "ACGTNMRWSYKVHDB"
+    assert se("GTN", dna2, fixed=True) == ([3], [5])
+    assert se("GTN", dna2, fixed=False) == ([3, 7, 9, 12], [5, 9, 11, 14])
+    assert se("---", "ACGTGCA", max_mismatch=3) == (list(range(-1, 8)), list(range(1, 10)))
+    assert se("---", "A") == ([], [])
+    assert se("ATA", "ATGGATACACAA") == ([5], [7])                  # test-matchPDict.R:15-17
+    with pytest.raises(ValueError, match="valid algos for your string matching problem"):
+        se("ATG", dna, algorithm="indels")
+    with pytest.raises(ValueError, match="empty patterns are not supported"):
+        se("", dna)
+    # vcountPattern("TG", Views) = c(1, 1)   (test-matchPattern.R:148)
+    v = R.Views(dna, [2, 9], [3, 3])
+    assert R.vcountPDict(R.SeqSet(["TG"]), v, backend=be).tolist() == [[1, 1]]
