@@ -128,12 +128,54 @@ def c5(scale):
     return {"config": "C5 (one of 8 shards)", "letters": n, "patterns": M, "pdict_build_s": t_build, **out}
 
 
+def p1(scale):
+    """Non-preprocessed dictionary: 1000 patterns of 15-40 letters, 2 % IUPAC
+    letters, countPDict(max.mismatch=2, fixed=FALSE) against 10 Mbp; the reference's own loop
+    (one matchPattern per pattern) is timed on one host core over 20 patterns."""
+    n = int(10e6 * scale)
+    M = max(20, int(1000 * scale))
+    g = np.random.Generator(np.random.PCG64(11))
+    subj = synth.subject_region(0, n, n, seed=12, with_n=False)
+    widths = g.integers(15, 41, M)
+    pats = []
+    for w in widths.tolist():
+        st = int(g.integers(0, n - w))
+        q = subj[st:st + w].copy()
+        amb = g.random(w) < 0.02
+        q[amb] = np.array([15, 3, 5, 10], dtype=np.uint8)[g.integers(0, 4, int(amb.sum()))]
+        pats.append(q)
+    pset = bs.DNAStringSet(pats)
+    ds = mp.DeviceSubject.from_xstring(subj)
+    out = {}
+    for mm, fixed in ((0, True), (2, False)):
+        c, dt = timed(lambda: bs.countPDict(pset, ds, max_mismatch=mm, fixed=fixed), 2)
+        out[f"mm{mm}_fixed{fixed}"] = {"seconds": dt, "Gbp_s": n / dt / 1e9,
+                                       "pattern_x_letters_per_s": M * n / dt,
+                                       "matches": int(c.sum()), "plan": L.bsgpu_last_plan().decode()}
+    cpu = None
+    try:
+        from oracle import ref, rlevel as R
+        if ref.available():
+            k = 20
+            oset = R.SeqSet(pats[:k])
+            t0 = time.perf_counter()
+            want = R.countPDict(oset, subj, max_mismatch=2, fixed=False, backend="ref")
+            dt = time.perf_counter() - t0
+            got = bs.countPDict(bs.DNAStringSet(pats[:k]), ds, max_mismatch=2, fixed=False)
+            cpu = {"patterns": k, "seconds": dt, "pattern_x_letters_per_s": k * n / dt,
+                   "algo": "shift-or (auto)", "cores": 1, "parity_with_gpu": bool((got == want).all())}
+    except Exception as e:                                      # noqa: BLE001
+        cpu = {"error": str(e)}
+    return {"config": "P1 (non-preprocessed dictionary)", "letters": n, "patterns": M, **out,
+            "cpu_reference": cpu}
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--only", default="C3,C3p,C4,C5")
+    ap.add_argument("--only", default="C3,C3p,C4,C5,P1")
     a = ap.parse_args()
-    todo = {"C3": c3, "C3p": c3prime, "C4": c4, "C5": c5}
+    todo = {"C3": c3, "C3p": c3prime, "C4": c4, "C5": c5, "P1": p1}
     for name in a.only.split(","):
         t0 = time.perf_counter()
         res = todo[name](a.scale)
