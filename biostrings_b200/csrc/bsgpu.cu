@@ -1324,8 +1324,6 @@ struct Workspace {
 	DevBuf<long long> ovf;                  // windows with too many IUPAC expansions
 	DevBuf<int64_t> slot_off;               // plain dictionaries: first slot of every segment
 	BsgpuPlainView plain = {};              // view of the last plain scan (for finalize_ends_kernel)
-	DevBuf<unsigned long long> bs_cand;     // byte-seed scan: candidate slices, one per block
-	DevBuf<int32_t> bs_ncand;
 	DevBuf<uint8_t> cub_temp;
 	unsigned long long *h_counters = nullptr;       // pinned
 	int *h_flags = nullptr;
@@ -1455,43 +1453,31 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 				int np = bi->t.s <= 11 ? 8 : (bi->t.s <= 23 ? 4 : 2);
 				if (env_np != nullptr && (atoi(env_np) == 4 || atoi(env_np) == 2) && atoi(env_np) < np)
 					np = atoi(env_np);
-				size_t smem = 8 * (size_t) BSGPU_BYTESEED_STAGES * byteseed_stage_bytes(np, bi->t.s);
+				size_t smem = (size_t) BSGPU_BYTESEED_SCAN_WARPS * BSGPU_BYTESEED_STAGES * byteseed_stage_bytes(np, bi->t.s);
 				int per_sm = 1;
 #define PREPARE_BYTESEED(NP) do { \
 	static bool attr_set = false; \
 	if (!attr_set) { \
 		CUDA_TRY(cudaFuncSetAttribute(scan_byteseed_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-			8 * BSGPU_BYTESEED_STAGES * (int) byteseed_stage_bytes(NP, NP == 8 ? 11 : (NP == 4 ? 23 : 32)))); \
+			BSGPU_BYTESEED_SCAN_WARPS * BSGPU_BYTESEED_STAGES * (int) byteseed_stage_bytes(NP, NP == 8 ? 11 : (NP == 4 ? 23 : 32)))); \
 		attr_set = true; \
 	} \
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_byteseed_kernel<NP>, 256, smem)); \
 } while (0)
 				if (np == 8) PREPARE_BYTESEED(8); else if (np == 4) PREPARE_BYTESEED(4); else PREPARE_BYTESEED(2);
 #undef PREPARE_BYTESEED
-				int grid = grid_for((nprobes + np - 1) / np, 256, std::max(per_sm, 1));
-				int64_t tiles_per_block = ((nprobes + np * 256 - 1) / (np * 256) + grid - 1) / grid + 1;
-				// candidate slices: 1/8 of the probes a block sees (typical: ~1 %)
-				int32_t cap = (int32_t) std::max<int64_t>(1024, tiles_per_block * np * 256 / 8);
-
-				if (ws->bs_cand.n < (size_t) grid * cap)
-					TRY(ws->bs_cand.alloc((size_t) grid * cap));
-				if (ws->bs_ncand.n < (size_t) grid)
-					TRY(ws->bs_ncand.alloc((size_t) grid));
+				// one tile per scan warp at least; the grid fills the device once
+				int64_t ntile = (nprobes + (int64_t) np * 32 - 1) / ((int64_t) np * 32);
+				int grid = (int) std::max<int64_t>(1, std::min<int64_t>(
+					(ntile + BSGPU_BYTESEED_SCAN_WARPS - 1) / BSGPU_BYTESEED_SCAN_WARPS,
+					(int64_t) g_num_sms * std::max(per_sm, 1)));
 #define LAUNCH_BYTESEED(NP) \
-	scan_byteseed_kernel<NP><<<grid, 256, smem, st>>>(S, bi->t, R, first, nprobes, end_lo, end_hi, \
-							  ws->bs_cand.p, ws->bs_ncand.p, cap)
+	scan_byteseed_kernel<NP><<<grid, 256, smem, st>>>(S, bi->t, R, first, nprobes, end_lo, end_hi)
 				{
 					KernelTimer kt("scan_byteseed_kernel", st);
 					if (np == 8) LAUNCH_BYTESEED(8); else if (np == 4) LAUNCH_BYTESEED(4); else LAUNCH_BYTESEED(2);
 				}
 #undef LAUNCH_BYTESEED
-				g_launches++;
-				CUDA_TRY(cudaGetLastError());
-				{
-					KernelTimer kt("confirm_byteseed_kernel", st);
-					confirm_byteseed_kernel<<<dim3(grid, 4), 256, 0, st>>>(S, bi->t, R, end_lo, end_hi,
-							ws->bs_cand.p, ws->bs_ncand.p, cap);
-				}
 				g_launches++;
 				CUDA_TRY(cudaGetLastError());
 			}
@@ -1940,7 +1926,7 @@ static void count_block_free(void *p)
 		if (g_count_live[i].first == p) {
 			auto blk = g_count_live[i];
 			g_count_live.erase(g_count_live.begin() + i);
-			if (g_count_blocks.size() < 4) {
+			if (g_count_blocks.size() < 8) {
 				g_count_blocks.push_back(blk);
 				return;
 			}
@@ -1956,7 +1942,7 @@ extern "C" void bsgpu_result_free(bsgpu_result *res)
 	count_block_free(res->counts);
 	free(res->dcounts);
 	free(res->which);
-	free(res->ends_offsets);
+	count_block_free(res->ends_offsets);
 	free(res->ends);
 	memset(res, 0, sizeof(*res));
 }
@@ -2071,7 +2057,9 @@ extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
 		CUDA_TRY(cudaStreamSynchronize(st));
 		if (matches_as == BSGPU_MATCHES_AS_ENDS) {
 			res->n_rows = M;
-			res->ends_offsets = (int64_t *) malloc(((size_t) M + 1) * sizeof(int64_t));
+			res->ends_offsets = (int64_t *) count_block_alloc(((size_t) M + 1) * sizeof(int64_t));
+			if (res->ends_offsets == nullptr)
+				return fail(BSGPU_ENOMEM, "out of host memory");
 			res->ends_offsets[0] = 0;
 			for (int32_t i = 0; i < M; i++)
 				res->ends_offsets[i + 1] = res->ends_offsets[i] + counts[i];

@@ -576,18 +576,25 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 		     :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// Probe g of the launch sits at concat index first + g * S.  Every warp runs its own
-// pipeline over tiles of NP * 32 consecutive probes: the letters under a tile
-// (NP * 32 * S + 20 bytes) are brought into the warp's shared-memory ring by one TMA bulk
-// copy, STAGES deep; lane l hashes the NP windows l, l + 32, ... of tile i while its NP
-// filter gathers of tile i - 1 are in flight, so the HBM stream, the hashing and the L2
-// gathers overlap and no block-wide barrier sits in the loop.
-// Probes the filter lets through (false positives, seed hits, matches: ~1 %) are appended
-// to the block's own slice of a candidate buffer and confirmed by confirm_byteseed_kernel,
-// one candidate per thread, so that the dependent table / pattern loads of the
-// confirmations never stall the scan.  A full slice falls back to confirming in place.
-// Dynamic shared memory: 8 warps * STAGES * byteseed_stage_bytes(NP, S).
+// Probe g of the launch sits at concat index first + g * S.  A block is SCAN_WARPS scan warps
+// and 8 - SCAN_WARPS confirm warps.
+// Scan warps: each runs its own pipeline over tiles of NP * 32 consecutive probes: the
+// letters under a tile (NP * 32 * S + 20 bytes) are brought into the warp's shared-memory
+// ring by one TMA bulk copy, STAGES deep; lane l hashes the NP windows l, l + 32, ... of
+// tile i while its NP filter gathers of tile i - 1 are in flight, so the HBM stream, the
+// hashing and the L2 gathers overlap and no block-wide barrier sits in the loop.
+// Probes the filter lets through (false positives, seed hits, matches: ~1 %) are pushed
+// into the block's candidate queue in shared memory.
+// Confirm warp: pops 32 candidates at a time and confirms them, one per lane, so that the
+// dependent table / pattern loads of the confirmations (two DRAM misses each) overlap the
+// scan instead of following it.  Producers never wait: when the queue is nearly full they
+// confirm their candidate themselves.
+// Dynamic shared memory: 7 warps * STAGES * byteseed_stage_bytes(NP, S).
 #define BSGPU_BYTESEED_STAGES 3
+#ifndef BSGPU_BYTESEED_SCAN_WARPS
+#define BSGPU_BYTESEED_SCAN_WARPS 6
+#endif
+#define BSGPU_BYTESEED_QUEUE 1024
 
 __host__ __device__ __forceinline__ uint32_t byteseed_stage_bytes(int np, int s)
 {
@@ -597,21 +604,78 @@ __host__ __device__ __forceinline__ uint32_t byteseed_stage_bytes(int np, int s)
 template <int NP>
 __global__ void __launch_bounds__(256, NP == 8 ? 2 : 4)
 scan_byteseed_kernel(BsgpuSubjectView S, BsgpuByteSeedView T, BsgpuReport R, int64_t first,
-		     int64_t nprobes, int64_t own_lo, int64_t own_hi,
-		     unsigned long long *__restrict__ cand, int32_t *__restrict__ ncand_out, int32_t cap)
+		     int64_t nprobes, int64_t own_lo, int64_t own_hi)
 {
-	constexpr int STAGES = BSGPU_BYTESEED_STAGES;
+	constexpr int STAGES = BSGPU_BYTESEED_STAGES, NSCAN = BSGPU_BYTESEED_SCAN_WARPS;
+	constexpr unsigned int QCAP = BSGPU_BYTESEED_QUEUE;
 	extern __shared__ __align__(128) uint8_t byteseed_smem[];
-	__shared__ __align__(8) uint64_t bars[8][STAGES];
-	__shared__ int ncand;
+	__shared__ __align__(8) uint64_t bars[NSCAN][STAGES];
+	__shared__ unsigned long long queue[QCAP];      // 0 = slot not written yet
+	constexpr int NCONF = 8 - NSCAN;
+	// q_heads[j]: first slot of the next batch confirm warp j will take (everything below the
+	// smallest of them has been consumed); q_tail: slots reserved; q_done: scan warps finished
+	__shared__ unsigned int q_heads[NCONF], q_tail, q_done;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+	for (unsigned int i = threadIdx.x; i < QCAP; i += blockDim.x)
+		queue[i] = 0ull;
+	if (threadIdx.x == 0) {
+		for (int j = 0; j < NCONF; j++)
+			q_heads[j] = 32u * j;
+		q_tail = 0;
+		q_done = 0;
+	}
+	__syncthreads();                // the only block-wide barrier
+
+	if (warp >= NSCAN) {
+		// ---- confirm warps: warp j takes the batches j, j + NCONF, ... of 32 queue slots ----
+		const int j = warp - NSCAN;
+		for (unsigned int k = j;; k += NCONF) {
+			const unsigned int lo = 32u * k;
+			unsigned int n;
+
+			for (;;) {
+				unsigned int done = *(volatile unsigned int *) &q_done;
+				unsigned int tail = *(volatile unsigned int *) &q_tail;
+
+				if (tail - lo >= 32u && tail >= lo) {
+					n = 32u;
+					break;
+				}
+				if (done == NSCAN) {
+					n = tail > lo ? tail - lo : 0u;
+					break;
+				}
+				__nanosleep(256);
+			}
+			if (n == 0u)
+				break;
+			unsigned long long c = 0ull;
+			if ((unsigned int) lane < n) {
+				volatile unsigned long long *slot = &queue[(lo + lane) % QCAP];
+				while ((c = *slot) == 0ull)
+					;               // reserved, about to be written
+				*slot = 0ull;
+			}
+			__syncwarp();
+			if (lane == 0)
+				*(volatile unsigned int *) &q_heads[j] = lo + 32u * NCONF;      // my next batch
+			if ((unsigned int) lane < n)
+				byteseed_confirm(S, T, R, c, own_lo, own_hi);
+			__syncwarp();
+			if (n < 32u)
+				break;
+		}
+		return;
+	}
+
+	// ---- scan warps ----
 	const int64_t tile = (int64_t) NP * 32;
 	const int64_t ntiles = (nprobes + tile - 1) / tile;
-	const int64_t gw = (int64_t) blockIdx.x * 8 + warp, nwarps = (int64_t) gridDim.x * 8;
+	const int64_t gw = (int64_t) blockIdx.x * NSCAN + warp, nwarps = (int64_t) gridDim.x * NSCAN;
 	const uint32_t stage_bytes = byteseed_stage_bytes(NP, T.s);
 	uint8_t *ring = byteseed_smem + (size_t) warp * STAGES * stage_bytes;
 	uint64_t *bar = bars[warp];
-	unsigned long long *my_cand = cand + (int64_t) blockIdx.x * cap;
 
 	// tile tl -> (first byte, 16-byte aligned source, bytes to copy)
 	auto issue = [&](int64_t tl, int stage) {
@@ -622,7 +686,7 @@ scan_byteseed_kernel(BsgpuSubjectView S, BsgpuByteSeedView T, BsgpuReport R, int
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 		tma_load_1d(ring + (size_t) stage * stage_bytes, S.bytes + base16, nbytes, &bar[stage]);
 	};
-	// filter verdicts of a tile -> candidate slice
+	// filter verdicts of a tile -> candidate queue
 	auto emit = [&](const uint4 (&b)[NP], const uint32_t (&xs)[NP], uint32_t live, int64_t b0) {
 		uint32_t rare = 0;
 #pragma unroll
@@ -643,26 +707,31 @@ scan_byteseed_kernel(BsgpuSubjectView S, BsgpuByteSeedView T, BsgpuReport R, int
 				x = q == k ? xs[k] : x;
 
 			rare &= rare - 1;
-			int slot = atomicAdd(&ncand, 1);
-			if (slot < cap)
-				my_cand[slot] = byteseed_candidate(p, x);
-			else            // slice full: right away
+			// at most 224 producers sit between this check and their reservation
+			unsigned int consumed = *(volatile unsigned int *) &q_heads[0];
+#pragma unroll
+			for (int j = 1; j < NCONF; j++)
+				consumed = min(consumed, *(volatile unsigned int *) &q_heads[j]);
+			// slots below consumed - 32 * (NCONF - 1) are free for sure
+			if (*(volatile unsigned int *) &q_tail + 32u * NCONF - consumed < QCAP - 256u) {
+				unsigned int slot = atomicAdd(&q_tail, 1u);
+
+				*(volatile unsigned long long *) &queue[slot % QCAP] = byteseed_candidate(p, x);
+			} else {        // queue nearly full (dense hits): confirm right here
 				byteseed_confirm_now(S, T, R, byteseed_candidate(p, x), own_lo, own_hi);
+			}
 		}
 	};
 
-	if (threadIdx.x == 0)
-		ncand = 0;
 	if (lane == 0) {
 		for (int k = 0; k < STAGES; k++)
 			mbar_init(&bar[k], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	__syncthreads();
-	if (lane == 0)
 		for (int k = 0; k < STAGES; k++)
 			if (gw + k * nwarps < ntiles)
 				issue(gw + k * nwarps, k);
+	}
+	__syncwarp();
 
 	uint4 b[NP];
 	uint32_t xs[NP], live = 0, phase = 0;
@@ -711,22 +780,10 @@ scan_byteseed_kernel(BsgpuSubjectView S, BsgpuByteSeedView T, BsgpuReport R, int
 	}
 	if (have_prev)
 		emit(b, xs, live, prev_b0);
-	__syncthreads();
-	if (threadIdx.x == 0)
-		ncand_out[blockIdx.x] = min(ncand, cap);
-}
-
-// One candidate per thread; block k takes the slice scan block k filled.
-__global__ void __launch_bounds__(256)
-confirm_byteseed_kernel(BsgpuSubjectView S, BsgpuByteSeedView T, BsgpuReport R, int64_t own_lo,
-			int64_t own_hi, const unsigned long long *__restrict__ cand,
-			const int32_t *__restrict__ ncand, int32_t cap)
-{
-	const unsigned long long *my_cand = cand + (int64_t) blockIdx.x * cap;
-	int n = ncand[blockIdx.x];
-
-	for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x)
-		byteseed_confirm(S, T, R, my_cand[i], own_lo, own_hi);
+	__syncwarp();
+	__threadfence_block();          // queue writes before the "done" count
+	if (lane == 0)
+		atomicAdd(&q_done, 1u);
 }
 
 // ------------------------------------------------------------------------------------

@@ -247,7 +247,7 @@ const char *bsgpu_last_plan(void);
 int64_t bsgpu_launch_count(void);
 
 /* Opt-in timing of the hot kernels (pack_subject_kernel, scan_byteseed_kernel,
- * confirm_byteseed_kernel, scan_tb_kernel, qscan_kernel) with CUDA events recorded on the
+ * match_plain_kernel, scan_tb_kernel, qscan_kernel) with CUDA events recorded on the
  * launching stream.  bsgpu_kernel_timing(1) starts collecting (at most 8192 launches),
  * bsgpu_kernel_times() waits for them, writes up to max_entries (name, milliseconds) pairs in
  * launch order, forgets them and returns how many it wrote (-1 on error). */
