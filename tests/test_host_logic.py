@@ -172,3 +172,37 @@ def test_seed_shape_table_is_complete():
         for mm in itertools.combinations(range(m), k):
             bad = sum(1 << x for x in mm)
             assert any((pl & bad) == 0 for pl in placed), (m, k, mm)
+
+
+def test_plain_dictionary_argument_checks():
+    """selectAlgo / .valid.algos (R/match-utils.R:36-85) as mirrored on the host side, product and
+    oracle restatement alike; no device needed."""
+    from oracle import rlevel as R
+    w = np.array([5, 9, 70], dtype=np.int32)
+    for sel in (mp.select_algo, R.select_algo):
+        assert sel("auto", w[:2], 0, 0, False, (True, True)) == "boyer-moore"
+        assert sel("auto", w[:2], 1, 0, False, (True, True)) == "shift-or"
+        assert sel("auto", w, 1, 0, False, (True, True)) == "naive-inexact"          # > 64 letters
+        assert sel("auto", w[:2], 1, 1, False, (True, True)) == "naive-inexact"      # min.mismatch
+        assert sel("auto", w[:2], 1, 0, False, (True, False)) == "naive-inexact"     # fixed differs
+        assert sel("auto", w[:2], 0, 0, False, (False, False)) == "shift-or"
+        assert sel("auto", w[:2], 2, 0, True, (True, True)) == "indels"
+        assert sel("naive-exact", w[:2], 0, 0, False, (True, True)) == "naive-exact"
+        with pytest.raises(ValueError, match="valid algos for your string matching problem"):
+            sel("boyer-moore", w[:2], 1, 0, False, (True, True))
+        with pytest.raises(ValueError, match="'min.mismatch' must be 0 when 'with.indels' is TRUE"):
+            sel("auto", w[:2], 2, 1, True, (True, True))
+        with pytest.raises(ValueError, match="empty patterns are not supported"):
+            sel("auto", np.array([3, 0]), 0, 0, False, (True, True))
+        with pytest.raises(ValueError, match="more than 20000 letters"):
+            sel("auto", np.array([3, 20001]), 0, 0, False, (True, True))
+    assert mp.normarg_algorithm("shift") == "shift-or" and mp.normarg_algorithm("auto") == "auto"
+    with pytest.raises(ValueError):
+        mp.normarg_algorithm("naive")                 # ambiguous abbreviation
+    with pytest.raises(ValueError, match="TRUE or FALSE"):
+        mp.normarg_with_indels(1)
+    # the restatement of match_naive_inexact on the examples of R/matchPattern.R:183-185
+    enc = R.encode
+    assert R.naive_match_ends(enc("TG"), enc("GTGACGTGCAT"), 0, 0, True, True) == [3, 8]
+    assert R.naive_match_ends(enc("---"), enc("ACGTGCA"), 3, 0, True, True) == list(range(1, 10))
+    assert R.naive_match_ends(enc("---"), enc("A"), 0, 0, True, True) == []
