@@ -14,9 +14,11 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "../../include/bsgpu.h"
 #include "bsgpu_qindex.cuh"
@@ -1898,51 +1900,72 @@ static int bits_for(unsigned long long v)
 	return b;
 }
 
-// Count vectors of results are recycled: a fresh 4 MB malloc() is mmap-backed and costs a
-// page fault per page on first touch, which shows in the end-to-end time of a 5 ms call.
-static std::vector<std::pair<void *, size_t>> g_count_blocks;   // free blocks
-static std::vector<std::pair<void *, size_t>> g_count_live;     // handed out
+// The big vectors of a result (counts, CSR offsets) live in pinned host blocks that are
+// recycled between calls: the device -> host copy lands in them directly (no staging copy, no
+// page faults of a fresh mmap-backed malloc), which is a third of the time of a 250 Mbp call.
+struct HostBlock {
+	void *p;
+	size_t bytes;
+	bool pinned;
+};
+static std::vector<HostBlock> g_free_blocks, g_live_blocks;
 
-static void *count_block_alloc(size_t bytes)
+static void *result_block_alloc(size_t bytes)
 {
-	for (size_t i = 0; i < g_count_blocks.size(); i++)
-		if (g_count_blocks[i].second >= bytes && g_count_blocks[i].second <= 2 * bytes + 4096) {
-			auto blk = g_count_blocks[i];
-			g_count_blocks.erase(g_count_blocks.begin() + i);
-			g_count_live.push_back(blk);
-			return blk.first;
+	for (size_t i = 0; i < g_free_blocks.size(); i++)
+		if (g_free_blocks[i].bytes >= bytes && g_free_blocks[i].bytes <= 2 * bytes + 4096) {
+			HostBlock blk = g_free_blocks[i];
+			g_free_blocks.erase(g_free_blocks.begin() + i);
+			g_live_blocks.push_back(blk);
+			return blk.p;
 		}
-	void *p = malloc(bytes);
-	if (p != nullptr && bytes >= (1u << 16) && bytes <= (64u << 20))
-		g_count_live.push_back(std::make_pair(p, bytes));
-	return p;
+	HostBlock blk = {nullptr, bytes, false};
+	if (bytes >= (1u << 16) && bytes <= (256u << 20) &&
+	    cudaMallocHost(&blk.p, bytes) == cudaSuccess) {
+		blk.pinned = true;
+	} else {
+		cudaGetLastError();
+		blk.p = malloc(bytes);
+	}
+	if (blk.p != nullptr)
+		g_live_blocks.push_back(blk);
+	return blk.p;
 }
 
-static void count_block_free(void *p)
+static void result_block_free(void *p)
 {
 	if (p == nullptr)
 		return;
-	for (size_t i = 0; i < g_count_live.size(); i++)
-		if (g_count_live[i].first == p) {
-			auto blk = g_count_live[i];
-			g_count_live.erase(g_count_live.begin() + i);
-			if (g_count_blocks.size() < 8) {
-				g_count_blocks.push_back(blk);
+	for (size_t i = 0; i < g_live_blocks.size(); i++)
+		if (g_live_blocks[i].p == p) {
+			HostBlock blk = g_live_blocks[i];
+			g_live_blocks.erase(g_live_blocks.begin() + i);
+			if (blk.pinned && g_free_blocks.size() < 8) {
+				g_free_blocks.push_back(blk);
 				return;
 			}
-			break;
+			if (blk.pinned)
+				cudaFreeHost(p);
+			else
+				free(p);
+			return;
 		}
-	free(p);
+	free(p);                // not one of ours: plain malloc
 }
+
+// offsets[i] = counts[0] + ... + counts[i-1], i = 0..M (64-bit), on the device
+struct Int32To64 {
+	__host__ __device__ __forceinline__ int64_t operator()(const int32_t &v) const { return (int64_t) v; }
+};
 
 extern "C" void bsgpu_result_free(bsgpu_result *res)
 {
 	if (res == nullptr)
 		return;
-	count_block_free(res->counts);
+	result_block_free(res->counts);
 	free(res->dcounts);
 	free(res->which);
-	count_block_free(res->ends_offsets);
+	result_block_free(res->ends_offsets);
 	free(res->ends);
 	memset(res, 0, sizeof(*res));
 }
@@ -1984,11 +2007,19 @@ extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
 	MatchParams mp = {max_nmis, min_nmis, fixedP != 0, fixedS != 0};
 	int32_t M = parts[0]->M;
 	res->M = M;
-	DevBuf<int32_t> d_counts;
-	TRY(d_counts.alloc((size_t) M));
-	CUDA_TRY(cudaMemsetAsync(d_counts.p, 0, (size_t) std::max(M, 1) * sizeof(int32_t), st));
-	int32_t *counts = nullptr;              // pinned staging for the device -> host copy
-	TRY(host_counts(ws, (size_t) M, &counts));
+	DevBuf<int32_t> d_counts;               // one spare element: the CSR scan reads M + 1 items
+	TRY(d_counts.alloc((size_t) M + 1));
+	CUDA_TRY(cudaMemsetAsync(d_counts.p, 0, ((size_t) M + 1) * sizeof(int32_t), st));
+	int32_t *counts = nullptr;              // where the device -> host copy of the counts lands
+	if (matches_as == BSGPU_MATCHES_AS_COUNTS) {
+		res->counts = (int32_t *) result_block_alloc((size_t) std::max(M, 1) * sizeof(int32_t));
+		if (res->counts == nullptr)
+			return fail(BSGPU_ENOMEM, "out of host memory");
+		res->n_counts = M;
+		counts = res->counts;           // pinned: no staging copy
+	} else {
+		TRY(host_counts(ws, (size_t) M, &counts));
+	}
 
 	// q-gram engine when the dictionary is eligible (whole-pattern TB or MTB bands, base-only
 	// patterns of <= 64 letters, fixedS): same results, far fewer index probes
@@ -2054,27 +2085,32 @@ extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
 				CUDA_TRY(cudaMemcpyAsync(res->ends, d_ends.p, (size_t) nrec * sizeof(int32_t),
 							 cudaMemcpyDeviceToHost, st));
 		}
-		CUDA_TRY(cudaStreamSynchronize(st));
 		if (matches_as == BSGPU_MATCHES_AS_ENDS) {
+			// CSR offsets = exclusive scan of the counts, on the device, straight into the
+			// result's pinned block
+			DevBuf<int64_t> d_off;
+			size_t temp = 0;
+			thrust::transform_iterator<Int32To64, const int32_t *> in(d_counts.p, Int32To64());
+
+			TRY(d_off.alloc((size_t) M + 1));
+			CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, temp, in, d_off.p, M + 1, st));
+			if (temp > ws->cub_temp.n)
+				TRY(ws->cub_temp.alloc(temp));
+			CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws->cub_temp.p, temp, in, d_off.p, M + 1, st));
+			g_launches += 2;
 			res->n_rows = M;
-			res->ends_offsets = (int64_t *) count_block_alloc(((size_t) M + 1) * sizeof(int64_t));
+			res->ends_offsets = (int64_t *) result_block_alloc(((size_t) M + 1) * sizeof(int64_t));
 			if (res->ends_offsets == nullptr)
 				return fail(BSGPU_ENOMEM, "out of host memory");
-			res->ends_offsets[0] = 0;
-			for (int32_t i = 0; i < M; i++)
-				res->ends_offsets[i + 1] = res->ends_offsets[i] + counts[i];
+			CUDA_TRY(cudaMemcpyAsync(res->ends_offsets, d_off.p, ((size_t) M + 1) * sizeof(int64_t),
+						 cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaStreamSynchronize(st));
 			return BSGPU_OK;
 		}
+		CUDA_TRY(cudaStreamSynchronize(st));
 	}
-	if (matches_as == BSGPU_MATCHES_AS_COUNTS) {
-		res->counts = (int32_t *) count_block_alloc((size_t) std::max(M, 1) * sizeof(int32_t));
-		if (res->counts == nullptr)
-			return fail(BSGPU_ENOMEM, "out of host memory");
-		res->n_counts = M;
-		memcpy(res->counts, counts, (size_t) M * sizeof(int32_t));
-	} else {
+	if (matches_as != BSGPU_MATCHES_AS_COUNTS)
 		which_from_counts(res, counts, M);
-	}
 	return BSGPU_OK;
 }
 
