@@ -170,7 +170,7 @@ def run_reference(args):
     host cores (the reference is single-threaded: one process per core, each on its own
     slice of the subject; the index is built once per process, outside the timed part).
     A step is a bounded sample: the slice per core is sized so that warmup + steps together
-    spend about a minute matching."""
+    spend about a minute matching (the whole run ends within a few minutes)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -181,8 +181,8 @@ def run_reference(args):
     chrom_len = int(args.subject_mbp * 1e6)
     pats = synth.dictionary(args.patterns, WIDTH, chrom_len, 1)
     nsteps = args.warmup + args.steps
-    # ~4 Mbp/s per core; 60 s of matching in total
-    per_core = int(min(1e6, max(2e4, 60 * 4e6 / max(nsteps, 1))))
+    # 1-4 Mbp/s per core: about a minute of matching in total
+    per_core = int(min(1e6, max(2e4, 40 * 4e6 / max(nsteps, 1))))
     span = max(1, (chrom_len - 40_000) // (cores * per_core))    # distinct step windows available
     times = []
     ctx = mpc.get_context("fork")
