@@ -317,6 +317,7 @@ struct bsgpu_pdict3parts {
 	bool plain = false;
 	DevBuf<uint8_t> d_pat;
 	DevBuf<int64_t> d_pat_off;
+	DevBuf<uint4> d_pat_head;
 	uint32_t nbuckets = 0;
 	bool all_singletons = true;
 	DevBuf<uint4> d_table;
@@ -986,6 +987,18 @@ extern "C" int bsgpu_patterns_build(const uint8_t *concat, const int32_t *widths
 	if (off[M] > 0)
 		CUDA_TRY(cudaMemcpy(p3->d_pat.p, concat, (size_t) off[M], cudaMemcpyHostToDevice));
 	TRY(p3->d_pat_off.upload(off.data(), off.size()));
+	{
+		// {offset, length, first 4 letters} of every pattern: one 16-byte load per pair
+		std::vector<uint4> head((size_t) M);
+		for (int32_t i = 0; i < M; i++) {
+			uint32_t w0 = 0;
+			for (int d = 0; d < 4 && d < widths[i]; d++)
+				w0 |= (uint32_t) concat[off[i] + d] << (8 * d);
+			head[i] = make_uint4((uint32_t) off[i], (uint32_t) ((uint64_t) off[i] >> 32),
+					     (uint32_t) widths[i], w0);
+		}
+		TRY(p3->d_pat_head.upload(head.data(), head.size()));
+	}
 	*out = p3.release();
 	return BSGPU_OK;
 }
@@ -1552,13 +1565,20 @@ static int run_plain(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, con
 	BsgpuPlainView P = {};
 	P.pat = p3->d_pat.p;
 	P.pat_off = p3->d_pat_off.p;
+	P.pat_head = p3->d_pat_head.p;
 	P.M = p3->M;
 	P.slot_off = ws->slot_off.p;
 	P.ext = ext;
 	P.nslots = slot_off[n];
 	ws->plain = P;
 	set_plan("plain_bruteforce patterns=%d slots=%lld", p3->M, (long long) P.nslots);
-	dim3 grid((unsigned) grid_for(P.nslots, 256, 8), (unsigned) std::min(p3->M, 1024));
+	// x covers the slots once, y splits the patterns so that a thread amortises its slot set-up
+	// over ~64 patterns while the grid still fills the device for short subjects
+	long long xblocks = std::max<long long>(1, std::min<long long>((P.nslots + 255) / 256, 1 << 20));
+	long long want_y = std::max<long long>(1, (long long) g_num_sms * 16 / xblocks);
+	unsigned ysplit = (unsigned) std::max<long long>(want_y, std::min<long long>((p3->M + 63) / 64, 64));
+	ysplit = (unsigned) std::min<long long>(ysplit, std::max(p3->M, 1));
+	dim3 grid((unsigned) xblocks, ysplit);
 	for (;;) {
 		unsigned long long rec_before = 0, nrec = 0;
 

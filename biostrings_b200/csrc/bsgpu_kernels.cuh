@@ -612,8 +612,9 @@ verify_flanks_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R,
 // ------------------------------------------------------------------------------------
 
 struct BsgpuPlainView {
-	const uint8_t *pat;          // concatenated pattern letters
+	const uint8_t *pat;          // concatenated pattern letters (+8 readable bytes)
 	const int64_t *pat_off;      // [M+1]
+	const uint4 *pat_head;       // [M] {offset lo, offset hi, length, first 4 letters}
 	int32_t M;
 	const int64_t *slot_off;     // [nseg+1]
 	int32_t ext;
@@ -635,7 +636,31 @@ __device__ __forceinline__ int find_slot_segment(const BsgpuPlainView &P, int ns
 	return lo;
 }
 
-// blockIdx.x strides over the slots, blockIdx.y over the patterns
+// number of the 4 letter pairs of two words that do not match (src/lowlevel_matching.c:26-56,
+// four bytes at a time); bytes whose 'keep' byte is 0 are ignored
+__device__ __forceinline__ int mismatches4(uint32_t p, uint32_t s, uint32_t keep, int fixedP, int fixedS)
+{
+	uint32_t x = fixedP ? (fixedS ? p ^ s : p & ~s) : (fixedS ? ~p & s : p & s);
+	// 0x80 in every byte of x that is not 0
+	uint32_t nz = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+
+	if (!fixedP && !fixedS)
+		nz = ~nz & 0x80808080u;         // (p & s) != 0 is the match
+	return __popc(nz & keep);
+}
+
+// the 4 bytes at b (any alignment; b - 3 .. b + 7 readable) as a little-endian word
+__device__ __forceinline__ uint32_t load_word_unaligned(const uint8_t *b)
+{
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(b) & ~(uintptr_t) 3);
+
+	return __funnelshift_r(__ldg(w), __ldg(w + 1), 8u * (uint32_t) (reinterpret_cast<uintptr_t>(b) & 3));
+}
+
+// blockIdx.x strides over the slots, blockIdx.y over the patterns.  A thread keeps the first
+// 4 subject letters of its shift in a register; most (pattern, shift) pairs are rejected by
+// one broadcast 16-byte load of the pattern's header and one 4-letter compare.  Shifts that
+// hang over an end of the segment take the letter-by-letter path.
 __global__ void __launch_bounds__(256)
 match_plain_kernel(BsgpuSubjectView S, BsgpuPlainView P, BsgpuReport R, int max_nmis, int min_nmis,
 		   int fixedP, int fixedS)
@@ -648,15 +673,33 @@ match_plain_kernel(BsgpuSubjectView S, BsgpuPlainView P, BsgpuReport R, int max_
 		int64_t L = __ldg(S.seg_len + seg);
 		int64_t Pshift = slot - __ldg(P.slot_off + seg) - P.ext;
 		const uint8_t *s = S.bytes + __ldg(S.seg_start + seg);
+		// first 4 letters at this shift; only used when the whole pattern lies inside the
+		// segment (the separator / guard bytes after the segment make the read safe)
+		uint32_t s0 = Pshift >= 0 && Pshift <= L ? load_word_unaligned(s + Pshift) : 0u;
 
 		for (int i = blockIdx.y; i < P.M; i += gridDim.y) {
-			int64_t po = __ldg(P.pat_off + i);
-			int plen = (int) (__ldg(P.pat_off + i + 1) - po);
+			uint4 h = __ldg(P.pat_head + i);
+			int64_t po = (int64_t) h.x | ((int64_t) h.y << 32);
+			int plen = (int) h.z;
 			int64_t minP = plen <= max_nmis ? 1 - plen : -max_nmis;
+			int nmis;
 
 			if (Pshift < minP || Pshift + plen > L - minP)
 				continue;
-			int nmis = count_mismatches(P.pat + po, plen, s, L, Pshift, max_nmis, fixedP, fixedS);
+			if (Pshift >= 0 && Pshift + plen <= L) {
+				uint32_t keep = plen >= 4 ? 0x80808080u : (0x80808080u >> (8 * (4 - plen)));
+
+				nmis = mismatches4(h.w, s0, keep, fixedP, fixedS);
+				for (int j = 4; j < plen && nmis <= max_nmis; j += 4) {
+					int left = plen - j;
+
+					keep = left >= 4 ? 0x80808080u : (0x80808080u >> (8 * (4 - left)));
+					nmis += mismatches4(load_word_unaligned(P.pat + po + j),
+							    load_word_unaligned(s + Pshift + j), keep, fixedP, fixedS);
+				}
+			} else {
+				nmis = count_mismatches(P.pat + po, plen, s, L, Pshift, max_nmis, fixedP, fixedS);
+			}
 			if (nmis > max_nmis || nmis < min_nmis)
 				continue;
 			if (R.mode == BSGPU_R_COUNT)
