@@ -318,6 +318,7 @@ struct bsgpu_pdict3parts {
 	DevBuf<uint8_t> d_pat;
 	DevBuf<int64_t> d_pat_off;
 	DevBuf<uint4> d_pat_head;
+	int32_t max_plen = 0;
 	uint32_t nbuckets = 0;
 	bool all_singletons = true;
 	DevBuf<uint4> d_table;
@@ -975,11 +976,15 @@ extern "C" int bsgpu_patterns_build(const uint8_t *concat, const int32_t *widths
 			return fail(BSGPU_EINVAL, "patterns with more than 20000 letters are not supported");
 		off[i + 1] = off[i] + widths[i];
 	}
+	int32_t max_plen = 0;
+	for (int32_t i = 0; i < M; i++)
+		max_plen = std::max(max_plen, widths[i]);
 	if (off[M] > 0 && concat == nullptr)
 		return fail(BSGPU_EINVAL, "bsgpu_patterns_build(): bad arguments");
 	TRY(ensure_device());
 	std::unique_ptr<bsgpu_pdict3parts> p3(new bsgpu_pdict3parts());
 	p3->plain = true;
+	p3->max_plen = max_plen;
 	p3->M = M;
 	p3->w = 0;
 	p3->high2low.assign(M, BSGPU_NA);
@@ -1548,11 +1553,23 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 static int run_plain(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, const MatchParams &mp,
 		     BsgpuReport R, bool rec_based, Workspace *ws, cudaStream_t st)
 {
-	if (subj->kind == SUBJ_CHUNK)
-		return fail(BSGPU_EUNSUPPORTED, "non-preprocessed dictionaries on subject chunks are "
-			    "not supported yet (use a PDict object or the whole subject)");
 	if (p3->M == 0)
 		return BSGPU_OK;
+	int64_t own_lo = INT64_MIN, own_hi = INT64_MAX;
+	if (subj->kind == SUBJ_CHUNK) {
+		// a match is owned by the chunk that holds its last letter; everything the pattern
+		// touches before it must be in the halo (letters missing from a chunk are not
+		// mismatches: only the ends of the whole subject are out of limits)
+		int64_t need_l = (int64_t) p3->max_plen - 1;
+
+		if (subj->open_left && subj->halo_left < need_l)
+			return fail(BSGPU_EINVAL, "subject chunk has an insufficient halo: need %lld "
+				    "letters before and %lld after the report range", (long long) need_l, 0ll);
+		if (!subj->own_from_start)
+			own_lo = subj->scan_lo;
+		if (!subj->own_to_end)
+			own_hi = subj->scan_hi;
+	}
 	int32_t n = subj->nseg;
 	int ext = mp.max_nmis;
 	std::vector<int64_t> slot_off((size_t) n + 1, 0);
@@ -1570,6 +1587,8 @@ static int run_plain(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, con
 	P.slot_off = ws->slot_off.p;
 	P.ext = ext;
 	P.nslots = slot_off[n];
+	P.own_lo = own_lo;
+	P.own_hi = own_hi;
 	ws->plain = P;
 	set_plan("plain_bruteforce patterns=%d slots=%lld", p3->M, (long long) P.nslots);
 	// x covers the slots once, y splits the patterns so that a thread amortises its slot set-up

@@ -619,6 +619,7 @@ struct BsgpuPlainView {
 	const int64_t *slot_off;     // [nseg+1]
 	int32_t ext;
 	int64_t nslots;
+	int64_t own_lo, own_hi;      // subject chunks: concat index range of the owned match ends
 };
 
 __device__ __forceinline__ int find_slot_segment(const BsgpuPlainView &P, int nseg, int64_t slot)
@@ -685,6 +686,9 @@ match_plain_kernel(BsgpuSubjectView S, BsgpuPlainView P, BsgpuReport R, int max_
 			int nmis;
 
 			if (Pshift < minP || Pshift + plen > L - minP)
+				continue;
+			int64_t e_idx = (s - S.bytes) + Pshift + plen - 1;      // concat index of the last letter
+			if (e_idx < P.own_lo || e_idx >= P.own_hi)
 				continue;
 			if (Pshift >= 0 && Pshift + plen <= L) {
 				uint32_t keep = plen >= 4 ? 0x80808080u : (0x80808080u >> (8 * (4 - plen)));

@@ -200,3 +200,39 @@ def test_through_the_dot_call_boundary():
             ref.match_set_xstring(pc[:3], [3, 0], s, 0, 0, 0, (1, 1), "naive-exact", ref.MATCHES_AS_COUNTS)
     finally:
         ref.use("ref")
+
+
+def test_chunked_subject_equals_whole():
+    """Overlap chunks for a non-preprocessed dictionary: a match belongs to the chunk
+    holding its last letter; only the ends of the whole subject are out of limits."""
+    from biostrings_b200 import matchpdict as mp
+    g = rng(9600)
+    s = letters(g, 6000)
+    pats = [s[i:i + int(g.integers(3, 30))].copy() for i in g.integers(0, 5900, 60)]
+    pats += [s[:12].copy(), s[-12:].copy()]                # overhang both ends with mismatches
+    pset = bs.DNAStringSet(pats)
+    maxw = max(len(p) for p in pats)
+    pat = mp.PlainPatterns(pset)
+    try:
+        for mx, fixed in ((0, (True, True)), (3, (False, False))):
+            with mp.DeviceSubject.from_xstring(s) as whole:
+                want = mp.match_parts([pat], whole, mx, 0, fixed, _lib.MATCHES_AS_COUNTS)
+                wo, we = mp.match_parts([pat], whole, mx, 0, fixed, _lib.MATCHES_AS_ENDS)
+            bounds = [0, 1, 40, 2048, 2049, 5990, s.size]
+            got = np.zeros_like(want)
+            rows = [[] for _ in pats]
+            for lo, hi in zip(bounds[:-1], bounds[1:]):
+                a = max(0, lo - (maxw - 1))
+                with mp.DeviceSubject.from_chunk(s[a:hi], a, s.size, lo, hi) as ch:
+                    got += mp.match_parts([pat], ch, mx, 0, fixed, _lib.MATCHES_AS_COUNTS)
+                    o, e = mp.match_parts([pat], ch, mx, 0, fixed, _lib.MATCHES_AS_ENDS)
+                    for i in range(len(pats)):
+                        rows[i].extend(e[o[i]:o[i + 1]].tolist())
+            assert (got == want).all() and want.sum() > 60
+            for i in range(len(pats)):
+                assert rows[i] == we[wo[i]:wo[i + 1]].tolist()
+        with mp.DeviceSubject.from_chunk(s[1000:2000], 1000, s.size, 1000, 2000) as ch:
+            with pytest.raises(bs.BsgpuError, match="insufficient halo"):
+                mp.match_parts([pat], ch, 0, 0, (True, True), _lib.MATCHES_AS_COUNTS)
+    finally:
+        pat.close()
