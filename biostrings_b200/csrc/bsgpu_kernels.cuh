@@ -8,7 +8,11 @@
 //                         (replaces walk_tb_nonfixed_subject, match_pdict_ACtree2.c:1124-1157)
 //   verify_flanks_kernel  head/tail mismatch counting + fan-out to TB duplicates
 //                         (replaces _match_pdict_all_flanks, src/match_pdict_utils.c:809-915)
+//   match_plain_kernel    non-preprocessed dictionaries: every (segment, shift) x pattern
+//                         (replaces the matchPattern loop of match_XStringSet_XString & co,
+//                          src/match_pdict.c:174-199, src/match_pattern.c:53-110)
 //   finalize_ends_kernel  sorted records -> end coordinates
+// The exact whole-pattern scan and the q-gram (MTB) scan are in bsgpu_qindex.cuh.
 #pragma once
 #include <cooperative_groups.h>
 #include "bsgpu_common.cuh"

@@ -1,20 +1,22 @@
-// bsgpu_qindex.cuh -- q-gram seed index + whole-pattern Hamming verification.
+// bsgpu_qindex.cuh -- the two seed-index engines, used where the reference's answer does not
+// depend on HOW candidates are found:
 //
-// Used where the reference's answer does not depend on HOW candidates are found:
-//   * a TB_PDict whose Trusted Band is the whole pattern (exact matching): contiguous
-//     q-mers of every pattern at offsets 0..s-1 are indexed and the subject is probed only
-//     at every s-th position (s = width-q+1): an occurrence starting at a is met exactly
-//     once, at the probe position p = a + ((-a) mod s).
-//   * an MTB_PDict (max.mismatch = k >= 1): the union over its k+1 Trusted Bands
-//     (R/matchPDict.R:335-377, src/MIndex_class.c:230-263) is exactly the set of alignments
-//     with min <= #mismatches <= max (pigeonhole), so any complete filter for Hamming
-//     distance <= k gives the same result.  One gapped shape of weight q applied at a small
-//     set of shifts (tools/find_seed_shapes.py) needs ONE directory probe per subject
-//     position and |shifts|*M/4^q candidates, instead of k+1 probes and
-//     sum_b M/4^w_b candidates for the reference's short bands.
-// Every candidate is verified against the whole pattern on the packed planes
-// (XOR + popcount), with letters outside the segment and non-base subject letters counted
-// as mismatches (src/lowlevel_matching.c:79-86), so the result is exact.
+//   scan_byteseed_kernel  a TB_PDict whose Trusted Band is the whole pattern (exact matching,
+//       w >= 17): 16-letter seeds of every pattern at offsets 0..S-1 (S = w - 15) are indexed
+//       and the subject is probed only at every S-th position: an occurrence starting at a is
+//       met exactly once, at the probe position p = a + ((-a) mod S).  The seeds are hashed from
+//       the raw encoded bytes (TMA-staged tiles), filtered by a blocked Bloom filter and
+//       confirmed byte for byte by dedicated warps -- no packed planes.
+//   qscan_kernel  an MTB_PDict (max.mismatch = k >= 1): the union over its k+1 Trusted Bands
+//       (R/matchPDict.R:335-377, src/MIndex_class.c:230-263) is exactly the set of alignments
+//       with min <= #mismatches <= max (pigeonhole), so any complete filter for Hamming
+//       distance <= k gives the same result.  One gapped shape of weight q applied at a small
+//       set of shifts (tools/find_seed_shapes.py) needs ONE directory probe per subject
+//       position and |shifts|*M/4^q candidates, instead of k+1 probes and
+//       sum_b M/4^w_b candidates for the reference's short bands.  Every candidate is
+//       verified against the whole pattern on the packed planes (XOR + popcount), with
+//       letters outside the segment and non-base subject letters counted as mismatches
+//       (src/lowlevel_matching.c:79-86), so the result is exact.
 #pragma once
 #include "bsgpu_kernels.cuh"
 
