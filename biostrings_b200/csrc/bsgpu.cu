@@ -407,6 +407,8 @@ static bool pick_shape(int m, int k, SeedShape *out)
 //   nparts == 1: parts[0] must be a whole-pattern Trusted Band (no head, no tail)
 //   nparts  > 1: the components of an MTB_PDict (band b = letters [headw_b, headw_b+w_b))
 // Returns the cached index; ->ok tells whether the dictionary is eligible.
+static int bits_for(unsigned long long v);
+
 static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const QIndex **out)
 {
 	const bsgpu_pdict3parts *p0 = parts[0];
@@ -581,14 +583,42 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 		dir[k2 >> 2].y |= cnt[k2] << (8 * (k2 & 3));
 		run += cnt[k2];
 	}
+	// entry word = [fingerprint][pattern id][shift index]; the fingerprint is up to 4 pattern
+	// letters from outside the seed (the first positions of the window the shape, placed at
+	// that shift, does not cover): a cheap pre-check before the pattern is loaded
+	v.shift_bits = bits_for((unsigned long long) std::max(v.nshifts - 1, 1));
+	v.id_bits = bits_for((unsigned long long) std::max(M - 1, 1));
+	if (v.shift_bits + v.id_bits > 32)
+		return done();
+	v.nfp = std::min(4, (32 - v.shift_bits - v.id_bits) / 2);
+	for (int s2 = 0; s2 < v.nshifts; s2++) {
+		int found = 0;
+
+		v.fp_pos[s2] = 0;
+		for (int x = 0; x < std::min(v.min_w, 32) && found < 4; x++) {
+			int rel = x - v.shift[s2];
+			bool in_seed = rel >= 0 && rel < sh.span && ((sh.mask >> rel) & 1);
+
+			if (!in_seed)
+				v.fp_pos[s2] |= (uint32_t) x << (8 * found++);
+		}
+		v.nfp = std::min(v.nfp, found);
+	}
 	std::vector<uint32_t> entries(nent ? nent : 1);
 	for (int i = 0; i < M; i++) {
 		if (p0->excluded[i])
 			continue;
 		if (nparts == 1 && p0->is_tb_dup[i])
 			continue;
-		for (int s2 = 0; s2 < v.nshifts; s2++)
-			entries[start[seed_key(i, v.shift[s2])]++] = ((uint32_t) i << 5) | (uint32_t) s2;
+		for (int s2 = 0; s2 < v.nshifts; s2++) {
+			uint32_t fp = 0;
+
+			for (int f = 0; f < v.nfp; f++)
+				fp |= (uint32_t) ((pat[i].x >> (2 * ((v.fp_pos[s2] >> (8 * f)) & 0xFFu))) & 3u) << (2 * f);
+			entries[start[seed_key(i, v.shift[s2])]++] =
+				(v.nfp ? fp << (v.shift_bits + v.id_bits) : 0u) |
+				((uint32_t) i << v.shift_bits) | (uint32_t) s2;
+		}
 	}
 	TRY(qi->d_bitmap.upload(bitmap.data(), bitmap.size()));
 	v.bitmap = qi->d_bitmap.p;

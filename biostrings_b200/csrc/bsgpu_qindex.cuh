@@ -28,7 +28,7 @@
 struct BsgpuQIndexView {
 	const uint32_t *bitmap;      // [2^key_bits / 32] bit = some entry has this directory key
 	const uint2 *dir;            // [2^key_bits / 4] {base offset, 4 x u8 counts}
-	const uint32_t *entries;     // id << 5 | shift index, grouped by seed key
+	const uint32_t *entries;     // fp | id << shift_bits | shift index (see q_ent_*), grouped by seed key
 	const ulonglong2 *pat;       // [M] 2-bit packed pattern letters (<= 64)
 	const unsigned long long *pat8;      // [M] the low 32 letters only (patterns of <= 32 letters)
 	const uint8_t *pat_len;      // [M]
@@ -46,7 +46,26 @@ struct BsgpuQIndexView {
 	int32_t const_len;           // > 0: every pattern has this many letters
 	int32_t nshifts;
 	int32_t shift[BSGPU_Q_MAX_SHIFTS];   // ascending
+	// entry word: [fingerprint: 2 * nfp bits][pattern id: id_bits][shift index: shift_bits]
+	int32_t shift_bits, id_bits;
+	int32_t nfp;                 // 0..4 pattern letters outside the seed kept in the entry
+	uint32_t fp_pos[BSGPU_Q_MAX_SHIFTS]; // per shift index: their pattern positions, one byte each
 };
+
+__host__ __device__ __forceinline__ int q_ent_shift(const BsgpuQIndexView &Q, uint32_t ent)
+{
+	return (int) (ent & ((1u << Q.shift_bits) - 1u));
+}
+
+__host__ __device__ __forceinline__ int q_ent_id(const BsgpuQIndexView &Q, uint32_t ent)
+{
+	return (int) ((ent >> Q.shift_bits) & ((1u << Q.id_bits) - 1u));
+}
+
+__host__ __device__ __forceinline__ uint32_t q_ent_fp(const BsgpuQIndexView &Q, uint32_t ent)
+{
+	return Q.nfp ? ent >> (Q.shift_bits + Q.id_bits) : 0u;
+}
 
 // Directory key of a window: multiply-shift hash of the letters under the shape.  It does
 // not have to be injective -- every candidate is verified against the whole pattern.
@@ -91,7 +110,7 @@ __device__ __forceinline__ void q_verify(const BsgpuSubjectView &S, const BsgpuQ
 		int64_t own_lo, int64_t own_hi)
 {
 	const uint64_t E = 0x5555555555555555ull;
-	int id = (int) (ent >> 5), ti = (int) (ent & 31u);
+	int id = q_ent_id(Q, ent), ti = q_ent_shift(Q, ent);
 	int t = Q.shift[ti];
 	int64_t a = p - t;
 	int len = Q.const_len > 0 ? Q.const_len : (int) __ldg(Q.pat_len + id);
@@ -196,8 +215,8 @@ __device__ __forceinline__ int q_lower_bound(const BsgpuSubjectView &S, const Bs
 					     uint32_t ent, int64_t p)
 {
 	const uint64_t E = 0x5555555555555555ull;
-	int id = (int) (ent >> 5);
-	int64_t a = p - Q.shift[ent & 31u];
+	int id = q_ent_id(Q, ent);
+	int64_t a = p - Q.shift[q_ent_shift(Q, ent)];
 	int64_t wi = a >> 5;
 	int sh = 2 * (int) (a & 31);
 	int len = Q.const_len > 0 ? Q.const_len : (int) __ldg(Q.pat_len + id);
@@ -294,48 +313,95 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 			for (int qq = 0; qq < QSCAN_GROUP; qq++)
 				have |= ((bw[qq] >> (key[qq] & 31u)) & 1u) << (g + qq);
 		}
-		// Phase 2, flattened: every lane walks the concatenation of the entry lists of its
-		// non-empty positions, one candidate per lane and iteration.
+		// Phase 2, flattened and software-pipelined: every lane walks the concatenation of the
+		// entry lists of its non-empty positions, one candidate per lane and iteration.  The
+		// three dependent gathers of a candidate (directory cell -> entry -> pattern) belong to
+		// three different candidates within one iteration: an iteration finishes the candidate
+		// whose pattern was requested last time, requests the pattern of the entry that arrived
+		// last time, requests the next entry, and requests the directory cell of the next
+		// position when the current list is about to end -- one round trip per iteration
+		// instead of three.
 		uint32_t cur = 0, end = 0;
 		int64_t pos = 0;
+		bool d_valid = false, e_valid = false, p_valid = false;
+		uint2 d_cell = make_uint2(0, 0);
+		uint32_t d_key = 0, e_ent = 0, p_ent = 0;
+		int d_r = 0, p_len = 0;
+		int64_t e_pos = 0, p_pos = 0;
+		uint64_t p_pat = 0, p_x = 0, p_iv = 0;
 		for (;;) {
-			if (cur == end && have != 0) {
-				int r = __ffs(have) - 1;
-				have &= have - 1;
-				uint64_t win = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
-				uint32_t key = q_key(Q, win);
-				uint2 G = __ldg(Q.dir + (key >> 2));
-
-				cur = G.x + q_prefix(G.y, (int) (key & 3u));
-				end = cur + ((G.y >> (8 * (key & 3u))) & 0xFFu);
-				pos = base + r;
-			}
-			bool busy = cur < end;
-			if (!__any_sync(FULL, busy || have != 0))
+			if (!__any_sync(FULL, cur < end || have != 0 || d_valid || e_valid || p_valid))
 				break;
-			if (busy) {
-				uint32_t ent = __ldg(Q.entries + cur++);
-				int lb;
+			// 1. the pattern requested in the previous iteration has arrived
+			if (p_valid) {
+				const uint64_t E = 0x5555555555555555ull;
+				uint64_t d = p_x ^ p_pat;
 
+				d = ((d | (d >> 1)) | p_iv) & (p_len >= 32 ? E : E & ((1ull << (2 * p_len)) - 1));
+				if (__popcll(d) <= max_nmis)
+					q_verify<LONG>(S, Q, R, p_ent, p_pos, max_nmis, min_nmis, own_lo, own_hi);
+				p_valid = false;
+			}
+			// 2. the entry requested in the previous iteration has arrived
+			if (e_valid) {
+				e_valid = false;
 				if (!LONG) {
-					const uint64_t E = 0x5555555555555555ull;
-					int id = (int) (ent >> 5);
-					int o = (int) (pos - base) - Q.shift[ent & 31u];   // window start, -31..31
-					int len = Q.const_len > 0 ? Q.const_len : (int) __ldg(Q.pat_len + id);
+					int id = q_ent_id(Q, e_ent), ti = q_ent_shift(Q, e_ent);
+					int o = (int) (e_pos - base) - Q.shift[ti];   // window start, -31..31
 					uint64_t lo_c = o >= 0 ? c0 : cm, hi_c = o >= 0 ? c1 : c0;
 					uint64_t lo_i = o >= 0 ? i0 : im, hi_i = o >= 0 ? i1 : i0;
-					int sh = 2 * (o & 31);
+					int sh = 2 * (o & 31), lb = 0;
 					uint64_t x = sh ? (lo_c >> sh) | (hi_c << (64 - sh)) : lo_c;
 					uint64_t iv = sh ? (lo_i >> sh) | (hi_i << (64 - sh)) : lo_i;
-					uint64_t d = x ^ __ldg(Q.pat8 + id);
 
-					d = ((d | (d >> 1)) | iv) & (len >= 32 ? E : E & ((1ull << (2 * len)) - 1));
-					lb = __popcll(d);
-				} else {
-					lb = q_lower_bound<LONG>(S, Q, ent, pos);
+					// the entry carries nfp pattern letters from outside the seed: most random
+					// candidates already exceed max_nmis on them and never load the pattern
+					if (Q.nfp) {
+						uint32_t fp = q_ent_fp(Q, e_ent), where = Q.fp_pos[ti];
+#pragma unroll
+						for (int f = 0; f < 4; f++)
+							if (f < Q.nfp) {
+								int at = 2 * (int) ((where >> (8 * f)) & 0xFFu);
+
+								lb += (int) ((((x >> at) ^ (fp >> (2 * f))) & 3u) != 0u ||
+									     ((iv >> at) & 1u) != 0u);
+							}
+					}
+					if (lb <= max_nmis) {
+						p_pat = __ldg(Q.pat8 + id);
+						p_len = Q.const_len > 0 ? Q.const_len : (int) __ldg(Q.pat_len + id);
+						p_x = x;
+						p_iv = iv;
+						p_ent = e_ent;
+						p_pos = e_pos;
+						p_valid = true;
+					}
+				} else if (q_lower_bound<LONG>(S, Q, e_ent, e_pos) <= max_nmis) {
+					q_verify<LONG>(S, Q, R, e_ent, e_pos, max_nmis, min_nmis, own_lo, own_hi);
 				}
-				if (lb <= max_nmis)
-					q_verify<LONG>(S, Q, R, ent, pos, max_nmis, min_nmis, own_lo, own_hi);
+			}
+			// 3. next entry of the current list, or start the list whose cell has arrived
+			if (cur == end && d_valid) {
+				cur = d_cell.x + q_prefix(d_cell.y, (int) (d_key & 3u));
+				end = cur + ((d_cell.y >> (8 * (d_key & 3u))) & 0xFFu);
+				pos = base + d_r;
+				d_valid = false;
+			}
+			if (cur < end) {
+				e_ent = __ldg(Q.entries + cur++);
+				e_pos = pos;
+				e_valid = true;
+			}
+			// 4. the current list is about to end: request the cell of the next position
+			if (!d_valid && have != 0 && cur + 1 >= end) {
+				int r = __ffs(have) - 1;
+				uint64_t win = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
+
+				have &= have - 1;
+				d_key = q_key(Q, win);
+				d_cell = __ldg(Q.dir + (d_key >> 2));
+				d_r = r;
+				d_valid = true;
 			}
 		}
 	}

@@ -404,10 +404,10 @@ def _match_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, mode, what,
         return ByPos_MIndex(pdict.width(), offsets, ends, names=pdict.names(), dups0=dups0)
     if dups0 is None:
         return ans
-    which_pp_excluded = np.flatnonzero(dups0.duplicated()) + 1
     if mode == MATCHES_AS_WHICH:
         return dups0.members(ans)                     # members(dups0, ans)
-    ans[which_pp_excluded - 1] = ans[dups0.togroup(which_pp_excluded) - 1]
+    # ans[which_pp_excluded] <- ans[togroup(dups0, which_pp_excluded)]
+    ans[dups0.which_duplicated - 1] = ans[dups0.rep_of_duplicated - 1]
     return ans
 
 

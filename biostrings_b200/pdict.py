@@ -104,6 +104,11 @@ class Dups:
         self._l2h_off = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(cnt, out=self._l2h_off[1:])
 
+        # which(duplicated(dups0)) and their representatives, used by every match call
+        # (R/matchPDict.R:410,441-443): computed once
+        self.which_duplicated = (highs + 1).astype(np.int64)
+        self.rep_of_duplicated = self._rep[highs].astype(np.int64)
+
     def __len__(self):
         return int(self.high2low.size)
 
