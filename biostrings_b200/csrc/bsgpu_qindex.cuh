@@ -256,29 +256,46 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 	// Warp-synchronous: all 32 lanes of a warp stay in every loop (lanes without work are
 	// predicated off), so the candidate loop below reconverges every iteration.
 	const unsigned FULL = 0xFFFFFFFFu;
+	__shared__ uint64_t wc_all[8][34], wi_all[8][34];
+	__shared__ uint16_t plist_all[8][1024];
 	int64_t word_lo = probe_lo >> 5, word_hi = (probe_hi + 31) >> 5;
 	int lane = threadIdx.x & 31;
+	uint64_t *wc = wc_all[threadIdx.x >> 5], *wi = wi_all[threadIdx.x >> 5];
+	uint16_t *plist = plist_all[threadIdx.x >> 5];
 	int64_t jb = word_lo + (int64_t) blockIdx.x * blockDim.x + (threadIdx.x & ~31);
 	int64_t stride = (int64_t) gridDim.x * blockDim.x;
 
 	for (; jb < word_hi; jb += stride) {
 		int64_t j = jb + lane;
 		int64_t base = j << 5;
-		uint64_t cm = 0, c0 = 0, c1 = 0, im = 0, i0 = 0, i1 = 0;
+		uint64_t c0 = 0, c1 = 0;
 		uint32_t m = 0;
 
-		if (j < word_hi) {
-			c0 = __ldcs(S.codes + j);
-			c1 = __ldcs(S.codes + j + 1);
-			if (!LONG) {
-				// the 96 letters around this word stay in registers: candidate windows
-				// (start within 31 letters before the probe position, <= 32 letters long)
-				// are cut from them without touching memory again
-				cm = j > 0 ? __ldcs(S.codes + j - 1) : 0;
-				im = j > 0 ? __ldcs(S.inv2 + j - 1) : ~0ull;
-				i0 = __ldcs(S.inv2 + j);
-				i1 = __ldcs(S.inv2 + j + 1);
+		if (!LONG) {
+			// the codes / not-a-base words jb-1 .. jb+32 of this batch go to the warp's shared
+			// memory: candidate windows (start within 31 letters before the probe position,
+			// <= 32 letters long) are cut from there by whichever lane takes the candidate
+			bool ld = j < word_hi + 2;          // the planes have spare words after the end
+
+			__syncwarp();
+			c0 = ld ? __ldcs(S.codes + j) : 0ull;
+			wc[lane + 1] = c0;
+			wi[lane + 1] = ld ? __ldcs(S.inv2 + j) : ~0ull;
+			if (lane == 0) {
+				wc[0] = jb > 0 ? __ldcs(S.codes + jb - 1) : 0ull;
+				wi[0] = jb > 0 ? __ldcs(S.inv2 + jb - 1) : ~0ull;
 			}
+			if (lane == 31) {
+				bool ld2 = j + 1 < word_hi + 2;
+
+				wc[33] = ld2 ? __ldcs(S.codes + j + 1) : 0ull;
+				wi[33] = ld2 ? __ldcs(S.inv2 + j + 1) : ~0ull;
+			}
+		}
+		if (j < word_hi) {
+			if (LONG)
+				c0 = __ldcs(S.codes + j);
+			c1 = __ldcs(S.codes + j + 1);
 			uint64_t v = (uint64_t) __ldcs(S.valid + j) | ((uint64_t) __ldcs(S.valid + j + 1) << 32);
 			m = q_valid_positions(Q, v);
 			if (Q.stride > 1) {
@@ -313,24 +330,41 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 			for (int qq = 0; qq < QSCAN_GROUP; qq++)
 				have |= ((bw[qq] >> (key[qq] & 31u)) & 1u) << (g + qq);
 		}
-		// Phase 2, flattened and software-pipelined: every lane walks the concatenation of the
-		// entry lists of its non-empty positions, one candidate per lane and iteration.  The
-		// three dependent gathers of a candidate (directory cell -> entry -> pattern) belong to
-		// three different candidates within one iteration: an iteration finishes the candidate
-		// whose pattern was requested last time, requests the pattern of the entry that arrived
-		// last time, requests the next entry, and requests the directory cell of the next
-		// position when the current list is about to end -- one round trip per iteration
-		// instead of three.
+		// Phase 2, balanced and software-pipelined.  The non-empty positions of the whole batch
+		// (32 words) are listed in shared memory and dealt round-robin to the lanes, so every
+		// lane gets the same number of positions whatever their distribution over the words.
+		// The three dependent gathers of a candidate (directory cell -> entry -> pattern)
+		// belong to three different candidates within one iteration: an iteration finishes the
+		// candidate whose pattern was requested last time, requests the pattern of the entry
+		// that arrived last time, requests the next entry, and requests the directory cell of
+		// the lane's next position when the current list is about to end -- one round trip
+		// per iteration instead of three.
+		int nitems;
+		{
+			int mine = __popc(have), before = mine;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				int up = __shfl_up_sync(FULL, before, d);
+				if (lane >= d)
+					before += up;
+			}
+			nitems = __shfl_sync(FULL, before, 31);
+			before -= mine;
+			for (uint32_t h = have; h != 0; h &= h - 1)
+				plist[before++] = (uint16_t) (lane * 32 + __ffs(h) - 1);
+			__syncwarp();
+		}
+		const int64_t base0 = jb << 5;
+		int it = lane;
 		uint32_t cur = 0, end = 0;
-		int64_t pos = 0;
+		int pos = 0;                    // position within the batch
 		bool d_valid = false, e_valid = false, p_valid = false;
 		uint2 d_cell = make_uint2(0, 0);
 		uint32_t d_key = 0, e_ent = 0, p_ent = 0;
-		int d_r = 0, p_len = 0;
-		int64_t e_pos = 0, p_pos = 0;
+		int d_pos = 0, e_pos = 0, p_pos = 0, p_len = 0;
 		uint64_t p_pat = 0, p_x = 0, p_iv = 0;
 		for (;;) {
-			if (!__any_sync(FULL, cur < end || have != 0 || d_valid || e_valid || p_valid))
+			if (!__any_sync(FULL, cur < end || it < nitems || d_valid || e_valid || p_valid))
 				break;
 			// 1. the pattern requested in the previous iteration has arrived
 			if (p_valid) {
@@ -339,7 +373,7 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 
 				d = ((d | (d >> 1)) | p_iv) & (p_len >= 32 ? E : E & ((1ull << (2 * p_len)) - 1));
 				if (__popcll(d) <= max_nmis)
-					q_verify<LONG>(S, Q, R, p_ent, p_pos, max_nmis, min_nmis, own_lo, own_hi);
+					q_verify<LONG>(S, Q, R, p_ent, base0 + p_pos, max_nmis, min_nmis, own_lo, own_hi);
 				p_valid = false;
 			}
 			// 2. the entry requested in the previous iteration has arrived
@@ -347,12 +381,10 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 				e_valid = false;
 				if (!LONG) {
 					int id = q_ent_id(Q, e_ent), ti = q_ent_shift(Q, e_ent);
-					int o = (int) (e_pos - base) - Q.shift[ti];   // window start, -31..31
-					uint64_t lo_c = o >= 0 ? c0 : cm, hi_c = o >= 0 ? c1 : c0;
-					uint64_t lo_i = o >= 0 ? i0 : im, hi_i = o >= 0 ? i1 : i0;
-					int sh = 2 * (o & 31), lb = 0;
-					uint64_t x = sh ? (lo_c >> sh) | (hi_c << (64 - sh)) : lo_c;
-					uint64_t iv = sh ? (lo_i >> sh) | (hi_i << (64 - sh)) : lo_i;
+					int at0 = e_pos - Q.shift[ti] + 32;     // window start, in letters from word jb-1
+					int w = at0 >> 5, sh = 2 * (at0 & 31), lb = 0;
+					uint64_t x = sh ? (wc[w] >> sh) | (wc[w + 1] << (64 - sh)) : wc[w];
+					uint64_t iv = sh ? (wi[w] >> sh) | (wi[w + 1] << (64 - sh)) : wi[w];
 
 					// the entry carries nfp pattern letters from outside the seed: most random
 					// candidates already exceed max_nmis on them and never load the pattern
@@ -376,15 +408,15 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 						p_pos = e_pos;
 						p_valid = true;
 					}
-				} else if (q_lower_bound<LONG>(S, Q, e_ent, e_pos) <= max_nmis) {
-					q_verify<LONG>(S, Q, R, e_ent, e_pos, max_nmis, min_nmis, own_lo, own_hi);
+				} else if (q_lower_bound<LONG>(S, Q, e_ent, base0 + e_pos) <= max_nmis) {
+					q_verify<LONG>(S, Q, R, e_ent, base0 + e_pos, max_nmis, min_nmis, own_lo, own_hi);
 				}
 			}
 			// 3. next entry of the current list, or start the list whose cell has arrived
 			if (cur == end && d_valid) {
 				cur = d_cell.x + q_prefix(d_cell.y, (int) (d_key & 3u));
 				end = cur + ((d_cell.y >> (8 * (d_key & 3u))) & 0xFFu);
-				pos = base + d_r;
+				pos = d_pos;
 				d_valid = false;
 			}
 			if (cur < end) {
@@ -392,15 +424,23 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 				e_pos = pos;
 				e_valid = true;
 			}
-			// 4. the current list is about to end: request the cell of the next position
-			if (!d_valid && have != 0 && cur + 1 >= end) {
-				int r = __ffs(have) - 1;
-				uint64_t win = r == 0 ? c0 : (c0 >> (2 * r)) | (c1 << (64 - 2 * r));
+			// 4. the current list is about to end: request the cell of the lane's next position
+			if (!d_valid && it < nitems && cur + 1 >= end) {
+				uint64_t k0, k1;
+				int r;
 
-				have &= have - 1;
-				d_key = q_key(Q, win);
+				d_pos = plist[it];
+				it += 32;
+				r = d_pos & 31;
+				if (!LONG) {
+					k0 = wc[(d_pos >> 5) + 1];
+					k1 = wc[(d_pos >> 5) + 2];
+				} else {
+					k0 = __ldg(S.codes + jb + (d_pos >> 5));
+					k1 = __ldg(S.codes + jb + (d_pos >> 5) + 1);
+				}
+				d_key = q_key(Q, r == 0 ? k0 : (k0 >> (2 * r)) | (k1 << (64 - 2 * r)));
 				d_cell = __ldg(Q.dir + (d_key >> 2));
-				d_r = r;
 				d_valid = true;
 			}
 		}
