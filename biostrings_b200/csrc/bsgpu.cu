@@ -544,7 +544,9 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 			qi->max_shift = t;
 		}
 	// --- entries, counting sort by seed key ---------------------------------------------------
-	v.key_bits = 24;
+	v.key_bits = 2 * sh.q;          // the key is the q shape letters themselves
+	if (v.key_bits > 24 || v.key_bits < 8)
+		return done();
 	v.mask2 = v.shape2 | (v.shape2 << 1);
 	v.const_len = min_w == max_w ? max_w : 0;
 	size_t nkeys = (size_t) 1 << v.key_bits;
@@ -553,7 +555,7 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 		// the window of 32 letters starting at pattern offset t, in the subject's layout
 		unsigned long long win = t == 0 ? pat[i].x
 			: (t < 32 ? (pat[i].x >> (2 * t)) | (pat[i].y << (64 - 2 * t)) : pat[i].y >> (2 * (t - 32)));
-		return q_key_of(win & v.mask2, v.key_bits);
+		return q_key(v, win);
 	};
 	size_t nent = 0;
 	for (int i = 0; i < M; i++) {

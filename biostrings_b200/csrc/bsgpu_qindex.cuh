@@ -23,7 +23,6 @@
 #define BSGPU_Q_MAX_RUNS 8
 #define BSGPU_Q_MAX_SHIFTS 32
 
-#define BSGPU_Q_HASH_C 0x9E3779B97F4A7C15ull
 
 struct BsgpuQIndexView {
 	const uint32_t *bitmap;      // [2^key_bits / 32] bit = some entry has this directory key
@@ -67,16 +66,21 @@ __host__ __device__ __forceinline__ uint32_t q_ent_fp(const BsgpuQIndexView &Q, 
 	return Q.nfp ? ent >> (Q.shift_bits + Q.id_bits) : 0u;
 }
 
-// Directory key of a window: multiply-shift hash of the letters under the shape.  It does
-// not have to be injective -- every candidate is verified against the whole pattern.
-__host__ __device__ __forceinline__ uint32_t q_key_of(uint64_t masked, int key_bits)
+// Directory key of a window: the letters under the shape, compacted run by run into 2q bits.
+// The key is injective on purpose: with a hash of the masked window (a random function onto
+// 2^24 keys) popular keys collect both more dictionary entries and more subject windows, and
+// the number of candidates per position doubles (measured 0.79 against 0.42 for 7 M entries).
+__host__ __device__ __forceinline__ uint32_t q_key(const BsgpuQIndexView &Q, uint64_t win)
 {
-	return (uint32_t) ((masked * BSGPU_Q_HASH_C) >> (64 - key_bits));
-}
-
-__device__ __forceinline__ uint32_t q_key(const BsgpuQIndexView &Q, uint64_t win)
-{
-	return q_key_of(win & Q.mask2, Q.key_bits);
+	uint32_t key = 0;
+	int at = 0;
+#pragma unroll
+	for (int i = 0; i < BSGPU_Q_MAX_RUNS; i++)
+		if (i < Q.nruns) {
+			key |= (uint32_t) ((win >> (2 * Q.run_src[i])) & ((1ull << (2 * Q.run_len[i])) - 1)) << at;
+			at += 2 * Q.run_len[i];
+		}
+	return key;
 }
 
 // 128-bit logical right shift by s (< 128) returning the low 64 bits
