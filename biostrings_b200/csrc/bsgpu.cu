@@ -535,6 +535,15 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 				v.nruns++;
 			}
 		}
+	for (int i = 0, at = 0; i < BSGPU_Q_MAX_RUNS; i++) {
+		bool used = i < v.nruns;
+
+		v.run_shift[i] = used ? 2 * v.run_src[i] : 0;
+		v.run_mask[i] = used ? (uint32_t) ((1ull << (2 * v.run_len[i])) - 1) : 0u;
+		v.run_dst[i] = used ? at : 0;
+		if (used)
+			at += 2 * v.run_len[i];
+	}
 	v.nshifts = 0;
 	for (int t = 0; t < 64; t++)
 		if ((sh.shifts >> t) & 1) {
