@@ -1878,12 +1878,14 @@ static int run_q(const QIndex *qi, const bsgpu_subject *subj, const MatchParams 
 		if (rec_based)
 			TRY(read_counter(ws, 1, &rec_before, st));
 		{
+			const char *env_g = getenv("BSGPU_Q_GRID");     // blocks per SM of the grid-stride launch
+			int qgrid = env_g != nullptr && atoi(env_g) > 0 ? atoi(env_g) : 1024;
 			KernelTimer kt("qscan_kernel", st);
 			if (qi->max_len > 32)
-				qscan_kernel<true><<<grid_for(nwords, 256, 8), 256, 0, st>>>(subj->view(), Q, R,
+				qscan_kernel<true><<<grid_for(nwords, 256, qgrid), 256, 0, st>>>(subj->view(), Q, R,
 						mp.max_nmis, mp.min_nmis, probe_lo, probe_hi, own_lo, own_hi);
 			else
-				qscan_kernel<false><<<grid_for(nwords, 256, 8), 256, 0, st>>>(subj->view(), Q, R,
+				qscan_kernel<false><<<grid_for(nwords, 256, qgrid), 256, 0, st>>>(subj->view(), Q, R,
 						mp.max_nmis, mp.min_nmis, probe_lo, probe_hi, own_lo, own_hi);
 		}
 		g_launches++;
