@@ -1454,6 +1454,14 @@ struct MatchParams {
 	int max_nmis, min_nmis, fixedP, fixedS;
 };
 
+// blocks per SM the grid-stride kernels of the Trusted-Band engine are capped at
+static int tb_grid(void)
+{
+	const char *env = getenv("BSGPU_TB_GRID");
+
+	return env != nullptr && atoi(env) > 0 ? atoi(env) : 64;
+}
+
 static unsigned int iupac_max_expansions(void)
 {
 	const char *env = getenv("BSGPU_MAX_IUPAC_EXPANSIONS");
@@ -1552,7 +1560,7 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 		 mp.fixedS ? "" : " + iupac_expansion");
 	{
 		KernelTimer kt("scan_tb_kernel", st);
-		scan_tb_kernel<<<grid_for(nwords, 256, 8), 256, 0, st>>>(S, I, R, C, direct, start_lo, start_hi);
+		scan_tb_kernel<<<grid_for(nwords, 256, tb_grid()), 256, 0, st>>>(S, I, R, C, direct, start_lo, start_hi);
 	}
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
@@ -1563,7 +1571,7 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 		if (ws->ovf.n < OVF_CAP)
 			TRY(ws->ovf.alloc(OVF_CAP));
 		TRY(write_counter(ws, 2, 0, st));
-		scan_tb_iupac_kernel<<<grid_for(nwords, 128, 16), 128, 0, st>>>(
+		scan_tb_iupac_kernel<<<grid_for(nwords, 128, 2 * tb_grid()), 128, 0, st>>>(
 			S, I, R, C, direct, start_lo, start_hi, iupac_max_expansions(), ws->ovf.p,
 			ws->counters.p + 2, OVF_CAP);
 		g_launches++;
@@ -1753,7 +1761,7 @@ static int run_part(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, cons
 					continue;       // rerun this slab
 				}
 				if (ncand > 0) {
-					verify_flanks_kernel<<<grid_for((long long) ncand, 256, 8), 256, 0, st>>>(
+					verify_flanks_kernel<<<grid_for((long long) ncand, 256, tb_grid()), 256, 0, st>>>(
 						subj->view(), p3->view(), R, ws->cand.p, ncand,
 						mp.max_nmis, mp.min_nmis, mp.fixedP, mp.fixedS);
 					g_launches++;
