@@ -540,7 +540,7 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 
 		v.run_shift[i] = used ? 2 * v.run_src[i] : 0;
 		v.run_mask[i] = used ? (uint32_t) ((1ull << (2 * v.run_len[i])) - 1) : 0u;
-		v.run_dst[i] = used ? at : 0;
+		v.run_mul[i] = used ? 1u << at : 0u;
 		if (used)
 			at += 2 * v.run_len[i];
 	}
@@ -602,6 +602,8 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 	if (v.shift_bits + v.id_bits > 32)
 		return done();
 	v.nfp = std::min(4, (32 - v.shift_bits - v.id_bits) / 2);
+	if (getenv("BSGPU_Q_NFP") != nullptr)
+		v.nfp = std::min(v.nfp, std::max(0, atoi(getenv("BSGPU_Q_NFP"))));
 	for (int s2 = 0; s2 < v.nshifts; s2++) {
 		int found = 0;
 

@@ -38,10 +38,10 @@ struct BsgpuQIndexView {
 	int32_t nruns;               // runs of consecutive shape offsets
 	int32_t run_src[BSGPU_Q_MAX_RUNS];   // first offset of the run
 	int32_t run_len[BSGPU_Q_MAX_RUNS];
-	// the same runs as the key extraction wants them: key |= ((win >> run_shift) & run_mask) << run_dst
+	// the same runs as the key extraction wants them: key += ((win >> run_shift) & run_mask) * run_mul
 	int32_t run_shift[BSGPU_Q_MAX_RUNS];
 	uint32_t run_mask[BSGPU_Q_MAX_RUNS]; // 0 for unused runs
-	int32_t run_dst[BSGPU_Q_MAX_RUNS];
+	uint32_t run_mul[BSGPU_Q_MAX_RUNS];  // 1 << (2 * letters of the runs before)
 	uint64_t shape1;             // 1 bit per letter
 	uint64_t shape2;             // the same, spread to the 2-bit layout (bit 2i)
 	uint64_t mask2;              // both bits of every shape letter in the 2-bit layout
@@ -81,7 +81,7 @@ __host__ __device__ __forceinline__ uint32_t q_key(const BsgpuQIndexView &Q, uin
 	for (int i = 0; i < BSGPU_Q_MAX_RUNS; i++) {
 		if (i >= Q.nruns)
 			break;
-		key |= ((uint32_t) (win >> Q.run_shift[i]) & Q.run_mask[i]) << Q.run_dst[i];
+		key += ((uint32_t) (win >> Q.run_shift[i]) & Q.run_mask[i]) * Q.run_mul[i];    // disjoint fields
 	}
 	return key;
 }
