@@ -9,6 +9,8 @@ behaviour); it needs the shared library and a CUDA device -- there is no CPU fal
 from ._lib import BsgpuError
 from .matchpdict import (DeviceSubject, countPDict, matchPDict, vcountPDict, vmatchPDict,
                          vwhichPDict, whichPDict)
+from .letterfreq import (dinucleotideFrequency, mkAllStrings, oligonucleotideFrequency,
+                         oligonucleotideTransitions, trinucleotideFrequency)
 from .mindex import ByPos_MIndex, extractAllMatches
 from .pdict import MTB_PDict, TB_PDict, make_pdict as PDict
 from .xstring import (DNA_BASES, DNAString, DNAStringSet, MaskedDNAString, XStringViews,
@@ -17,4 +19,5 @@ from .xstring import (DNA_BASES, DNAString, DNAStringSet, MaskedDNAString, XStri
 __all__ = ["PDict", "TB_PDict", "MTB_PDict", "matchPDict", "countPDict", "whichPDict",
            "vcountPDict", "vwhichPDict", "vmatchPDict", "ByPos_MIndex", "extractAllMatches", "DNAString",
            "DNAStringSet", "XStringViews", "MaskedDNAString", "DeviceSubject", "DNA_BASES",
-           "encode_dna", "decode_dna", "BsgpuError"]
+           "encode_dna", "decode_dna", "BsgpuError", "oligonucleotideFrequency", "dinucleotideFrequency",
+           "trinucleotideFrequency", "oligonucleotideTransitions", "mkAllStrings"]

@@ -25,6 +25,8 @@ SYMBOLS = [
     "bsgpu_vmatch_PDict3Parts_XStringSet", "bsgpu_mindex_combine",
     "bsgpu_last_plan", "bsgpu_launch_count", "bsgpu_probe_peaks",
     "bsgpu_kernel_timing", "bsgpu_kernel_times", "bsgpu_patterns_build",
+    "bsgpu_oligo_frequency", "bsgpu_oligo_count_device", "bsgpu_XString_oligo_frequency",
+    "bsgpu_XStringSet_oligo_frequency",
 ]
 
 
@@ -94,6 +96,10 @@ def lib():
     L.bsgpu_launch_count.restype = i64
     L.bsgpu_probe_peaks.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), i64]
     L.bsgpu_patterns_build.argtypes = [vp, vp, i32, C.POINTER(vp)]
+    L.bsgpu_oligo_frequency.argtypes = [vp] + [C.c_int] * 5 + [vp, vp]
+    L.bsgpu_oligo_count_device.argtypes = [vp] + [C.c_int] * 3 + [vp, vp]
+    L.bsgpu_XString_oligo_frequency.argtypes = [vp, i64] + [C.c_int] * 4 + [vp, vp]
+    L.bsgpu_XStringSet_oligo_frequency.argtypes = [vp, vp, i32] + [C.c_int] * 5 + [vp, vp]
     L.bsgpu_kernel_timing.argtypes = [C.c_int]
     L.bsgpu_kernel_times.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     _lib = L

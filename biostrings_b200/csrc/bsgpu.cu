@@ -22,6 +22,7 @@
 
 #include "../../include/bsgpu.h"
 #include "bsgpu_qindex.cuh"
+#include "bsgpu_oligo.cuh"
 
 // ---------------------------------------------------------------------------------------
 // errors
@@ -2474,6 +2475,182 @@ extern "C" int bsgpu_mindex_combine(const bsgpu_result *const *comps, int ncomps
 	res->ends = (int32_t *) malloc(std::max<size_t>(all.size(), 1) * sizeof(int32_t));
 	memcpy(res->ends, all.data(), all.size() * sizeof(int32_t));
 	return BSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// oligonucleotideFrequency (XString_oligo_frequency / XStringSet_oligo_frequency,
+// src/letter_frequency.c:634-738)
+// ---------------------------------------------------------------------------------------
+
+template <typename CT>
+static int launch_oligo(const bsgpu_subject *subj, const BsgpuOligoParams &P, CT *d_out, cudaStream_t st)
+{
+	size_t shmem = P.replicas > 0 ? ((size_t) P.replicas << (2 * P.w)) * sizeof(uint32_t) : 0;
+
+	if (shmem > 48 * 1024)
+		CUDA_TRY(cudaFuncSetAttribute(oligo_freq_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+					      (int) shmem));
+	{
+		KernelTimer kt("oligo_freq_kernel", st);
+		oligo_freq_kernel<CT><<<grid_for(P.nwords, 256, 8), 256, shmem, st>>>(subj->view(), P, d_out);
+	}
+	g_launches++;
+	CUDA_TRY(cudaGetLastError());
+	return BSGPU_OK;
+}
+
+static int check_oligo_width_step(int width, int step)
+{
+	// src/utils.c:101-102
+	if (width < 1 || width > 15)
+		return fail(BSGPU_EINVAL, "_new_TwobitEncodingBuffer(): 'buflength' must be >= 1 and <= 15");
+	// R/letterFrequency.R:26-34
+	if (step < 1)
+		return fail(BSGPU_EINVAL, "'step' must be a positive integer");
+	return BSGPU_OK;
+}
+
+static int check_oligo_args(const bsgpu_subject *subj, int width, int step)
+{
+	if (subj == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_oligo_frequency(): NULL subject");
+	return check_oligo_width_step(width, step);
+}
+
+static BsgpuOligoParams oligo_params(const bsgpu_subject *subj, int width, int step, int invert,
+				     bool per_segment)
+{
+	BsgpuOligoParams P = {};
+
+	P.w = width;
+	P.step = step;
+	P.invert = invert != 0;
+	P.per_segment = per_segment;
+	P.coord_step = subj->kind == SUBJ_CHUNK;
+	// one row of at most 4^7 counters: per-block tables in shared memory, replicated while
+	// they are small so that the lanes of a warp do not pile up on 4 or 16 counters
+	if (!per_segment && width <= 7) {
+		int r = width <= 6 ? (4096 >> (2 * width)) : 1;
+
+		P.replicas = std::max(1, std::min(32, r));
+	}
+	P.scan_lo = subj->scan_lo;
+	P.scan_hi = subj->scan_hi;
+	P.nwords = subj->total / 32;
+	return P;
+}
+
+extern "C" int bsgpu_oligo_count_device(const bsgpu_subject *subj, int width, int step,
+		int invert_twobit_order, unsigned long long *d_counts, void *stream)
+{
+	TRY(check_oligo_args(subj, width, step));
+	if (d_counts == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_oligo_count_device(): NULL d_counts");
+	TRY(ensure_device());
+	cudaStream_t st = (cudaStream_t) stream;
+	TRY(ensure_packed(subj, st));
+	set_plan("oligo_freq w=%d step=%d rows=1 table=%s", width, step, width <= 7 ? "shared" : "global");
+	return launch_oligo<unsigned long long>(subj, oligo_params(subj, width, step, invert_twobit_order, false),
+						d_counts, st);
+}
+
+extern "C" int bsgpu_oligo_frequency(const bsgpu_subject *subj, int width, int step,
+		int invert_twobit_order, int collapsed, int as_prob, int32_t *counts_out, double *freq_out)
+{
+	TRY(check_oligo_args(subj, width, step));
+	if ((as_prob ? (void *) freq_out : (void *) counts_out) == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_oligo_frequency(): NULL output");
+	TRY(ensure_device());
+	const size_t ncol = (size_t) 1 << (2 * width);
+	const size_t nrow = collapsed ? 1 : (size_t) subj->nseg;
+
+	if (nrow * ncol > (size_t) INT32_MAX)
+		return fail(BSGPU_EINVAL, "allocMatrix: too many elements specified");
+	if (nrow == 0)
+		return BSGPU_OK;
+	cudaStream_t st = 0;
+	TRY(ensure_packed(subj, st));
+	BsgpuOligoParams P = oligo_params(subj, width, step, invert_twobit_order, !collapsed);
+	set_plan("oligo_freq w=%d step=%d rows=%zu table=%s", width, step, nrow, P.replicas ? "shared" : "global");
+	if (collapsed) {
+		// 64-bit counters: a collapsed set may hold more than 2^31 windows of one kind
+		DevBuf<unsigned long long> d_out;
+		std::vector<unsigned long long> h(ncol);
+
+		TRY(d_out.alloc(ncol));
+		CUDA_TRY(cudaMemsetAsync(d_out.p, 0, ncol * sizeof(unsigned long long), st));
+		TRY(launch_oligo<unsigned long long>(subj, P, d_out.p, st));
+		CUDA_TRY(cudaMemcpyAsync(h.data(), d_out.p, ncol * sizeof(unsigned long long),
+					 cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		if (!as_prob) {
+			for (size_t c = 0; c < ncol; c++)
+				counts_out[c] = (int32_t) (uint32_t) h[c];      // the reference's int wraps too
+			return BSGPU_OK;
+		}
+		// normalize_oligo_freqs(), src/letter_frequency.c:286-301: sum left to right, a row
+		// whose sum is 0 is left alone
+		double sum = 0.0;
+		for (size_t c = 0; c < ncol; c++)
+			sum += (freq_out[c] = (double) h[c]);
+		if (sum != 0.0)
+			for (size_t c = 0; c < ncol; c++)
+				freq_out[c] /= sum;
+		return BSGPU_OK;
+	}
+	// one row per sequence: row-major on the device (the counters of a sequence are
+	// neighbours), column-major for the caller as allocMatrix() lays it out
+	DevBuf<uint32_t> d_out;
+	std::vector<uint32_t> h(nrow * ncol);
+
+	TRY(d_out.alloc(nrow * ncol));
+	CUDA_TRY(cudaMemsetAsync(d_out.p, 0, nrow * ncol * sizeof(uint32_t), st));
+	TRY(launch_oligo<uint32_t>(subj, P, d_out.p, st));
+	CUDA_TRY(cudaMemcpyAsync(h.data(), d_out.p, nrow * ncol * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	for (size_t i = 0; i < nrow; i++) {
+		const uint32_t *row = h.data() + i * ncol;
+
+		if (!as_prob) {
+			for (size_t c = 0; c < ncol; c++)
+				counts_out[i + c * nrow] = (int32_t) row[c];
+			continue;
+		}
+		double sum = 0.0;
+		for (size_t c = 0; c < ncol; c++)
+			sum += (double) row[c];
+		for (size_t c = 0; c < ncol; c++)
+			freq_out[i + c * nrow] = sum != 0.0 ? (double) row[c] / sum : (double) row[c];
+	}
+	return BSGPU_OK;
+}
+
+// XString_oligo_frequency, src/letter_frequency.c:634
+extern "C" int bsgpu_XString_oligo_frequency(const uint8_t *x, int64_t x_length, int width, int step,
+		int invert_twobit_order, int as_prob, int32_t *counts_out, double *freq_out)
+{
+	bsgpu_subject *subj = nullptr;
+
+	TRY(check_oligo_width_step(width, step));
+	TRY(bsgpu_subject_xstring(x, x_length, &subj));
+	int rc = bsgpu_oligo_frequency(subj, width, step, invert_twobit_order, 1, as_prob, counts_out, freq_out);
+	bsgpu_subject_free(subj);
+	return rc;
+}
+
+// XStringSet_oligo_frequency, src/letter_frequency.c:667
+extern "C" int bsgpu_XStringSet_oligo_frequency(const uint8_t *concat, const int32_t *widths, int32_t n,
+		int width, int step, int invert_twobit_order, int collapsed, int as_prob,
+		int32_t *counts_out, double *freq_out)
+{
+	bsgpu_subject *subj = nullptr;
+
+	TRY(check_oligo_width_step(width, step));
+	TRY(bsgpu_subject_set(concat, widths, n, &subj));
+	int rc = bsgpu_oligo_frequency(subj, width, step, invert_twobit_order, collapsed, as_prob,
+				       counts_out, freq_out);
+	bsgpu_subject_free(subj);
+	return rc;
 }
 
 // ---------------------------------------------------------------------------------------

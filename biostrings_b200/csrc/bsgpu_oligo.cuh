@@ -1,0 +1,114 @@
+// bsgpu_oligo.cuh -- oligonucleotideFrequency on the packed subject planes.
+//
+//   oligo_freq_kernel     counts every width-letter window made of base letters only, at the
+//                         0-based starts that are multiples of `step` inside its sequence
+//                         (replaces update_int_oligo_freqs / update_double_oligo_freqs,
+//                          src/letter_frequency.c:183-267, i.e. the rolling
+//                          _shift_twobit_signature walk of src/utils.c:123-146)
+//
+// The reference rolls a 2-bit signature along the sequence and resets it at every non-base
+// letter; all three of its step regimes (step = 1, 1 < step < width, step >= width) count the
+// same thing: window [s, s + width) is counted iff s % step == 0, s + width <= length and all
+// of its letters are A/C/G/T.  On the 2-bit code plane a window is a 2*width-bit field at bit
+// 2*s and "all base letters" is a run of width set bits in the validity plane, so one thread
+// takes one 32-letter word of the planes, finds the valid window starts in it with width - 1
+// shift-ANDs and visits only those.  Separator and guard letters are not base letters, hence
+// no window straddles two sequences and the sequence of a window is the one holding its start.
+#pragma once
+#include "bsgpu_kernels.cuh"
+
+struct BsgpuOligoParams {
+	int32_t w;              // window width, 1..15 (src/utils.c:101-102)
+	int32_t step;           // >= 1
+	int32_t invert;         // fast.moving.side = "left": first letter least significant
+	int32_t per_segment;    // 1: out[segment * 4^w + code], 0: one row
+	int32_t coord_step;     // chunk subjects: starts are judged in subject coordinates
+	int32_t replicas;       // copies of the table in shared memory (0 = global atomics)
+	int64_t scan_lo, scan_hi;       // only windows whose last letter is in [scan_lo, scan_hi)
+	int64_t nwords;
+};
+
+// offset of a window in the reference's table: sum of code(letter i) * 4^(w-1-i)
+// (endianness 0, src/utils.c:135-142), or * 4^i when the two-bit order is inverted.
+__device__ __forceinline__ uint32_t oligo_offset(uint32_t field, int w, int invert)
+{
+	if (invert)
+		return field;
+	uint32_t r = __brev(field) >> (32 - 2 * w);             // digits reversed, bits of a digit swapped
+
+	return ((r & 0x55555555u) << 1) | ((r >> 1) & 0x55555555u);
+}
+
+template <typename CT>
+__global__ void __launch_bounds__(256)
+oligo_freq_kernel(BsgpuSubjectView S, BsgpuOligoParams P, CT *__restrict__ out)
+{
+	extern __shared__ uint32_t sh_hist[];
+	const uint32_t ncol = 1u << (2 * P.w);
+	const uint32_t cmask = ncol - 1;
+	const int tid = threadIdx.x;
+
+	if (P.replicas > 0) {
+		for (uint32_t k = tid; k < ncol * P.replicas; k += blockDim.x)
+			sh_hist[k] = 0;
+		__syncthreads();
+	}
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (int64_t j = (int64_t) blockIdx.x * blockDim.x + tid; j < P.nwords; j += stride) {
+		uint64_t vv = (uint64_t) __ldg(S.valid + j) | ((uint64_t) __ldg(S.valid + j + 1) << 32);
+		uint64_t run = vv;
+
+		for (int k = 1; k < P.w; k++)
+			run &= vv >> k;
+		uint32_t starts = (uint32_t) run;       // bit i: letters i .. i+w-1 are all base letters
+		if (starts == 0)
+			continue;
+		uint64_t lo = __ldg(S.codes + j), hi = __ldg(S.codes + j + 1);
+		int64_t p0 = j * 32;
+		int seg = 0;
+		bool seg_known = S.nseg == 1;
+
+		while (starts != 0) {
+			int i = __ffs(starts) - 1;
+
+			starts &= starts - 1;
+			int64_t p = p0 + i, e = p + P.w - 1;
+			if (e < P.scan_lo || e >= P.scan_hi)
+				continue;
+			if (!seg_known) {
+				seg = find_segment(S, p);
+				seg_known = true;
+			} else {
+				while (seg + 1 < S.nseg && __ldg(S.seg_start + seg + 1) <= p)
+					seg++;
+			}
+			if (P.step > 1) {
+				int64_t local = p - __ldg(S.seg_start + seg);
+
+				if (P.coord_step)
+					local += __ldg(S.seg_coord + seg);
+				if (local % P.step != 0)
+					continue;
+			}
+			uint64_t f = i == 0 ? lo : (lo >> (2 * i)) | (hi << (64 - 2 * i));
+			uint32_t code = oligo_offset((uint32_t) f & cmask, P.w, P.invert);
+
+			if (P.replicas > 0)
+				atomicAdd(&sh_hist[code * P.replicas + (tid & (P.replicas - 1))], 1u);
+			else
+				atomicAdd(out + (P.per_segment ? (size_t) seg * ncol : (size_t) 0) + code, (CT) 1);
+		}
+	}
+	if (P.replicas > 0) {
+		__syncthreads();
+		for (uint32_t c = tid; c < ncol; c += blockDim.x) {
+			uint32_t sum = 0;
+
+			for (int r = 0; r < P.replicas; r++)
+				sum += sh_hist[c * P.replicas + r];
+			if (sum != 0)
+				atomicAdd(out + c, (CT) sum);
+		}
+	}
+}

@@ -238,6 +238,45 @@ int bsgpu_vmatch_PDict3Parts_XStringSet(const bsgpu_pdict3parts *p3,
 int bsgpu_mindex_combine(const bsgpu_result *const *components, int ncomponents,
 		bsgpu_result *res);
 
+/* ------------------------------------------------------------------------------------
+ * oligonucleotideFrequency.  Replaces
+ *     XString_oligo_frequency(x, width, step, as_prob, as_array, fast_moving_side,
+ *                             with_labels, base_codes)     src/letter_frequency.c:634
+ *     XStringSet_oligo_frequency(..., simplify_as, ...)     src/letter_frequency.c:667
+ * i.e. the rolling two-bit signature walk of update_int_oligo_freqs /
+ * update_double_oligo_freqs (src/letter_frequency.c:183-267): the window of `width` letters
+ * starting at 0-based position s of a sequence is counted iff s % step == 0 and all its
+ * letters are A/C/G/T.  Entry `offset` of a row is the window whose letters spell offset in
+ * base 4 (A=0 C=1 G=2 T=3), first letter most significant (fast.moving.side = "right",
+ * invert_twobit_order = 0) or least significant ("left" / as.array, 1).
+ *   collapsed = 1: one row of 4^width entries over all sequences of the subject (a
+ *                  DNAString, or simplify.as = "collapsed")
+ *   collapsed = 0: nseq x 4^width, column-major like allocMatrix() (simplify.as = "matrix";
+ *                  "list" is its rows).  nseq * 4^width must fit an R matrix (< 2^31).
+ *   as_prob = 0: counts_out (int32); as_prob = 1: freq_out (double), every row divided by
+ *                  its sum as normalize_oligo_freqs() does (:286-301; all-zero rows stay 0).
+ * Chunk subjects count the windows whose last letter lies in the chunk's report range, with
+ * `step` judged in whole-subject coordinates, so the tables of the chunks of a sharded
+ * sequence add up to the table of the sequence.  Labels, dim and dimnames
+ * (format_oligo_freqs, :414-452) are the host layer's job.
+ * Errors: width outside 1..15 ("_new_TwobitEncodingBuffer(): 'buflength' must be >= 1 and
+ * <= 15", src/utils.c:101-102), step < 1 (R/letterFrequency.R:26-34).
+ * ------------------------------------------------------------------------------------ */
+int bsgpu_oligo_frequency(const bsgpu_subject *subject, int width, int step,
+		int invert_twobit_order, int collapsed, int as_prob,
+		int32_t *counts_out, double *freq_out);
+/* Device-side twin for callers that own the device (bench, multi-GPU sharding): adds the
+ * collapsed table of `subject` into d_counts[4^width] (DEVICE pointer, 64-bit counters) on
+ * `stream`; asynchronous. */
+int bsgpu_oligo_count_device(const bsgpu_subject *subject, int width, int step,
+		int invert_twobit_order, unsigned long long *d_counts, void *stream);
+/* Host-buffer entry points with the reference's .Call shapes (upload + count + free). */
+int bsgpu_XString_oligo_frequency(const uint8_t *x, int64_t x_length, int width, int step,
+		int invert_twobit_order, int as_prob, int32_t *counts_out, double *freq_out);
+int bsgpu_XStringSet_oligo_frequency(const uint8_t *concat, const int32_t *widths, int32_t n,
+		int width, int step, int invert_twobit_order, int collapsed, int as_prob,
+		int32_t *counts_out, double *freq_out);
+
 /* Human-readable description of the engine the last match/count call used, e.g.
  * "byteseed_hash S=10 seed=16 filter_bytes=19779008 buckets=6593006 ..." or
  * "qgram_hamming q=12 shifts=7 entries=6930000" or "tb_hash w=12 buckets=2097152 + verify". */
@@ -247,7 +286,7 @@ const char *bsgpu_last_plan(void);
 int64_t bsgpu_launch_count(void);
 
 /* Opt-in timing of the hot kernels (pack_subject_kernel, scan_byteseed_kernel,
- * match_plain_kernel, scan_tb_kernel, qscan_kernel) with CUDA events recorded on the
+ * match_plain_kernel, scan_tb_kernel, qscan_kernel, oligo_freq_kernel) with CUDA events recorded on the
  * launching stream.  bsgpu_kernel_timing(1) starts collecting (at most 8192 launches),
  * bsgpu_kernel_times() waits for them, writes up to max_entries (name, milliseconds) pairs in
  * launch order, forgets them and returns how many it wrote (-1 on error). */

@@ -10,6 +10,8 @@ R calls them (src/R_init_Biostrings.c:27-147):
     match_PDict3Parts_XStringViews          -> RefPPTB.match_views
     vmatch_PDict3Parts_XStringSet           -> RefPPTB.vmatch_set
     ByPos_MIndex_combine / _endIndex        -> mindex_combine / mindex_endindex
+    XString_oligo_frequency / XStringSet_oligo_frequency (src/letter_frequency.c:634,667)
+                                            -> oligo_frequency_xstring / oligo_frequency_set
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
 """
@@ -82,6 +84,13 @@ def lib():
             L.ref_vmatch_set_set.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_int] + [C.c_int] * 5 + \
                 [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        if hasattr(L, "ref_oligo_frequency_xstring"):
+            L.ref_oligo_frequency_xstring.argtypes = [C.c_void_p] + [C.c_int] * 7
+            L.ref_oligo_frequency_set.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_char_p]
+            L.ref_result_dim.argtypes = [C.c_void_p]
+            L.ref_result_labels.restype = C.c_long
+            L.ref_result_labels.argtypes = [C.c_int, C.c_char_p, C.c_long]
+            L.ref_result_list_flat_double.argtypes = [C.c_void_p]
         L.ref_result_length.restype = C.c_long
         L.ref_result_list_lengths.restype = C.c_long
         L.ref_result_list_lengths.argtypes = [C.c_void_p]
@@ -129,8 +138,12 @@ def _fetch_result(release=True, L=None):
     elif t == _VECSXP:
         lens = np.empty(n, dtype=np.int32)
         total = L.ref_result_list_lengths(_ptr(lens))
-        flat = np.empty(total, dtype=np.int32)
-        L.ref_result_list_flat(_ptr(flat))
+        if hasattr(L, "ref_result_list_elt_type") and L.ref_result_list_elt_type() == _REALSXP:
+            flat = np.empty(total, dtype=np.float64)
+            L.ref_result_list_flat_double(_ptr(flat))
+        else:
+            flat = np.empty(total, dtype=np.int32)
+            L.ref_result_list_flat(_ptr(flat))
         out, off = [], 0
         for k in lens.tolist():
             if k < 0:
@@ -265,6 +278,47 @@ def vmatch_set_set(pat_concat, pat_widths, subj_concat, subj_widths, max_mismatc
                                 int(fixed[1]), algo.encode(), collapse, int(is_double), _ptr(w),
                                 len(w), mode), L)
     return _fetch_result(L=L)
+
+
+# ---- oligonucleotideFrequency (src/letter_frequency.c:634,667) ---------------------------------
+
+def _fetch_labelled(L):
+    """(values, dim tuple or None, [labels per dimension or None]) of the current result."""
+    dim = (C.c_int * 3)()
+    nd = L.ref_result_dim(dim)
+    dims = tuple(dim[i] for i in range(nd)) if nd > 0 else None
+    labels = []
+    buf = C.create_string_buffer(1 << 26)
+    for which in range(max(nd, 1)):
+        k = L.ref_result_labels(which, buf, len(buf))
+        if k < 0:
+            raise RuntimeError("label buffer too small")
+        labels.append(buf.value.decode("latin1").split("\n")[:-1] if k > 0 else None)
+    return _fetch_result(L=L), dims, labels
+
+
+def oligo_frequency_xstring(x, width, step=1, as_prob=False, as_array=False,
+                            fast_moving_side="right", with_labels=True):
+    """XString_oligo_frequency (the .Call behind oligonucleotideFrequency() on a DNAString,
+    R/letterFrequency.R:564-586).  Returns (values, dim, labels)."""
+    L = lib()
+    xb = _u8(x)
+    _check(L.ref_oligo_frequency_xstring(_ptr(xb), len(xb), int(width), int(step), int(as_prob),
+                                         int(as_array), int(fast_moving_side != "right"),
+                                         int(with_labels)), L)
+    return _fetch_labelled(L)
+
+
+def oligo_frequency_set(concat, widths, width, step=1, as_prob=False, as_array=False,
+                        fast_moving_side="right", with_labels=True, simplify_as="matrix"):
+    """XStringSet_oligo_frequency (R/letterFrequency.R:588-612).  "matrix": values is the
+    column-major N x 4^width matrix, flat."""
+    L = lib()
+    cb, wb = _u8(concat), _i32(widths)
+    _check(L.ref_oligo_frequency_set(_ptr(cb), _ptr(wb), len(wb), int(width), int(step),
+                                     int(as_prob), int(as_array), int(fast_moving_side != "right"),
+                                     int(with_labels), simplify_as.encode()), L)
+    return _fetch_labelled(L)
 
 
 def stash_result():

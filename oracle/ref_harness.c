@@ -17,6 +17,8 @@
  *   ByPos_MIndex_endIndex / _combine  src/MIndex_class.c:134,230
  *   ACtree2_nnodes / _has_all_flinks / _compute_all_flinks
  *                                     src/match_pdict_ACtree2.c:681,972,981
+ *   XString_oligo_frequency / XStringSet_oligo_frequency
+ *                                     src/letter_frequency.c:634,667
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -55,6 +57,10 @@ SEXP match_XStringSet_XStringViews(SEXP pattern, SEXP subject, SEXP views_start,
 SEXP vmatch_XStringSet_XStringSet(SEXP pattern, SEXP subject, SEXP max_mismatch, SEXP min_mismatch,
 		SEXP with_indels, SEXP fixed, SEXP algorithm, SEXP collapse, SEXP weight,
 		SEXP matches_as, SEXP envir);
+SEXP XString_oligo_frequency(SEXP x, SEXP width, SEXP step, SEXP as_prob, SEXP as_array,
+		SEXP fast_moving_side, SEXP with_labels, SEXP base_codes);
+SEXP XStringSet_oligo_frequency(SEXP x, SEXP width, SEXP step, SEXP as_prob, SEXP as_array,
+		SEXP fast_moving_side, SEXP with_labels, SEXP simplify_as, SEXP base_codes);
 SEXP ByPos_MIndex_endIndex(SEXP x_high2low, SEXP x_ends, SEXP x_width0);
 SEXP ByPos_MIndex_combine(SEXP ends_listlist);
 
@@ -451,7 +457,131 @@ int ref_mindex_endindex(int M, const int *high2low, const int *width0)
 	GUARD_END(0, -1)
 }
 
+/* ---- oligonucleotideFrequency (src/letter_frequency.c:634,667) ---------------- */
+
+static SEXP new_named_base_codes(void)
+{
+	static const char *const letters[4] = {"A", "C", "G", "T"};
+	SEXP codes = new_base_codes(), names = NEW_CHARACTER(4);
+	int i;
+
+	for (i = 0; i < 4; i++)
+		SET_STRING_ELT(names, i, Rf_mkChar(letters[i]));
+	SET_NAMES(codes, names);
+	return codes;
+}
+
+int ref_oligo_frequency_xstring(const unsigned char *x, int x_length, int width, int step,
+		int as_prob, int as_array, int fast_moving_side_is_left, int with_labels)
+{
+	GUARD_BEGIN
+	minir_set_generation(2);
+	result = XString_oligo_frequency(
+			minir_new_XString("DNAString", (const char *) x, x_length),
+			Rf_ScalarInteger(width), Rf_ScalarInteger(step),
+			Rf_ScalarLogical(as_prob), Rf_ScalarLogical(as_array),
+			Rf_mkString(fast_moving_side_is_left ? "left" : "right"),
+			Rf_ScalarLogical(with_labels), new_named_base_codes());
+	GUARD_END(0, -1)
+}
+
+/* simplify_as: "matrix" | "list" | "collapsed" (R/letterFrequency.R:66-75) */
+int ref_oligo_frequency_set(const unsigned char *concat, const int *widths, int n, int width,
+		int step, int as_prob, int as_array, int fast_moving_side_is_left, int with_labels,
+		const char *simplify_as)
+{
+	GUARD_BEGIN
+	minir_set_generation(2);
+	result = XStringSet_oligo_frequency(
+			new_set("DNAStringSet", n, concat, widths),
+			Rf_ScalarInteger(width), Rf_ScalarInteger(step),
+			Rf_ScalarLogical(as_prob), Rf_ScalarLogical(as_array),
+			Rf_mkString(fast_moving_side_is_left ? "left" : "right"),
+			Rf_ScalarLogical(with_labels), Rf_mkString(simplify_as),
+			new_named_base_codes());
+	GUARD_END(0, -1)
+}
+
 /* ---- result access ---------------------------------------------------------- */
+
+/* dim attribute of the result (or of its first list element): returns ndim, fills out[3] */
+int ref_result_dim(int *out)
+{
+	SEXP x = result, dim;
+	int i;
+
+	if (x == NULL)
+		return -1;
+	if (x->type == VECSXP && x->length > 0)
+		x = VECTOR_ELT(x, 0);
+	dim = GET_DIM(x);
+	if (dim == R_NilValue)
+		return 0;
+	for (i = 0; i < LENGTH(dim) && i < 3; i++)
+		out[i] = INTEGER(dim)[i];
+	return LENGTH(dim);
+}
+
+/* Labels of the result (or of its first list element) joined with '\n': names() of a vector,
+ * else dimnames()[[which]].  Returns the number of labels, 0 when there are none, -1 when
+ * buf is too small. */
+long ref_result_labels(int which, char *buf, long buflen)
+{
+	SEXP x = result, labels;
+	long i, used = 0;
+
+	if (x == NULL)
+		return -1;
+	if (x->type == VECSXP && x->length > 0)
+		x = VECTOR_ELT(x, 0);
+	labels = GET_NAMES(x);
+	if (labels == R_NilValue || labels == NULL) {
+		SEXP dn = GET_DIMNAMES(x);
+
+		if (dn == R_NilValue || which >= LENGTH(dn))
+			return 0;
+		labels = VECTOR_ELT(dn, which);
+	}
+	if (labels == R_NilValue)
+		return 0;
+	for (i = 0; i < labels->length; i++) {
+		const char *s = CHAR(STRING_ELT(labels, i));
+		long k = (long) strlen(s);
+
+		if (used + k + 2 > buflen)
+			return -1;
+		memcpy(buf + used, s, (size_t) k);
+		used += k;
+		buf[used++] = '\n';
+	}
+	buf[used] = 0;
+	return labels->length;
+}
+
+/* type of the first non-NULL element of a list result */
+int ref_result_list_elt_type(void)
+{
+	long i;
+
+	for (i = 0; i < result->length; i++)
+		if (VECTOR_ELT(result, i) != R_NilValue)
+			return VECTOR_ELT(result, i)->type;
+	return NILSXP;
+}
+
+void ref_result_list_flat_double(double *out)
+{
+	long i;
+
+	for (i = 0; i < result->length; i++) {
+		SEXP e = VECTOR_ELT(result, i);
+
+		if (e == R_NilValue)
+			continue;
+		memcpy(out, REAL(e), (size_t) LENGTH(e) * sizeof(double));
+		out += LENGTH(e);
+	}
+}
 
 int ref_result_type(void) { return result == NULL ? -1 : result->type; }
 long ref_result_length(void) { return result == NULL ? -1 : result->length; }

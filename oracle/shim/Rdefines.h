@@ -27,6 +27,7 @@ enum {
 
 typedef struct minir_sexp *SEXP;
 typedef int Rboolean;
+typedef ptrdiff_t R_xlen_t;
 
 struct minir_slot {
 	char *name;
@@ -101,6 +102,19 @@ SEXP GET_SLOT(SEXP x, SEXP name);
 SEXP SET_SLOT(SEXP x, SEXP name, SEXP value);
 void SET_NAMES(SEXP x, SEXP names);
 SEXP GET_NAMES(SEXP x);
+/* dim / dimnames attributes (src/letter_frequency.c); kept beside the slots */
+void SET_DIM(SEXP x, SEXP dim);
+SEXP GET_DIM(SEXP x);
+void SET_DIMNAMES(SEXP x, SEXP dimnames);
+SEXP GET_DIMNAMES(SEXP x);
+SEXP Rf_alloc3DArray(int type, int nrow, int ncol, int nface);
+#define alloc3DArray Rf_alloc3DArray
+int Rf_asLogical(SEXP x);
+#define asLogical Rf_asLogical
+SEXP Rf_list2(SEXP a, SEXP b);
+SEXP Rf_list3(SEXP a, SEXP b, SEXP c);
+#define list2 Rf_list2
+#define list3 Rf_list3
 SEXP MAKE_CLASS(const char *name);
 SEXP NEW_OBJECT(SEXP classdef);
 

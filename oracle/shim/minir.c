@@ -139,9 +139,31 @@ SEXP minir_alloc(int type, long length)
 
 SEXP Rf_allocVector(int type, long length) { return minir_alloc(type, length); }
 
+static SEXP new_dim(int n, int d0, int d1, int d2)
+{
+	SEXP dim = minir_alloc(INTSXP, n);
+
+	((int *) dim->data)[0] = d0;
+	((int *) dim->data)[1] = d1;
+	if (n > 2)
+		((int *) dim->data)[2] = d2;
+	return dim;
+}
+
 SEXP Rf_allocMatrix(int type, int nrow, int ncol)
 {
-	return minir_alloc(type, (long) nrow * ncol);
+	SEXP x = minir_alloc(type, (long) nrow * ncol);
+
+	SET_DIM(x, new_dim(2, nrow, ncol, 0));
+	return x;
+}
+
+SEXP Rf_alloc3DArray(int type, int nrow, int ncol, int nface)
+{
+	SEXP x = minir_alloc(type, (long) nrow * ncol * nface);
+
+	SET_DIM(x, new_dim(3, nrow, ncol, nface));
+	return x;
 }
 
 static void free_sexp(SEXP x)
@@ -379,6 +401,53 @@ void SET_NAMES(SEXP x, SEXP names)
 }
 
 SEXP GET_NAMES(SEXP x) { return x->names; }
+
+/* dim / dimnames live in the slot list under names no S4 class uses */
+static SEXP get_attr(SEXP x, const char *nm)
+{
+	struct minir_slot *s;
+
+	for (s = x->slots; s != NULL; s = s->next)
+		if (strcmp(s->name, nm) == 0)
+			return s->value;
+	return R_NilValue;
+}
+
+void SET_DIM(SEXP x, SEXP dim) { SET_SLOT(x, Rf_install(".dim"), dim); }
+SEXP GET_DIM(SEXP x) { return get_attr(x, ".dim"); }
+void SET_DIMNAMES(SEXP x, SEXP dimnames) { SET_SLOT(x, Rf_install(".dimnames"), dimnames); }
+SEXP GET_DIMNAMES(SEXP x) { return get_attr(x, ".dimnames"); }
+
+int Rf_asLogical(SEXP x)
+{
+	if (x->length < 1)
+		return NA_LOGICAL;
+	if (x->type == LGLSXP || x->type == INTSXP)
+		return ((int *) x->data)[0];
+	if (x->type == REALSXP)
+		return ((double *) x->data)[0] != 0.0;
+	return NA_LOGICAL;
+}
+
+/* pairlists are only used as dimnames containers here: a plain list serves */
+SEXP Rf_list2(SEXP a, SEXP b)
+{
+	SEXP x = minir_alloc(VECSXP, 2);
+
+	SET_VECTOR_ELT(x, 0, a);
+	SET_VECTOR_ELT(x, 1, b);
+	return x;
+}
+
+SEXP Rf_list3(SEXP a, SEXP b, SEXP c)
+{
+	SEXP x = minir_alloc(VECSXP, 3);
+
+	SET_VECTOR_ELT(x, 0, a);
+	SET_VECTOR_ELT(x, 1, b);
+	SET_VECTOR_ELT(x, 2, c);
+	return x;
+}
 
 SEXP MAKE_CLASS(const char *name) { return Rf_mkChar(name); }
 

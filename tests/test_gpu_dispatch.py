@@ -142,3 +142,55 @@ def test_mindex_combine_entry_point():
             ref.use("ref")
     assert_same_ends(outs["ref"], outs["dispatch"])
     assert sum(e is not None for e in outs["ref"]) > 50
+
+
+def test_oligo_frequency_through_the_dot_call_boundary():
+    """XString_oligo_frequency / XStringSet_oligo_frequency (src/letter_frequency.c:634,667)
+    of biostrings_b200/csrc/letter_frequency_gpu.c against the reference's own: values, dim,
+    names / dimnames of every result shape, and the error text."""
+    g = rng(1234)
+    x = random_dna(g, 20_000)
+    x[g.integers(0, x.size, 300)] = IUPAC_AMBIG[g.integers(0, len(IUPAC_AMBIG), 300)]
+    widths = g.integers(0, 200, 150).astype(np.int32)
+    concat = x[:int(widths.sum())]
+
+    def both(fn, *a, **kw):
+        out = []
+        for which in ("ref", "dispatch"):
+            ref.use(which)
+            try:
+                out.append(fn(*a, **kw))
+            finally:
+                ref.use("ref")
+        return out
+
+    def same_table(a, b):
+        (va, da, la), (vb, db, lb) = a, b
+        assert da == db and la == lb
+        if isinstance(va, list):
+            assert len(va) == len(vb)
+            for p, q in zip(va, vb):
+                assert p.dtype == q.dtype and np.array_equal(p, q)
+        else:
+            assert va.dtype == vb.dtype and np.array_equal(va, vb)
+
+    for width, step in [(1, 1), (2, 1), (3, 3), (4, 2), (6, 1), (8, 5)]:
+        for kw in ({}, {"as_prob": True}, {"fast_moving_side": "left"}, {"with_labels": False},
+                   {"as_array": True, "fast_moving_side": "left"}):
+            if kw.get("as_array") and width > 4:
+                continue
+            same_table(*both(ref.oligo_frequency_xstring, x, width, step, **kw))
+        for simplify_as in ("matrix", "list", "collapsed"):
+            for kw in ({}, {"as_prob": True}, {"with_labels": False}):
+                if width > 6:
+                    continue
+                same_table(*both(ref.oligo_frequency_set, concat, widths, width, step,
+                                 simplify_as=simplify_as, **kw))
+    same_table(*both(ref.oligo_frequency_set, concat, widths, 2, simplify_as="list", as_array=True,
+                     fast_moving_side="left"))
+    ref.use("dispatch")
+    try:
+        with pytest.raises(ref.RefError, match="'buflength' must be >= 1 and <= 15"):
+            ref.oligo_frequency_xstring(x, 16)
+    finally:
+        ref.use("ref")
