@@ -27,6 +27,8 @@ SYMBOLS = [
     "bsgpu_kernel_timing", "bsgpu_kernel_times", "bsgpu_patterns_build",
     "bsgpu_oligo_frequency", "bsgpu_oligo_count_device", "bsgpu_XString_oligo_frequency",
     "bsgpu_XStringSet_oligo_frequency",
+    "bsgpu_subject_fasta", "bsgpu_fasta_info_free", "bsgpu_subject_nsequences", "bsgpu_subject_element",
+    "bsgpu_subject_download",
 ]
 
 
@@ -44,6 +46,12 @@ class Result(C.Structure):
                 ("dcounts", C.POINTER(C.c_double)), ("n_which", C.c_int64),
                 ("which", C.POINTER(C.c_int32)), ("n_rows", C.c_int64),
                 ("ends_offsets", C.POINTER(C.c_int64)), ("ends", C.POINTER(C.c_int32))]
+
+
+class FastaInfo(C.Structure):
+    _fields_ = [("nrec", C.c_int32), ("ninvalid", C.c_int64), ("nletters", C.c_int64),
+                ("widths", C.POINTER(C.c_int32)), ("desc_offset", C.POINTER(C.c_int64)),
+                ("desc_length", C.POINTER(C.c_int32))]
 
 
 _lib = None
@@ -100,6 +108,12 @@ def lib():
     L.bsgpu_oligo_count_device.argtypes = [vp] + [C.c_int] * 3 + [vp, vp]
     L.bsgpu_XString_oligo_frequency.argtypes = [vp, i64] + [C.c_int] * 4 + [vp, vp]
     L.bsgpu_XStringSet_oligo_frequency.argtypes = [vp, vp, i32] + [C.c_int] * 5 + [vp, vp]
+    L.bsgpu_subject_fasta.argtypes = [vp, i64, vp, C.c_int, C.POINTER(vp), C.POINTER(FastaInfo)]
+    L.bsgpu_fasta_info_free.argtypes = [C.POINTER(FastaInfo)]
+    L.bsgpu_fasta_info_free.restype = None
+    L.bsgpu_subject_nsequences.argtypes = [vp]
+    L.bsgpu_subject_element.argtypes = [vp, i32, C.POINTER(vp)]
+    L.bsgpu_subject_download.argtypes = [vp, vp, vp]
     L.bsgpu_kernel_timing.argtypes = [C.c_int]
     L.bsgpu_kernel_times.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     _lib = L

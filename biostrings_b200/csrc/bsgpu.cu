@@ -23,6 +23,7 @@
 #include "../../include/bsgpu.h"
 #include "bsgpu_qindex.cuh"
 #include "bsgpu_oligo.cuh"
+#include "bsgpu_fasta.cuh"
 
 // ---------------------------------------------------------------------------------------
 // errors
@@ -1141,6 +1142,7 @@ static int ensure_packed(const bsgpu_subject *s, cudaStream_t st);
 // srcs[i] points at host letters of segment i (may alias one big buffer).
 // set_concat != NULL: the segments are the consecutive pieces of one packed host buffer
 // (a DNAStringSet): it is uploaded as is and laid out by scatter_set_kernel on the device.
+// one_src may be a device pointer (bsgpu_subject_element): the copy kind is inferred.
 static int subject_finish(bsgpu_subject *s, const uint8_t *const *srcs, const uint8_t *one_src,
 			  const uint8_t *set_concat = nullptr)
 {
@@ -1167,7 +1169,7 @@ static int subject_finish(bsgpu_subject *s, const uint8_t *const *srcs, const ui
 					 (size_t) (s->total + 64 - seg_end)));
 		if (s->seg_len[0] > 0)
 			CUDA_TRY(cudaMemcpyAsync(s->d_bytes.p + s->seg_start[0], one_src ? one_src : srcs[0],
-						 (size_t) s->seg_len[0], cudaMemcpyHostToDevice));
+						 (size_t) s->seg_len[0], cudaMemcpyDefault));
 	} else {
 		CUDA_TRY(cudaMemsetAsync(s->d_bytes.p, BSGPU_SEP_BYTE, (size_t) s->total + 64));
 	}
@@ -1376,6 +1378,192 @@ extern "C" int bsgpu_subject_repack(bsgpu_subject *s, void *stream)
 
 extern "C" void bsgpu_subject_free(bsgpu_subject *s) { delete s; }
 extern "C" int64_t bsgpu_subject_nletters(const bsgpu_subject *s) { return s ? s->nletters : 0; }
+
+// ---------------------------------------------------------------------------------------
+// Subject ingestion: FASTA text -> resident subject (read_fasta_files, src/read_fasta_files.c:412)
+// ---------------------------------------------------------------------------------------
+
+extern "C" void bsgpu_fasta_info_free(bsgpu_fasta_info *info)
+{
+	if (info == nullptr)
+		return;
+	free(info->widths);
+	free(info->desc_offset);
+	free(info->desc_length);
+	memset(info, 0, sizeof(*info));
+}
+
+extern "C" int bsgpu_subject_fasta(const uint8_t *text, int64_t nbytes, const int32_t *lkup, int lkup_length,
+		bsgpu_subject **out, bsgpu_fasta_info *info)
+{
+	if (out == nullptr || info == nullptr || nbytes < 0 || (nbytes > 0 && text == nullptr) ||
+	    lkup == nullptr || lkup_length < 0)
+		return fail(BSGPU_EINVAL, "bsgpu_subject_fasta(): bad arguments");
+	*out = nullptr;
+	memset(info, 0, sizeof(*info));
+	TRY(ensure_device());
+	// translate_byte(): keys >= lkup_length and NA entries are not letters of the alphabet
+	int16_t lk16[256];
+	for (int k = 0; k < 256; k++)
+		lk16[k] = k < lkup_length && lkup[k] != BSGPU_NA ? (int16_t) (lkup[k] & 0xFF) : (int16_t) -1;
+	const int64_t nchunks = (nbytes + BSGPU_FASTA_CHUNK - 1) / BSGPU_FASTA_CHUNK;
+	const size_t padded = (size_t) ((nbytes + 15) / 16 * 16 + 16);
+	DevBuf<uint8_t> d_text;
+	DevBuf<int16_t> d_lkup;
+	DevBuf<BsgpuFastaSummary> d_sums;
+	DevBuf<BsgpuFastaResolved> d_res;
+	std::vector<BsgpuFastaSummary> sums((size_t) nchunks);
+	std::vector<BsgpuFastaResolved> res;
+
+	TRY(d_text.alloc(padded));
+	{
+		size_t tail = std::min<size_t>(padded, 32);             // covers everything past the text
+
+		CUDA_TRY(cudaMemsetAsync(d_text.p + (padded - tail), '\n', tail));
+	}
+	if (nbytes > 0)
+		CUDA_TRY(cudaMemcpyAsync(d_text.p, text, (size_t) nbytes, cudaMemcpyHostToDevice));
+	TRY(d_lkup.upload(lk16, 256));
+	TRY(d_sums.alloc((size_t) nchunks));
+	if (nchunks > 0) {
+		KernelTimer kt("fasta_summary_kernel", 0);
+		fasta_summary_kernel<<<(unsigned) ((nchunks + 127) / 128), 128>>>(d_text.p, nbytes, nchunks, d_lkup.p, d_sums.p);
+		g_launches++;
+	}
+	CUDA_TRY(cudaGetLastError());
+	if (nchunks > 0)
+		CUDA_TRY(cudaMemcpy(sums.data(), d_sums.p, (size_t) nchunks * sizeof(BsgpuFastaSummary),
+				    cudaMemcpyDeviceToHost));
+	BsgpuFastaTotals t = fasta_resolve(sums, res);
+	if (t.first_seqline >= 0 && (t.first_header < 0 || t.first_seqline < t.first_header)) {
+		// src/read_fasta_files.c:322-327; lines are counted like the reference counts them
+		long long lineno = 1;
+		for (int64_t i = 0; i < t.first_seqline; i++)
+			lineno += text[i] == '\n';
+		return fail(BSGPU_EINVAL, "\">\" expected at beginning of line %lld", lineno);
+	}
+	if (t.nrec > INT32_MAX)
+		return fail(BSGPU_EUNSUPPORTED, "more than INT_MAX FASTA records");
+	const int32_t nrec = (int32_t) t.nrec;
+	std::unique_ptr<bsgpu_subject> s(new bsgpu_subject());
+	int64_t pos = BSGPU_GUARD + t.kept + nrec;      // one separator after every record
+
+	s->kind = SUBJ_SET;
+	s->nseg = nrec;
+	s->nletters = t.kept;
+	s->total = ((pos + BSGPU_GUARD + 127) / 128) * 128;
+	if (s->total >= (1ll << BSGPU_POS_BITS))
+		return fail(BSGPU_EUNSUPPORTED, "subject too long for one device buffer (%lld letters)",
+			    (long long) s->total);
+	TRY(s->d_bytes.alloc((size_t) s->total + 64));
+	CUDA_TRY(cudaMemsetAsync(s->d_bytes.p, BSGPU_SEP_BYTE, (size_t) s->total + 64));
+	TRY(s->d_seg_start.alloc((size_t) nrec));
+	DevBuf<int64_t> d_desc_off;
+	TRY(d_desc_off.alloc((size_t) nrec));
+	if (nchunks > 0) {
+		TRY(d_res.upload(res.data(), (size_t) nchunks));
+		KernelTimer kt("fasta_emit_kernel", 0);
+		fasta_emit_kernel<<<(unsigned) ((nchunks + 127) / 128), 128>>>(d_text.p, nbytes, nchunks, d_lkup.p, d_res.p,
+				s->d_bytes.p, s->d_seg_start.p, d_desc_off.p);
+		g_launches++;
+	}
+	CUDA_TRY(cudaGetLastError());
+	s->seg_start.resize((size_t) nrec);
+	s->seg_len.resize((size_t) nrec);
+	s->seg_coord.assign((size_t) nrec, 0);
+	std::vector<int64_t> desc_off((size_t) nrec);
+	if (nrec > 0) {
+		CUDA_TRY(cudaMemcpy(s->seg_start.data(), s->d_seg_start.p, (size_t) nrec * sizeof(int64_t),
+				    cudaMemcpyDeviceToHost));
+		CUDA_TRY(cudaMemcpy(desc_off.data(), d_desc_off.p, (size_t) nrec * sizeof(int64_t),
+				    cudaMemcpyDeviceToHost));
+	}
+	CUDA_TRY(cudaDeviceSynchronize());
+	for (int32_t r = 0; r < nrec; r++) {
+		int64_t end = r + 1 < nrec ? s->seg_start[(size_t) r + 1] - 1 : pos - 1;
+		int64_t len = end - s->seg_start[(size_t) r];
+
+		if (len < 0 || len > INT32_MAX)
+			return fail(BSGPU_EUNSUPPORTED, "FASTA record %d has more than INT_MAX letters", r + 1);
+		s->seg_len[(size_t) r] = (int32_t) len;
+	}
+	TRY(s->d_seg_len.upload(s->seg_len.data(), (size_t) nrec));
+	TRY(s->d_seg_coord.upload(s->seg_coord.data(), (size_t) nrec));
+	s->scan_lo = BSGPU_GUARD;
+	s->scan_hi = pos;
+	s->packed = false;
+	s->iupac_ready = false;
+	// what the host layer needs to build names(): where every description starts and ends
+	info->nrec = nrec;
+	info->ninvalid = t.invalid;
+	info->nletters = t.kept;
+	info->widths = (int32_t *) malloc((size_t) std::max(nrec, 1) * sizeof(int32_t));
+	info->desc_offset = (int64_t *) malloc((size_t) std::max(nrec, 1) * sizeof(int64_t));
+	info->desc_length = (int32_t *) malloc((size_t) std::max(nrec, 1) * sizeof(int32_t));
+	if (info->widths == nullptr || info->desc_offset == nullptr || info->desc_length == nullptr) {
+		bsgpu_fasta_info_free(info);
+		return fail(BSGPU_ENOMEM, "out of host memory");
+	}
+	for (int32_t r = 0; r < nrec; r++) {
+		int64_t a = desc_off[(size_t) r];
+		const uint8_t *nl = a < nbytes ? (const uint8_t *) memchr(text + a, '\n', (size_t) (nbytes - a)) : nullptr;
+		int64_t e = nl != nullptr ? nl - text : nbytes;
+
+		if (nl != nullptr && e > a && text[e - 1] == '\r')      // delete_trailing_LF_or_CRLF
+			e--;
+		info->widths[r] = s->seg_len[(size_t) r];
+		info->desc_offset[r] = a;
+		info->desc_length[r] = (int32_t) std::min<int64_t>(e - a, INT32_MAX);
+	}
+	set_plan("fasta_ingest bytes=%lld chunks=%lld records=%d letters=%lld invalid=%lld", (long long) nbytes,
+		 (long long) nchunks, nrec, (long long) t.kept, (long long) t.invalid);
+	*out = s.release();
+	return BSGPU_OK;
+}
+
+extern "C" int32_t bsgpu_subject_nsequences(const bsgpu_subject *subj) { return subj ? subj->nseg : 0; }
+
+extern "C" int bsgpu_subject_element(const bsgpu_subject *set, int32_t i, bsgpu_subject **out)
+{
+	if (set == nullptr || out == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_subject_element(): bad arguments");
+	*out = nullptr;
+	if (i < 0 || i >= set->nseg)
+		return fail(BSGPU_EINVAL, "subscript out of bounds");
+	TRY(ensure_device());
+	std::unique_ptr<bsgpu_subject> s(new bsgpu_subject());
+	s->kind = SUBJ_XSTRING;
+	s->nseg = 1;
+	s->seg_len.assign(1, set->seg_len[(size_t) i]);
+	s->seg_coord.assign(1, 0);
+	s->nletters = set->seg_len[(size_t) i];
+	TRY(subject_finish(s.get(), nullptr, set->d_bytes.p + set->seg_start[(size_t) i]));
+	*out = s.release();
+	return BSGPU_OK;
+}
+
+extern "C" int bsgpu_subject_download(const bsgpu_subject *subj, uint8_t *concat_out, int32_t *widths_out)
+{
+	if (subj == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_subject_download(): NULL subject");
+	TRY(ensure_device());
+	if (widths_out != nullptr)
+		for (int32_t r = 0; r < subj->nseg; r++)
+			widths_out[r] = subj->seg_len[(size_t) r];
+	if (concat_out == nullptr || subj->nseg == 0)
+		return BSGPU_OK;
+	// the records lie back to back with one separator in between: one copy, then close the gaps
+	int64_t first = subj->seg_start[0];
+	int64_t last = subj->seg_start[(size_t) subj->nseg - 1] + subj->seg_len[(size_t) subj->nseg - 1];
+	std::vector<uint8_t> stage((size_t) (last - first) + 1);
+	CUDA_TRY(cudaMemcpy(stage.data(), subj->d_bytes.p + first, (size_t) (last - first), cudaMemcpyDeviceToHost));
+	size_t off = 0;
+	for (int32_t r = 0; r < subj->nseg; r++) {
+		memcpy(concat_out + off, stage.data() + (subj->seg_start[(size_t) r] - first), (size_t) subj->seg_len[(size_t) r]);
+		off += (size_t) subj->seg_len[(size_t) r];
+	}
+	return BSGPU_OK;
+}
 
 // ---------------------------------------------------------------------------------------
 // Workspace: candidate / record buffers and counters (per process, grown on demand)

@@ -1,0 +1,226 @@
+// bsgpu_fasta.cuh -- FASTA text -> encoded letters in the subject layout, on the device
+// (subject ingestion).
+//
+// Replaces the two passes of read_fasta_files() over parse_FASTA_file()
+// (src/read_fasta_files.c:240-352,412-451) for one in-memory file:
+//   * lines end at LF; a CR right before that LF belongs to the line end
+//     (delete_trailing_LF_or_CRLF), any other CR is an ordinary byte;
+//   * empty lines and lines starting with ';' are ignored (:283-294);
+//   * a line starting with '>' opens a new record, the rest of the line is its description
+//     (:297-321);
+//   * every other line is sequence data: each byte goes through the integer lookup `lkup`
+//     (translate(), :31-50); bytes the lookup does not know are dropped and counted
+//     ("ignored %lld invalid one-letter sequence codes", :388-391), the others are appended to
+//     the current record;
+//   * a non-empty sequence line before the first '>' is an error (:322-327).
+// The reference reads lines into a 200001-byte buffer; a longer sequence line is simply read in
+// pieces (same result), a longer description or comment line is an error there ("line is too
+// long", :286-291) and accepted here.
+//
+// Parallel formulation.  The text is cut into chunks of BSGPU_FASTA_CHUNK bytes, one thread per
+// chunk walks its bytes with the small state machine above.  What a chunk cannot know locally is
+// the class of the line it starts in the middle of, so pass 1 (fasta_summary_kernel) counts the
+// letters of that first partial line as if it were sequence data, separately from the lines that
+// start inside the chunk; the host resolves the classes and prefix sums over the chunk summaries
+// (fasta_resolve, one step per chunk), and pass 2 (fasta_emit_kernel) walks the chunk again
+// and stores every kept letter at  guard + letters before + record index  -- the concat layout
+// of bsgpu_subject with one separator after every record -- and the start of every record.
+// The walk itself (fasta_walk_chunk) is plain C++ shared by both kernels and by the host-side
+// check in tests/hostcheck/, which runs it on the CPU against the reference's parser.
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+#ifdef __CUDACC__
+#define BSGPU_HD __host__ __device__ __forceinline__
+#else
+#define BSGPU_HD inline
+#endif
+
+#define BSGPU_FASTA_CHUNK 512           // bytes per thread (multiple of 16)
+#define BSGPU_FASTA_GUARD 128           // = BSGPU_GUARD: letters in front of the first record
+
+enum { BSGPU_FASTA_SEQ = 0, BSGPU_FASTA_SKIP = 1, BSGPU_FASTA_PASS = 2 };
+
+struct BsgpuFastaSummary {
+	int32_t kept_head, invalid_head;        // first partial line, if it is sequence data
+	int32_t kept_rest, invalid_rest;        // lines that start in this chunk
+	int32_t headers;                        // description lines that start in this chunk
+	int32_t class_out;                      // class of the line the chunk ends in; PASS = no line starts here
+	int32_t first_header;                   // offset in the chunk of its first description line, or -1
+	int32_t first_seqline;                  // offset of the first non-empty sequence line starting here, or -1
+};
+
+struct BsgpuFastaResolved {
+	int64_t kept_before;                    // letters kept in front of this chunk
+	int32_t headers_before;                 // records opened in front of this chunk
+	int32_t class_in;                       // class of the line the chunk starts in the middle of
+};
+
+// 16 text bytes at offset i (multiple of 16; the buffer is padded to a multiple of 16)
+BSGPU_HD void bsgpu_fasta_load16(const uint8_t *text, int64_t i, uint32_t w[4])
+{
+#ifdef __CUDA_ARCH__
+	uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + i));
+
+	w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+#else
+	for (int k = 0; k < 4; k++)
+		w[k] = (uint32_t) text[i + 4 * k] | ((uint32_t) text[i + 4 * k + 1] << 8) |
+		       ((uint32_t) text[i + 4 * k + 2] << 16) | ((uint32_t) text[i + 4 * k + 3] << 24);
+#endif
+}
+
+// Walks chunk [a, b) of text[0, n).  EMIT = false: fills *sum.  EMIT = true: `in` holds the
+// resolved state in front of the chunk; kept letters go to out[], record starts to seg_start[]
+// and the offsets of the description texts (the byte after '>') to desc_off[].
+// lkup: 256 entries, < 0 = not a letter of the alphabet.
+template <bool EMIT>
+BSGPU_HD void fasta_walk_chunk(const uint8_t *text, int64_t n, int64_t a, int64_t b, const int16_t *lkup,
+			       BsgpuFastaSummary *sum, BsgpuFastaResolved in, uint8_t *out,
+			       int64_t *seg_start, int64_t *desc_off)
+{
+	bool at_line_start = a == 0 || text[a - 1] == '\n';
+	bool in_head = !at_line_start, saw_line_start = false;
+	int cls = at_line_start || !EMIT ? BSGPU_FASTA_SEQ : in.class_in;
+	int32_t kept_head = 0, invalid_head = 0, kept_rest = 0, invalid_rest = 0, headers = 0;
+	int32_t first_header = -1, first_seqline = -1;
+	int64_t kept = in.kept_before;
+	int64_t hdrs = in.headers_before;
+
+	for (int64_t i0 = a; i0 < b; i0 += 16) {
+		uint32_t w[4];
+
+		bsgpu_fasta_load16(text, i0, w);
+#pragma unroll
+		for (int k = 0; k < 16; k++) {
+			int64_t i = i0 + k;
+
+			if (i >= b)
+				break;
+			uint32_t c = (w[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+			bool cr_of_crlf = c == '\r' && i + 1 < n && text[i + 1] == '\n';
+
+			if (at_line_start) {
+				in_head = false;
+				saw_line_start = true;
+				if (c == '>') {
+					cls = BSGPU_FASTA_SKIP;
+					headers++;
+					if (first_header < 0)
+						first_header = (int32_t) (i - a);
+					if (EMIT) {
+						seg_start[hdrs] = BSGPU_FASTA_GUARD + kept + hdrs;
+						desc_off[hdrs] = i + 1;
+						hdrs++;
+					}
+				} else if (c == ';') {
+					cls = BSGPU_FASTA_SKIP;
+				} else {
+					cls = BSGPU_FASTA_SEQ;
+					if (c != '\n' && !cr_of_crlf && first_seqline < 0)
+						first_seqline = (int32_t) (i - a);
+				}
+			}
+			at_line_start = c == '\n';
+			if (c == '\n' || cls != BSGPU_FASTA_SEQ || cr_of_crlf)
+				continue;
+			int code = lkup[c];
+			if (code < 0) {
+				if (in_head)
+					invalid_head++;
+				else
+					invalid_rest++;
+				continue;
+			}
+			if (EMIT) {
+				if (hdrs > 0)
+					out[BSGPU_FASTA_GUARD + kept + hdrs - 1] = (uint8_t) code;
+				kept++;
+			} else if (in_head) {
+				kept_head++;
+			} else {
+				kept_rest++;
+			}
+		}
+	}
+	if (!EMIT) {
+		sum->kept_head = kept_head;
+		sum->invalid_head = invalid_head;
+		sum->kept_rest = kept_rest;
+		sum->invalid_rest = invalid_rest;
+		sum->headers = headers;
+		sum->class_out = saw_line_start ? cls : BSGPU_FASTA_PASS;
+		sum->first_header = first_header;
+		sum->first_seqline = first_seqline;
+	}
+}
+
+struct BsgpuFastaTotals {
+	int64_t kept = 0, invalid = 0, nrec = 0;
+	int64_t first_header = -1;      // byte offset of the first description line
+	int64_t first_seqline = -1;     // byte offset of the first non-empty sequence line
+};
+
+// Host step between the two passes: classes of the lines that straddle chunk boundaries and the
+// prefix sums of kept letters / records.  One iteration per chunk.
+static inline BsgpuFastaTotals fasta_resolve(const std::vector<BsgpuFastaSummary> &sums,
+					     std::vector<BsgpuFastaResolved> &res)
+{
+	BsgpuFastaTotals t;
+	int cls = BSGPU_FASTA_SEQ;      // class of the line the previous chunk ended in
+
+	res.resize(sums.size());
+	for (size_t c = 0; c < sums.size(); c++) {
+		const BsgpuFastaSummary &s = sums[c];
+
+		res[c].kept_before = t.kept;
+		res[c].headers_before = (int32_t) t.nrec;
+		res[c].class_in = cls;
+		if (cls == BSGPU_FASTA_SEQ) {   // only counted when the chunk starts inside a line
+			t.kept += s.kept_head;
+			t.invalid += s.invalid_head;
+		}
+		t.kept += s.kept_rest;
+		t.invalid += s.invalid_rest;
+		t.nrec += s.headers;
+		int64_t base = (int64_t) c * BSGPU_FASTA_CHUNK;
+		if (t.first_header < 0 && s.first_header >= 0)
+			t.first_header = base + s.first_header;
+		if (t.first_seqline < 0 && s.first_seqline >= 0)
+			t.first_seqline = base + s.first_seqline;
+		if (s.class_out != BSGPU_FASTA_PASS)
+			cls = s.class_out;
+	}
+	return t;
+}
+
+#ifdef __CUDACC__
+__global__ void __launch_bounds__(128)
+fasta_summary_kernel(const uint8_t *__restrict__ text, int64_t n, int64_t nchunks,
+		     const int16_t *__restrict__ lkup, BsgpuFastaSummary *__restrict__ sums)
+{
+	int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (c >= nchunks)
+		return;
+	int64_t a = c * BSGPU_FASTA_CHUNK, b = a + BSGPU_FASTA_CHUNK < n ? a + BSGPU_FASTA_CHUNK : n;
+	BsgpuFastaResolved none = {0, 0, BSGPU_FASTA_SEQ};
+
+	fasta_walk_chunk<false>(text, n, a, b, lkup, sums + c, none, nullptr, nullptr, nullptr);
+}
+
+__global__ void __launch_bounds__(128)
+fasta_emit_kernel(const uint8_t *__restrict__ text, int64_t n, int64_t nchunks,
+		  const int16_t *__restrict__ lkup, const BsgpuFastaResolved *__restrict__ res,
+		  uint8_t *__restrict__ out, int64_t *__restrict__ seg_start, int64_t *__restrict__ desc_off)
+{
+	int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (c >= nchunks)
+		return;
+	int64_t a = c * BSGPU_FASTA_CHUNK, b = a + BSGPU_FASTA_CHUNK < n ? a + BSGPU_FASTA_CHUNK : n;
+
+	fasta_walk_chunk<true>(text, n, a, b, lkup, nullptr, res[c], out, seg_start, desc_off);
+}
+#endif

@@ -1,0 +1,163 @@
+"""readDNAStringSet (FASTA) on the GPU: subject ingestion.
+
+Mirror of R/XStringSet-io.R:45-55,203-260 (readDNAStringSet(format="fasta") ->
+.read_fasta_files -> .Call "read_fasta_files") over bsgpu_subject_fasta() of the C ABI: the
+file text is uploaded once, the line rules and the letter translation of
+src/read_fasta_files.c:240-352 run on the device and the letters land in the resident subject
+layout.  `read_fasta_to_device` keeps them there (a genome read once serves any number of
+matchPDict / countPDict / oligonucleotideFrequency calls without touching the host again);
+`readDNAStringSet` also brings them back as a DNAStringSet, like the reference returns.
+"""
+import ctypes as C
+import gzip
+import warnings
+
+import numpy as np
+
+from . import _lib
+from ._lib import NA_INTEGER
+from .matchpdict import DeviceSubject
+from .xstring import DNA_CODES, DNAStringSet
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def dna_lkup():
+    """get_seqtype_conversion_lookup("B", "DNA") (R/seqtype.R): the DNA alphabet in both cases
+    -> codes, NA elsewhere, as long as the largest letter + 1."""
+    keys = {}
+    for letter, code in DNA_CODES.items():
+        keys[ord(letter)] = code
+        keys[ord(letter.lower())] = code
+    lkup = np.full(max(keys) + 1, NA_INTEGER, dtype=np.int32)
+    for k, v in keys.items():
+        lkup[k] = v
+    return lkup
+
+
+def _normarg_nrec(nrec):
+    # R/XStringSet-io.R:.normarg_nrec
+    if isinstance(nrec, bool) or not isinstance(nrec, (int, float, np.integer, np.floating)):
+        raise ValueError("'nrec' must be a single integer value")
+    nrec = int(nrec)
+    return -1 if nrec < 0 else nrec
+
+
+def _normarg_skip(skip):
+    if isinstance(skip, bool) or not isinstance(skip, (int, float, np.integer, np.floating)):
+        raise ValueError("'skip' must be a single non-negative integer value")
+    skip = int(skip)
+    if skip < 0:
+        raise ValueError("'skip' cannot be negative")
+    return skip
+
+
+def _read_text(filepath):
+    if isinstance(filepath, (bytes, bytearray, memoryview)):
+        return bytes(filepath)
+    with open(filepath, "rb") as f:
+        head = f.read(2)
+    if head == b"\x1f\x8b":                         # the reference reads gzip-ed files too
+        with gzip.open(filepath, "rb") as f:
+            return f.read()
+    with open(filepath, "rb") as f:
+        return f.read()
+
+
+def _cut(text, nrec, skip, seek_first_rec):
+    """nrec / skip / seek.first.rec of parse_FASTA_file (src/read_fasta_files.c:276-316) applied
+    to the text before it is uploaded: records are delimited by the lines that start with '>'."""
+    if nrec < 0 and skip == 0 and not seek_first_rec:
+        return text
+    arr = np.frombuffer(text, dtype=np.uint8)
+    gt = np.flatnonzero(arr == ord(">"))
+    starts = gt[(gt == 0) | (arr[np.maximum(gt - 1, 0)] == ord("\n"))]
+    if seek_first_rec:
+        if starts.size == 0:
+            raise ValueError("no FASTA record found")
+        lo = int(starts[0])
+    else:
+        lo = 0
+    if skip > 0:
+        lo = int(starts[skip]) if skip < starts.size else len(text)
+    hi = len(text)
+    if nrec >= 0 and skip + nrec < starts.size:
+        hi = int(starts[skip + nrec])
+    return text[lo:hi]
+
+
+def read_fasta_to_device(filepath, nrec=-1, skip=0, seek_first_rec=False, use_names=True, lkup=None):
+    """-> (DeviceSubject of kind "set", widths int32[nrec], names or None).  `filepath`: a path
+    (plain or gzip-ed) or the file content as bytes."""
+    nrec, skip = _normarg_nrec(nrec), _normarg_skip(skip)
+    if not isinstance(seek_first_rec, (bool, np.bool_)):
+        raise ValueError("'seek.first.rec' must be TRUE or FALSE")
+    name = filepath if isinstance(filepath, str) else "<memory>"
+    text = _cut(_read_text(filepath), nrec, skip, bool(seek_first_rec))
+    lk = dna_lkup() if lkup is None else np.ascontiguousarray(lkup, dtype=np.int32)
+    buf = np.frombuffer(text, dtype=np.uint8)
+    h = C.c_void_p()
+    info = _lib.FastaInfo()
+    rc = _lib.lib().bsgpu_subject_fasta(_ptr(buf) if buf.size else None, buf.size, _ptr(lk), lk.size,
+                                        C.byref(h), C.byref(info))
+    if rc != 0:
+        msg = _lib.lib().bsgpu_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise _lib.BsgpuError(rc, f"reading FASTA file {name}: {msg}")
+        raise _lib.BsgpuError(rc, msg)
+    try:
+        n = info.nrec
+        widths = np.ctypeslib.as_array(info.widths, shape=(max(n, 1),))[:n].astype(np.int32)
+        names = None
+        if use_names:
+            offs = np.ctypeslib.as_array(info.desc_offset, shape=(max(n, 1),))[:n]
+            lens = np.ctypeslib.as_array(info.desc_length, shape=(max(n, 1),))[:n]
+            names = [text[int(o):int(o) + int(k)].decode("latin1") for o, k in zip(offs, lens)]
+        if info.ninvalid:
+            warnings.warn(f"reading FASTA file {name}: ignored {info.ninvalid} invalid one-letter "
+                          "sequence codes")
+    finally:
+        _lib.lib().bsgpu_fasta_info_free(C.byref(info))
+    return DeviceSubject(h, "set", n), widths, names
+
+
+def device_subject_element(dset, i):
+    """One sequence of a resident set as a resident single-sequence subject (0-based i)."""
+    h = C.c_void_p()
+    _lib.check(_lib.lib().bsgpu_subject_element(dset.handle, int(i), C.byref(h)))
+    return DeviceSubject(h, "xstring", dset_width(dset, i))
+
+
+def dset_width(dset, i):
+    n = _lib.lib().bsgpu_subject_nsequences(dset.handle)
+    widths = np.zeros(max(n, 1), dtype=np.int32)
+    _lib.check(_lib.lib().bsgpu_subject_download(dset.handle, None, _ptr(widths)))
+    return int(widths[i])
+
+
+def download_set(dset, names=None):
+    """The letters of a resident set back in host memory as a DNAStringSet."""
+    n = _lib.lib().bsgpu_subject_nsequences(dset.handle)
+    widths = np.zeros(max(n, 1), dtype=np.int32)
+    _lib.check(_lib.lib().bsgpu_subject_download(dset.handle, None, _ptr(widths)))
+    widths = widths[:n]
+    concat = np.zeros(max(int(widths.sum()), 1), dtype=np.uint8)
+    _lib.check(_lib.lib().bsgpu_subject_download(dset.handle, _ptr(concat), None))
+    return DNAStringSet(concat=concat[:int(widths.sum())], widths=widths, names=names)
+
+
+def readDNAStringSet(filepath, format="fasta", nrec=-1, skip=0, seek_first_rec=False, use_names=True):
+    """R/XStringSet-io.R:203-260 for format="fasta" (one file or a list of files)."""
+    if format != "fasta":
+        raise ValueError("only format=\"fasta\" is on this path")
+    if isinstance(filepath, (list, tuple)):
+        parts = [readDNAStringSet(f, format, nrec, skip, seek_first_rec, use_names) for f in filepath]
+        names = sum((p.names or [] for p in parts), []) if use_names else None
+        return DNAStringSet(concat=np.concatenate([p.concat for p in parts]) if parts else np.zeros(0, np.uint8),
+                            widths=np.concatenate([p.widths for p in parts]) if parts else np.zeros(0, np.int32),
+                            names=names)
+    dset, widths, names = read_fasta_to_device(filepath, nrec, skip, seek_first_rec, use_names)
+    with dset:
+        return download_set(dset, names)

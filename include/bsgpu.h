@@ -143,6 +143,44 @@ void bsgpu_subject_free(bsgpu_subject *subj);
 int64_t bsgpu_subject_nletters(const bsgpu_subject *subj);	/* letters that are scanned */
 
 /* ------------------------------------------------------------------------------------
+ * Subject ingestion: FASTA text -> resident subject.  Replaces
+ *     read_fasta_files(filexp_list, nrec, skip, seek_first_rec, use_names, elementType, lkup)
+ *                                                          src/read_fasta_files.c:412
+ * for one in-memory file read whole (nrec = -1, skip = 0, seek_first_rec = FALSE; the host
+ * layer cuts the text for other values): parse_FASTA_file()'s line rules (:240-352) and
+ * translate() (:31-50) run on the device, one thread per 512-byte chunk, and the letters land
+ * directly in the subject layout -- the text is uploaded once and never re-read by the host.
+ * `lkup`: the reference's integer lookup (byte -> code, BSGPU_NA = not a letter; keys >=
+ * lkup_length are not letters), e.g. get_seqtype_conversion_lookup("B", "DNA").
+ * The result is a set subject (one sequence per record) usable with bsgpu_vmatch /
+ * bsgpu_oligo_frequency; bsgpu_subject_element() makes a single-sequence subject from one
+ * record (device-to-device), which is how a chromosome read once stays resident for repeated
+ * matchPDict / countPDict calls; bsgpu_subject_download() brings the encoded letters back
+ * for callers that want the XStringSet in host memory like the reference returns it.
+ * `info` (fields allocated by the library, release with bsgpu_fasta_info_free): widths, and
+ * for names() the offset and length of every description text inside `text`.
+ * Errors: "\">\" expected at beginning of line %d" (:322-327).  ninvalid != 0 is the
+ * reference's warning "ignored %lld invalid one-letter sequence codes" (:388-391).
+ * ------------------------------------------------------------------------------------ */
+typedef struct bsgpu_fasta_info {
+	int32_t nrec;
+	int64_t ninvalid;
+	int64_t nletters;
+	int32_t *widths;	/* [nrec] */
+	int64_t *desc_offset;	/* [nrec] byte offset in `text` of the description (after '>') */
+	int32_t *desc_length;	/* [nrec] */
+} bsgpu_fasta_info;
+
+int bsgpu_subject_fasta(const uint8_t *text, int64_t nbytes, const int32_t *lkup, int lkup_length,
+		bsgpu_subject **out, bsgpu_fasta_info *info);
+void bsgpu_fasta_info_free(bsgpu_fasta_info *info);
+int32_t bsgpu_subject_nsequences(const bsgpu_subject *subj);
+int bsgpu_subject_element(const bsgpu_subject *set, int32_t i, bsgpu_subject **out);
+/* encoded letters of all sequences back to back (concat_out, may be NULL) and their widths
+ * (widths_out[nsequences], may be NULL) */
+int bsgpu_subject_download(const bsgpu_subject *subj, uint8_t *concat_out, int32_t *widths_out);
+
+/* ------------------------------------------------------------------------------------
  * Results (library-allocated host memory; release with bsgpu_result_free()).
  *   COUNTS: counts[M]                                   src/match_reporting.c:163-166
  *   WHICH:  which[n_which], ascending 1-based ids        src/match_reporting.c:150-161
@@ -286,7 +324,8 @@ const char *bsgpu_last_plan(void);
 int64_t bsgpu_launch_count(void);
 
 /* Opt-in timing of the hot kernels (pack_subject_kernel, scan_byteseed_kernel,
- * match_plain_kernel, scan_tb_kernel, qscan_kernel, oligo_freq_kernel) with CUDA events recorded on the
+ * match_plain_kernel, scan_tb_kernel, qscan_kernel, oligo_freq_kernel,
+ * fasta_summary_kernel, fasta_emit_kernel) with CUDA events recorded on the
  * launching stream.  bsgpu_kernel_timing(1) starts collecting (at most 8192 launches),
  * bsgpu_kernel_times() waits for them, writes up to max_entries (name, milliseconds) pairs in
  * launch order, forgets them and returns how many it wrote (-1 on error). */

@@ -335,3 +335,48 @@ def mindex_combine():
 
 def release():
     lib().ref_release()
+
+
+# ---- read_fasta_files (src/read_fasta_files.c:412) ----------------------------------------------
+
+def dna_lkup():
+    """get_seqtype_conversion_lookup("B", "DNA") (R/seqtype.R): byte -> DNA code for the letters
+    of DNA_ALPHABET in both cases, NA elsewhere; as long as the largest letter + 1."""
+    codes = {"A": 1, "C": 2, "G": 4, "T": 8, "M": 3, "R": 5, "W": 9, "S": 6, "Y": 10, "K": 12,
+             "V": 7, "H": 11, "D": 13, "B": 14, "N": 15, "-": 16, "+": 32, ".": 64}
+    keys = {}
+    for letter, code in codes.items():
+        keys[ord(letter)] = code
+        keys[ord(letter.lower())] = code
+    lkup = np.full(max(keys) + 1, NA_INTEGER, dtype=np.int32)
+    for k, v in keys.items():
+        lkup[k] = v
+    return lkup
+
+
+def read_fasta(text, lkup=None, nrec=-1, skip=0, seek_first_rec=False, use_names=True):
+    """read_fasta_files() on one in-memory file -> (widths int32[n], concat uint8, names or None,
+    warning text).  `text`: bytes."""
+    L = lib()
+    L.ref_read_fasta.argtypes = [C.c_char_p, C.c_long, C.c_void_p, C.c_int] + [C.c_int] * 4
+    L.ref_result_set_widths.restype = C.c_long
+    L.ref_result_set_widths.argtypes = [C.c_void_p]
+    L.ref_result_set_concat.argtypes = [C.c_void_p]
+    L.ref_result_set_names.restype = C.c_long
+    L.ref_result_set_names.argtypes = [C.c_char_p, C.c_long]
+    lk = dna_lkup() if lkup is None else _i32(lkup)
+    L.ref_clear_warning()
+    text = bytes(text)
+    _check(L.ref_read_fasta(text, len(text), _ptr(lk), len(lk), nrec, skip, int(seek_first_rec),
+                            int(use_names)), L)
+    n = L.ref_result_set_length()
+    widths = np.empty(n, dtype=np.int32)
+    total = L.ref_result_set_widths(_ptr(widths))
+    concat = np.empty(total, dtype=np.uint8)
+    L.ref_result_set_concat(_ptr(concat))
+    buf = C.create_string_buffer(len(text) + 16)
+    k = L.ref_result_set_names(buf, len(buf))
+    names = buf.value.decode("latin1").split("\n")[:-1] if k > 0 else ([] if use_names and n == 0 else None)
+    warn = L.ref_last_warning().decode("latin1")
+    L.ref_release()
+    return widths, concat, names, warn

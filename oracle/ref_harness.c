@@ -19,6 +19,7 @@
  *                                     src/match_pdict_ACtree2.c:681,972,981
  *   XString_oligo_frequency / XStringSet_oligo_frequency
  *                                     src/letter_frequency.c:634,667
+ *   read_fasta_files                  src/read_fasta_files.c:412
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -61,6 +62,8 @@ SEXP XString_oligo_frequency(SEXP x, SEXP width, SEXP step, SEXP as_prob, SEXP a
 		SEXP fast_moving_side, SEXP with_labels, SEXP base_codes);
 SEXP XStringSet_oligo_frequency(SEXP x, SEXP width, SEXP step, SEXP as_prob, SEXP as_array,
 		SEXP fast_moving_side, SEXP with_labels, SEXP simplify_as, SEXP base_codes);
+SEXP read_fasta_files(SEXP filexp_list, SEXP nrec, SEXP skip, SEXP seek_first_rec,
+		SEXP use_names, SEXP elementType, SEXP lkup);
 SEXP ByPos_MIndex_endIndex(SEXP x_high2low, SEXP x_ends, SEXP x_width0);
 SEXP ByPos_MIndex_combine(SEXP ends_listlist);
 
@@ -500,6 +503,77 @@ int ref_oligo_frequency_set(const unsigned char *concat, const int *widths, int 
 			Rf_ScalarLogical(with_labels), Rf_mkString(simplify_as),
 			new_named_base_codes());
 	GUARD_END(0, -1)
+}
+
+/* ---- read_fasta_files (src/read_fasta_files.c:412) ----------------------------- */
+
+/* One in-memory file; `lkup` is the integer lookup R builds with
+ * get_seqtype_conversion_lookup("B", "DNA") (NA for bytes that are not DNA letters). */
+int ref_read_fasta(const char *text, long nbytes, const int *lkup, int lkup_length,
+		int nrec, int skip, int seek_first_rec, int use_names)
+{
+	SEXP files, names;
+
+	GUARD_BEGIN
+	minir_set_generation(2);
+	files = NEW_LIST(1);
+	SET_VECTOR_ELT(files, 0, minir_new_filexp(text, nbytes));
+	names = NEW_CHARACTER(1);
+	SET_STRING_ELT(names, 0, Rf_mkChar("<memory>"));
+	SET_NAMES(files, names);
+	result = read_fasta_files(files, Rf_ScalarInteger(nrec), Rf_ScalarInteger(skip),
+			Rf_ScalarLogical(seek_first_rec), Rf_ScalarLogical(use_names),
+			Rf_mkString("DNAString"),
+			lkup != NULL ? new_int(lkup_length, lkup) : R_NilValue);
+	GUARD_END(0, -1)
+}
+
+/* XStringSet results: number of elements, widths, the letters back to back, names */
+int ref_result_set_length(void) { return get_XVectorList_length(result); }
+
+long ref_result_set_widths(int *out)
+{
+	XVectorList_holder h = hold_XVectorList(result);
+	long total = 0;
+	int i;
+
+	for (i = 0; i < h.length; i++)
+		total += (out[i] = get_elt_from_XRawList_holder(&h, i).length);
+	return total;
+}
+
+void ref_result_set_concat(unsigned char *out)
+{
+	XVectorList_holder h = hold_XVectorList(result);
+	int i;
+
+	for (i = 0; i < h.length; i++) {
+		Chars_holder e = get_elt_from_XRawList_holder(&h, i);
+
+		memcpy(out, e.ptr, (size_t) e.length);
+		out += e.length;
+	}
+}
+
+long ref_result_set_names(char *buf, long buflen)
+{
+	SEXP names = get_XVectorList_names(result);
+	long i, used = 0;
+
+	if (names == R_NilValue)
+		return 0;
+	for (i = 0; i < names->length; i++) {
+		const char *s = CHAR(STRING_ELT(names, i));
+		long n = (long) strlen(s);
+
+		if (used + n + 2 > buflen)
+			return -1;
+		memcpy(buf + used, s, (size_t) n);
+		used += n;
+		buf[used++] = '\n';
+	}
+	buf[used] = 0;
+	return names->length;
 }
 
 /* ---- result access ---------------------------------------------------------- */

@@ -5,5 +5,8 @@
 
 typedef struct int_ae { size_t _buflength; size_t _nelt; int *elts; } IntAE;
 typedef struct int_aeae { size_t _buflength; size_t _nelt; IntAE **elts; } IntAEAE;
+typedef struct llong_ae { size_t _buflength; size_t _nelt; long long *elts; } LLongAE;
+/* strings only (src/read_fasta_files.c keeps the description lines in one) */
+typedef struct char_aeae { size_t _buflength; size_t _nelt; char **elts; } CharAEAE;
 
 #endif

@@ -20,6 +20,15 @@ void IntAE_uniq(IntAE *ae, size_t offset);
 SEXP new_INTEGER_from_IntAE(const IntAE *ae);
 IntAE *new_IntAE_from_CHARACTER(SEXP x, int keyshift);
 
+LLongAE *new_LLongAE(size_t buflength, size_t nelt, long long val);
+size_t LLongAE_get_nelt(const LLongAE *ae);
+void LLongAE_insert_at(LLongAE *ae, size_t at, long long val);
+CharAEAE *new_CharAEAE(size_t buflength, size_t nelt);
+size_t CharAEAE_get_nelt(const CharAEAE *aeae);
+void CharAEAE_append_string(CharAEAE *aeae, const char *string);
+SEXP new_CHARACTER_from_CharAEAE(const CharAEAE *aeae);
+void list_as_data_frame(SEXP x, int nrow);
+
 IntAEAE *new_IntAEAE(size_t buflength, size_t nelt);
 size_t IntAEAE_get_nelt(const IntAEAE *aeae);
 void IntAEAE_sum_and_shift(const IntAEAE *aeae1, const IntAEAE *aeae2, int shift);

@@ -17,6 +17,24 @@ SEXP new_XInteger_from_tag(const char *classname, SEXP tag);
 SEXP new_XRaw_from_tag(const char *classname, SEXP tag);
 SEXP alloc_XRawList(const char *classname, const char *element_type, SEXP width);
 SEXP alloc_XRaw(const char *classname, int length);
+SEXP get_XVectorList_names(SEXP x);
+
+/* io_utils: an in-memory "file" behind an external pointer (see minir_new_filexp) */
+int filexp_gets(SEXP filexp, char *buf, int buf_size, int *EOL_in_buf);
+void filexp_seek(SEXP filexp, long long int offset, int whence);
+long long int filexp_tell(SEXP filexp);
+int filexp_puts(SEXP filexp, const char *s);
+int delete_trailing_LF_or_CRLF(const char *buf, int buf_len);
+
+static inline int translate_byte(char byte, const int *lkup, int lkup_length)
+{
+	int key = (unsigned char) byte;
+
+	return key >= lkup_length ? NA_INTEGER : lkup[key];
+}
+
+void Ocopy_bytes_from_i1i2_with_lkup(int i1, int i2, char *dest, int dest_nbytes,
+		const char *src, int src_nbytes, const int *lkup, int lkup_length);
 void Ocopy_bytes_to_i1i2_with_lkup(int i1, int i2,
 		char *dest, int dest_nbytes,
 		const char *src, int src_nbytes,

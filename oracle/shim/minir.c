@@ -656,6 +656,70 @@ void IntAE_uniq(IntAE *ae, size_t offset)
 	ae->_nelt = i1 + 1;
 }
 
+LLongAE *new_LLongAE(size_t buflength, size_t nelt, long long val)
+{
+	LLongAE *ae = ae_track(xmalloc(sizeof(*ae)));
+	size_t i;
+
+	ae->_buflength = buflength > nelt ? buflength : nelt;
+	ae->_nelt = nelt;
+	ae->elts = ae->_buflength ? xmalloc(ae->_buflength * sizeof(long long)) : NULL;
+	for (i = 0; i < nelt; i++)
+		ae->elts[i] = val;
+	return ae;
+}
+
+size_t LLongAE_get_nelt(const LLongAE *ae) { return ae->_nelt; }
+
+void LLongAE_insert_at(LLongAE *ae, size_t at, long long val)
+{
+	if (ae->_nelt >= ae->_buflength) {
+		ae->_buflength = ae->_buflength ? 2 * ae->_buflength : 16;
+		ae->elts = realloc(ae->elts, ae->_buflength * sizeof(long long));
+	}
+	memmove(ae->elts + at + 1, ae->elts + at, (ae->_nelt - at) * sizeof(long long));
+	ae->elts[at] = val;
+	ae->_nelt++;
+}
+
+CharAEAE *new_CharAEAE(size_t buflength, size_t nelt)
+{
+	CharAEAE *aeae = ae_track(xmalloc(sizeof(*aeae)));
+
+	(void) nelt;
+	aeae->_buflength = buflength;
+	aeae->_nelt = 0;
+	aeae->elts = buflength ? xmalloc(buflength * sizeof(char *)) : NULL;
+	return aeae;
+}
+
+size_t CharAEAE_get_nelt(const CharAEAE *aeae) { return aeae->_nelt; }
+
+void CharAEAE_append_string(CharAEAE *aeae, const char *string)
+{
+	if (aeae->_nelt >= aeae->_buflength) {
+		aeae->_buflength = aeae->_buflength ? 2 * aeae->_buflength : 16;
+		aeae->elts = realloc(aeae->elts, aeae->_buflength * sizeof(char *));
+	}
+	aeae->elts[aeae->_nelt++] = strdup(string);
+}
+
+SEXP new_CHARACTER_from_CharAEAE(const CharAEAE *aeae)
+{
+	SEXP x = NEW_CHARACTER((long) aeae->_nelt);
+	size_t i;
+
+	for (i = 0; i < aeae->_nelt; i++)
+		SET_STRING_ELT(x, (long) i, Rf_mkChar(aeae->elts[i]));
+	return x;
+}
+
+/* IN-PLACE coercion in S4Vectors; here the list just remembers its row count */
+void list_as_data_frame(SEXP x, int nrow)
+{
+	SET_SLOT(x, Rf_install(".nrow"), Rf_ScalarInteger(nrow));
+}
+
 SEXP new_INTEGER_from_IntAE(const IntAE *ae)
 {
 	SEXP ans = NEW_INTEGER((long) ae->_nelt);
@@ -844,9 +908,113 @@ SEXP alloc_XRaw(const char *classname, int length)
 	return new_XRaw_from_tag(classname, NEW_RAW(length));
 }
 
+/* One RAW pool holding the elements back to back (what XVector does for small sets). */
 SEXP alloc_XRawList(const char *classname, const char *element_type, SEXP width)
 {
-	Rf_error("minir: alloc_XRawList() is not needed on the PDict path");
+	int n = LENGTH(width), i;
+	size_t total = 0, off = 0;
+	const char **ptrs = xmalloc((size_t) (n ? n : 1) * sizeof(char *));
+	SEXP pool, x;
+
+	(void) element_type;
+	for (i = 0; i < n; i++)
+		total += (size_t) INTEGER(width)[i];
+	pool = NEW_RAW((long) (total ? total : 1));
+	for (i = 0; i < n; i++) {
+		ptrs[i] = (const char *) RAW(pool) + off;
+		off += (size_t) INTEGER(width)[i];
+	}
+	x = minir_new_XStringSet(classname, n, ptrs, INTEGER(width));
+	SET_SLOT(x, Rf_install(".pool"), pool);
+	if (GET_NAMES(width) != R_NilValue)	/* XVector propagates names(width) */
+		set_XVectorList_names(x, GET_NAMES(width));
+	free(ptrs);
+	return x;
+}
+
+SEXP get_XVectorList_names(SEXP x)
+{
+	struct minir_slot *s;
+
+	for (s = x->slots; s != NULL; s = s->next)
+		if (strcmp(s->name, "NAMES") == 0)
+			return s->value;
+	return R_NilValue;
+}
+
+void Ocopy_bytes_from_i1i2_with_lkup(int i1, int i2, char *dest, int dest_nbytes,
+		const char *src, int src_nbytes, const int *lkup, int lkup_length)
+{
+	Rf_error("minir: Ocopy_bytes_from_i1i2_with_lkup() is only used when writing FASTA");
+}
+
+/* ---- XVector io_utils: a "file" is an in-memory buffer behind an external pointer ---- */
+
+SEXP minir_new_filexp(const char *data, long nbytes)
+{
+	SEXP holder = NEW_RAW((long) sizeof(struct minir_memfile));	/* owned by the pointer */
+	struct minir_memfile *f = (struct minir_memfile *) RAW(holder);
+
+	f->data = data;
+	f->nbytes = nbytes;
+	f->pos = 0;
+	return R_MakeExternalPtr(f, R_NilValue, holder);
+}
+
+/* fgets() semantics plus XVector's end-of-line detection: a sentinel in the last byte of the
+ * buffer tells whether the buffer was filled; not filled, or filled up to a newline, means the
+ * end of the line (or of the file) is in the buffer.  Returns 0 at end of file. */
+int filexp_gets(SEXP filexp, char *buf, int buf_size, int *EOL_in_buf)
+{
+	struct minir_memfile *f = R_ExternalPtrAddr(filexp);
+	int n = 0;
+
+	if (f->pos >= f->nbytes)
+		return 0;
+	buf[buf_size - 1] = 'N';
+	while (n < buf_size - 1 && f->pos < f->nbytes) {
+		char c = f->data[f->pos++];
+
+		buf[n++] = c;
+		if (c == '\n')
+			break;
+	}
+	buf[n] = 0;
+	*EOL_in_buf = buf[buf_size - 1] == 'N' || buf[buf_size - 2] == '\n';
+	return *EOL_in_buf ? 2 : 1;
+}
+
+void filexp_seek(SEXP filexp, long long int offset, int whence)
+{
+	struct minir_memfile *f = R_ExternalPtrAddr(filexp);
+
+	(void) whence;			/* only SEEK_SET is used */
+	f->pos = (long) offset;
+}
+
+long long int filexp_tell(SEXP filexp)
+{
+	return ((struct minir_memfile *) R_ExternalPtrAddr(filexp))->pos;
+}
+
+int filexp_puts(SEXP filexp, const char *s)
+{
+	Rf_error("minir: filexp_puts() is only used when writing FASTA");
+}
+
+int delete_trailing_LF_or_CRLF(const char *buf, int buf_len)
+{
+	if (buf_len == -1)
+		buf_len = (int) strlen(buf);
+	if (buf_len == 0)
+		return 0;
+	if (buf[--buf_len] != '\n')
+		return ++buf_len;
+	if (buf_len == 0)
+		return 0;
+	if (buf[--buf_len] != '\r')
+		return ++buf_len;
+	return buf_len;
 }
 
 void Ocopy_bytes_to_i1i2_with_lkup(int i1, int i2, char *dest, int dest_nbytes,

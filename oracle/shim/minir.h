@@ -15,6 +15,8 @@ void minir_release_scratch(void);       /* what the end of a .Call does in R */
 void minir_free_object(SEXP x);         /* demote a persistent object to scratch */
 void minir_free_AEbufs(void);
 
+struct minir_memfile { const char *data; long nbytes; long pos; };
+SEXP minir_new_filexp(const char *data, long nbytes);
 SEXP minir_new_XString(const char *classname, const char *ptr, int length);
 SEXP minir_new_XStringSet(const char *classname, int n, const char *const *ptrs,
 			  const int *widths);
