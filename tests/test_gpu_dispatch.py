@@ -194,3 +194,43 @@ def test_oligo_frequency_through_the_dot_call_boundary():
             ref.oligo_frequency_xstring(x, 16)
     finally:
         ref.use("ref")
+
+
+def test_read_fasta_files_through_the_dot_call_boundary():
+    """read_fasta_files (src/read_fasta_files.c:412) of biostrings_b200/csrc/read_fasta_files_gpu.c
+    against the reference's own on the same in-memory files: widths, letters, names, the
+    invalid-letter warning, nrec / skip / seek.first.rec and the error texts."""
+    from tests.test_fasta_hostlogic import TEXTS, rand_fasta
+
+    def both(text, **kw):
+        out = []
+        for which in ("ref", "dispatch"):
+            ref.use(which)
+            try:
+                out.append(ref.read_fasta(text, **kw))
+            finally:
+                ref.use("ref")
+        return out
+
+    def same_set(a, b):
+        assert a[0].tolist() == b[0].tolist() and np.array_equal(a[1], b[1])
+        assert a[2] == b[2] and a[3] == b[3]
+
+    for text in TEXTS:
+        same_set(*both(text))
+        same_set(*both(text, use_names=False))
+    g = rng(808)
+    for k in range(6):
+        text = rand_fasta(g, int(g.integers(1, 30)), crlf=bool(k % 2), line=int(g.integers(1, 600)))
+        same_set(*both(text))
+        for nrec, skip in [(3, 0), (-1, 2), (2, 4), (0, 0), (50, 1)]:
+            same_set(*both(text, nrec=nrec, skip=skip))
+            same_set(*both(b"junk\n" + text, nrec=nrec, skip=skip, seek_first_rec=True))
+    ref.use("dispatch")
+    try:
+        with pytest.raises(ref.RefError, match='reading FASTA file <memory>: ">" expected at beginning of line 4'):
+            ref.read_fasta(b"\n;c\n\nAC\n>r\n")
+        with pytest.raises(ref.RefError, match="no FASTA record found"):
+            ref.read_fasta(b"junk\n", seek_first_rec=True)
+    finally:
+        ref.use("ref")
