@@ -2722,6 +2722,7 @@ static BsgpuOligoParams oligo_params(const bsgpu_subject *subj, int width, int s
 
 		P.replicas = std::max(1, std::min(32, r));
 	}
+	P.fast = !per_segment && step == 1 && getenv("BSGPU_OLIGO_GENERIC") == nullptr;
 	P.scan_lo = subj->scan_lo;
 	P.scan_hi = subj->scan_hi;
 	P.nwords = subj->total / 32;

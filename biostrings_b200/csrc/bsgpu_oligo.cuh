@@ -14,6 +14,14 @@
 // takes one 32-letter word of the planes, finds the valid window starts in it with width - 1
 // shift-ANDs and visits only those.  Separator and guard letters are not base letters, hence
 // no window straddles two sequences and the sequence of a window is the one holding its start.
+//
+// One table over everything with step = 1 (a DNAString, or a collapsed set: the common case)
+// needs neither the sequence nor the position of a window, and the kernel was bound by
+// instruction issue (about 40 instructions per window with run-time 64-bit shifts), so that
+// case has its own fully unrolled path: the 48 letters a word's windows can touch are three
+// 32-bit words; for the "first letter most significant" order they are digit-reversed ONCE
+// per thread and pre-shifted by 2*(17 - width) bits, after which window i is the 2*width-bit
+// field at the compile-time offset 2*(31 - i): one funnel shift and one AND per window.
 #pragma once
 #include "bsgpu_kernels.cuh"
 
@@ -24,6 +32,7 @@ struct BsgpuOligoParams {
 	int32_t per_segment;    // 1: out[segment * 4^w + code], 0: one row
 	int32_t coord_step;     // chunk subjects: starts are judged in subject coordinates
 	int32_t replicas;       // copies of the table in shared memory (0 = global atomics)
+	int32_t fast;           // step == 1 and one row: the unrolled path
 	int64_t scan_lo, scan_hi;       // only windows whose last letter is in [scan_lo, scan_hi)
 	int64_t nwords;
 };
@@ -37,6 +46,24 @@ __device__ __forceinline__ uint32_t oligo_offset(uint32_t field, int w, int inve
 	uint32_t r = __brev(field) >> (32 - 2 * w);             // digits reversed, bits of a digit swapped
 
 	return ((r & 0x55555555u) << 1) | ((r >> 1) & 0x55555555u);
+}
+
+// digits (bit pairs) of a 32-bit word in reverse order
+__device__ __forceinline__ uint32_t oligo_rev16(uint32_t x)
+{
+	uint32_t r = __brev(x);
+
+	return ((r & 0x55555555u) << 1) | ((r >> 1) & 0x55555555u);
+}
+
+template <typename CT>
+__device__ __forceinline__ void oligo_bump(uint32_t code, const BsgpuOligoParams &P, uint32_t *sh_hist,
+					   CT *__restrict__ out, int tid)
+{
+	if (P.replicas > 0)
+		atomicAdd(&sh_hist[code * P.replicas + (tid & (P.replicas - 1))], 1u);
+	else
+		atomicAdd(out + code, (CT) 1);
 }
 
 template <typename CT>
@@ -66,6 +93,46 @@ oligo_freq_kernel(BsgpuSubjectView S, BsgpuOligoParams P, CT *__restrict__ out)
 			continue;
 		uint64_t lo = __ldg(S.codes + j), hi = __ldg(S.codes + j + 1);
 		int64_t p0 = j * 32;
+
+		if (P.fast) {
+			// windows whose last letter is in [scan_lo, scan_hi): starts i in [a, b)
+			int64_t a = P.scan_lo - p0 - P.w + 1, b = P.scan_hi - p0 - P.w + 1;
+
+			if (a > 0)
+				starts = a >= 32 ? 0u : starts & (0xFFFFFFFFu << (int) a);
+			if (b < 32)
+				starts = b <= 0 ? 0u : starts & (0xFFFFFFFFu >> (32 - (int) b));
+			if (starts == 0)
+				continue;
+			uint32_t q0, q1, q2;
+
+			if (P.invert) {         // letter m at bits 2m: window i starts at bit 2i
+				q0 = (uint32_t) lo;
+				q1 = (uint32_t) (lo >> 32);
+				q2 = (uint32_t) hi;
+			} else {                // 48 letters reversed: window i at bit 2 * (31 - i) after the pre-shift
+				uint32_t r0 = oligo_rev16((uint32_t) hi), r1 = oligo_rev16((uint32_t) (lo >> 32)),
+					 r2 = oligo_rev16((uint32_t) lo);
+				uint32_t s0 = 2u * (17u - (uint32_t) P.w);      // 4 .. 32
+
+				q0 = __funnelshift_rc(r0, r1, s0);
+				q1 = __funnelshift_rc(r1, r2, s0);
+				q2 = __funnelshift_rc(r2, 0u, s0);
+			}
+			// either way window number i of `starts` is now the field at bit 2 * i
+			if (!P.invert)
+				starts = __brev(starts);
+#pragma unroll
+			for (int i = 0; i < 32; i++) {
+				if (!(starts & (1u << i)))
+					continue;
+				uint32_t f = i < 16 ? __funnelshift_r(q0, q1, 2 * (i & 15))
+						    : __funnelshift_r(q1, q2, 2 * (i & 15));
+
+				oligo_bump<CT>(f & cmask, P, sh_hist, out, tid);
+			}
+			continue;
+		}
 		int seg = 0;
 		bool seg_known = S.nseg == 1;
 

@@ -147,12 +147,15 @@ def oligo_frequency_device(dsubj, width, step=1, invert=False, collapsed=True, a
     return out
 
 
-def _format(values, width, labels, invert, as_array):
-    """format_oligo_freqs(), src/letter_frequency.c:414-430."""
+def _format(values, width, labels, invert, as_array, names=None):
+    """format_oligo_freqs(), src/letter_frequency.c:414-430.  `names`: the labels when the
+    caller already has them (the rows of a list share one list of names)."""
     if as_array:
         arr = values.reshape((4,) * width, order="F")
         return _freq(arr, dimnames=tuple(list(DNA_BASES) for _ in range(width)) if labels else None)
-    return _freq(values, names=_all_oligos(list(DNA_BASES), width, invert) if labels else None)
+    if labels and names is None:
+        names = _all_oligos(list(DNA_BASES), width, invert)
+    return _freq(values, names=names if labels else None)
 
 
 def oligonucleotideFrequency(x, width, step=1, as_prob=False, as_array=False,
@@ -197,7 +200,9 @@ def oligonucleotideFrequency(x, width, step=1, as_prob=False, as_array=False,
         # set_oligo_freqs_colnames(), src/letter_frequency.c:432-446
         names = _all_oligos(list(DNA_BASES), width, invert) if with_labels else None
         return _freq(mat, dimnames=(None, names) if with_labels else None)
-    return [_format(np.ascontiguousarray(mat[i]), width, with_labels, invert, as_array) for i in range(nrow)]
+    names = _all_oligos(list(DNA_BASES), width, invert) if with_labels and not as_array else None
+    return [_format(np.ascontiguousarray(mat[i]), width, with_labels, invert, as_array, names)
+            for i in range(nrow)]
 
 
 def dinucleotideFrequency(x, step=1, as_prob=False, as_matrix=False, fast_moving_side="right",

@@ -284,7 +284,7 @@ def vmatch_set_set(pat_concat, pat_widths, subj_concat, subj_widths, max_mismatc
 
 def _fetch_labelled(L):
     """(values, dim tuple or None, [labels per dimension or None]) of the current result."""
-    dim = (C.c_int * 3)()
+    dim = (C.c_int * 16)()
     nd = L.ref_result_dim(dim)
     dims = tuple(dim[i] for i in range(nd)) if nd > 0 else None
     labels = []

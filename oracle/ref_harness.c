@@ -578,7 +578,7 @@ long ref_result_set_names(char *buf, long buflen)
 
 /* ---- result access ---------------------------------------------------------- */
 
-/* dim attribute of the result (or of its first list element): returns ndim, fills out[3] */
+/* dim attribute of the result (or of its first list element): returns ndim, fills out[16] */
 int ref_result_dim(int *out)
 {
 	SEXP x = result, dim;
@@ -591,7 +591,7 @@ int ref_result_dim(int *out)
 	dim = GET_DIM(x);
 	if (dim == R_NilValue)
 		return 0;
-	for (i = 0; i < LENGTH(dim) && i < 3; i++)
+	for (i = 0; i < LENGTH(dim) && i < 16; i++)
 		out[i] = INTEGER(dim)[i];
 	return LENGTH(dim);
 }

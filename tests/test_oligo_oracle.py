@@ -161,9 +161,44 @@ def test_reference_expectations(backend):
 
 # ---- the kernel's plane arithmetic, modelled ---------------------------------------------------
 
-def model_plane_counts(segs, width, step, invert):
+M32 = 0xFFFFFFFF
+
+
+def _brev(x):
+    return int(f"{x & M32:032b}"[::-1], 2)
+
+
+def _rev16(x):
+    r = _brev(x)
+    return ((r & 0x55555555) << 1 | (r >> 1) & 0x55555555) & M32
+
+
+def _shf_r(lo, hi, s):                    # __funnelshift_r (shift & 31) / _rc (clamped to 32)
+    return ((hi << 32 | lo) >> s) & M32
+
+
+def model_fast_word(lo, hi, starts, width, invert, ncol):
+    """The unrolled path of oligo_freq_kernel for one word: the table offsets it bumps."""
+    if invert:
+        q0, q1, q2 = lo & M32, lo >> 32, hi & M32
+    else:
+        r0, r1, r2 = _rev16(hi & M32), _rev16(lo >> 32), _rev16(lo & M32)
+        s0 = 2 * (17 - width)
+        q0, q1, q2 = _shf_r(r0, r1, min(s0, 32)), _shf_r(r1, r2, min(s0, 32)), _shf_r(r2, 0, min(s0, 32))
+        starts = _brev(starts)
+    out = []
+    for i in range(32):
+        if not (starts >> i) & 1:
+            continue
+        f = _shf_r(q0, q1, 2 * (i & 15)) if i < 16 else _shf_r(q1, q2, 2 * (i & 15))
+        out.append(f & (ncol - 1))
+    return out
+
+
+def model_plane_counts(segs, width, step, invert, fast=False):
     """What oligo_freq_kernel computes, word by word, on the concat layout
-    [128 guard][seg][sep]...: returns rows (one per segment)."""
+    [128 guard][seg][sep]...: returns rows (one per segment); fast = its unrolled path
+    (step 1, one row: everything lands in row 0)."""
     guard = 128
     pos, starts_ = guard, []
     for s in segs:
@@ -193,6 +228,15 @@ def model_plane_counts(segs, width, step, invert):
             run &= vv >> k
         st = run & 0xFFFFFFFF
         lo, hi = codes[j], codes[j + 1]
+        if fast:
+            a, b = 128 - 32 * j - width + 1, pos - 32 * j - width + 1      # scan_lo, scan_hi
+            if a > 0:
+                st = 0 if a >= 32 else st & (M32 << a) & M32
+            if b < 32:
+                st = 0 if b <= 0 else st & (M32 >> (32 - b))
+            for field in model_fast_word(lo, hi, st, width, invert, ncol):
+                rows[0, field] += 1
+            continue
         for i in range(32):
             if not (st >> i) & 1:
                 continue
@@ -217,3 +261,28 @@ def test_plane_arithmetic_of_the_kernel(width, step, invert):
     rows = model_plane_counts(segs, width, step, invert)
     for s, row in zip(segs, rows):
         assert np.array_equal(row, LF.oligo_counts(s, width, step, invert))
+
+
+@pytest.mark.parametrize("width", list(range(1, 16)))
+@pytest.mark.parametrize("invert", [False, True])
+def test_unrolled_path_of_the_kernel(width, invert):
+    """field extraction of the step = 1 / one-row path: digit reversal of the three words, the
+    pre-shift by 2 * (17 - width), compile-time offsets -- for every width."""
+    g = rng(777 + width)
+    segs = [noisy_dna(g, int(n)) for n in (0, 1, 47, 32, 33, 97, 300, 0, 64)]
+    if width <= 10:
+        rows = model_plane_counts(segs, width, 1, invert, fast=True)
+        want = sum(LF.oligo_counts(s, width, 1, invert) for s in segs)
+        assert np.array_equal(rows[0], want)
+        return
+    # wide windows: compare the offsets themselves instead of 4^width-entry tables
+    s = random_dna(g, 96)
+    two = LF._TWOBIT[s]
+    lo = sum(int(two[i]) << (2 * i) for i in range(32))
+    hi = sum(int(two[32 + i]) << (2 * i) for i in range(32))
+    got = model_fast_word(lo, hi, M32, width, invert, 1 << (2 * width))
+    want = []
+    for i in range(32):
+        digits = [int(two[i + k]) for k in range(width)]
+        want.append(sum(d * 4 ** (k if invert else width - 1 - k) for k, d in enumerate(digits)))
+    assert sorted(got) == sorted(want)

@@ -111,6 +111,21 @@ def bench_fasta(x, sample):
                          "achieved": (2 * len(text) + L) / (dev * 1e-3) / 1e9, "peak": HBM_GBS,
                          "frac": (2 * len(text) + L) / (dev * 1e-3) / 1e9 / HBM_GBS},
             "plan": _lib.lib().bsgpu_last_plan().decode()}
+    # the same text in pinned host memory: the upload runs at PCIe speed
+    try:
+        import torch
+        pinned = torch.empty(len(text), dtype=torch.uint8, pin_memory=True)
+        pview = pinned.numpy()
+        pview[:] = np.frombuffer(text, dtype=np.uint8)
+
+        def run_pinned():
+            dset, widths, names = bs.read_fasta_to_device(pview)
+            dset.close()
+        _, wall_p = kernel_ms(run_pinned, 3)
+        line["call_ms_pinned_text"] = wall_p
+        line["GB_s_call_pinned_text"] = len(text) / (wall_p * 1e-3) / 1e9
+    except Exception as e:                          # measurement only
+        line["pinned_error"] = repr(e)
     if ref.available():
         ts = fasta_text(x[:sample])
         t0 = time.perf_counter()
