@@ -10,6 +10,8 @@
           read_fasta_files() on one core over a 20 MB sample.
 
     python tools/bench_widen.py [--mbp 250] > profiles/r01_widen.jsonl
+    ncu --set full ... -k regex:"oligo_freq|fasta_" -c 4 python tools/bench_widen.py --profile --mbp 50
+        (--profile: one launch each of oligo_freq_kernel w=6 / w=12 and the two FASTA kernels)
 """
 import argparse
 import json
@@ -146,9 +148,17 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--mbp", type=int, default=250)
     ap.add_argument("--sample-mbp", type=int, default=20)
+    ap.add_argument("--profile", action="store_true")
     a = ap.parse_args()
     L, sample = a.mbp * 1_000_000, a.sample_mbp * 1_000_000
     x = synth.subject_region(0, L, L)
+    if a.profile:
+        with bs.DeviceSubject.from_xstring(x) as d:
+            for w in (6, 12):
+                oligo_frequency_device(d, w, 1, False, True, False)
+        dset, _, _ = bs.read_fasta_to_device(fasta_text(x))
+        dset.close()
+        sys.exit(0)
     for ln in bench_oligo(x, sample):
         print(json.dumps(ln), flush=True)
     for ln in bench_fasta(x, sample):
