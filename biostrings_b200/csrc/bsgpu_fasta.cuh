@@ -24,7 +24,8 @@
 // start inside the chunk; the host resolves the classes and prefix sums over the chunk summaries
 // (fasta_resolve, one step per chunk), and pass 2 (fasta_emit_kernel) walks the chunk again
 // and stores every kept letter at  guard + letters before + record index  -- the concat layout
-// of bsgpu_subject with one separator after every record -- and the start of every record.
+// of bsgpu_subject with one separator after every record -- and the start of every record
+// (16 letters per store wherever a 16-byte block of the output belongs to one thread).
 // The walk itself (fasta_walk_chunk) is plain C++ shared by both kernels and by the host-side
 // check in tests/hostcheck/, which runs it on the CPU against the reference's parser.
 #pragma once
@@ -71,6 +72,55 @@ BSGPU_HD void bsgpu_fasta_load16(const uint8_t *text, int64_t i, uint32_t w[4])
 #endif
 }
 
+// Output staging of the emit pass: a thread's letters go to consecutive positions, so they are
+// collected per 16-byte block of the output and a block this thread filled completely is
+// written with ONE 16-byte store (byte stores cost a partial-sector write in L2 each); blocks
+// shared with a neighbouring thread are written byte by byte, only the bytes that are ours.
+struct BsgpuFastaOut {
+	uint8_t *out;
+	int64_t blk;            // 16-aligned position of the block being filled, -1 = none
+	uint64_t lo, hi;        // its bytes 0..7 / 8..15
+	uint32_t mask;          // which of them are set
+};
+
+BSGPU_HD void fasta_out_flush(BsgpuFastaOut &o)
+{
+	if (o.blk < 0 || o.mask == 0)
+		return;
+	if (o.mask == 0xFFFFu) {
+#ifdef __CUDA_ARCH__
+		*reinterpret_cast<uint4 *>(o.out + o.blk) =
+			make_uint4((uint32_t) o.lo, (uint32_t) (o.lo >> 32), (uint32_t) o.hi, (uint32_t) (o.hi >> 32));
+#else
+		for (int k = 0; k < 16; k++)
+			o.out[o.blk + k] = (uint8_t) ((k < 8 ? o.lo >> (8 * k) : o.hi >> (8 * (k - 8))) & 0xFF);
+#endif
+	} else {
+		for (int k = 0; k < 16; k++)
+			if (o.mask & (1u << k))
+				o.out[o.blk + k] = (uint8_t) ((k < 8 ? o.lo >> (8 * k) : o.hi >> (8 * (k - 8))) & 0xFF);
+	}
+	o.mask = 0;
+}
+
+BSGPU_HD void fasta_out_put(BsgpuFastaOut &o, int64_t pos, uint32_t byte)
+{
+	int64_t b = pos & ~(int64_t) 15;
+	int k = (int) (pos & 15);
+
+	if (b != o.blk) {
+		fasta_out_flush(o);
+		o.blk = b;
+		o.lo = o.hi = 0;
+		o.mask = 0;
+	}
+	if (k < 8)
+		o.lo |= (uint64_t) byte << (8 * k);
+	else
+		o.hi |= (uint64_t) byte << (8 * (k - 8));
+	o.mask |= 1u << k;
+}
+
 // Walks chunk [a, b) of text[0, n).  EMIT = false: fills *sum.  EMIT = true: `in` holds the
 // resolved state in front of the chunk; kept letters go to out[], record starts to seg_start[]
 // and the offsets of the description texts (the byte after '>') to desc_off[].
@@ -87,6 +137,7 @@ BSGPU_HD void fasta_walk_chunk(const uint8_t *text, int64_t n, int64_t a, int64_
 	int32_t first_header = -1, first_seqline = -1;
 	int64_t kept = in.kept_before;
 	int64_t hdrs = in.headers_before;
+	BsgpuFastaOut o = {out, -1, 0, 0, 0};
 
 	for (int64_t i0 = a; i0 < b; i0 += 16) {
 		uint32_t w[4];
@@ -110,6 +161,10 @@ BSGPU_HD void fasta_walk_chunk(const uint8_t *text, int64_t n, int64_t a, int64_
 					if (first_header < 0)
 						first_header = (int32_t) (i - a);
 					if (EMIT) {
+						// the separator behind the previous record is ours too: writing it
+						// keeps the blocks around record boundaries whole
+						if (hdrs > 0)
+							fasta_out_put(o, BSGPU_FASTA_GUARD + kept + hdrs - 1, 0x80u);
 						seg_start[hdrs] = BSGPU_FASTA_GUARD + kept + hdrs;
 						desc_off[hdrs] = i + 1;
 						hdrs++;
@@ -135,7 +190,7 @@ BSGPU_HD void fasta_walk_chunk(const uint8_t *text, int64_t n, int64_t a, int64_
 			}
 			if (EMIT) {
 				if (hdrs > 0)
-					out[BSGPU_FASTA_GUARD + kept + hdrs - 1] = (uint8_t) code;
+					fasta_out_put(o, BSGPU_FASTA_GUARD + kept + hdrs - 1, (uint32_t) code);
 				kept++;
 			} else if (in_head) {
 				kept_head++;
@@ -144,6 +199,8 @@ BSGPU_HD void fasta_walk_chunk(const uint8_t *text, int64_t n, int64_t a, int64_
 			}
 		}
 	}
+	if (EMIT)
+		fasta_out_flush(o);
 	if (!EMIT) {
 		sum->kept_head = kept_head;
 		sum->invalid_head = invalid_head;

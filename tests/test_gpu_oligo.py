@@ -89,6 +89,7 @@ def test_sets(simplify_as, as_prob):
     concat = noisy_dna(g, int(widths.sum()))
     sset = bs.DNAStringSet(concat=concat, widths=widths)
     for width, step in [(1, 1), (2, 1), (3, 3), (4, 2), (6, 1), (7, 5)]:
+        names = all_strings(width)
         got = bs.oligonucleotideFrequency(sset, width, step=step, as_prob=as_prob, simplify_as=simplify_as)
         want = LF.xstringset_oligo_frequency(concat, widths, width, step, as_prob=as_prob,
                                              simplify_as=simplify_as)
@@ -101,14 +102,14 @@ def test_sets(simplify_as, as_prob):
                 assert np.array_equal(r, want)
         if simplify_as == "matrix":
             assert got.shape == (len(widths), 4 ** width)
-            assert got.dimnames == (None, all_strings(width))
+            assert got.dimnames == (None, names)
             assert np.array_equal(np.asarray(got), want)
         elif simplify_as == "list":
             assert len(got) == len(want)
             for a, b in zip(got, want):
-                assert np.array_equal(np.asarray(a), b) and a.names == all_strings(width)
+                assert np.array_equal(np.asarray(a), b) and a.names == names
         else:
-            assert np.array_equal(np.asarray(got), want) and got.names == all_strings(width)
+            assert np.array_equal(np.asarray(got), want) and got.names == names
 
 
 def test_reference_expectations_on_the_gpu():
