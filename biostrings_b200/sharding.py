@@ -71,3 +71,19 @@ def sharded_count(count_fn, subject_len, halo, rank, world, fetch, reduce=all_re
     a, b = chunk_range(lo, hi, subject_len, halo[0], halo[1])
     counts = count_fn(fetch(a, b), a, subject_len, lo, hi)
     return reduce(counts)
+
+
+def sharded_oligo_frequency(count_fn, subject_len, width, rank, world, fetch, reduce=all_reduce_counts):
+    """Host-side driver of a sharded oligonucleotideFrequency(x, width, step) of one long sequence
+    (SURVEY 8f rank 4 on the 8e sharding): rank r counts the windows whose LAST letter n (1-based)
+    lies in (lo_r, hi_r], which needs the width-1 letters in front of lo_r and nothing behind hi_r;
+    window starts are judged against `step` in whole-sequence coordinates, so the per-rank tables
+    add up to the table of the sequence (one all-reduce of 4^width counters).
+
+    count_fn(chunk, chunk_start, subject_len, lo, hi) -> table of that chunk (torch tensor); the
+    device path passes DeviceSubject.from_chunk + bsgpu_oligo_frequency / bsgpu_oligo_count_device,
+    the CPU tests pass the oracle.
+    """
+    lo, hi = shard_bounds(subject_len, world, rank)
+    a, b = chunk_range(lo, hi, subject_len, width - 1, 0)
+    return reduce(count_fn(fetch(a, b), a, subject_len, lo, hi))

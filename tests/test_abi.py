@@ -82,6 +82,41 @@ def test_no_device_means_no_compute():
     import biostrings_b200 as bs
     with pytest.raises(bs.BsgpuError, match="no CPU fallback"):
         bs.PDict(["ACGT"])
+    # the rows beside the dictionary path refuse the same way
+    out = np.zeros(16, np.int32)
+    assert L.bsgpu_XString_oligo_frequency(s.ctypes.data_as(C.c_void_p), 4, 2, 1, 0, 0,
+                                           out.ctypes.data_as(C.c_void_p), None) == -2
+    with pytest.raises(bs.BsgpuError, match="no CPU fallback"):
+        bs.oligonucleotideFrequency("ACGT", 2)
+    with pytest.raises(bs.BsgpuError, match="no CPU fallback"):
+        bs.readDNAStringSet(b">a\nACGT\n")
+
+
+def test_argument_errors_of_the_new_rows_need_no_device():
+    """width / step of oligonucleotideFrequency are validated before a device is needed, with
+    the reference's texts (src/utils.c:101-102; R/letterFrequency.R:16-75)."""
+    L = _lib.lib()
+    s = np.array([1, 2, 4, 8], np.uint8)
+    out = np.zeros(16, np.int32)
+    for width, step, msg in [(0, 1, "'buflength' must be >= 1 and <= 15"),
+                             (16, 1, "'buflength' must be >= 1 and <= 15"),
+                             (2, 0, "'step' must be a positive integer")]:
+        rc = L.bsgpu_XString_oligo_frequency(s.ctypes.data_as(C.c_void_p), 4, width, step, 0, 0,
+                                             out.ctypes.data_as(C.c_void_p), None)
+        assert rc == -1 and msg in L.bsgpu_last_error().decode()
+    import biostrings_b200 as bs
+    for kw, msg in [(dict(width="a"), "'width' must be a single integer"),
+                    (dict(width=0), "'width' must be an integer >= 1"),
+                    (dict(width=2, step=0), "'step' must be a positive integer"),
+                    (dict(width=2, as_prob=1), "'as.prob' must be TRUE or FALSE"),
+                    (dict(width=2, fast_moving_side="up"), "should be one of"),
+                    (dict(width=2, with_labels=None), "'with.labels' must be TRUE or FALSE")]:
+        with pytest.raises(ValueError, match=msg):
+            bs.oligonucleotideFrequency("ACGT", **kw)
+    with pytest.raises(ValueError, match="'skip' cannot be negative"):
+        bs.readDNAStringSet(b">a\nA\n", skip=-1)
+    assert bs.mkAllStrings(["A", "T"], 2) == ["AA", "AT", "TA", "TT"]      # test-matchPDict.R:127
+    assert bs.mkAllStrings(bs.DNA_BASES, 0) == [""]
 
 
 def test_product_never_imports_the_oracle():

@@ -88,3 +88,37 @@ def test_two_rank_sharded_count_equals_whole():
     for i in range(len(pats)):
         got = out[0][i] + out[1][i]
         assert got == ([] if want_ends[i] is None else want_ends[i].tolist())
+
+
+def _oligo_worker(rank, port, out, width, step):
+    from oracle import letterfreq as LF
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    s, _ = _make_case()
+
+    def count_fn(chunk, chunk_start, subject_len, lo, hi):
+        # what a chunk subject makes oligo_freq_kernel do: windows whose last letter (1-based)
+        # is in (lo, hi], starts judged against `step` in whole-sequence coordinates
+        table = np.zeros(4 ** width, dtype=np.int64)
+        for st in range(0, len(chunk) - width + 1):
+            g0 = chunk_start + st
+            if g0 % step or not (lo < g0 + width <= hi):
+                continue
+            table += LF.oligo_counts(chunk[st:st + width], width)
+        return torch.from_numpy(table)
+
+    total = sharding.sharded_oligo_frequency(count_fn, len(s), width, rank, WORLD, lambda a, b: s[a:b])
+    if rank == 0:
+        out["total"] = total.numpy().tolist()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("width,step", [(3, 1), (5, 3)])
+def test_two_rank_sharded_oligo_frequency_equals_whole(width, step):
+    from oracle import letterfreq as LF
+    s, _ = _make_case()
+    mgr = tmp.Manager()
+    out = mgr.dict()
+    tmp.spawn(_oligo_worker, args=(_free_port(), out, width, step), nprocs=WORLD, join=True)
+    assert out["total"] == LF.oligo_counts(s, width, step).tolist()
