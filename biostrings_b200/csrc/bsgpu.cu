@@ -1410,10 +1410,12 @@ extern "C" int bsgpu_subject_fasta(const uint8_t *text, int64_t nbytes, const in
 	const size_t padded = (size_t) ((nbytes + 15) / 16 * 16 + 16);
 	DevBuf<uint8_t> d_text;
 	DevBuf<int16_t> d_lkup;
+	const int64_t ngroups = (nchunks + BSGPU_FASTA_GROUP - 1) / BSGPU_FASTA_GROUP;
 	DevBuf<BsgpuFastaSummary> d_sums;
-	DevBuf<BsgpuFastaResolved> d_res;
-	std::vector<BsgpuFastaSummary> sums((size_t) nchunks);
-	std::vector<BsgpuFastaResolved> res;
+	DevBuf<BsgpuFastaGroup> d_groups;
+	DevBuf<BsgpuFastaResolved> d_res, d_bases;
+	std::vector<BsgpuFastaGroup> groups((size_t) ngroups);
+	std::vector<BsgpuFastaResolved> bases;
 
 	TRY(d_text.alloc(padded));
 	{
@@ -1431,10 +1433,17 @@ extern "C" int bsgpu_subject_fasta(const uint8_t *text, int64_t nbytes, const in
 		g_launches++;
 	}
 	CUDA_TRY(cudaGetLastError());
-	if (nchunks > 0)
-		CUDA_TRY(cudaMemcpy(sums.data(), d_sums.p, (size_t) nchunks * sizeof(BsgpuFastaSummary),
+	// between the passes: the chunk summaries stay on the device, only one summary per 64 chunks
+	// crosses PCIe for the host's sequential step
+	TRY(d_groups.alloc((size_t) ngroups));
+	if (ngroups > 0) {
+		fasta_group_kernel<<<(unsigned) ((ngroups + 127) / 128), 128>>>(d_sums.p, nchunks, ngroups, d_groups.p);
+		g_launches++;
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpy(groups.data(), d_groups.p, (size_t) ngroups * sizeof(BsgpuFastaGroup),
 				    cudaMemcpyDeviceToHost));
-	BsgpuFastaTotals t = fasta_resolve(sums, res);
+	}
+	BsgpuFastaTotals t = fasta_resolve_groups(groups, bases);
 	if (t.first_seqline >= 0 && (t.first_header < 0 || t.first_seqline < t.first_header)) {
 		// src/read_fasta_files.c:322-327; lines are counted like the reference counts them
 		long long lineno = 1;
@@ -1461,7 +1470,11 @@ extern "C" int bsgpu_subject_fasta(const uint8_t *text, int64_t nbytes, const in
 	DevBuf<int64_t> d_desc_off;
 	TRY(d_desc_off.alloc((size_t) nrec));
 	if (nchunks > 0) {
-		TRY(d_res.upload(res.data(), (size_t) nchunks));
+		TRY(d_bases.upload(bases.data(), (size_t) ngroups));
+		TRY(d_res.alloc((size_t) nchunks));
+		fasta_expand_kernel<<<(unsigned) ((ngroups + 127) / 128), 128>>>(d_sums.p, nchunks, ngroups, d_bases.p, d_res.p);
+		g_launches++;
+		CUDA_TRY(cudaGetLastError());
 		KernelTimer kt("fasta_emit_kernel", 0);
 		fasta_emit_kernel<<<(unsigned) ((nchunks + 127) / 128), 128>>>(d_text.p, nbytes, nchunks, d_lkup.p, d_res.p,
 				s->d_bytes.p, s->d_seg_start.p, d_desc_off.p);

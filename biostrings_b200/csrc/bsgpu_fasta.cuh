@@ -21,8 +21,10 @@
 // chunk walks its bytes with the small state machine above.  What a chunk cannot know locally is
 // the class of the line it starts in the middle of, so pass 1 (fasta_summary_kernel) counts the
 // letters of that first partial line as if it were sequence data, separately from the lines that
-// start inside the chunk; the host resolves the classes and prefix sums over the chunk summaries
-// (fasta_resolve, one step per chunk), and pass 2 (fasta_emit_kernel) walks the chunk again
+// start inside the chunk; the summaries are folded 64 to 1 on the device for both classes a group may
+// start in, the host resolves classes and prefix sums over those few thousand group summaries
+// (fasta_resolve_groups) and the device expands them back to one state per chunk; pass 2
+// (fasta_emit_kernel) walks the chunk again
 // and stores every kept letter at  guard + letters before + record index  -- the concat layout
 // of bsgpu_subject with one separator after every record -- and the start of every record
 // (16 letters per store wherever a 16-byte block of the output belongs to one thread).
@@ -213,41 +215,111 @@ BSGPU_HD void fasta_walk_chunk(const uint8_t *text, int64_t n, int64_t a, int64_
 	}
 }
 
+// ---- between the passes: line classes across chunk boundaries, prefix sums ---------------------
+// The chunk summaries stay on the device.  BSGPU_FASTA_GROUP consecutive chunks are folded into one
+// group summary for BOTH classes the group may start in (fasta_group_kernel, one thread per group),
+// the host walks the few thousand group summaries (fasta_resolve_groups), and
+// fasta_expand_kernel replays every group from its resolved base to give each chunk its state.
+
+#define BSGPU_FASTA_GROUP 64
+
+struct BsgpuFastaGroup {
+	int64_t kept[2], invalid[2];    // indexed by the class the group starts in (SEQ, SKIP)
+	int32_t class_out[2];           // class of the line the group ends in, given that class
+	int64_t headers;
+	int64_t first_header;           // byte offset of the first description line in the group, or -1
+	int64_t first_seqline;          // byte offset of the first non-empty sequence line starting in it, or -1
+};
+
+BSGPU_HD void fasta_fold_group(const BsgpuFastaSummary *sums, int64_t c0, int64_t c1, BsgpuFastaGroup *g)
+{
+	for (int h = 0; h < 2; h++) {
+		int cls = h;
+		int64_t kept = 0, invalid = 0;
+
+		for (int64_t c = c0; c < c1; c++) {
+			const BsgpuFastaSummary s = sums[c];
+
+			if (cls == BSGPU_FASTA_SEQ) {   // the first partial line of the chunk is sequence data
+				kept += s.kept_head;
+				invalid += s.invalid_head;
+			}
+			kept += s.kept_rest;
+			invalid += s.invalid_rest;
+			if (s.class_out != BSGPU_FASTA_PASS)
+				cls = s.class_out;
+		}
+		g->kept[h] = kept;
+		g->invalid[h] = invalid;
+		g->class_out[h] = cls;
+	}
+	int64_t headers = 0, first_header = -1, first_seqline = -1;
+
+	for (int64_t c = c0; c < c1; c++) {
+		const BsgpuFastaSummary s = sums[c];
+
+		headers += s.headers;
+		if (first_header < 0 && s.first_header >= 0)
+			first_header = c * BSGPU_FASTA_CHUNK + s.first_header;
+		if (first_seqline < 0 && s.first_seqline >= 0)
+			first_seqline = c * BSGPU_FASTA_CHUNK + s.first_seqline;
+	}
+	g->headers = headers;
+	g->first_header = first_header;
+	g->first_seqline = first_seqline;
+}
+
+// state of every chunk of one group, replayed from the group's resolved base
+BSGPU_HD void fasta_expand_group(const BsgpuFastaSummary *sums, int64_t c0, int64_t c1,
+				 BsgpuFastaResolved base, BsgpuFastaResolved *res)
+{
+	int cls = base.class_in;
+	int64_t kept = base.kept_before;
+	int64_t headers = base.headers_before;
+
+	for (int64_t c = c0; c < c1; c++) {
+		const BsgpuFastaSummary s = sums[c];
+
+		res[c].kept_before = kept;
+		res[c].headers_before = (int32_t) headers;
+		res[c].class_in = cls;
+		if (cls == BSGPU_FASTA_SEQ)
+			kept += s.kept_head;
+		kept += s.kept_rest;
+		headers += s.headers;
+		if (s.class_out != BSGPU_FASTA_PASS)
+			cls = s.class_out;
+	}
+}
+
 struct BsgpuFastaTotals {
 	int64_t kept = 0, invalid = 0, nrec = 0;
 	int64_t first_header = -1;      // byte offset of the first description line
 	int64_t first_seqline = -1;     // byte offset of the first non-empty sequence line
 };
 
-// Host step between the two passes: classes of the lines that straddle chunk boundaries and the
-// prefix sums of kept letters / records.  One iteration per chunk.
-static inline BsgpuFastaTotals fasta_resolve(const std::vector<BsgpuFastaSummary> &sums,
-					     std::vector<BsgpuFastaResolved> &res)
+// Host step: one iteration per group.  bases[g] = state in front of group g.
+static inline BsgpuFastaTotals fasta_resolve_groups(const std::vector<BsgpuFastaGroup> &groups,
+						    std::vector<BsgpuFastaResolved> &bases)
 {
 	BsgpuFastaTotals t;
-	int cls = BSGPU_FASTA_SEQ;      // class of the line the previous chunk ended in
+	int cls = BSGPU_FASTA_SEQ;      // the text starts at a line start: the value is never used
 
-	res.resize(sums.size());
-	for (size_t c = 0; c < sums.size(); c++) {
-		const BsgpuFastaSummary &s = sums[c];
+	bases.resize(groups.size());
+	for (size_t g = 0; g < groups.size(); g++) {
+		const BsgpuFastaGroup &G = groups[g];
 
-		res[c].kept_before = t.kept;
-		res[c].headers_before = (int32_t) t.nrec;
-		res[c].class_in = cls;
-		if (cls == BSGPU_FASTA_SEQ) {   // only counted when the chunk starts inside a line
-			t.kept += s.kept_head;
-			t.invalid += s.invalid_head;
-		}
-		t.kept += s.kept_rest;
-		t.invalid += s.invalid_rest;
-		t.nrec += s.headers;
-		int64_t base = (int64_t) c * BSGPU_FASTA_CHUNK;
-		if (t.first_header < 0 && s.first_header >= 0)
-			t.first_header = base + s.first_header;
-		if (t.first_seqline < 0 && s.first_seqline >= 0)
-			t.first_seqline = base + s.first_seqline;
-		if (s.class_out != BSGPU_FASTA_PASS)
-			cls = s.class_out;
+		bases[g].kept_before = t.kept;
+		bases[g].headers_before = (int32_t) t.nrec;
+		bases[g].class_in = cls;
+		t.kept += G.kept[cls];
+		t.invalid += G.invalid[cls];
+		t.nrec += G.headers;
+		if (t.first_header < 0 && G.first_header >= 0)
+			t.first_header = G.first_header;
+		if (t.first_seqline < 0 && G.first_seqline >= 0)
+			t.first_seqline = G.first_seqline;
+		cls = G.class_out[cls];
 	}
 	return t;
 }
@@ -265,6 +337,32 @@ fasta_summary_kernel(const uint8_t *__restrict__ text, int64_t n, int64_t nchunk
 	BsgpuFastaResolved none = {0, 0, BSGPU_FASTA_SEQ};
 
 	fasta_walk_chunk<false>(text, n, a, b, lkup, sums + c, none, nullptr, nullptr, nullptr);
+}
+
+__global__ void __launch_bounds__(128)
+fasta_group_kernel(const BsgpuFastaSummary *__restrict__ sums, int64_t nchunks, int64_t ngroups,
+		   BsgpuFastaGroup *__restrict__ groups)
+{
+	int64_t g = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (g >= ngroups)
+		return;
+	int64_t c0 = g * BSGPU_FASTA_GROUP, c1 = c0 + BSGPU_FASTA_GROUP < nchunks ? c0 + BSGPU_FASTA_GROUP : nchunks;
+
+	fasta_fold_group(sums, c0, c1, groups + g);
+}
+
+__global__ void __launch_bounds__(128)
+fasta_expand_kernel(const BsgpuFastaSummary *__restrict__ sums, int64_t nchunks, int64_t ngroups,
+		    const BsgpuFastaResolved *__restrict__ bases, BsgpuFastaResolved *__restrict__ res)
+{
+	int64_t g = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (g >= ngroups)
+		return;
+	int64_t c0 = g * BSGPU_FASTA_GROUP, c1 = c0 + BSGPU_FASTA_GROUP < nchunks ? c0 + BSGPU_FASTA_GROUP : nchunks;
+
+	fasta_expand_group(sums, c0, c1, bases[g], res);
 }
 
 __global__ void __launch_bounds__(128)

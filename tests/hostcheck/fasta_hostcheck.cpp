@@ -25,7 +25,23 @@ extern "C" int fasta_hostcheck(const uint8_t *text, int64_t n, const int16_t *lk
 
 		fasta_walk_chunk<false>(padded.data(), n, a, b, lkup, &sums[(size_t) c], none, nullptr, nullptr, nullptr);
 	}
-	BsgpuFastaTotals t = fasta_resolve(sums, res);
+	// the between-passes step exactly as bsgpu_subject_fasta() runs it: fold 64 chunks to one group
+	// summary, resolve the groups, expand back to one state per chunk
+	int64_t ngroups = (nchunks + BSGPU_FASTA_GROUP - 1) / BSGPU_FASTA_GROUP;
+	std::vector<BsgpuFastaGroup> groups((size_t) ngroups);
+	std::vector<BsgpuFastaResolved> bases;
+	for (int64_t g = 0; g < ngroups; g++) {
+		int64_t c0 = g * BSGPU_FASTA_GROUP, c1 = c0 + BSGPU_FASTA_GROUP < nchunks ? c0 + BSGPU_FASTA_GROUP : nchunks;
+
+		fasta_fold_group(sums.data(), c0, c1, &groups[(size_t) g]);
+	}
+	BsgpuFastaTotals t = fasta_resolve_groups(groups, bases);
+	res.resize((size_t) nchunks);
+	for (int64_t g = 0; g < ngroups; g++) {
+		int64_t c0 = g * BSGPU_FASTA_GROUP, c1 = c0 + BSGPU_FASTA_GROUP < nchunks ? c0 + BSGPU_FASTA_GROUP : nchunks;
+
+		fasta_expand_group(sums.data(), c0, c1, bases[(size_t) g], res.data());
+	}
 	totals[0] = t.kept;
 	totals[1] = t.invalid;
 	totals[2] = t.nrec;

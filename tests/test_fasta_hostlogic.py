@@ -192,3 +192,16 @@ def test_nrec_skip_seek_first_rec_cut_equals_reference():
         ref.read_fasta(b"junk\nmore junk\n", seek_first_rec=True)
     with pytest.raises(ValueError, match="no FASTA record found"):
         _cut(b"junk\nmore junk\n", -1, 0, True)
+
+
+def test_chunk_walk_lines_longer_than_a_group(hostcheck):
+    """description, comment and sequence lines longer than a group of 64 chunks (32 KiB): the
+    class a group starts in is only known to the host step (both hypotheses are folded on the
+    device), including groups in which no line starts at all."""
+    g = rng(31337)
+    seq = np.frombuffer(b"ACGTNacgtX", dtype=np.uint8)[g.integers(0, 10, 150_000)].tobytes()
+    text = (b">" + b"d" * 70_000 + b"\n" + seq[:100_000] + b"\n;" + b"c" * 40_000 + b"\r\n" +
+            seq[100_000:] + b"\n>r2\n" + b"A" * 33_000 + b"\r\n>r3 " + b"x" * 66_000)
+    same(walk(hostcheck, text), OF.read_fasta(text))
+    for cut in (32_768, 32_769, 65_536, 98_304 + 17):
+        same(walk(hostcheck, text[:cut]), OF.read_fasta(text[:cut]))

@@ -132,3 +132,15 @@ def test_resident_genome_serves_the_matching_calls():
                                   np.asarray(bs.oligonucleotideFrequency(bs.DNAString(seqs[2]), 6)))
         with pytest.raises(bs.BsgpuError, match="subscript out of bounds"):
             bs.device_subject_element(dset, 4)
+
+
+def test_lines_longer_than_a_group_of_chunks():
+    """classes carried over whole groups of 64 chunks (tests/test_fasta_hostlogic.py has the
+    same text on the CPU walk)."""
+    g = rng(31337)
+    seq = np.frombuffer(b"ACGTNacgtX", dtype=np.uint8)[g.integers(0, 10, 150_000)].tobytes()
+    text = (b">" + b"d" * 70_000 + b"\n" + seq[:100_000] + b"\n;" + b"c" * 40_000 + b"\r\n" +
+            seq[100_000:] + b"\n>r2\n" + b"A" * 33_000 + b"\r\n>r3 " + b"x" * 66_000)
+    same(gpu_parse(text), OF.read_fasta(text))
+    for cut in (32_768, 32_769, 65_536, 98_304 + 17):
+        same(gpu_parse(text[:cut]), OF.read_fasta(text[:cut]))
