@@ -9,7 +9,7 @@ behaviour); it needs the shared library and a CUDA device -- there is no CPU fal
 from ._lib import BsgpuError
 from .matchpdict import (DeviceSubject, countPDict, matchPDict, vcountPDict, vmatchPDict,
                          vwhichPDict, whichPDict)
-from .io import device_subject_element, download_set, read_fasta_to_device, readDNAStringSet
+from .io import device_subject_element, device_subject_from_letters, download_set, read_fasta_to_device, readDNAStringSet
 from .letterfreq import (dinucleotideFrequency, mkAllStrings, oligonucleotideFrequency,
                          oligonucleotideTransitions, trinucleotideFrequency)
 from .mindex import ByPos_MIndex, extractAllMatches
@@ -22,4 +22,4 @@ __all__ = ["PDict", "TB_PDict", "MTB_PDict", "matchPDict", "countPDict", "whichP
            "DNAStringSet", "XStringViews", "MaskedDNAString", "DeviceSubject", "DNA_BASES",
            "encode_dna", "decode_dna", "BsgpuError", "oligonucleotideFrequency", "dinucleotideFrequency",
            "trinucleotideFrequency", "oligonucleotideTransitions", "mkAllStrings", "readDNAStringSet",
-           "read_fasta_to_device", "device_subject_element", "download_set"]
+           "read_fasta_to_device", "device_subject_element", "device_subject_from_letters", "download_set"]

@@ -1167,7 +1167,7 @@ static int subject_finish(bsgpu_subject *s, const uint8_t *const *srcs, const ui
 		CUDA_TRY(cudaMemsetAsync(s->d_bytes.p, BSGPU_SEP_BYTE, (size_t) s->seg_start[0]));
 		CUDA_TRY(cudaMemsetAsync(s->d_bytes.p + seg_end, BSGPU_SEP_BYTE,
 					 (size_t) (s->total + 64 - seg_end)));
-		if (s->seg_len[0] > 0)
+		if (s->seg_len[0] > 0 && (one_src != nullptr || srcs != nullptr))      // else: filled by the caller
 			CUDA_TRY(cudaMemcpyAsync(s->d_bytes.p + s->seg_start[0], one_src ? one_src : srcs[0],
 						 (size_t) s->seg_len[0], cudaMemcpyDefault));
 	} else {
@@ -1530,6 +1530,59 @@ extern "C" int bsgpu_subject_fasta(const uint8_t *text, int64_t nbytes, const in
 	}
 	set_plan("fasta_ingest bytes=%lld chunks=%lld records=%d letters=%lld invalid=%lld", (long long) nbytes,
 		 (long long) nchunks, nrec, (long long) t.kept, (long long) t.invalid);
+	*out = s.release();
+	return BSGPU_OK;
+}
+
+// DNAString(<character>) straight onto the device: the letters are uploaded as they are and
+// translated by encode_letters_kernel (replaces the copy-with-lookup loop behind
+// new_XString_from_CHARACTER, src/XString_class.c:134-159,191-218 + XVector's
+// Ocopy_bytes_from_i1i2_with_lkup, with the tables of R/XStringCodec-class.R:114-166).
+extern "C" int bsgpu_subject_letters(const uint8_t *letters, int64_t length, const int32_t *lkup, int lkup_length,
+		bsgpu_subject **out)
+{
+	if (out == nullptr || length < 0 || (length > 0 && letters == nullptr) || lkup == nullptr || lkup_length < 0)
+		return fail(BSGPU_EINVAL, "bsgpu_subject_letters(): bad arguments");
+	*out = nullptr;
+	if (length > INT32_MAX)
+		return fail(BSGPU_EINVAL, "subject longer than INT_MAX letters (use chunks or views)");
+	TRY(ensure_device());
+	int16_t lk16[256];
+	for (int k = 0; k < 256; k++)
+		lk16[k] = k < lkup_length && lkup[k] != BSGPU_NA ? (int16_t) (lkup[k] & 0xFF) : (int16_t) -1;
+	std::unique_ptr<bsgpu_subject> s(new bsgpu_subject());
+	s->kind = SUBJ_XSTRING;
+	s->nseg = 1;
+	s->seg_len.assign(1, (int32_t) length);
+	s->seg_coord.assign(1, 0);
+	s->nletters = length;
+	TRY(subject_finish(s.get(), nullptr, nullptr));         // layout and guards; no letters yet
+	if (length > 0) {
+		const size_t padded = (size_t) ((length + 15) / 16 * 16);
+		DevBuf<uint8_t> d_src;
+		DevBuf<int16_t> d_lkup;
+		DevBuf<unsigned long long> d_bad;
+		unsigned long long bad = ~0ull;
+
+		TRY(d_src.alloc(padded));
+		CUDA_TRY(cudaMemcpyAsync(d_src.p, letters, (size_t) length, cudaMemcpyHostToDevice));
+		TRY(d_lkup.upload(lk16, 256));
+		TRY(d_bad.upload(&bad, 1));
+		{
+			KernelTimer kt("encode_letters_kernel", 0);
+			encode_letters_kernel<<<grid_for((long long) (padded / 16), 256, 16), 256>>>(d_src.p, length, d_lkup.p,
+					s->d_bytes.p + s->seg_start[0], d_bad.p);
+		}
+		g_launches++;
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpy(&bad, d_bad.p, sizeof(bad), cudaMemcpyDeviceToHost));
+		if (bad != ~0ull) {
+			// XVector's lookup copy stops at the first letter the lookup does not know
+			int c = letters[bad];
+
+			return fail(BSGPU_EINVAL, "key %d (char '%c') not in lookup table", c, c);
+		}
+	}
 	*out = s.release();
 	return BSGPU_OK;
 }

@@ -325,6 +325,43 @@ static inline BsgpuFastaTotals fasta_resolve_groups(const std::vector<BsgpuFasta
 }
 
 #ifdef __CUDACC__
+// Letters -> codes through the lookup, 16 per thread (one 16-byte load and store); the smallest
+// index of a letter the lookup does not know lands in *first_bad.  src is padded to a multiple
+// of 16 bytes, dst + 16 * k is 16-byte aligned (the subject's guard is 128 letters); the last,
+// partial group is stored byte by byte so that the guard behind the sequence stays intact.
+__global__ void __launch_bounds__(256)
+encode_letters_kernel(const uint8_t *__restrict__ src, int64_t n, const int16_t *__restrict__ lkup,
+		      uint8_t *__restrict__ dst, unsigned long long *__restrict__ first_bad)
+{
+	int64_t ngroups = (n + 15) / 16;
+	int64_t stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (int64_t g = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+		uint32_t w[4], o[4] = {0, 0, 0, 0};
+		int64_t i0 = g * 16;
+
+		bsgpu_fasta_load16(src, i0, w);
+#pragma unroll
+		for (int k = 0; k < 16; k++) {
+			if (i0 + k >= n)
+				break;
+			int code = lkup[(w[k >> 2] >> (8 * (k & 3))) & 0xFFu];
+
+			if (code < 0) {
+				atomicMin(first_bad, (unsigned long long) (i0 + k));
+				code = 0;
+			}
+			o[k >> 2] |= (uint32_t) code << (8 * (k & 3));
+		}
+		if (i0 + 16 <= n) {
+			*reinterpret_cast<uint4 *>(dst + i0) = make_uint4(o[0], o[1], o[2], o[3]);
+		} else {
+			for (int k = 0; i0 + k < n; k++)
+				dst[i0 + k] = (uint8_t) ((o[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+		}
+	}
+}
+
 __global__ void __launch_bounds__(128)
 fasta_summary_kernel(const uint8_t *__restrict__ text, int64_t n, int64_t nchunks,
 		     const int16_t *__restrict__ lkup, BsgpuFastaSummary *__restrict__ sums)

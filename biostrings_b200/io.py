@@ -126,6 +126,22 @@ def read_fasta_to_device(filepath, nrec=-1, skip=0, seek_first_rec=False, use_na
     return DeviceSubject(h, "set", n), widths, names
 
 
+def device_subject_from_letters(letters, lkup=None):
+    """DNAString(<character>) with the encoding done on the device: `letters` (str, bytes or a
+    uint8 array of ASCII codes) are uploaded as they are and translated by the library
+    (R/XStringCodec-class.R:114-166; error text of XVector's lookup copy for a letter that is
+    not in the DNA alphabet)."""
+    if isinstance(letters, str):
+        letters = letters.encode("latin1")
+    buf = letters if isinstance(letters, np.ndarray) else np.frombuffer(bytes(letters), dtype=np.uint8)
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    lk = dna_lkup() if lkup is None else np.ascontiguousarray(lkup, dtype=np.int32)
+    h = C.c_void_p()
+    _lib.check(_lib.lib().bsgpu_subject_letters(_ptr(buf) if buf.size else None, buf.size, _ptr(lk), lk.size,
+                                                C.byref(h)))
+    return DeviceSubject(h, "xstring", int(buf.size))
+
+
 def device_subject_element(dset, i):
     """One sequence of a resident set as a resident single-sequence subject (0-based i)."""
     h = C.c_void_p()

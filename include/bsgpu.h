@@ -125,6 +125,14 @@ int32_t bsgpu_pdict3parts_tb_width(const bsgpu_pdict3parts *p3);
 typedef struct bsgpu_subject bsgpu_subject;
 
 int bsgpu_subject_xstring(const uint8_t *s, int64_t length, bsgpu_subject **out);
+/* The same from LETTERS (ASCII): DNAString(<character>) with the encoding done on the device.
+ * Replaces the copy-with-lookup behind new_XString_from_CHARACTER (src/XString_class.c:191-218
+ * -> _copy_CHARSXP_to_Chars_holder :134-159 -> XVector's Ocopy_bytes_from_i1i2_with_lkup; the
+ * tables of src/XString_class.c:18-65 and R/XStringCodec-class.R:114-166).  `lkup`: byte -> code, BSGPU_NA = not a letter, as for
+ * bsgpu_subject_fasta.  Error: "key %d (char '%c') not in lookup table" for the first such
+ * letter, XVector's text. */
+int bsgpu_subject_letters(const uint8_t *letters, int64_t length, const int32_t *lkup, int lkup_length,
+		bsgpu_subject **out);
 int bsgpu_subject_views(const uint8_t *s, int64_t length,
 		const int32_t *views_start, const int32_t *views_width, int32_t nviews,
 		bsgpu_subject **out);
@@ -325,7 +333,7 @@ int64_t bsgpu_launch_count(void);
 
 /* Opt-in timing of the hot kernels (pack_subject_kernel, scan_byteseed_kernel,
  * match_plain_kernel, scan_tb_kernel, qscan_kernel, oligo_freq_kernel,
- * fasta_summary_kernel, fasta_emit_kernel) with CUDA events recorded on the
+ * fasta_summary_kernel, fasta_emit_kernel, encode_letters_kernel) with CUDA events recorded on the
  * launching stream.  bsgpu_kernel_timing(1) starts collecting (at most 8192 launches),
  * bsgpu_kernel_times() waits for them, writes up to max_entries (name, milliseconds) pairs in
  * launch order, forgets them and returns how many it wrote (-1 on error). */

@@ -144,3 +144,29 @@ def test_lines_longer_than_a_group_of_chunks():
     same(gpu_parse(text), OF.read_fasta(text))
     for cut in (32_768, 32_769, 65_536, 98_304 + 17):
         same(gpu_parse(text[:cut]), OF.read_fasta(text[:cut]))
+
+
+def test_letters_encoded_on_the_device():
+    """DNAString(<character>) with the translation done by encode_letters_kernel
+    (bsgpu_subject_letters): same resident subject as uploading host-encoded codes, the
+    reference's error text for a letter outside the alphabet (first such letter)."""
+    g = rng(21)
+    for n in (0, 1, 15, 16, 17, 4095, 100_003):
+        letters = np.frombuffer(b"ACGTacgtNnMRWSYKVHDB-+.", dtype=np.uint8)[g.integers(0, 23, n)]
+        with bs.device_subject_from_letters(letters) as d:
+            got = bs.download_set(d)
+        assert got.widths.tolist() == [n]
+        assert np.array_equal(got.concat, bs.encode_dna(letters.tobytes()))
+    s = random_dna(g, 60_000)
+    text = bs.decode_dna(s)
+    pdict = bs.PDict([s[100:125], s[59_975:60_000], random_dna(g, 25)])
+    with bs.device_subject_from_letters(text) as d:
+        assert np.array_equal(bs.countPDict(pdict, d), bs.countPDict(pdict, bs.DNAString(s)))
+        assert np.array_equal(np.asarray(bs.oligonucleotideFrequency(d, 5)),
+                              np.asarray(bs.oligonucleotideFrequency(bs.DNAString(s), 5)))
+    bad = bytearray(text[:5000].encode())
+    bad[4000], bad[1234] = ord("!"), ord("Z")
+    with pytest.raises(bs.BsgpuError, match=r"key 90 \(char 'Z'\) not in lookup table"):
+        bs.device_subject_from_letters(bytes(bad))
+    with pytest.raises(ValueError, match=r"key 90 \(char 'Z'\) not in lookup table"):
+        bs.encode_dna(bytes(bad))

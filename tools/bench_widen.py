@@ -81,6 +81,30 @@ def bench_oligo(x, sample):
     return lines
 
 
+def bench_letters(x):
+    """DNAString(<character>) -> resident subject: letters translated on the device against the
+    host-side table lookup (numpy) followed by the upload of the codes."""
+    dec = np.zeros(256, np.uint8)
+    for letter, code in bs.xstring.DNA_CODES.items():
+        dec[code] = ord(letter)
+    letters = dec[x]
+
+    def run():
+        bs.device_subject_from_letters(letters).close()
+    k, wall = kernel_ms(run, 3)
+    t0 = time.perf_counter()
+    codes = bs.encode_dna(letters.tobytes())
+    t_host = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    bs.DeviceSubject.from_xstring(codes).close()
+    t_up = (time.perf_counter() - t0) * 1e3
+    return [{"what": "DNAString(<letters>) -> resident subject", "letters": int(x.size), "kernel_ms": k,
+             "call_ms_host_api": wall, "host_numpy_encode_ms": t_host, "host_encoded_upload_ms": t_up,
+             "roofline": {"bound": "hbm", "unit": "GB/s", "algorithmic_bytes": 2 * int(x.size),
+                          "achieved": 2 * x.size / (sum(k.values()) * 1e-3) / 1e9, "peak": HBM_GBS,
+                          "frac": 2 * x.size / (sum(k.values()) * 1e-3) / 1e9 / HBM_GBS}}]
+
+
 def fasta_text(x, line=60):
     n = x.size
     dec = np.zeros(256, np.uint8)
@@ -162,4 +186,6 @@ if __name__ == "__main__":
     for ln in bench_oligo(x, sample):
         print(json.dumps(ln), flush=True)
     for ln in bench_fasta(x, sample):
+        print(json.dumps(ln), flush=True)
+    for ln in bench_letters(x):
         print(json.dumps(ln), flush=True)
