@@ -227,6 +227,37 @@ def workload_config(args, world):
 # GPU arm
 # ----------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(local):
+    """Best effort: run this rank on the CPUs of its GPU's NUMA node BEFORE it allocates its pinned
+    host buffer, so that the buffer the end-to-end leg streams over PCIe lives in the memory next
+    to that GPU's root port instead of crossing the inter-socket link (with 8 ranks per box the
+    e2e leg is one host-memory -> PCIe stream per GPU).  Returns what was done (for `config`), or
+    None when the topology cannot be read.  BENCH_NUMA=0 disables it."""
+    if os.environ.get("BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                if part:
+                    lo_, _, hi_ = part.partition("-")
+                    cpus.update(range(int(lo_), int(hi_ or lo_) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if len(allowed) < 2:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"gpu_pci": bus, "numa_node": node, "cpus": len(allowed)}
+    except Exception:           # no sysfs, no such attribute, not permitted: leave the rank where it is
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -241,6 +272,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the PDict path has no CPU fallback)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     L = _lib.lib()
     _lib.check(L.bsgpu_set_device(local))
     if world > 1:
@@ -412,7 +444,8 @@ def run_ours(args):
                "h2d_bytes_per_step": int(b - a), "d2h_bytes_per_step": int(4 * M),
                "ms_per_step": 1e3 * te.item(),
                "call": "DeviceSubject.from_chunk(pinned host bytes) + countPDict (bsgpu_subject_chunk + "
-                       "bsgpu_match through the C ABI), counts read back to the host"}
+                       "bsgpu_match through the C ABI), counts read back to the host",
+               "host_binding": numa if numa is not None else "none (topology not readable or BENCH_NUMA=0)"}
 
     if rank != 0:
         if world > 1:
