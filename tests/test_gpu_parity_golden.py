@@ -137,3 +137,19 @@ def test_mtb_pdict_small():
         assert inb == b
     assert bs.countPDict(pd, s, max_mismatch=1).tolist() == [len(e or []) for e in ends]
     assert pd.duplicated().tolist() == [False, False, True, False]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variable", [False, True])
+def test_seeded_dictionaries_of_the_reference_tests(seed, variable):
+    """tests/testthat/test-matchPDict.R:176-234 re-expressed (see tests/test_oracle_golden.py):
+    six windows cut from a 150-letter target, shuffled, must come back at exactly their places."""
+    from tests.test_oracle_golden import seeded_dictionary
+    target, pats, starts, widths = seeded_dictionary(seed, variable)
+    kw = dict(tb_start=1, tb_width=min(widths)) if variable else {}
+    pd = bs.PDict(bs.DNAStringSet(pats), **kw)
+    res = bs.matchPDict(pd, bs.DNAString(target))
+    assert [None if e is None else e.tolist() for e in res.startIndex()] == [[s] for s in starts]
+    assert [None if e is None else e.tolist() for e in res.endIndex()] == \
+        [[s + w - 1] for s, w in zip(starts, widths)]
+    assert bs.countPDict(pd, bs.DNAString(target)).tolist() == [1] * 6

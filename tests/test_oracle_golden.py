@@ -195,3 +195,60 @@ def test_plain_dictionary_known_answers(be):
     # vcountPattern("TG", Views) = c(1, 1)   (test-matchPattern.R:148)
     v = R.Views(dna, [2, 9], [3, 3])
     assert R.vcountPDict(R.SeqSet(["TG"]), v, backend=be).tolist() == [[1, 1]]
+
+
+# ---- the reference's seeded tests, re-expressed (test-matchPDict.R:176-234, test-PDict.R:174-221) ----
+# They draw a 150-letter target with R's RNG (set.seed(1) + sample), cut L = 6 windows out of it
+# with successiveIRanges(), shuffle them and expect every window back at exactly its place.  R's
+# RNG cannot be replayed without R, so the same construction runs on our own seeded target: the
+# expectations are properties of the construction, not of the particular random draw.
+
+def successive_ranges(widths, gaps):
+    """IRanges::successiveIRanges(width, gapwidth): 1-based starts of back-to-back ranges."""
+    starts, pos = [], 1
+    for i, w in enumerate(widths):
+        starts.append(pos)
+        pos += w + (gaps[i] if i < len(gaps) else 0)
+    return starts
+
+
+def seeded_dictionary(seed, variable):
+    from tests.helpers import random_dna, rng
+    g = rng(seed)
+    target = random_dna(g, 150, gc=0.5)
+    W, n = 20, 6
+    n_cut = g.integers(0, 6, n) if variable else np.zeros(n, dtype=np.int64)
+    widths = (W - n_cut).tolist()
+    starts = successive_ranges(widths, (1 + n_cut[:-1]).tolist())
+    order = g.permutation(n)
+    pats = [target[starts[i] - 1:starts[i] - 1 + widths[i]].copy() for i in order]
+    return target, pats, [starts[i] for i in order], [widths[i] for i in order]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_constant_width_dictionary(be, seed):    # test-matchPDict.R:176-201, test-PDict.R:174-192
+    target, pats, starts, widths = seeded_dictionary(seed, variable=False)
+    pd = R.PDict(R.SeqSet(pats), backend=be)
+    assert len(pd) == 6 and pd.width().tolist() == [20] * 6
+    tp = pd.threeparts_list[0]
+    assert tp.head_or_none() is None and tp.tail_or_none() is None and tp.tb.widths.tolist() == [20] * 6
+    res = R.matchPDict(pd, target)
+    assert L(res.startIndex()) == [[s] for s in starts]
+    assert L(res.endIndex()) == [[s + 19] for s in starts]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_variable_width_dictionary(be, seed):    # test-matchPDict.R:203-234, test-PDict.R:194-221
+    target, pats, starts, widths = seeded_dictionary(seed, variable=True)
+    mw = min(widths)
+    pd = R.PDict(R.SeqSet(pats), tb_start=1, tb_width=mw, backend=be)
+    assert len(pd) == 6 and pd.width().tolist() == widths
+    tp = pd.threeparts_list[0]
+    assert tp.head_or_none() is None and tp.tb.widths.tolist() == [mw] * 6
+    assert tp.tail.widths.tolist() == [w - mw for w in widths]
+    for i, p in enumerate(pats):                # tail(pdict) == substring(x, min width + 1)
+        a = int(tp.tail.offsets[i]) if hasattr(tp.tail, "offsets") else sum(tp.tail.widths[:i])
+        assert tp.tail.concat[a:a + widths[i] - mw].tolist() == p[mw:].tolist()
+    res = R.matchPDict(pd, target)
+    assert L(res.startIndex()) == [[s] for s in starts]
+    assert L(res.endIndex()) == [[s + w - 1] for s, w in zip(starts, widths)]
