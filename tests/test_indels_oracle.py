@@ -83,3 +83,70 @@ def test_edges():
     for p, k in [("ACGTACGTACGT", 2), ("ACGTACGTACGTA", 2), ("A", 1), ("AC", 1), ("TTTT", 3), ("ACGTAC", 5)]:
         assert OI.count_indels([enc(p)], S, k) == ref_counts([enc(p)], S, k), (p, k)
     assert OI.count_indels([enc("ACG")], enc(""), 1) == ref_counts([enc("ACG")], enc(""), 1)
+
+
+# ---- the device-ready core (biostrings_b200/csrc/bsgpu_indels.cuh) compiled for the CPU ----------
+
+@pytest.fixture(scope="module")
+def hostcheck(tmp_path_factory):
+    import ctypes as C
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path_factory.mktemp("hostcheck") / "indels_hostcheck.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so,
+                           os.path.join(root, "tests", "hostcheck", "indels_hostcheck.cpp")])
+    L = C.CDLL(so)
+    L.indels_hostcheck.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
+                                   C.c_int, C.c_int, C.c_int, C.c_void_p]
+    return L
+
+
+def core_counts(L, pats, S, k, fixed=(True, True)):
+    concat = np.ascontiguousarray(np.concatenate(pats), dtype=np.uint8)
+    widths = np.array([len(p) for p in pats], dtype=np.int32)
+    S = np.ascontiguousarray(S, dtype=np.uint8)
+    counts = np.zeros(len(pats), dtype=np.int64)
+    rc = L.indels_hostcheck(concat.ctypes.data, widths.ctypes.data, len(pats), S.ctypes.data, S.size,
+                            k, int(fixed[0]), int(fixed[1]), counts.ctypes.data)
+    assert rc == 0
+    return counts.tolist()
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5])
+def test_device_core_equals_reference(hostcheck, k):
+    g = rng(500 + k)
+    S = random_dna(g, 4000)
+    S[g.integers(0, 4000, 30)] = 15
+    pats = []
+    for _ in range(60):
+        w = int(g.integers(k + 1, 30))
+        a = int(g.integers(0, 4000 - 40))
+        p = S[a:a + w].copy()
+        for _ in range(int(g.integers(0, k + 2))):
+            kind, at = int(g.integers(3)), int(g.integers(0, len(p)))
+            if kind == 0:
+                p[at] = [1, 2, 4, 8][int(g.integers(4))]
+            elif kind == 1 and len(p) > k + 1:
+                p = np.delete(p, at)
+            else:
+                p = np.insert(p, at, [1, 2, 4, 8][int(g.integers(4))])
+        pats.append(p.astype(np.uint8))
+    pats += [S[:k + 1].copy(), S[-(k + 3):].copy(), np.concatenate([random_dna(g, 3), S[:10]])]   # subject edges
+    assert core_counts(hostcheck, pats, S, k) == ref_counts(pats, S, k)
+
+
+@pytest.mark.parametrize("fixed", [(True, True), (False, False), (True, False), (False, True)])
+def test_device_core_fixed_modes(hostcheck, fixed):
+    g = rng(9)
+    codes = np.array([1, 2, 4, 8, 1, 2, 4, 8, 15, 3, 5, 10], dtype=np.uint8)
+    S = codes[g.integers(0, len(codes), 1500)]
+    pats = [codes[g.integers(0, len(codes), int(g.integers(4, 16)))] for _ in range(30)]
+    pats += [S[a:a + 12].copy() for a in g.integers(0, 1400, 10)]
+    assert core_counts(hostcheck, pats, S, 3, fixed) == ref_counts(pats, S, 3, fixed)
+
+
+def test_device_core_short_subjects(hostcheck):
+    for s, p, k in [("ACGTACGTAC", "ACGTACGTACGT", 2), ("ACGTACGTAC", "ACGTACGTACGTA", 2), ("AC", "ACG", 1),
+                    ("A", "AC", 1), ("ACGT", "TTTTT", 4)]:
+        assert core_counts(hostcheck, [enc(p)], enc(s), k) == ref_counts([enc(p)], enc(s), k), (s, p, k)
