@@ -24,6 +24,7 @@
 #include "bsgpu_qindex.cuh"
 #include "bsgpu_oligo.cuh"
 #include "bsgpu_fasta.cuh"
+#include "bsgpu_indels.cuh"
 
 // ---------------------------------------------------------------------------------------
 // errors
@@ -2728,6 +2729,173 @@ extern "C" int bsgpu_mindex_combine(const bsgpu_result *const *comps, int ncomps
 	memcpy(res->ends_offsets, off.data(), ((size_t) rows + 1) * sizeof(int64_t));
 	res->ends = (int32_t *) malloc(std::max<size_t>(all.size(), 1) * sizeof(int32_t));
 	memcpy(res->ends, all.data(), all.size() * sizeof(int32_t));
+	return BSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Matching with indels on a non-preprocessed dictionary (countPDict / whichPDict /
+// vcountPDict / vwhichPDict with with.indels=TRUE: _match_pattern_indels,
+// src/match_pattern_indels.c:58-107).  EXPERIMENTAL: the per-position core (bsgpu_indels.cuh) is
+// checked against the reference on the CPU, the kernels around it have not been validated on
+// a device yet, so the entry point refuses to run unless BSGPU_EXPERIMENTAL_INDELS is set.
+// ---------------------------------------------------------------------------------------
+
+// first[pattern][y] = first pattern position whose letter matches subject byte y, or -1
+__global__ void __launch_bounds__(256)
+indels_first_kernel(const uint8_t *__restrict__ pat, const int64_t *__restrict__ pat_off, int M,
+		    int fixedP, int fixedS, int16_t *__restrict__ first)
+{
+	int pid = blockIdx.x, y = threadIdx.x;
+
+	if (pid >= M)
+		return;
+	const uint8_t *P = pat + pat_off[pid];
+	int plen = (int) (pat_off[pid + 1] - pat_off[pid]), at = -1;
+
+	for (int n = 0; n < plen; n++)
+		if (bsgpu_indels_match(P[n], (uint32_t) y, fixedP, fixedS)) {
+			at = n;
+			break;
+		}
+	first[(size_t) pid * 256 + y] = (int16_t) at;
+}
+
+// One thread per (letter of the subject, pattern of this grid row): the candidate match that
+// starts at the letter, if any, as {pattern << 34 | concat index, width << 8 | nedit}.
+__global__ void __launch_bounds__(128)
+indels_candidates_kernel(BsgpuSubjectView S, const uint8_t *__restrict__ pat, const int64_t *__restrict__ pat_off,
+			 int M, const int16_t *__restrict__ first, int max_nmis, int fixedP, int fixedS,
+			 int64_t scan_lo, int64_t scan_hi, unsigned long long *__restrict__ keys,
+			 uint32_t *__restrict__ vals, unsigned long long *__restrict__ n_out,
+			 unsigned long long capacity)
+{
+	int64_t stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (int64_t p = scan_lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; p < scan_hi; p += stride) {
+		int seg = S.nseg == 1 ? 0 : find_segment(S, p);
+		int64_t lo = __ldg(S.seg_start + seg), L = __ldg(S.seg_len + seg);
+
+		if (p < lo || p >= lo + L)
+			continue;                       // a separator
+		for (int pid = blockIdx.y; pid < M; pid += gridDim.y) {
+			int64_t o = __ldg(pat_off + pid);
+			int plen = (int) (__ldg(pat_off + pid + 1) - o);
+			BsgpuIndelCand c;
+
+			if (plen <= max_nmis)
+				continue;               // not an indels pattern (src/match_pattern.c:98-99)
+			if (!bsgpu_indels_candidate(pat + o, plen, first + (size_t) pid * 256, S.bytes + lo, L, p - lo,
+						    max_nmis, fixedP, fixedS, &c))
+				continue;
+			unsigned long long at = atomicAdd(n_out, 1ull);
+			if (at < capacity) {
+				keys[at] = ((unsigned long long) pid << BSGPU_POS_BITS) | (unsigned long long) p;
+				vals[at] = ((uint32_t) c.width << 8) | (uint32_t) c.nedit;
+			}
+		}
+	}
+}
+
+extern "C" int bsgpu_count_indels(const bsgpu_pdict3parts *plain, const bsgpu_subject *subj, int max_mismatch,
+		int fixedP, int fixedS, int per_sequence, int32_t *counts_out)
+{
+	if (getenv("BSGPU_EXPERIMENTAL_INDELS") == nullptr)
+		return fail(BSGPU_EUNSUPPORTED, "with.indels=TRUE is not supported yet: the indels engine has not "
+			    "been validated on a device (BSGPU_EXPERIMENTAL_INDELS=1 enables it)");
+	if (plain == nullptr || subj == nullptr || counts_out == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_count_indels(): bad arguments");
+	if (!plain->plain)
+		return fail(BSGPU_EINVAL, "at the moment, matchPDict() and family only support indels on a "
+			    "non-preprocessed pattern dictionary, sorry");
+	if (max_mismatch < 1 || max_mismatch > BSGPU_INDELS_MAX_K)
+		return fail(BSGPU_EUNSUPPORTED, "with.indels=TRUE needs 1 <= max.mismatch <= %d here", BSGPU_INDELS_MAX_K);
+	if (subj->kind == SUBJ_CHUNK)
+		return fail(BSGPU_EUNSUPPORTED, "with.indels=TRUE is not supported on subject chunks");
+	TRY(ensure_device());
+	const int32_t M = plain->M;
+	const int64_t N = per_sequence ? subj->nseg : 1;
+
+	if ((int64_t) M * N > INT32_MAX)
+		return fail(BSGPU_EINVAL, "allocMatrix: too many elements specified");
+	for (int64_t i = 0; i < (int64_t) M * N; i++)
+		counts_out[i] = 0;
+	if (M == 0 || subj->nseg == 0)
+		return BSGPU_OK;
+	std::vector<int64_t> pat_off((size_t) M + 1);
+	CUDA_TRY(cudaMemcpy(pat_off.data(), plain->d_pat_off.p, ((size_t) M + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+	for (int32_t i = 0; i < M; i++)
+		if (pat_off[(size_t) i + 1] - pat_off[(size_t) i] <= max_mismatch)
+			return fail(BSGPU_EUNSUPPORTED, "with.indels=TRUE: pattern %d is not longer than max.mismatch "
+				    "(the reference counts such patterns with its mismatch-only loop)", i + 1);
+	cudaStream_t st = 0;
+	DevBuf<int16_t> d_first;
+	DevBuf<unsigned long long> d_keys, d_n;
+	DevBuf<uint32_t> d_vals;
+	unsigned long long n = 0, zero = 0;
+	size_t cap = 1u << 20;
+
+	TRY(d_first.alloc((size_t) M * 256));
+	indels_first_kernel<<<M, 256, 0, st>>>(plain->d_pat.p, plain->d_pat_off.p, M, fixedP != 0, fixedS != 0, d_first.p);
+	g_launches++;
+	CUDA_TRY(cudaGetLastError());
+	TRY(d_n.alloc(1));
+	long long nletters = subj->scan_hi - subj->scan_lo;
+	dim3 grid((unsigned) grid_for(nletters, 128, 8), (unsigned) std::min(M, 64));
+	for (;;) {
+		TRY(d_keys.alloc(cap));
+		TRY(d_vals.alloc(cap));
+		CUDA_TRY(cudaMemcpyAsync(d_n.p, &zero, sizeof(zero), cudaMemcpyHostToDevice, st));
+		{
+			KernelTimer kt("indels_candidates_kernel", st);
+			indels_candidates_kernel<<<grid, 128, 0, st>>>(subj->view(), plain->d_pat.p, plain->d_pat_off.p, M,
+					d_first.p, max_mismatch, fixedP != 0, fixedS != 0, subj->scan_lo, subj->scan_hi,
+					d_keys.p, d_vals.p, d_n.p, (unsigned long long) cap);
+		}
+		g_launches++;
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpy(&n, d_n.p, sizeof(n), cudaMemcpyDeviceToHost));
+		if (n <= cap)
+			break;
+		cap = (size_t) n + (size_t) n / 8;      // everything is recomputed into the larger buffers
+	}
+	set_plan("indels_bruteforce patterns=%d letters=%lld candidates=%llu", M, nletters, n);
+	if (n == 0)
+		return BSGPU_OK;
+	std::vector<unsigned long long> keys((size_t) n);
+	std::vector<uint32_t> vals((size_t) n);
+	CUDA_TRY(cudaMemcpy(keys.data(), d_keys.p, (size_t) n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	CUDA_TRY(cudaMemcpy(vals.data(), d_vals.p, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	// ascending (pattern, concat index) = per pattern, per sequence, ascending start
+	std::vector<size_t> order((size_t) n);
+	for (size_t i = 0; i < (size_t) n; i++)
+		order[i] = i;
+	std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });
+	// the best-local-match filter restarts with every (pattern, sequence): each view / set element
+	// is an independent subject (src/match_pdict.c:267-293,348-384)
+	std::vector<BsgpuIndelCand> run;
+	int64_t run_pid = -1, run_seg = -1;
+	auto flush = [&]() {
+		if (run.empty())
+			return;
+		int64_t k = bsgpu_indels_best_local(run.data(), (int64_t) run.size(), nullptr, nullptr);
+		counts_out[per_sequence ? run_pid + run_seg * (int64_t) M : run_pid] += (int32_t) k;
+		run.clear();
+	};
+	for (size_t q = 0; q < (size_t) n; q++) {
+		size_t i = order[q];
+		int64_t pid = (int64_t) (keys[i] >> BSGPU_POS_BITS), pos = (int64_t) (keys[i] & BSGPU_POS_MASK);
+		int64_t seg = std::upper_bound(subj->seg_start.begin(), subj->seg_start.end(), pos) - subj->seg_start.begin() - 1;
+
+		if (pid != run_pid || seg != run_seg) {
+			flush();
+			run_pid = pid;
+			run_seg = seg;
+		}
+		BsgpuIndelCand c = {(int32_t) (pos - subj->seg_start[(size_t) seg] + 1), (int32_t) (vals[i] >> 8),
+				    (int32_t) (vals[i] & 0xFFu)};
+		run.push_back(c);
+	}
+	flush();
 	return BSGPU_OK;
 }
 

@@ -6,6 +6,7 @@ Trusted-Band component followed by ByPos_MIndex_combine (R/matchPDict.R:335-377)
 bsgpu_match() call here: the components are merged on the device.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -290,9 +291,22 @@ def _check_plain_args(pset, max_mismatch, min_mismatch, with_indels, fixed, algo
                          "whichPDict(), vcountPDict() and vwhichPDict() support indels")
     algo = select_algo(normarg_algorithm(algorithm), np.asarray(pset.widths), max_mismatch,
                        min_mismatch, with_indels, fixed)
-    if algo == "indels":
+    if algo == "indels" and not os.environ.get("BSGPU_EXPERIMENTAL_INDELS"):
+        # the indels engine (bsgpu_count_indels) is written and its core checked on the CPU, but
+        # not validated on a device yet: refused unless explicitly enabled
         raise _lib.BsgpuError(-5, "with.indels=TRUE is not supported on the GPU path")
     return algo
+
+
+def _count_indels(pat, dsubj, max_mismatch, fixed, per_sequence):
+    """EXPERIMENTAL (BSGPU_EXPERIMENTAL_INDELS): bsgpu_count_indels() -> int32[M] or [M, N]."""
+    M = _lib.lib().bsgpu_pdict3parts_length(pat.handle)
+    N = dsubj.length if per_sequence else 1
+    out = np.zeros(max(M * N, 1), dtype=np.int32)
+    _lib.check(_lib.lib().bsgpu_count_indels(pat.handle, dsubj.handle, max_mismatch, int(fixed[0]),
+                                             int(fixed[1]), int(per_sequence), _ptr(out)))
+    out = out[:M * N]
+    return out.reshape((M, N), order="F") if per_sequence else out
 
 
 # ---- .checkUserArgsWhenTrustedBandIsFull / .checkMaxMismatch (R/matchPDict.R:118-141) --------
@@ -353,9 +367,14 @@ def _match_plain(pset, subject, max_mismatch, min_mismatch, with_indels, fixed, 
         max_mismatch = normarg_max_mismatch(max_mismatch)
         min_mismatch = normarg_min_mismatch(min_mismatch, max_mismatch)
         fixed = normarg_fixed(fixed)
-        _check_plain_args(pset, max_mismatch, min_mismatch, with_indels, fixed, algorithm, mode)
+        algo = _check_plain_args(pset, max_mismatch, min_mismatch, with_indels, fixed, algorithm, mode)
         pat = PlainPatterns(pset)
-        ans = match_parts([pat], dsubj, max_mismatch, min_mismatch, fixed, mode)
+        if algo == "indels":
+            ans = _count_indels(pat, dsubj, max_mismatch, fixed, False)
+            if mode == MATCHES_AS_WHICH:
+                ans = (np.flatnonzero(ans) + 1).astype(np.int32)
+        else:
+            ans = match_parts([pat], dsubj, max_mismatch, min_mismatch, fixed, mode)
     finally:
         if pat is not None:
             pat.close()
@@ -470,8 +489,22 @@ def _vmatch_plain(pset, subject, max_mismatch, min_mismatch, with_indels, fixed,
                 weight = np.resize(weight, M)
         else:
             collapse = 0
-        _check_plain_args(pset, max_mismatch, min_mismatch, with_indels, fixed, algorithm, mode)
+        algo = _check_plain_args(pset, max_mismatch, min_mismatch, with_indels, fixed, algorithm, mode)
         pat = PlainPatterns(pset)
+        if algo == "indels":
+            mat = _count_indels(pat, dsubj, max_mismatch, fixed, True)
+            if mode == MATCHES_AS_WHICH:
+                return [(np.flatnonzero(mat[:, j]) + 1).astype(np.int32) for j in range(N)]
+            if collapse == 0:
+                return mat
+            # src/match_pdict.c:85-127: subjects outer, patterns inner
+            ans = np.zeros(M if collapse == 1 else N, dtype=np.float64 if weight.dtype.kind == "f" else np.int32)
+            for j in range(N):
+                if collapse == 1:
+                    ans += mat[:, j] * weight[j]
+                else:
+                    ans[j] = sum((mat[i, j] * weight[i] for i in range(M)), ans.dtype.type(0))
+            return ans
         ans = vmatch_parts([pat], dsubj, max_mismatch, min_mismatch, fixed, collapse, weight, mode)
     finally:
         if pat is not None:
