@@ -2865,37 +2865,8 @@ extern "C" int bsgpu_count_indels(const bsgpu_pdict3parts *plain, const bsgpu_su
 	std::vector<uint32_t> vals((size_t) n);
 	CUDA_TRY(cudaMemcpy(keys.data(), d_keys.p, (size_t) n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
 	CUDA_TRY(cudaMemcpy(vals.data(), d_vals.p, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-	// ascending (pattern, concat index) = per pattern, per sequence, ascending start
-	std::vector<size_t> order((size_t) n);
-	for (size_t i = 0; i < (size_t) n; i++)
-		order[i] = i;
-	std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });
-	// the best-local-match filter restarts with every (pattern, sequence): each view / set element
-	// is an independent subject (src/match_pdict.c:267-293,348-384)
-	std::vector<BsgpuIndelCand> run;
-	int64_t run_pid = -1, run_seg = -1;
-	auto flush = [&]() {
-		if (run.empty())
-			return;
-		int64_t k = bsgpu_indels_best_local(run.data(), (int64_t) run.size(), nullptr, nullptr);
-		counts_out[per_sequence ? run_pid + run_seg * (int64_t) M : run_pid] += (int32_t) k;
-		run.clear();
-	};
-	for (size_t q = 0; q < (size_t) n; q++) {
-		size_t i = order[q];
-		int64_t pid = (int64_t) (keys[i] >> BSGPU_POS_BITS), pos = (int64_t) (keys[i] & BSGPU_POS_MASK);
-		int64_t seg = std::upper_bound(subj->seg_start.begin(), subj->seg_start.end(), pos) - subj->seg_start.begin() - 1;
-
-		if (pid != run_pid || seg != run_seg) {
-			flush();
-			run_pid = pid;
-			run_seg = seg;
-		}
-		BsgpuIndelCand c = {(int32_t) (pos - subj->seg_start[(size_t) seg] + 1), (int32_t) (vals[i] >> 8),
-				    (int32_t) (vals[i] & 0xFFu)};
-		run.push_back(c);
-	}
-	flush();
+	bsgpu_indels_counts_from_candidates(keys.data(), vals.data(), (size_t) n, BSGPU_POS_BITS, subj->seg_start, M,
+					    per_sequence != 0, counts_out);
 	return BSGPU_OK;
 }
 

@@ -229,3 +229,48 @@ BSGPU_HD int64_t bsgpu_indels_best_local(const BsgpuIndelCand *cands, int64_t n,
 	}
 	return nout;
 }
+
+#include <algorithm>
+#include <vector>
+
+// Host step of the engine: candidates as the kernel emits them -- key = pattern << pos_bits | concat
+// index of the candidate's first letter, val = width << 8 | nedit, in any order -- to counts.  The
+// filter restarts with every (pattern, sequence): each view / set element is an independent subject
+// (src/match_pdict.c:267-293,348-384).  seg_start: concat index of the first letter of every
+// sequence, ascending.  counts: M entries, or M x N column-major when per_sequence.
+static inline void bsgpu_indels_counts_from_candidates(const unsigned long long *keys, const uint32_t *vals,
+		size_t n, int pos_bits, const std::vector<int64_t> &seg_start, int32_t M, bool per_sequence,
+		int32_t *counts)
+{
+	const unsigned long long pos_mask = (1ull << pos_bits) - 1;
+	std::vector<size_t> order(n);
+	std::vector<BsgpuIndelCand> run;
+	int64_t run_pid = -1, run_seg = -1;
+
+	for (size_t i = 0; i < n; i++)
+		order[i] = i;
+	std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });
+	auto flush = [&]() {
+		if (run.empty())
+			return;
+		int64_t k = bsgpu_indels_best_local(run.data(), (int64_t) run.size(), nullptr, nullptr);
+
+		counts[per_sequence ? run_pid + run_seg * (int64_t) M : run_pid] += (int32_t) k;
+		run.clear();
+	};
+	for (size_t q = 0; q < n; q++) {
+		size_t i = order[q];
+		int64_t pid = (int64_t) (keys[i] >> pos_bits), pos = (int64_t) (keys[i] & pos_mask);
+		int64_t seg = std::upper_bound(seg_start.begin(), seg_start.end(), pos) - seg_start.begin() - 1;
+
+		if (pid != run_pid || seg != run_seg) {
+			flush();
+			run_pid = pid;
+			run_seg = seg;
+		}
+		BsgpuIndelCand c = {(int32_t) (pos - seg_start[(size_t) seg] + 1), (int32_t) (vals[i] >> 8),
+				    (int32_t) (vals[i] & 0xFFu)};
+		run.push_back(c);
+	}
+	flush();
+}

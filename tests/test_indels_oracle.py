@@ -150,3 +150,39 @@ def test_device_core_short_subjects(hostcheck):
     for s, p, k in [("ACGTACGTAC", "ACGTACGTACGT", 2), ("ACGTACGTAC", "ACGTACGTACGTA", 2), ("AC", "ACG", 1),
                     ("A", "AC", 1), ("ACGT", "TTTTT", 4)]:
         assert core_counts(hostcheck, [enc(p)], enc(s), k) == ref_counts([enc(p)], enc(s), k), (s, p, k)
+
+
+def test_engine_host_step_on_several_sequences(hostcheck):
+    """bsgpu_count_indels() minus the device: candidates of every (letter, pattern) of a
+    multi-sequence subject in the concat layout, in scrambled order, through the host step
+    (sort by (pattern, position), filter restarted per sequence) -- summed and per sequence."""
+    import ctypes as C
+    g = rng(4711)
+    S = random_dna(g, 5000)
+    cuts = [(0, 1800), (1700, 2600), (2600, 2600), (4000, 5000)]     # overlapping, empty, tail
+    seqs = [S[a:b] for a, b in cuts]
+    k = 2
+    pats = []
+    for _ in range(30):
+        a = int(g.integers(0, 4900))
+        p = S[a:a + int(g.integers(k + 1, 25))].copy()
+        if g.random() < 0.5 and len(p) > k + 2:
+            p = np.delete(p, int(g.integers(0, len(p))))
+        pats.append(p.astype(np.uint8))
+    concat = np.ascontiguousarray(np.concatenate(pats))
+    widths = np.array([len(p) for p in pats], dtype=np.int32)
+    sconcat = np.ascontiguousarray(np.concatenate(seqs))
+    slen = np.array([len(s) for s in seqs], dtype=np.int32)
+    hostcheck.indels_engine_hostcheck.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                                  C.c_int32] + [C.c_int] * 4 + [C.c_void_p]
+    per = np.stack([np.array(ref_counts(pats, s, k)) for s in seqs], axis=1)
+    for per_sequence in (0, 1):
+        out = np.zeros(len(pats) * (len(seqs) if per_sequence else 1), dtype=np.int32)
+        rc = hostcheck.indels_engine_hostcheck(concat.ctypes.data, widths.ctypes.data, len(pats),
+                                               sconcat.ctypes.data, slen.ctypes.data, len(seqs), k, 1, 1,
+                                               per_sequence, out.ctypes.data)
+        assert rc == 0
+        if per_sequence:
+            assert np.array_equal(out.reshape((len(pats), len(seqs)), order="F"), per)
+        else:
+            assert out.tolist() == per.sum(axis=1).tolist()
