@@ -2735,9 +2735,9 @@ extern "C" int bsgpu_mindex_combine(const bsgpu_result *const *comps, int ncomps
 // ---------------------------------------------------------------------------------------
 // Matching with indels on a non-preprocessed dictionary (countPDict / whichPDict /
 // vcountPDict / vwhichPDict with with.indels=TRUE: _match_pattern_indels,
-// src/match_pattern_indels.c:58-107).  EXPERIMENTAL: the per-position core (bsgpu_indels.cuh) is
-// checked against the reference on the CPU, the kernels around it have not been validated on
-// a device yet, so the entry point refuses to run unless BSGPU_EXPERIMENTAL_INDELS is set.
+// src/match_pattern_indels.c:58-107).  The per-position core (bsgpu_indels.cuh) is checked
+// against the reference on the CPU (tests/test_indels_oracle.py), the whole engine on the device
+// (tests/test_gpu_indels.py).
 // ---------------------------------------------------------------------------------------
 
 // first[pattern][y] = first pattern position whose letter matches subject byte y, or -1
@@ -2799,9 +2799,6 @@ indels_candidates_kernel(BsgpuSubjectView S, const uint8_t *__restrict__ pat, co
 extern "C" int bsgpu_count_indels(const bsgpu_pdict3parts *plain, const bsgpu_subject *subj, int max_mismatch,
 		int fixedP, int fixedS, int per_sequence, int32_t *counts_out)
 {
-	if (getenv("BSGPU_EXPERIMENTAL_INDELS") == nullptr)
-		return fail(BSGPU_EUNSUPPORTED, "with.indels=TRUE is not supported yet: the indels engine has not "
-			    "been validated on a device (BSGPU_EXPERIMENTAL_INDELS=1 enables it)");
 	if (plain == nullptr || subj == nullptr || counts_out == nullptr)
 		return fail(BSGPU_EINVAL, "bsgpu_count_indels(): bad arguments");
 	if (!plain->plain)

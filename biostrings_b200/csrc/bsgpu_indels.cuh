@@ -1,10 +1,8 @@
 // bsgpu_indels.cuh -- matching with indels on a non-preprocessed dictionary: the per-position core.
 //
-// EXPERIMENTAL: used by bsgpu_count_indels() (bsgpu.cu), which refuses to run unless
-// BSGPU_EXPERIMENTAL_INDELS is set, because the kernels around this core have not been validated
-// on a device yet.  The core itself is plain host/device C++ and is checked on the CPU against the
-// reference's own _match_pattern_indels (tests/hostcheck/indels_hostcheck.cpp,
-// tests/test_indels_oracle.py).
+// Used by bsgpu_count_indels() (bsgpu.cu).  The core is plain host/device C++ and is checked on
+// the CPU against the reference's own _match_pattern_indels (tests/hostcheck/indels_hostcheck.cpp,
+// tests/test_indels_oracle.py); the engine around it on the device (tests/test_gpu_indels.py).
 //
 // The reference (src/match_pattern_indels.c:58-107) walks the subject once per pattern; at every
 // position j0 whose letter matches some pattern letter it takes the FIRST such pattern position i0

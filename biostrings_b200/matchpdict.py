@@ -291,15 +291,11 @@ def _check_plain_args(pset, max_mismatch, min_mismatch, with_indels, fixed, algo
                          "whichPDict(), vcountPDict() and vwhichPDict() support indels")
     algo = select_algo(normarg_algorithm(algorithm), np.asarray(pset.widths), max_mismatch,
                        min_mismatch, with_indels, fixed)
-    if algo == "indels" and not os.environ.get("BSGPU_EXPERIMENTAL_INDELS"):
-        # the indels engine (bsgpu_count_indels) is written and its core checked on the CPU, but
-        # not validated on a device yet: refused unless explicitly enabled
-        raise _lib.BsgpuError(-5, "with.indels=TRUE is not supported on the GPU path")
     return algo
 
 
 def _count_indels(pat, dsubj, max_mismatch, fixed, per_sequence):
-    """EXPERIMENTAL (BSGPU_EXPERIMENTAL_INDELS): bsgpu_count_indels() -> int32[M] or [M, N]."""
+    """with.indels=TRUE: bsgpu_count_indels() -> int32[M] or [M, N] (R/matchPDict.R:171-191)."""
     M = _lib.lib().bsgpu_pdict3parts_length(pat.handle)
     N = dsubj.length if per_sequence else 1
     out = np.zeros(max(M * N, 1), dtype=np.int32)

@@ -285,15 +285,14 @@ int bsgpu_mindex_combine(const bsgpu_result *const *components, int ncomponents,
 		bsgpu_result *res);
 
 /* ------------------------------------------------------------------------------------
- * EXPERIMENTAL -- matching with indels on a non-preprocessed dictionary (`plain` from
+ * Matching with indels on a non-preprocessed dictionary (`plain` from
  * bsgpu_patterns_build): the counts behind countPDict / whichPDict / vcountPDict / vwhichPDict
  * with with.indels=TRUE, i.e. the number of "best local matches" _match_pattern_indels reports
  * per pattern (src/match_pattern_indels.c:22-107), every view / set element being an
  * independent subject.  counts_out: M entries, or M x N column-major when per_sequence != 0.
  * The per-position core (csrc/bsgpu_indels.cuh) equals the reference on the CPU
- * (tests/test_indels_oracle.py); the kernels around it have not been validated on a device,
- * so the call fails with BSGPU_EUNSUPPORTED unless the environment variable
- * BSGPU_EXPERIMENTAL_INDELS is set.  Limits: 1 <= max_mismatch <= 15, every pattern longer than
+ * (tests/test_indels_oracle.py), the engine equals it on the device (tests/test_gpu_indels.py).
+ * Limits: 1 <= max_mismatch <= 15, every pattern longer than
  * max_mismatch, no subject chunks, min.mismatch = 0 (R/match-utils.R:54-57).
  * ------------------------------------------------------------------------------------ */
 int bsgpu_count_indels(const bsgpu_pdict3parts *plain, const bsgpu_subject *subject, int max_mismatch,

@@ -1,10 +1,6 @@
-"""EXPERIMENTAL: `with.indels=TRUE` on the GPU (bsgpu_count_indels) against the reference's own
-_match_pattern_indels.  The engine's per-position core is checked on the CPU
-(tests/test_indels_oracle.py); its kernels have not been validated on a device yet, so the entry
-point is disabled unless BSGPU_EXPERIMENTAL_INDELS is set -- and so are these tests:
-
-    BSGPU_EXPERIMENTAL_INDELS=1 python -m pytest tests/test_gpu_indels.py -m gpu
-"""
+"""`with.indels=TRUE` on the GPU (bsgpu_count_indels) against the reference's own
+_match_pattern_indels (src/match_pattern_indels.c:58-107).  The engine's per-position core is
+also checked on the CPU (tests/test_indels_oracle.py)."""
 import os
 
 import numpy as np
@@ -15,10 +11,7 @@ from oracle import indels as OI
 from oracle import ref
 from tests.helpers import random_dna, rng
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("BSGPU_EXPERIMENTAL_INDELS"),
-                                 reason="the indels engine is not validated on a device yet "
-                                        "(BSGPU_EXPERIMENTAL_INDELS=1 enables it)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def want_counts(pats, S, k, fixed=(True, True)):

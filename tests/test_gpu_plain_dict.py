@@ -150,8 +150,8 @@ def test_errors():
         bs.matchPDict(bs.PDict(["ACGT", "GGGG"]), "ACGT", max_mismatch=1, with_indels=True)
     with pytest.raises(ValueError, match="support indels"):
         bs.matchPDict(bs.DNAStringSet(["ACGT"]), "ACGT", max_mismatch=1, with_indels=True)
-    with pytest.raises(bs.BsgpuError, match="not supported on the GPU path"):
-        bs.countPDict(bs.DNAStringSet(["ACGT"]), "ACGT", max_mismatch=1, with_indels=True)
+    # with.indels=TRUE is served by the indels engine (tests/test_gpu_indels.py)
+    assert bs.countPDict(bs.DNAStringSet(["ACGT"]), "ACGT", max_mismatch=1, with_indels=True).tolist() == [1]
     with pytest.raises(ValueError, match="XStringSet object"):
         bs.countPDict(bs.DNAStringSet(["ACGT"]), bs.DNAStringSet(["ACGT"]))
 
