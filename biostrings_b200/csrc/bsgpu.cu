@@ -22,6 +22,7 @@
 
 #include "../../include/bsgpu.h"
 #include "bsgpu_qindex.cuh"
+#include "bsgpu_xseed.cuh"
 #include "bsgpu_oligo.cuh"
 #include "bsgpu_fasta.cuh"
 #include "bsgpu_indels.cuh"
@@ -316,6 +317,7 @@ struct bsgpu_pdict3parts {
 	std::vector<uint8_t> is_tb_dup;         // had a non-NA high2low at build time
 	mutable std::unique_ptr<struct QIndex> qcache;  // q-gram index built on first use
 	mutable std::unique_ptr<struct ByteSeedIndex> bcache;   // byte-seed index (exact, no planes)
+	mutable std::unique_ptr<struct XSeedIndex> xcache;      // extended-seed index (exact, w >= 25)
 	// non-preprocessed dictionary (bsgpu_patterns_build): the letters only, no Trusted Band
 	bool plain = false;
 	DevBuf<uint8_t> d_pat;
@@ -773,6 +775,138 @@ static int get_byteseed(const bsgpu_pdict3parts *p3, const ByteSeedIndex **out)
 	bi->t.s = s2;
 	bi->t.w = w;
 	bi->ok = true;
+	return done();
+}
+
+// Extended-seed index for exact dictionaries of width >= 25 (scan_xseed_kernel,
+// bsgpu_xseed.cuh): every (pattern, offset t) is filed under the filter block of its 10-letter
+// core [t, t + 10) and, inside it, under the 18-letter extended seed of its group.
+struct XSeedIndex {
+	bool ok = false;
+	BsgpuXSeedView t = {};
+	DevBuf<uint4> d_table;
+	DevBuf<BsgpuFilterBlock> d_filter;
+	DevBuf<uint8_t> d_tb;
+	size_t nent = 0;
+	uint64_t nfilter = 0;
+};
+
+static int get_xseed(const bsgpu_pdict3parts *p3, const XSeedIndex **out)
+{
+	*out = nullptr;
+	if (p3->xcache) {
+		*out = p3->xcache.get();
+		return BSGPU_OK;
+	}
+	std::unique_ptr<XSeedIndex> xi(new XSeedIndex());
+	auto done = [&]() {
+		p3->xcache = std::move(xi);
+		*out = p3->xcache.get();
+		return BSGPU_OK;
+	};
+	const int K = BSGPU_XSEED_CORE, E = BSGPU_XSEED_EXT;
+	int M = p3->M, w = p3->w, s2 = std::min(w - K + 1, 32);
+	const char *env = getenv("BSGPU_XSEED_STRIDE");
+
+	if (env != nullptr && atoi(env) >= 2 * E)
+		s2 = std::min(s2, atoi(env));
+	if (getenv("BSGPU_NO_XSEED") != nullptr || getenv("BSGPU_NO_BYTESEED") != nullptr || w < BSGPU_XSEED_MIN_W ||
+	    p3->has_head || p3->has_tail || !p3->all_singletons || M == 0)
+		return done();
+	// the entry id (pattern * S + offset) and >= 6 fingerprint bits share 31 bits
+	while (s2 >= 2 * E && (uint64_t) M * s2 + 2 > (1ull << 25))
+		s2--;
+	if (s2 < 2 * E)
+		return done();          // a very large dictionary: the byte-seed engine adapts its stride further
+	uint32_t id_bits = 1;
+	while (((uint64_t) 1 << id_bits) < (uint64_t) M * s2 + 2)
+		id_bits++;
+	uint32_t fp_mask = 0x7FFFFFFFu & ~((1u << id_bits) - 1u);
+	size_t nent = 0;
+	for (int i = 0; i < M; i++)
+		if (!p3->excluded[i] && !p3->is_tb_dup[i])
+			nent += s2;
+	if (nent == 0)
+		return done();
+	const char *env_l = getenv("BSGPU_SAMPLE_LOAD");
+	double load = env_l ? atof(env_l) / 100.0 : 1.5;
+	load = std::min(3.0, std::max(0.25, load));
+	uint64_t nb = std::max<uint64_t>(16, (uint64_t) ((double) nent / load));
+	// filter blocks are addressed by the packed core itself: 4^10 of them (32 MB) when the dictionary
+	// brings ~16 entries per block, fewer (leading core bits) for small dictionaries; more than ~24
+	// entries per block would drown the filter in false positives: the byte-seed engine takes over
+	const char *env_f = getenv("BSGPU_XSEED_FILTER_LOAD");          // target entries per 32-byte block
+	double fload = env_f ? atof(env_f) : 8.0;
+	fload = std::max(1.0, fload);
+	const char *env_k = getenv("BSGPU_XSEED_KBITS");
+	int kbits = env_k != nullptr && atoi(env_k) == 8 ? 8 : 4;
+	uint32_t fshift = 0;
+	while (fshift < 10 && (double) nent / (double) ((1u << 20) >> (fshift + 1)) <= fload)
+		fshift++;
+	uint64_t nf = (1u << 20) >> fshift;
+	if ((double) nent / (double) nf > 24.0)
+		return done();
+	std::vector<uint4> table(nb, make_uint4(BSGPU_S_EMPTY, BSGPU_S_EMPTY, BSGPU_S_EMPTY, BSGPU_S_EMPTY));
+	std::vector<BsgpuFilterBlock> filter(nf);
+	memset(filter.data(), 0, nf * sizeof(BsgpuFilterBlock));
+	std::vector<uint8_t> buf((size_t) w + 2 * 32, 0);
+	for (int i = 0; i < M; i++) {
+		if (p3->excluded[i] || p3->is_tb_dup[i])
+			continue;
+		memcpy(buf.data() + 32, p3->tb.data() + (size_t) i * w, (size_t) w);
+		for (int t = 0; t < s2; t++) {
+			// the 32 bytes from 8 before the core; letters outside the pattern never reach the
+			// digest of the entry's own group (t < S/2: [t, t + 18) <= w; else t >= 8)
+			uint32_t wd[8], xc, x0, x1;
+			int grp = xseed_group_of(t, s2);
+
+			memcpy(wd, buf.data() + 32 + t - E, 32);        // little-endian host, as on the device
+			if (grp == 0) {
+				wd[0] = wd[1] = 0;
+			} else {
+				wd[4] &= 0xFFFFu;
+				wd[5] = wd[6] = 0;
+			}
+			xseed_digests(wd, xc, x0, x1);
+			uint32_t x = grp ? x1 : x0, e = (uint32_t) i * s2 + t, b, fp;
+
+			byteseed_table_slot(xseed_payload(x, grp), (uint32_t) nb, b, fp);
+			uint32_t word = sampled_fp_of(fp, id_bits, fp_mask) | e;
+			for (;;) {
+				uint32_t *slot = &table[b].x;
+				int z = 0;
+				while (z < 4 && (slot[z] & BSGPU_S_EMPTY) != BSGPU_S_EMPTY)
+					z++;
+				if (z < 4) {
+					slot[z] = (slot[z] & BSGPU_S_OVERFLOW) | word;
+					break;
+				}
+				table[b].w |= BSGPU_S_OVERFLOW;
+				b = b + 1 == nb ? 0 : b + 1;
+			}
+			xseed_set(filter[xseed_block(xc, fshift)].v, x, grp, kbits);
+		}
+	}
+	TRY(xi->d_filter.upload(filter.data(), filter.size()));
+	TRY(xi->d_table.upload(table.data(), table.size()));
+	{
+		std::vector<uint8_t> tbp((size_t) M * w + 8, 0);        // word loads may run 7 bytes over
+		memcpy(tbp.data(), p3->tb.data(), (size_t) M * w);
+		TRY(xi->d_tb.upload(tbp.data(), tbp.size()));
+	}
+	xi->nent = nent;
+	xi->t.filter = xi->d_filter.p;
+	xi->t.filter_shift = fshift;
+	xi->t.kbits = kbits;
+	xi->nfilter = nf;
+	xi->t.table = xi->d_table.p;
+	xi->t.nbuckets = (uint32_t) nb;
+	xi->t.tb = xi->d_tb.p;
+	xi->t.id_bits = id_bits;
+	xi->t.fp_mask = fp_mask;
+	xi->t.s = s2;
+	xi->t.w = w;
+	xi->ok = true;
 	return done();
 }
 
@@ -1638,6 +1772,7 @@ extern "C" int bsgpu_subject_download(const bsgpu_subject *subj, uint8_t *concat
 
 struct Workspace {
 	DevBuf<unsigned long long> cand, rec, rec2;
+	DevBuf<unsigned int> xseed_counts;      // candidates per scan block (scan_xseed_kernel)
 	DevBuf<unsigned long long> counters;    // [0] = candidates, [1] = records
 	DevBuf<int> flags;
 	DevBuf<long long> ovf;                  // windows with too many IUPAC expansions
@@ -1761,6 +1896,89 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 	BsgpuIndexView I = p3->view();
 
 	if (direct && mp.fixedS) {
+		// exact dictionary of width >= 25, letters only: short core + extended seeds, one probe
+		// every S = w - 9 letters (bsgpu_xseed.cuh)
+		const XSeedIndex *xi = nullptr;
+		TRY(get_xseed(p3, &xi));
+		if (xi != nullptr && xi->ok) {
+			int64_t S_ = xi->t.s;
+			// S == 16: probes at p = 8 (mod 16), so that a probe's 32 bytes [p - 8, p + 24) are two
+			// aligned 16-byte chunks (the concat buffer is 16-byte aligned); any fixed phase works
+			bool aligned = S_ == 16 && getenv("BSGPU_XSEED_UNALIGNED") == nullptr;
+			int64_t phase = aligned ? 8 : 0;
+			int64_t lo_p = std::max<int64_t>(start_lo, 32);         // matches start behind the guard (128)
+			int64_t first = lo_p + ((phase - lo_p) % S_ + S_) % S_;
+			int64_t probe_hi = start_hi + S_ - 1;           // exclusive
+			int64_t nprobes = probe_hi > first ? (probe_hi - first + S_ - 1) / S_ : 0;
+
+			set_plan("byteseed_hash xseed core=%d ext=%d S=%d filter_bytes=%llu buckets=%u table_bytes=%llu "
+				 "entries_per_bucket=%.2f%s", BSGPU_XSEED_CORE, BSGPU_XSEED_EXT, xi->t.s,
+				 (unsigned long long) xi->nfilter * 32, xi->t.nbuckets,
+				 (unsigned long long) xi->t.nbuckets * 16, (double) xi->nent / xi->t.nbuckets,
+				 aligned ? " aligned" : "");
+			if (nprobes > 0) {
+				const char *env_np = getenv("BSGPU_XSEED_NP");
+				int np = xi->t.s <= 16 ? 4 : 2;
+				if (env_np != nullptr && (atoi(env_np) == 4 || atoi(env_np) == 2))
+					np = atoi(env_np);
+				size_t smem = (size_t) BSGPU_XSEED_WARPS * BSGPU_XSEED_STAGES * xseed_stage_bytes(np, xi->t.s, aligned);
+				int per_sm = 1;
+				const char *env_v = getenv("BSGPU_XSEED_VARIANT");     // experiments (tools/bench_exact.py)
+				int var = env_v ? atoi(env_v) : 0;
+#define PREPARE_XSEED(NP, AL, KB, V) do { \
+	static bool attr_set = false; \
+	if (!attr_set) { \
+		CUDA_TRY(cudaFuncSetAttribute(scan_xseed_kernel<NP, AL, KB, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+			BSGPU_XSEED_WARPS * BSGPU_XSEED_STAGES * (int) xseed_stage_bytes(NP, AL ? 16 : 32, AL))); \
+		attr_set = true; \
+	} \
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_xseed_kernel<NP, AL, KB, V>, 256, smem)); \
+} while (0)
+#define LAUNCH_XSEED(NP, AL, KB, V) \
+	scan_xseed_kernel<NP, AL, KB, V><<<grid, 256, smem, st>>>(S, xi->t, first, nprobes, ws->cand.p, cap, ws->xseed_counts.p)
+#define XSEED_DISPATCH(WHAT) do { \
+	if (var == 16 && aligned && np == 4 && xi->t.kbits == 4) { WHAT(4, true, 4, 16); } \
+	else if (xi->t.kbits == 8) { \
+		if (aligned) { if (np == 4) WHAT(4, true, 8, 0); else WHAT(2, true, 8, 0); } \
+		else { if (np == 4) WHAT(4, false, 8, 0); else WHAT(2, false, 8, 0); } \
+	} else { \
+		if (aligned) { if (np == 4) WHAT(4, true, 4, 0); else WHAT(2, true, 4, 0); } \
+		else { if (np == 4) WHAT(4, false, 4, 0); else WHAT(2, false, 4, 0); } \
+	} \
+} while (0)
+				XSEED_DISPATCH(PREPARE_XSEED);
+				int64_t ntile = (nprobes + (int64_t) np * 32 - 1) / ((int64_t) np * 32);
+				int grid = (int) std::max<int64_t>(1, std::min<int64_t>(
+					(ntile + BSGPU_XSEED_WARPS - 1) / BSGPU_XSEED_WARPS,
+					(int64_t) g_num_sms * std::max(per_sm, 1)));
+				// candidate slices: one per scan warp, sized for every probe passing both tests
+				int64_t cap = xseed_warp_capacity(nprobes, np, grid);
+				size_t nslices = (size_t) grid * BSGPU_XSEED_WARPS;
+				if ((size_t) cap * nslices > ws->cand.n)
+					TRY(ws->cand.alloc((size_t) cap * nslices));
+				if (nslices > ws->xseed_counts.n)
+					TRY(ws->xseed_counts.alloc(nslices));
+				{
+					KernelTimer kt("scan_xseed_kernel", st);
+					XSEED_DISPATCH(LAUNCH_XSEED);
+				}
+				g_launches++;
+				CUDA_TRY(cudaGetLastError());
+				{
+					KernelTimer kt("confirm_xseed_kernel", st);
+					const char *env_c = getenv("BSGPU_XSEED_CONFIRM_BLOCKS");
+					int cx = env_c != nullptr && atoi(env_c) > 0 ? atoi(env_c) : 4;
+					confirm_xseed_kernel<<<dim3((unsigned) cx, (unsigned) grid), 256, 0, st>>>(
+						S, xi->t, R, ws->cand.p, cap, ws->xseed_counts.p, end_lo, end_hi);
+				}
+#undef PREPARE_XSEED
+#undef LAUNCH_XSEED
+#undef XSEED_DISPATCH
+				g_launches++;
+				CUDA_TRY(cudaGetLastError());
+			}
+			return BSGPU_OK;
+		}
 		// exact dictionary, letters only: one probe every S letters
 		const ByteSeedIndex *bi = nullptr;
 		TRY(get_byteseed(p3, &bi));

@@ -55,29 +55,47 @@ def subject_region(lo, hi, chrom_len, seed=3, gc=0.41, with_n=True, out=None):
     return res
 
 
+PLANT_BLOCKS = 64
+
+
+def planted_blocks(chrom_len):
+    """The 1 Mi-letter blocks of a chromosome the planted patterns are cut from: up to
+    PLANT_BLOCKS of them, evenly spaced over the whole chromosome."""
+    nb = max(1, chrom_len // BLOCK)
+    step = max(1, -(-nb // PLANT_BLOCKS))
+    return np.arange(0, nb, step, dtype=np.int64)
+
+
 def dictionary(M, width, chrom_len, n_chrom, seed=2, frac_planted=0.10, frac_dup=0.01,
-               subject_seed=3, gc=0.41, nsub=0, sub_lo=0):
+               subject_seed=3, gc=0.41, nsub=0, sub_lo=0, with_n=True):
     """M patterns of `width` letters: i.i.d. random, `frac_planted` of them cut from the
-    synthetic subject (from the first 4 Mi letters after the telomere of every chromosome,
-    so every rank of a sharded run sees hits), optionally with up to `nsub` substitutions
-    at positions >= sub_lo, and `frac_dup` exact duplicates of other patterns.
-    Returns a uint8 array [M, width]."""
+    synthetic subject (generated with the same `with_n`) at positions spread over the WHOLE length of every chromosome (uniform
+    inside up to 64 evenly spaced 1 Mi-letter blocks per chromosome, so any window of a few Mbp
+    and every rank of a sharded run sees hits; windows holding an N stay random), optionally
+    with up to `nsub` substitutions at positions >= sub_lo, and `frac_dup` exact duplicates of
+    other patterns.  Returns a uint8 array [M, width]."""
     g = np.random.Generator(np.random.PCG64(seed))
     pats = BASES[g.integers(0, 4, size=(M, width), dtype=np.uint8)]
     n_pl = int(M * frac_planted)
     if n_pl:
-        span = min(4 * BLOCK, chrom_len // 4)
         rows = g.choice(M, size=n_pl, replace=False)
         chrom = g.integers(0, n_chrom, size=n_pl)
-        pos = g.integers(20_000, 20_000 + span - width, size=n_pl)
-        regions = {}
-        for c in range(n_chrom):
-            regions[c] = subject_region(c * chrom_len, c * chrom_len + 20_000 + span, chrom_len,
-                                        subject_seed, gc)
-        for r, c, p in zip(rows.tolist(), chrom.tolist(), pos.tolist()):
-            w = regions[c][p:p + width]
-            if (w != 15).all():
-                pats[r] = w
+        blocks = planted_blocks(chrom_len)
+        blk = blocks[g.integers(0, blocks.size, size=n_pl)]
+        span = min(BLOCK, chrom_len) - width
+        off = g.integers(0, max(span, 1), size=n_pl)
+        order = np.lexsort((blk, chrom))
+        cur = (-1, -1)
+        letters = None
+        for k in order.tolist():
+            c, b = int(chrom[k]), int(blk[k])
+            if (c, b) != cur:
+                a = c * chrom_len + b * BLOCK
+                letters = subject_region(a, min(a + BLOCK, (c + 1) * chrom_len), chrom_len, subject_seed, gc, with_n)
+                cur = (c, b)
+            w = letters[off[k]:off[k] + width]
+            if w.size == width and (w != 15).all():
+                pats[rows[k]] = w
         if nsub:
             k = g.integers(0, nsub + 1, size=n_pl)
             for r, kk in zip(rows.tolist(), k.tolist()):

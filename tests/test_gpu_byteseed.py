@@ -1,5 +1,8 @@
-"""The exact-dictionary engine (scan_byteseed_kernel + confirm_byteseed_kernel) against the
-reference on the GPU: every stride / tile regime (S = w - 15 from 2 to 32, NP = 8 / 4 / 2),
+"""The exact-dictionary engines against the reference on the GPU: scan_byteseed_kernel (16-letter
+seeds, S = w - 15 from 2 to 32, NP = 8 / 4 / 2) and, for w >= 25, scan_xseed_kernel (10-letter
+core + 18-letter extended seeds, S = w - 9 from 16 to 32, aligned and unaligned tiles, NP = 4 / 2,
+4 or 8 filter bits per seed):
+every stride / tile regime,
 subjects spanning many TMA tiles, sequence sets and views (separators), overlap chunks
 (ownership by end position), non-base letters in the subject, and repeats dense enough to
 overflow the candidate slices (the confirm-in-place fallback)."""
@@ -45,8 +48,40 @@ def cut(g, s, w, k):
     return pats
 
 
-@pytest.mark.parametrize("w", [17, 18, 25, 26, 27, 28, 38, 39, 40, 46, 47, 48, 64, 65, 100, 130])
-def test_exact_dictionary_all_strides(w):
+ENGINES = {"xseed": {}, "xseed_np2": {"BSGPU_XSEED_NP": "2"}, "xseed_np4": {"BSGPU_XSEED_NP": "4"},
+           "xseed_kbits8": {"BSGPU_XSEED_KBITS": "8"},
+           "xseed_unaligned": {"BSGPU_XSEED_UNALIGNED": "1"}, "byteseed": {"BSGPU_NO_XSEED": "1"}}
+
+
+@pytest.fixture(params=["xseed", "byteseed"])
+def engine(request, monkeypatch):
+    for k, v in ENGINES[request.param].items():
+        monkeypatch.setenv(k, v)
+    return request.param
+
+
+def expect_engine(engine, w):
+    assert plan().startswith("byteseed_hash"), plan()
+    assert ("xseed" in plan()) == (engine.startswith("xseed") and w >= 25), plan()
+
+
+@pytest.mark.parametrize("variant", ["xseed_np2", "xseed_np4", "xseed_kbits8", "xseed_unaligned"])
+@pytest.mark.parametrize("w", [25, 31])
+def test_xseed_tile_variants(w, variant, monkeypatch):
+    for k, v in ENGINES[variant].items():
+        monkeypatch.setenv(k, v)
+    g = rng(7050 + w)
+    s = subject(g, 300_000)
+    pats = cut(g, s, w, 600) + [random_dna(g, w) for _ in range(300)]
+    prod, orac = both(pats)
+    got = bs.countPDict(prod, s)
+    expect_engine(variant, w)
+    assert got.tolist() == R.countPDict(orac, s).tolist()
+    assert_same_ends(bs.matchPDict(prod, s).endIndex(), R.matchPDict(orac, s).endIndex())
+
+
+@pytest.mark.parametrize("w", [17, 18, 25, 26, 27, 28, 38, 39, 40, 41, 42, 46, 47, 48, 64, 65, 100, 130])
+def test_exact_dictionary_all_strides(w, engine):
     g = rng(7000 + w)
     s = subject(g, 150_000)
     pats = cut(g, s, w, 400) + [random_dna(g, w) for _ in range(200)]
@@ -55,7 +90,7 @@ def test_exact_dictionary_all_strides(w):
         p[~np.isin(p, [1, 2, 4, 8])] = 1
     prod, orac = both(pats)
     got = bs.countPDict(prod, s)
-    assert plan().startswith("byteseed_hash"), plan()
+    expect_engine(engine, w)
     assert got.tolist() == R.countPDict(orac, s).tolist()
     assert bs.whichPDict(prod, s).tolist() == R.whichPDict(orac, s).tolist()
     assert_same_ends(bs.matchPDict(prod, s).endIndex(), R.matchPDict(orac, s).endIndex())
@@ -97,7 +132,7 @@ def test_short_widths_keep_the_plain_scan():
     assert plan().startswith("tb_hash"), plan()
 
 
-def test_sets_views_and_collapse():
+def test_sets_views_and_collapse(engine):
     g = rng(7200)
     genome = subject(g, 60_000)
     pats = cut(g, genome, 25, 300)
@@ -106,7 +141,7 @@ def test_sets_views_and_collapse():
     pset, oset = bs.DNAStringSet(reads), R.SeqSet(reads)
     a, b = bs.vcountPDict(prod, pset), R.vcountPDict(orac, oset)
     assert a.shape == b.shape and (a == b).all() and a.sum() > 50
-    assert plan().startswith("byteseed_hash"), plan()
+    expect_engine(engine, 25)
     for collapse in (1, 2):
         w = g.integers(1, 5, len(reads) if collapse == 1 else len(pats)).astype(np.int32)
         got = bs.vcountPDict(prod, pset, collapse=collapse, weight=w)
@@ -123,7 +158,7 @@ def test_sets_views_and_collapse():
 
 
 @pytest.mark.parametrize("w", [25, 40])
-def test_chunks_own_matches_by_end(w):
+def test_chunks_own_matches_by_end(w, engine):
     from biostrings_b200 import matchpdict as mp
     g = rng(7300 + w)
     s = subject(g, 90_000)
@@ -148,7 +183,7 @@ def test_chunks_own_matches_by_end(w):
         assert rows[i] == we[wo[i]:wo[i + 1]].tolist()
 
 
-def test_dense_repeats_overflow_the_candidate_slices():
+def test_dense_repeats_overflow_the_candidate_slices(engine):
     """Every probe of a periodic subject is a seed hit: the candidate slices fill up and the
     scan confirms in place."""
     g = rng(7400)
@@ -157,7 +192,7 @@ def test_dense_repeats_overflow_the_candidate_slices():
     pats = [np.tile(np.roll(unit, r), 4)[:25].copy() for r in range(7)] + cut(g, random_dna(g, 5000), 25, 50)
     prod, orac = both(pats)
     got = bs.countPDict(prod, s)
-    assert plan().startswith("byteseed_hash"), plan()
+    expect_engine(engine, 25)
     want = R.countPDict(orac, s)
     assert got.tolist() == want.tolist()
     assert int(got[:7].sum()) == s.size - 24

@@ -9,7 +9,11 @@ Mbp-million-patterns there:
   * the whole subject == the sum over 5 overlap chunks (the sharding of SURVEY 8e);
   * max.mismatch 2 finds everything max.mismatch 0 finds, and min.mismatch = 1 removes
     exactly those;
-  * a 5 Mbp window of it, counted by the compiled reference, agrees bit for bit.
+  * a 5 Mbp window of it (200 000 of the patterns), counted by the compiled reference, agrees bit
+    for bit -- for max.mismatch 0 AND for PDict(max.mismatch=2), which is the recall check of
+    the q-gram filter at size (a missed alignment cannot hide behind the precision properties).
+BASELINE configurations 3, 4, 5 at their full dictionary sizes: the same kind of sample parity
+against the compiled reference (biostrings_b200/workloads.py generates the inputs).
 """
 import warnings
 
@@ -17,7 +21,7 @@ import numpy as np
 import pytest
 
 import biostrings_b200 as bs
-from biostrings_b200 import _lib, matchpdict as mp, sharding, synth
+from biostrings_b200 import _lib, matchpdict as mp, sharding, synth, workloads
 from oracle import ref, rlevel as R
 
 pytestmark = pytest.mark.gpu
@@ -107,3 +111,111 @@ def test_mtb_full_size(world):
     inside = (s >= 1) & (e <= N)
     assert inside.all()                                  # 40 N-runs at both ends: nothing overhangs
     assert (mismatches(subj, pats, rows, e) <= 2).all()
+    if ref.available():
+        # recall at size: every alignment the reference's three Trusted Bands (8/8/9) find
+        # (tests/testthat/test-matchPDict.R:63-76 semantics), counts AND ends
+        lo2, n2 = 30_000_000, 5_000_000
+        sample = subj[lo2:lo2 + n2]
+        sub = np.sort(np.random.default_rng(1).choice(M, 200_000, replace=False))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            od = R.PDict(R.SeqSet(concat=pats[sub].reshape(-1), widths=np.full(sub.size, W, np.int32)),
+                         max_mismatch=2, backend="ref")
+            pdsub = bs.PDict(bs.DNAStringSet(concat=pats[sub].reshape(-1), widths=np.full(sub.size, W, np.int32)),
+                             max_mismatch=2)
+        want = R.countPDict(od, sample, max_mismatch=2)
+        got = bs.countPDict(pdsub, sample, max_mismatch=2)
+        assert _lib.lib().bsgpu_last_plan().decode().startswith("qgram_hamming")
+        assert want.sum() > 300 and (got == want).all()
+        # the same window inside the resident 250 Mbp subject: counts of the sub-dictionary's rows
+        # restricted to ends inside the window agree with the whole-subject ends
+        sel = (e > lo2 + W) & (e <= lo2 + n2 - W)
+        whole = np.bincount(rows[sel], minlength=M)[sub]
+        we = R.matchPDict(od, sample, max_mismatch=2).endIndex()
+        inner = np.array([0 if v is None else int(((v > W) & (v <= n2 - W)).sum()) for v in we])
+        assert (whole == inner).all()
+
+
+def _sample_parity(pd_gpu, pd_ref, sample, **kw):
+    got = bs.countPDict(pd_gpu, sample, **kw)
+    want = R.countPDict(pd_ref, sample, **kw)
+    assert (got == want).all(), (int((got != want).sum()), int(got.sum()), int(want.sum()))
+    return int(want.sum())
+
+
+@pytest.mark.skipif(not ref.available(), reason="needs the compiled reference")
+def test_c3_solexa_shape_sample_parity():
+    """BASELINE config 3: 1M 36-mers, PDict(tb.start=1, tb.end=12), countPDict(max.mismatch=2) on
+    100 Mbp: properties at size, and 200 000 of the patterns x a 4 Mbp window against the reference."""
+    n = 100_000_000
+    pats = workloads.c3_dictionary(1_000_000, n)
+    subj = workloads.c3_subject(0, n, n)
+    dset = bs.DNAStringSet(concat=pats.reshape(-1), widths=np.full(pats.shape[0], 36, np.int32))
+    pd = bs.PDict(dset, tb_start=1, tb_end=12)
+    with mp.DeviceSubject.from_xstring(subj) as ds:
+        c0 = bs.countPDict(pd, ds)
+        c2 = bs.countPDict(pd, ds, max_mismatch=2)
+        c21 = bs.countPDict(pd, ds, max_mismatch=2, min_mismatch=1)
+    assert (c2 - c21 == c0).all() and c2.sum() > c0.sum() > 20_000
+    lo2, n2 = 48_000_000, 4_000_000
+    sub = np.sort(np.random.default_rng(2).choice(pats.shape[0], 200_000, replace=False))
+    sset = dict(concat=pats[sub].reshape(-1), widths=np.full(sub.size, 36, np.int32))
+    pg = bs.PDict(bs.DNAStringSet(**sset), tb_start=1, tb_end=12)
+    po = R.PDict(R.SeqSet(**sset), tb_start=1, tb_end=12, backend="ref")
+    sample = subj[lo2:lo2 + n2]
+    assert _sample_parity(pg, po, sample, max_mismatch=2) > 300
+    assert _sample_parity(pg, po, sample, max_mismatch=2, min_mismatch=1) > 100
+    assert _sample_parity(pg, po, sample) > 100
+
+
+@pytest.mark.skipif(not ref.available(), reason="needs the compiled reference")
+def test_c4_reads_sample_parity():
+    """BASELINE config 4: vcountPDict of 100k 25-mers against 150 bp reads, collapse=1 / 2 on a
+    100 000-read slice against the reference (weights 1 and a seeded integer weight)."""
+    probes = workloads.c4_probes(100_000)
+    reads = workloads.c4_reads(3_000_000, 3_100_000, probes)
+    pg = bs.PDict(bs.DNAStringSet(concat=probes.reshape(-1), widths=np.full(probes.shape[0], 25, np.int32)))
+    po = R.PDict(R.SeqSet(concat=probes.reshape(-1), widths=np.full(probes.shape[0], 25, np.int32)), backend="ref")
+    rg = bs.DNAStringSet(concat=reads.reshape(-1), widths=np.full(reads.shape[0], 150, np.int32))
+    ro = R.SeqSet(concat=reads.reshape(-1), widths=np.full(reads.shape[0], 150, np.int32))
+    g = np.random.default_rng(4)
+    # (the reference restarts its walk for every read: ~30 s per call on this slice)
+    for collapse, w in ((1, g.integers(1, 9, reads.shape[0]).astype(np.int32)),
+                        (2, np.ones(probes.shape[0], dtype=np.int32))):
+        got = np.asarray(bs.vcountPDict(pg, rg, collapse=collapse, weight=w))
+        want = np.asarray(R.vcountPDict(po, ro, collapse=collapse, weight=w))
+        assert got.sum() > 4000 and np.array_equal(got, want)
+    wg, wo = bs.vwhichPDict(pg, rg), R.vwhichPDict(po, ro)
+    assert [v.tolist() for v in wg] == [v.tolist() for v in wo]
+
+
+@pytest.mark.skipif(not ref.available(), reason="needs the compiled reference")
+def test_c5_variable_width_iupac_sample_parity():
+    """BASELINE config 5: 2M patterns of 15-40 letters, PDict(tb.start=1, tb.width=15), fixed=FALSE
+    on a genome with isolated IUPAC letters: the whole dictionary on one 16 Mbp stretch (properties)
+    and 200 000 of the patterns x a 2 Mbp window against the reference, fixed=FALSE and fixed=TRUE."""
+    concat, widths = workloads.c5_dictionary(2_000_000)
+    offs = np.concatenate([[0], np.cumsum(widths, dtype=np.int64)])
+    B = synth.BLOCK
+    nb = 3_100_000_000 // B - 1
+    step = -(-nb // 64)
+    lo = 20 * step * B                                   # a planted block, away from the ends
+    subj = workloads.c5_genome_region(lo - 4_000_000, lo + 12_000_000)
+    assert 8_000 < int((~np.isin(subj, synth.BASES)).sum()) < 24_000          # ~1e-3 ambiguity letters
+    pd = bs.PDict(bs.DNAStringSet(concat=concat, widths=widths), tb_start=1, tb_width=15)
+    with mp.DeviceSubject.from_xstring(subj) as ds, warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cf = bs.countPDict(pd, ds, fixed=False)
+        ct = bs.countPDict(pd, ds)
+    assert (cf >= ct).all() and cf.sum() > ct.sum() > 1000
+    sub = np.sort(np.random.default_rng(5).choice(widths.size, 200_000, replace=False))
+    sc = np.concatenate([concat[offs[i]:offs[i + 1]] for i in sub.tolist()])
+    sw = widths[sub]
+    pg = bs.PDict(bs.DNAStringSet(concat=sc, widths=sw), tb_start=1, tb_width=15)
+    po = R.PDict(R.SeqSet(concat=sc, widths=sw), tb_start=1, tb_width=15, backend="ref")
+    sample = subj[4_000_000 - 500_000:4_000_000 + 1_500_000]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert _sample_parity(pg, po, sample, fixed=False) > 50
+        assert _sample_parity(pg, po, sample) > 50
+        assert _sample_parity(pg, po, sample, max_mismatch=1, fixed=False) > 50
