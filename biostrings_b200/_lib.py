@@ -28,7 +28,7 @@ SYMBOLS = [
     "bsgpu_oligo_frequency", "bsgpu_oligo_count_device", "bsgpu_XString_oligo_frequency",
     "bsgpu_XStringSet_oligo_frequency",
     "bsgpu_subject_fasta", "bsgpu_fasta_info_free", "bsgpu_subject_nsequences", "bsgpu_subject_element",
-    "bsgpu_subject_download", "bsgpu_subject_letters", "bsgpu_count_indels",
+    "bsgpu_subject_download", "bsgpu_subject_letters", "bsgpu_count_indels", "bsgpu_count_host",
 ]
 
 
@@ -116,6 +116,7 @@ def lib():
     L.bsgpu_subject_download.argtypes = [vp, vp, vp]
     L.bsgpu_subject_letters.argtypes = [vp, i64, vp, C.c_int, C.POINTER(vp)]
     L.bsgpu_count_indels.argtypes = [vp, vp] + [C.c_int] * 4 + [vp]
+    L.bsgpu_count_host.argtypes = [C.POINTER(vp), C.c_int, vp, i64, i64, i64, i64, i64] + [C.c_int] * 4 + [vp, vp, vp]
     L.bsgpu_kernel_timing.argtypes = [C.c_int]
     L.bsgpu_kernel_times.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     _lib = L

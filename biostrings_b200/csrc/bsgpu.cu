@@ -2742,6 +2742,227 @@ extern "C" int bsgpu_count_device(const bsgpu_pdict3parts *const *parts, int npa
 }
 
 // ---------------------------------------------------------------------------------------
+// countPDict on a subject that lives in HOST memory: the upload is cut into slices and slice
+// k is scanned while slice k + 1 crosses PCIe, so a call costs the copy plus one slice of
+// scanning instead of copy + scan.  The subject lands in a staging buffer the library keeps
+// between calls (no allocation, no guard fill when the length repeats); the counts leave the
+// device once, after the caller's reduction if there is one (d_counts).
+// ---------------------------------------------------------------------------------------
+
+struct StageState {
+	bsgpu_subject *subj = nullptr;
+	cudaStream_t copy = nullptr;
+	std::vector<cudaEvent_t> arrived;       // slice k is on the device
+	cudaEvent_t scanned = nullptr;          // the previous call is done with the staging buffer
+	bool scanned_pending = false;
+	DevBuf<int32_t> d_counts;
+};
+static StageState g_stage;
+
+static int64_t stage_slice_letters(void)
+{
+	const char *env = getenv("BSGPU_HOST_SLICE_MB");
+	double mb = env != nullptr && atof(env) > 0 ? atof(env) : 16.0;
+
+	return std::max<int64_t>(1 << 16, ((int64_t) (mb * 1048576.0)) & ~(int64_t) 4095);
+}
+
+// the range-limited counting step shared by the slices: true when the dictionary's engine can
+// count straight into d_counts (no record buffer, no union)
+static bool counts_directly(const bsgpu_pdict3parts *const *parts, int nparts, const bsgpu_subject *subj,
+			    const QIndex *qi)
+{
+	bool useq = qi != nullptr && qi->ok;
+
+	return nparts == 1 || (useq && subj->kind != SUBJ_VIEWS);
+}
+
+extern "C" int bsgpu_count_host(const bsgpu_pdict3parts *const *parts, int nparts,
+		const uint8_t *letters, int64_t length, int64_t chunk_start, int64_t subject_len,
+		int64_t report_lo, int64_t report_hi,
+		int max_nmis, int min_nmis, int fixedP, int fixedS,
+		int32_t *counts_out, int32_t *d_counts, void *stream)
+{
+	if (parts == nullptr || nparts < 1 || parts[0] == nullptr || length < 0 || (length > 0 && letters == nullptr) ||
+	    chunk_start < 0 || chunk_start + length > subject_len || length > INT32_MAX)
+		return fail(BSGPU_EINVAL, "bsgpu_count_host(): bad arguments");
+	if (max_nmis < 0 || min_nmis < 0)
+		return fail(BSGPU_EINVAL, "'max.mismatch' and 'min.mismatch' must be non-negative integers");
+	for (int p = 0; p < nparts; p++)
+		if (parts[p] == nullptr || parts[p]->M != parts[0]->M)
+			return fail(BSGPU_EINVAL, "cannot combine MIndex objects of different lengths");
+	TRY(ensure_device());
+	Workspace *ws;
+	TRY(workspace(&ws));
+	cudaStream_t st = (cudaStream_t) stream;
+	MatchParams mp = {max_nmis, min_nmis, fixedP != 0, fixedS != 0};
+	const int32_t M = parts[0]->M;
+	StageState &G = g_stage;
+
+	if (G.copy == nullptr) {
+		CUDA_TRY(cudaStreamCreateWithFlags(&G.copy, cudaStreamNonBlocking));
+		CUDA_TRY(cudaEventCreateWithFlags(&G.scanned, cudaEventDisableTiming));
+	}
+	// ---- the staging subject: rebuilt only when the length changes -------------------------
+	report_lo = std::max(report_lo, chunk_start);
+	report_hi = std::min(report_hi, chunk_start + length);
+	if (report_hi < report_lo)
+		report_hi = report_lo;
+	if (G.subj == nullptr || G.subj->seg_len[0] != (int32_t) length) {
+		if (G.scanned_pending)
+			CUDA_TRY(cudaEventSynchronize(G.scanned));
+		G.scanned_pending = false;
+		delete G.subj;
+		G.subj = nullptr;
+		std::unique_ptr<bsgpu_subject> s(new bsgpu_subject());
+		s->kind = SUBJ_CHUNK;
+		s->nseg = 1;
+		s->seg_len.assign(1, (int32_t) length);
+		s->seg_coord.assign(1, chunk_start);
+		TRY(subject_finish(s.get(), nullptr, nullptr));         // guards only; the letters come in slices
+		G.subj = s.release();
+	}
+	bsgpu_subject *s = G.subj;
+	if (s->seg_coord[0] != chunk_start) {
+		s->seg_coord[0] = chunk_start;
+		CUDA_TRY(cudaMemcpyAsync(s->d_seg_coord.p, s->seg_coord.data(), sizeof(int64_t), cudaMemcpyHostToDevice, st));
+	}
+	const int64_t seg0 = s->seg_start[0];
+	const int64_t all_lo = seg0 + (report_lo - chunk_start), all_hi = seg0 + (report_hi - chunk_start);
+	const bool from_start = report_lo <= 0, to_end = report_hi >= subject_len;
+	const bool open_l = chunk_start > 0, open_r = chunk_start + length < subject_len;
+	const int64_t halo_l = report_lo - chunk_start, halo_r = chunk_start + length - report_hi;
+	s->nletters = report_hi - report_lo;
+	s->packed = false;
+	s->iupac_ready = false;
+
+	const QIndex *qi = nullptr;
+	if (mp.fixedS)
+		TRY(get_qindex(parts, nparts, &qi));
+	bool useq = qi != nullptr && qi->ok;
+	if (d_counts == nullptr) {
+		if (G.d_counts.n < (size_t) M + 1)
+			TRY(G.d_counts.alloc((size_t) M + 1));
+		d_counts = G.d_counts.p;
+		CUDA_TRY(cudaMemsetAsync(d_counts, 0, ((size_t) M + 1) * sizeof(int32_t), st));
+	}
+	// letters a reported match may touch behind its owner position (tails, the long end of
+	// variable-width patterns, the words the packed scans read ahead)
+	int64_t margin = 256;
+	for (int p = 0; p < nparts; p++)
+		margin = std::max<int64_t>(margin, 256 + parts[p]->max_T + parts[p]->max_plen);
+	const int64_t SL = std::max(stage_slice_letters(), 8 * margin);
+	const int nslices = (int) std::max<int64_t>(1, (length + SL - 1) / SL);
+	// fixedS = FALSE builds its IUPAC plane over the whole subject on first use: no slices there
+	const bool pipelined = counts_directly(parts, nparts, s, qi) && nslices > 1 && (mp.fixedS || parts[0]->plain) &&
+			       getenv("BSGPU_HOST_NO_PIPELINE") == nullptr;
+
+	// the previous call's scans must be done with the buffer before it is overwritten
+	if (G.scanned_pending)
+		CUDA_TRY(cudaStreamWaitEvent(G.copy, G.scanned, 0));
+	while ((int) G.arrived.size() < nslices) {
+		cudaEvent_t e;
+		CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		G.arrived.push_back(e);
+	}
+	for (int k = 0; k < nslices; k++) {
+		int64_t a = (int64_t) k * SL, b = std::min(length, a + SL);
+
+		CUDA_TRY(cudaMemcpyAsync(s->d_bytes.p + seg0 + a, letters + a, (size_t) (b - a), cudaMemcpyHostToDevice, G.copy));
+		CUDA_TRY(cudaEventRecord(G.arrived[k], G.copy));
+	}
+	int rc = BSGPU_OK;
+	if (!pipelined) {
+		// whole subject at once (records / union needed, or a short subject)
+		CUDA_TRY(cudaStreamWaitEvent(st, G.arrived[nslices - 1], 0));
+		s->scan_lo = all_lo;
+		s->scan_hi = all_hi;
+		s->open_left = open_l;
+		s->open_right = open_r;
+		s->halo_left = halo_l;
+		s->halo_right = halo_r;
+		s->own_from_start = from_start;
+		s->own_to_end = to_end;
+		rc = bsgpu_count_device(parts, nparts, s, max_nmis, min_nmis, fixedP, fixedS, d_counts, st, nullptr);
+	} else {
+		BsgpuReport R = {};
+		R.mode = BSGPU_R_COUNT;
+		R.M = M;
+		R.counts = d_counts;
+		int64_t lo = all_lo, packed_words = 0;
+		const int64_t nwords = s->total / 32;
+		// the exact engines read the letters themselves, everything else the packed planes
+		bool letters_only = parts[0]->plain;
+		if (!useq && nparts == 1 && !parts[0]->plain && !parts[0]->has_head && !parts[0]->has_tail &&
+		    parts[0]->all_singletons && mp.fixedS) {
+			const XSeedIndex *xi = nullptr;
+			const ByteSeedIndex *bi = nullptr;
+			TRY(get_xseed(parts[0], &xi));
+			if (xi == nullptr || !xi->ok)
+				TRY(get_byteseed(parts[0], &bi));
+			letters_only = (xi != nullptr && xi->ok) || (bi != nullptr && bi->ok);
+		}
+		const bool need_planes = !letters_only;
+
+		if (need_planes && s->d_codes.n < (size_t) nwords + 4) {
+			TRY(s->d_codes.alloc((size_t) nwords + 4));
+			TRY(s->d_valid.alloc((size_t) nwords + 4));
+			TRY(s->d_inv2.alloc((size_t) nwords + 4));
+			CUDA_TRY(cudaMemsetAsync(s->d_codes.p + nwords, 0, 4 * sizeof(uint64_t), st));
+			CUDA_TRY(cudaMemsetAsync(s->d_valid.p + nwords, 0, 4 * sizeof(uint32_t), st));
+			CUDA_TRY(cudaMemsetAsync(s->d_inv2.p + nwords, 0xFF, 4 * sizeof(uint64_t), st));
+		}
+		for (int k = 0; k < nslices && rc == BSGPU_OK; k++) {
+			const bool last = k == nslices - 1;
+			int64_t b = std::min(length, (int64_t) (k + 1) * SL);
+			int64_t hi = last ? all_hi : std::min(all_hi, std::max(lo, seg0 + b - margin));
+
+			CUDA_TRY(cudaStreamWaitEvent(st, G.arrived[k], 0));
+			if (need_planes) {
+				// planes of the words whose letters are all here (the last slice takes the guard words too)
+				int64_t w1 = last ? nwords : (seg0 + b) / 32;
+
+				if (w1 > packed_words) {
+					KernelTimer kt("pack_subject_kernel", st);
+					pack_subject_kernel<<<grid_for(2 * (w1 - packed_words), 256, 8), 256, 0, st>>>(
+						s->d_bytes.p + 32 * packed_words, w1 - packed_words, s->d_codes.p + packed_words,
+						s->d_valid.p + packed_words, s->d_inv2.p + packed_words);
+					g_launches++;
+					CUDA_TRY(cudaGetLastError());
+					packed_words = w1;
+				}
+				s->packed = true;
+			}
+			if (hi <= lo && !last)
+				continue;
+			s->scan_lo = lo;
+			s->scan_hi = hi;
+			s->own_from_start = from_start && k == 0;
+			s->own_to_end = to_end && last;
+			s->open_left = k == 0 ? open_l : true;
+			s->open_right = last ? open_r : true;
+			s->halo_left = k == 0 ? halo_l : (int64_t) 1 << 40;
+			s->halo_right = last ? halo_r : (int64_t) 1 << 40;
+			if (useq)
+				rc = run_q(qi, s, mp, R, false, ws, st);
+			else
+				rc = run_parts_tb(parts, nparts, s, mp, R, false, ws, st);
+			lo = hi;
+		}
+		s->packed = false;
+	}
+	CUDA_TRY(cudaEventRecord(G.scanned, st));
+	G.scanned_pending = true;
+	if (rc != BSGPU_OK)
+		return rc;
+	if (counts_out != nullptr) {
+		CUDA_TRY(cudaMemcpyAsync(counts_out, d_counts, (size_t) M * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+	}
+	return BSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // vmatch: vcountPDict / vwhichPDict on a set of subjects (src/match_pdict.c:320-346,386-432)
 // ---------------------------------------------------------------------------------------
 

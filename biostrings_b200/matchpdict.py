@@ -176,6 +176,27 @@ def match_parts(parts, dsubj, max_mismatch, min_mismatch, fixed, mode):
     return _take_result(res, mode)
 
 
+def count_parts_host(parts, letters, max_mismatch, min_mismatch, fixed, chunk_start=0, subject_len=None,
+                     report=None, out=None, d_counts=None, stream=None):
+    """bsgpu_count_host(): countPDict on letters that live in host memory (a whole subject, or
+    one overlap chunk of it), the upload pipelined with the scan.  out: int32[M] host array to
+    fill (allocated when missing); d_counts: device pointer of an int32[M] vector to ADD the
+    counts to (then nothing is copied back unless `out` is given); stream: CUDA stream handle."""
+    letters = np.ascontiguousarray(letters, dtype=np.uint8)
+    n = int(letters.size)
+    subject_len = n if subject_len is None else int(subject_len)
+    lo, hi = (chunk_start, chunk_start + n) if report is None else report
+    M = _lib.lib().bsgpu_pdict3parts_length(parts[0].handle)
+    if out is None and d_counts is None:
+        out = np.empty(M, dtype=np.int32)
+    _lib.check(_lib.lib().bsgpu_count_host(_parts_array(parts), len(parts), _ptr(letters), n, int(chunk_start),
+                                           subject_len, int(lo), int(hi), max_mismatch, min_mismatch,
+                                           int(fixed[0]), int(fixed[1]), _ptr(out),
+                                           None if d_counts is None else C.c_void_p(d_counts),
+                                           None if stream is None else C.c_void_p(stream)))
+    return out
+
+
 def vmatch_parts(parts, dsubj, max_mismatch, min_mismatch, fixed, collapse, weight, mode):
     res = _lib.Result()
     w = None
@@ -391,10 +412,17 @@ def _match_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, mode, what,
             raise ValueError("'pdict' must be a PDict or XStringSet object")
         return _match_plain(pset, subject, max_mismatch, min_mismatch, with_indels, fixed,
                             algorithm, mode, what)
-    try:
-        dsubj, owned = _subject_to_device(subject)
-    except ValueError as e:
-        raise ValueError(str(e).replace("vmatchPDict", "v" + what)) from None
+    host_letters = None
+    if mode in (MATCHES_AS_COUNTS, MATCHES_AS_WHICH) and \
+            isinstance(subject, (DNAString, str, bytes, np.ndarray)):
+        # a single sequence in host memory: upload and scan pipelined (bsgpu_count_host)
+        host_letters = encode_dna(subject)
+        dsubj, owned = None, False
+    else:
+        try:
+            dsubj, owned = _subject_to_device(subject)
+        except ValueError as e:
+            raise ValueError(str(e).replace("vmatchPDict", "v" + what)) from None
     try:
         dups0 = pdict.dups()
         max_mismatch = normarg_max_mismatch(max_mismatch)
@@ -410,7 +438,12 @@ def _match_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, mode, what,
         _check_args_full_tb(parts, max_mismatch, fixed)
         if isinstance(pdict, MTB_PDict):
             _check_max_mismatch(max_mismatch, len(parts))
-        ans = match_parts(parts, dsubj, max_mismatch, min_mismatch, fixed, mode)
+        if host_letters is not None:
+            ans = count_parts_host(parts, host_letters, max_mismatch, min_mismatch, fixed)
+            if mode == MATCHES_AS_WHICH:
+                ans = (np.flatnonzero(ans) + 1).astype(np.int32)    # sort(ids)+1, src/match_reporting.c:150-161
+        else:
+            ans = match_parts(parts, dsubj, max_mismatch, min_mismatch, fixed, mode)
     finally:
         if owned:
             dsubj.close()

@@ -245,6 +245,28 @@ int bsgpu_vmatch(const bsgpu_pdict3parts *const *parts, int nparts,
 		int collapse, int weight_is_double, const void *weight, int64_t weight_length,
 		int matches_as, bsgpu_result *res);
 
+/* ------------------------------------------------------------------------------------
+ * countPDict on a subject in HOST memory, upload pipelined with the scan: what
+ *     match_PDict3Parts_XString(pptb, head, tail, subject, max, min, fixed,
+ *                               "MATCHES_AS_COUNTS", envir)      src/match_pdict.c:153
+ * amounts to when `subject` (or one overlap chunk of it) still has to cross PCIe.
+ * The letters are copied in slices (BSGPU_HOST_SLICE_MB, default 16) on a copy stream and slice
+ * k is scanned on `stream` while slice k + 1 is in flight; the staging buffer, the events and
+ * the device count vector persist between calls.  letters/length: the chunk (pinned host
+ * memory makes the copies asynchronous); chunk_start / subject_len / report_lo / report_hi as in
+ * bsgpu_subject_chunk (0, length, 0, length for a whole XString).  d_counts != NULL: the counts
+ * are ADDED to this device vector (the caller zeroes / reduces it); counts_out != NULL: the
+ * counts are copied to this host vector and the call returns when they are there; with
+ * counts_out == NULL the call only enqueues work and the caller synchronises `stream`.
+ * Dictionaries whose engine needs records on the host side (MTB_PDict without the q-gram
+ * index, fixedS = FALSE) are uploaded whole and then counted.
+ * ------------------------------------------------------------------------------------ */
+int bsgpu_count_host(const bsgpu_pdict3parts *const *parts, int nparts,
+		const uint8_t *letters, int64_t length, int64_t chunk_start, int64_t subject_len,
+		int64_t report_lo, int64_t report_hi,
+		int max_mismatch, int min_mismatch, int fixedP, int fixedS,
+		int32_t *counts_out, int32_t *d_counts, void *stream);
+
 /*
  * Device-side counting for callers that own the device (bench, multi-GPU sharding):
  * adds the per-pattern match counts of `subject` into d_counts[M], a DEVICE pointer
