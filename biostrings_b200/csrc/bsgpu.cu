@@ -2762,7 +2762,7 @@ static StageState g_stage;
 static int64_t stage_slice_letters(void)
 {
 	const char *env = getenv("BSGPU_HOST_SLICE_MB");
-	double mb = env != nullptr && atof(env) > 0 ? atof(env) : 16.0;
+	double mb = env != nullptr && atof(env) > 0 ? atof(env) : 32.0;
 
 	return std::max<int64_t>(1 << 16, ((int64_t) (mb * 1048576.0)) & ~(int64_t) 4095);
 }

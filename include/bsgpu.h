@@ -250,7 +250,7 @@ int bsgpu_vmatch(const bsgpu_pdict3parts *const *parts, int nparts,
  *     match_PDict3Parts_XString(pptb, head, tail, subject, max, min, fixed,
  *                               "MATCHES_AS_COUNTS", envir)      src/match_pdict.c:153
  * amounts to when `subject` (or one overlap chunk of it) still has to cross PCIe.
- * The letters are copied in slices (BSGPU_HOST_SLICE_MB, default 16) on a copy stream and slice
+ * The letters are copied in slices (BSGPU_HOST_SLICE_MB, default 32) on a copy stream and slice
  * k is scanned on `stream` while slice k + 1 is in flight; the staging buffer, the events and
  * the device count vector persist between calls.  letters/length: the chunk (pinned host
  * memory makes the copies asynchronous); chunk_start / subject_len / report_lo / report_hi as in
