@@ -333,6 +333,9 @@ struct bsgpu_pdict3parts {
 	DevBuf<int32_t> d_grp_off, d_grp_keys;
 	DevBuf<uint8_t> d_tb, d_head, d_tail;
 	DevBuf<int64_t> d_head_off, d_tail_off;
+	DevBuf<ulonglong2> d_flank2;            // packed head / tail of every key (XOR + popcount check)
+	DevBuf<uint16_t> d_flank_len;
+	bool flanks_all_packed = false;         // every non-excluded key: base-only flanks of <= 32 letters
 
 	BsgpuIndexView view() const
 	{
@@ -358,6 +361,8 @@ struct bsgpu_pdict3parts {
 		I.tail = has_tail ? d_tail.p : nullptr;
 		I.tail_off = d_tail_off.p;
 		I.all_singletons = all_singletons;
+		I.flank2 = d_flank2.p;
+		I.flank_len = d_flank_len.p;
 		return I;
 	}
 };
@@ -974,6 +979,46 @@ static int upload_flank(int M, const uint8_t *concat, const int32_t *widths, Dev
 	return BSGPU_OK;
 }
 
+// Head and tail of every key 2-bit packed for the in-scan XOR + popcount verification
+// (tb_hit, direct == 2).  A key qualifies when both flanks are base letters only and at most 32
+// letters long; flanks_all_packed tells run_part() that no key needs the byte-wise kernel.
+static int upload_packed_flanks(bsgpu_pdict3parts *p3)
+{
+	int M = p3->M;
+	std::vector<ulonglong2> f2((size_t) std::max(M, 1), make_ulonglong2(0, 0));
+	std::vector<uint16_t> fl((size_t) std::max(M, 1), 0);
+	bool all = true;
+
+	for (int i = 0; i < M; i++) {
+		int64_t h0 = p3->has_head ? p3->h_head_off[i] : 0, t0 = p3->has_tail ? p3->h_tail_off[i] : 0;
+		int hl = p3->has_head ? (int) (p3->h_head_off[i + 1] - h0) : 0;
+		int tl = p3->has_tail ? (int) (p3->h_tail_off[i + 1] - t0) : 0;
+		bool ok = hl <= 32 && tl <= 32;
+		unsigned long long h = 0, t = 0;
+
+		for (int d = 0; ok && d < hl; d++) {
+			uint32_t b = p3->h_head[(size_t) h0 + d];
+			ok = bsgpu_is_base(b);
+			h |= (unsigned long long) bsgpu_base_code(b) << (2 * d);
+		}
+		for (int d = 0; ok && d < tl; d++) {
+			uint32_t b = p3->h_tail[(size_t) t0 + d];
+			ok = bsgpu_is_base(b);
+			t |= (unsigned long long) bsgpu_base_code(b) << (2 * d);
+		}
+		if (ok) {
+			f2[i] = make_ulonglong2(h, t);
+			fl[i] = (uint16_t) (hl | (tl << 6) | (1 << 15));
+		} else if (!(i < (int) p3->excluded.size() && p3->excluded[i])) {
+			all = false;
+		}
+	}
+	p3->flanks_all_packed = all && (p3->has_head || p3->has_tail || !p3->all_singletons);
+	TRY(p3->d_flank2.upload(f2.data(), f2.size()));
+	TRY(p3->d_flank_len.upload(fl.data(), fl.size()));
+	return BSGPU_OK;
+}
+
 extern "C" int bsgpu_pdict3parts_build(int algo, int32_t M,
 		const uint8_t *tb_concat, const int32_t *tb_widths,
 		const uint8_t *head_concat, const int32_t *head_widths,
@@ -1136,6 +1181,7 @@ extern "C" int bsgpu_pdict3parts_build(int algo, int32_t M,
 	if (pp_exclude != nullptr)
 		for (int i = 0; i < M; i++)
 			p3->excluded[i] = pp_exclude[i] != BSGPU_NA;
+	TRY(upload_packed_flanks(p3));
 	*out = guard.release();
 	return BSGPU_OK;
 }
@@ -1203,8 +1249,10 @@ extern "C" int bsgpu_pdict3parts_set_flanks(bsgpu_pdict3parts *p3,
 			 p3->max_H, nullptr, p3->h_head, p3->h_head_off));
 	TRY(upload_flank(p3->M, tail_concat, tail_widths, p3->d_tail, p3->d_tail_off, p3->has_tail,
 			 p3->max_T, &p3->tail_len, p3->h_tail, p3->h_tail_off));
+	TRY(upload_packed_flanks(p3));
 	p3->qcache.reset();
 	p3->bcache.reset();
+	p3->xcache.reset();
 	return BSGPU_OK;
 }
 
@@ -1215,8 +1263,10 @@ extern "C" int bsgpu_pdict3parts_blank_dups(bsgpu_pdict3parts *p3)
 	TRY(ensure_device());
 	TRY(upload_groups(p3, true));
 	std::fill(p3->high2low.begin(), p3->high2low.end(), BSGPU_NA);
+	TRY(upload_packed_flanks(p3));
 	p3->qcache.reset();
 	p3->bcache.reset();
+	p3->xcache.reset();
 	return BSGPU_OK;
 }
 
@@ -1772,7 +1822,9 @@ extern "C" int bsgpu_subject_download(const bsgpu_subject *subj, uint8_t *concat
 
 struct Workspace {
 	DevBuf<unsigned long long> cand, rec, rec2;
-	DevBuf<unsigned int> xseed_counts;      // candidates per scan block (scan_xseed_kernel)
+	DevBuf<unsigned int> xseed_counts;      // candidates per scan warp (scan_xseed_kernel)
+	DevBuf<int32_t> row_cursor, big_rows;   // count - scan - write of the hit records
+	unsigned long long rec_known = 0;       // counters[1] as of the last host read / write (no read-back needed)
 	DevBuf<unsigned long long> counters;    // [0] = candidates, [1] = records
 	DevBuf<int> flags;
 	DevBuf<long long> ovf;                  // windows with too many IUPAC expansions
@@ -1868,11 +1920,19 @@ static int read_counter(Workspace *ws, int which, unsigned long long *out, cudaS
 				 sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
 	*out = ws->h_counters[which];
+	if (which == 1)
+		ws->rec_known = *out;
 	return BSGPU_OK;
 }
 
 static int write_counter(Workspace *ws, int which, unsigned long long v, cudaStream_t st)
 {
+	if (which == 1)
+		ws->rec_known = v;
+	if (v == 0) {           // stream-ordered, nothing to wait for
+		CUDA_TRY(cudaMemsetAsync(ws->counters.p + which, 0, sizeof(unsigned long long), st));
+		return BSGPU_OK;
+	}
 	ws->h_counters[2] = v;
 	CUDA_TRY(cudaMemcpyAsync(ws->counters.p + which, ws->h_counters + 2,
 				 sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
@@ -1895,7 +1955,7 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 	BsgpuSubjectView S = subj->view();
 	BsgpuIndexView I = p3->view();
 
-	if (direct && mp.fixedS) {
+	if (direct == 1 && mp.fixedS) {
 		// exact dictionary of width >= 25, letters only: short core + extended seeds, one probe
 		// every S = w - 9 letters (bsgpu_xseed.cuh)
 		const XSeedIndex *xi = nullptr;
@@ -2032,11 +2092,13 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 	TRY(ensure_packed(subj, st));
 	S = subj->view();
 	set_plan("tb_hash w=%d buckets=%u table_bytes=%llu%s%s", p3->w, p3->nbuckets,
-		 (unsigned long long) p3->nbuckets * 16, direct ? "" : " + verify_flanks",
+		 (unsigned long long) p3->nbuckets * 16,
+		 direct == 1 ? "" : (direct == 2 ? " + packed flank check in the scan" : " + verify_flanks"),
 		 mp.fixedS ? "" : " + iupac_expansion");
 	{
 		KernelTimer kt("scan_tb_kernel", st);
-		scan_tb_kernel<<<grid_for(nwords, 256, tb_grid()), 256, 0, st>>>(S, I, R, C, direct, start_lo, start_hi);
+		scan_tb_kernel<<<grid_for(nwords, 256, tb_grid()), 256, 0, st>>>(S, I, R, C, direct, start_lo, start_hi,
+										  mp.max_nmis, mp.min_nmis);
 	}
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
@@ -2127,7 +2189,7 @@ static int run_plain(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, con
 		unsigned long long rec_before = 0, nrec = 0;
 
 		if (rec_based)
-			TRY(read_counter(ws, 1, &rec_before, st));
+			rec_before = ws->rec_known;
 		{
 			KernelTimer kt("match_plain_kernel", st);
 			match_plain_kernel<<<grid, 256, 0, st>>>(subj->view(), P, R, mp.max_nmis, mp.min_nmis,
@@ -2174,6 +2236,9 @@ static int run_part(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, cons
 				    (long long) need_l, (long long) need_r);
 	}
 	bool direct = !p3->has_head && !p3->has_tail && p3->all_singletons;
+	// every key's flanks are packed and the subject is taken literally: the scan verifies its own
+	// hits (XOR + popcount), no candidate buffer and no host synchronisation
+	bool inline_flanks = !direct && p3->flanks_all_packed && mp.fixedS && getenv("BSGPU_NO_PACKED_FLANKS") == nullptr;
 	BsgpuReport C = {};
 	int64_t lo = subj->scan_lo, hi = subj->scan_hi;
 
@@ -2199,9 +2264,9 @@ static int run_part(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, cons
 			subj->iupac_ready = true;
 		}
 	}
-	if (direct && !rec_based) {
+	if ((direct || inline_flanks) && !rec_based) {
 		// fully asynchronous: counts straight from the scan
-		TRY(launch_scans(p3, subj, mp, R, C, 1, lo, hi, ws, st));
+		TRY(launch_scans(p3, subj, mp, R, C, direct ? 1 : 2, lo, hi, ws, st));
 	} else {
 		if (!allow_sync)
 			return fail(BSGPU_EUNSUPPORTED, "internal: this configuration needs host synchronisation");
@@ -2213,9 +2278,9 @@ static int run_part(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, cons
 			unsigned long long rec_before = 0, ncand = 0, nrec = 0;
 
 			if (rec_based)
-				TRY(read_counter(ws, 1, &rec_before, st));
-			if (direct) {
-				TRY(launch_scans(p3, subj, mp, R, C, 1, a, b, ws, st));
+				rec_before = ws->rec_known;
+			if (direct || inline_flanks) {
+				TRY(launch_scans(p3, subj, mp, R, C, direct ? 1 : 2, a, b, ws, st));
 			} else {
 				TRY(grow(ws->cand, CAND_MIN, 0, st));
 				TRY(write_counter(ws, 0, 0, st));
@@ -2312,7 +2377,7 @@ static int run_q(const QIndex *qi, const bsgpu_subject *subj, const MatchParams 
 			unsigned long long rec_before = 0, nrec = 0, ncand = 0;
 
 			if (rec_based)
-				TRY(read_counter(ws, 1, &rec_before, st));
+				rec_before = ws->rec_known;
 			TRY(write_counter(ws, 0, 0, st));
 			qprobe_kernel<<<grid_for(nw, 256, 8), 256, 0, st>>>(subj->view(), Q, a, b, ws->cand.p,
 					ws->counters.p + 0, ws->cand.n);
@@ -2360,7 +2425,7 @@ static int run_q(const QIndex *qi, const bsgpu_subject *subj, const MatchParams 
 		unsigned long long rec_before = 0, nrec = 0;
 
 		if (rec_based)
-			TRY(read_counter(ws, 1, &rec_before, st));
+			rec_before = ws->rec_known;
 		{
 			const char *env_g = getenv("BSGPU_Q_GRID");     // blocks per SM of the grid-stride launch
 			int qgrid = env_g != nullptr && atoi(env_g) > 0 ? atoi(env_g) : 1024;
@@ -2628,16 +2693,52 @@ extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
 			TRY(run_q(qi, subj, mp, R, true, ws, st));
 		else
 			TRY(run_parts_tb(parts, nparts, subj, mp, R, true, ws, st));
-		TRY(read_counter(ws, 1, &nrec, st));
-		TRY(sort_records(ws, nrec, BSGPU_POS_BITS + bits_for((unsigned long long) std::max(M - 1, 1)),
-				 nparts > 1, &nrec, st));
+		nrec = ws->rec_known;           // read back by the engine after its last slab
+		// Rows without a global sort (count - scan - write, see bsgpu_kernels.cuh) whenever every
+		// alignment was reported once; the union of several Trusted-Band components (duplicates
+		// to drop) keeps the sort + unique path.
+		const bool compact = (nparts == 1 || (useq && subj->kind != SUBJ_VIEWS)) && getenv("BSGPU_ENDS_SORT") == nullptr;
 		DevBuf<int32_t> d_ends;
+		DevBuf<int64_t> d_off;
+		size_t temp = 0;
+		thrust::transform_iterator<Int32To64, const int32_t *> in(d_counts.p, Int32To64());
+		const unsigned long long *ordered = ws->rec.p;
+
+		TRY(d_off.alloc((size_t) M + 1));
+		if (compact && nrec > 0) {
+			const int rgrid = grid_for((long long) nrec, 256, 8);
+
+			TRY(grow(ws->rec2, (size_t) nrec, 0, st));
+			if (ws->row_cursor.n < (size_t) M + 2)
+				TRY(ws->row_cursor.alloc((size_t) M + 2));
+			if (ws->big_rows.n < (size_t) M + 1)
+				TRY(ws->big_rows.alloc((size_t) M + 1));
+			CUDA_TRY(cudaMemsetAsync(ws->row_cursor.p, 0, ((size_t) M + 2) * sizeof(int32_t), st));
+			count_rows_kernel<<<rgrid, 256, 0, st>>>(ws->rec.p, nrec, d_counts.p);
+			CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, temp, in, d_off.p, M + 1, st));
+			if (temp > ws->cub_temp.n)
+				TRY(ws->cub_temp.alloc(temp));
+			CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws->cub_temp.p, temp, in, d_off.p, M + 1, st));
+			write_rows_kernel<<<rgrid, 256, 0, st>>>(ws->rec.p, nrec, d_off.p, ws->row_cursor.p, ws->rec2.p);
+			// row_cursor[M + 1] = number of long rows
+			order_rows_kernel<<<grid_for(M, 256, 16), 256, 0, st>>>(ws->rec2.p, d_off.p, d_counts.p, M,
+					ws->big_rows.p, ws->row_cursor.p + M + 1);
+			bitonic_rows_kernel<<<256, 1024, 0, st>>>(ws->rec2.p, d_off.p, d_counts.p, ws->big_rows.p,
+								   ws->row_cursor.p + M + 1);
+			g_launches += 6;
+			CUDA_TRY(cudaGetLastError());
+			ordered = ws->rec2.p;
+		} else if (!compact) {
+			TRY(sort_records(ws, nrec, BSGPU_POS_BITS + bits_for((unsigned long long) std::max(M - 1, 1)),
+					 nparts > 1, &nrec, st));
+			ordered = ws->rec.p;
+		}
 		TRY(d_ends.alloc((size_t) nrec));
 		if (nrec > 0) {
 			finalize_ends_kernel<<<grid_for((long long) nrec, 256, 8), 256, 0, st>>>(
 				subj->view(), parts[0]->has_tail ? parts[0]->d_tail_off.p : nullptr,
-				tbpos ? 1 : 0, parts[0]->plain ? ws->plain : BsgpuPlainView{}, ws->rec.p, nrec,
-				d_ends.p, d_counts.p);
+				tbpos ? 1 : 0, parts[0]->plain ? ws->plain : BsgpuPlainView{}, ordered, nrec,
+				d_ends.p, compact ? nullptr : d_counts.p);
 			g_launches++;
 			CUDA_TRY(cudaGetLastError());
 		}
@@ -2650,20 +2751,15 @@ extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
 			if (nrec > 0)
 				CUDA_TRY(cudaMemcpyAsync(res->ends, d_ends.p, (size_t) nrec * sizeof(int32_t),
 							 cudaMemcpyDeviceToHost, st));
-		}
-		if (matches_as == BSGPU_MATCHES_AS_ENDS) {
 			// CSR offsets = exclusive scan of the counts, on the device, straight into the
 			// result's pinned block
-			DevBuf<int64_t> d_off;
-			size_t temp = 0;
-			thrust::transform_iterator<Int32To64, const int32_t *> in(d_counts.p, Int32To64());
-
-			TRY(d_off.alloc((size_t) M + 1));
-			CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, temp, in, d_off.p, M + 1, st));
-			if (temp > ws->cub_temp.n)
-				TRY(ws->cub_temp.alloc(temp));
-			CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws->cub_temp.p, temp, in, d_off.p, M + 1, st));
-			g_launches += 2;
+			if (!(compact && nrec > 0)) {
+				CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, temp, in, d_off.p, M + 1, st));
+				if (temp > ws->cub_temp.n)
+					TRY(ws->cub_temp.alloc(temp));
+				CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws->cub_temp.p, temp, in, d_off.p, M + 1, st));
+				g_launches += 2;
+			}
 			res->n_rows = M;
 			res->ends_offsets = (int64_t *) result_block_alloc(((size_t) M + 1) * sizeof(int64_t));
 			if (res->ends_offsets == nullptr)
@@ -2723,7 +2819,7 @@ extern "C" int bsgpu_count_device(const bsgpu_pdict3parts *const *parts, int npa
 			TRY(run_q(qi, subj, mp, R, true, ws, st));
 		else
 			TRY(run_parts_tb(parts, nparts, subj, mp, R, true, ws, st));
-		TRY(read_counter(ws, 1, &nrec, st));
+		nrec = ws->rec_known;           // read back by the engine after its last slab
 		TRY(sort_records(ws, nrec, BSGPU_POS_BITS + bits_for((unsigned long long) std::max(M - 1, 1)),
 				 true, &nrec, st));
 		if (nrec > 0) {
@@ -3053,7 +3149,7 @@ extern "C" int bsgpu_vmatch(const bsgpu_pdict3parts *const *parts, int nparts,
 		TRY(run_q(qi, subj, mp, R, true, ws, st));
 	else
 		TRY(run_parts_tb(parts, nparts, subj, mp, R, true, ws, st));
-	TRY(read_counter(ws, 1, &nrec, st));
+	nrec = ws->rec_known;
 	bool uniq = matches_as == BSGPU_MATCHES_AS_WHICH;
 	TRY(sort_records(ws, nrec, BSGPU_SEGKEY_BITS + bits_for((unsigned long long) std::max<int64_t>(N - 1, 1)),
 			 uniq, &nrec, st));

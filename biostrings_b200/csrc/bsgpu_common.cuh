@@ -93,6 +93,10 @@ struct BsgpuIndexView {
 	const uint8_t *tail;
 	const int64_t *tail_off;     // [M+1]
 	int32_t all_singletons;      // every TB group has exactly one key
+	// head / tail of every key 2-bit packed (letter i at bits 2i) for the XOR + popcount check;
+	// flank_len = |head| | |tail| << 6 | (1 << 15 if both are base-only and <= 32 letters)
+	const ulonglong2 *flank2;    // [M] {head, tail}
+	const uint16_t *flank_len;   // [M]
 };
 
 struct BsgpuReport {

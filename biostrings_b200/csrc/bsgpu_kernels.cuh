@@ -207,12 +207,67 @@ __device__ __forceinline__ void report_match(const BsgpuReport &R, const BsgpuSu
 	}
 }
 
-// A confirmed Trusted-Band hit of TB id 'tb_id' ending at concat index e.
-// direct != 0: no head/tail and singleton TB groups -> report right away; otherwise the
-// hit becomes a candidate record (tb_id << 34 | e) for verify_flanks_kernel.
-__device__ __forceinline__ void tb_hit(const BsgpuIndexView &I, const BsgpuSubjectView &S,
-		const BsgpuReport &R, const BsgpuReport &C, int direct, int tb_id, int64_t e)
+// Mismatches of a 2-bit packed flank (len <= 32 base letters, letter i at bits 2i) against the
+// subject letters [a, a + len): XOR of the code planes, the two bits of a letter folded together,
+// ORed with the "not a base" plane, popcount.  Letters outside the segment [lo, lo + L) count as
+// mismatches (src/lowlevel_matching.c:79-86); so do non-base subject letters, which is the
+// fixedS = TRUE table for a base-only pattern (src/lowlevel_matching.c:26-56).
+__device__ __forceinline__ int packed_flank_mismatches(const BsgpuSubjectView &S, int64_t a, int len,
+		uint64_t pat, int64_t lo, int64_t L)
 {
+	const uint64_t E = 0x5555555555555555ull;
+
+	if (len == 0)
+		return 0;
+	int64_t wi = a >> 5;
+	int sh = 2 * (int) (a & 31);
+	uint64_t c0 = __ldg(S.codes + wi), c1 = __ldg(S.codes + wi + 1);
+	uint64_t i0 = __ldg(S.inv2 + wi), i1 = __ldg(S.inv2 + wi + 1);
+	uint64_t x = sh ? (c0 >> sh) | (c1 << (64 - sh)) : c0;
+	uint64_t iv = sh ? (i0 >> sh) | (i1 << (64 - sh)) : i0;
+	uint64_t d = x ^ pat;
+
+	d = ((d | (d >> 1)) | iv) & E;
+	int nbefore = (int) min((int64_t) len, max((int64_t) 0, lo - a));
+	int nafter = (int) min((int64_t) len, max((int64_t) 0, a + len - (lo + L)));
+	if (nbefore)
+		d |= E & (nbefore >= 32 ? ~0ull : (1ull << (2 * nbefore)) - 1);
+	if (nafter)
+		d |= E & ~((len - nafter) >= 32 ? ~0ull : (1ull << (2 * (len - nafter))) - 1);
+	d &= len >= 32 ? E : E & ((1ull << (2 * len)) - 1);
+	return __popcll(d);
+}
+
+// A confirmed Trusted-Band hit of TB id 'tb_id' ending at concat index e.
+// direct == 1: no head/tail and singleton TB groups -> report right away;
+// direct == 2: every key's head and tail are packed (base-only, <= 32 letters) and fixedS = TRUE:
+//              the keys of the TB group {key0} U low2high[key0] (src/match_pdict_utils.c:153-181)
+//              are verified right here, head + tail mismatches by XOR + popcount against
+//              max / min.mismatch (src/match_pdict_utils.c:183-214 counts the same letters);
+// direct == 0: the hit becomes a candidate record (tb_id << 34 | e) for verify_flanks_kernel.
+__device__ __forceinline__ void tb_hit(const BsgpuIndexView &I, const BsgpuSubjectView &S,
+		const BsgpuReport &R, const BsgpuReport &C, int direct, int tb_id, int64_t e,
+		int max_nmis = 0, int min_nmis = 0)
+{
+	if (direct == 2) {
+		int seg = S.nseg == 1 ? 0 : find_segment(S, e);
+		int64_t lo = __ldg(S.seg_start + seg), L = __ldg(S.seg_len + seg);
+		int g0 = __ldg(I.grp_off + tb_id), g1 = __ldg(I.grp_off + tb_id + 1);
+
+		for (int g = g0; g < g1; g++) {
+			int key = g == g0 ? tb_id : __ldg(I.grp_keys + g);      // the leader comes first
+			uint32_t fl = __ldg(I.flank_len + key);
+			int hl = (int) (fl & 63u), tl = (int) ((fl >> 6) & 63u);
+			ulonglong2 f = __ldg(I.flank2 + key);
+			int nmis = packed_flank_mismatches(S, e - I.w - hl + 1, hl, f.x, lo, L);
+
+			if (nmis <= max_nmis)
+				nmis += packed_flank_mismatches(S, e + 1, tl, f.y, lo, L);
+			if (nmis <= max_nmis && nmis >= min_nmis)
+				report_match(R, S, key, seg, e - lo + 1, e, tl);
+		}
+		return;
+	}
 	if (!direct) {
 		append_record(C, ((unsigned long long) tb_id << BSGPU_POS_BITS) | (unsigned long long) e);
 		return;
@@ -326,7 +381,7 @@ __device__ __forceinline__ uint32_t window_mask(const uint32_t *__restrict__ pla
 
 __global__ void __launch_bounds__(256)
 scan_tb_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R, BsgpuReport C,
-	       int direct, int64_t start_lo, int64_t start_hi)
+	       int direct, int64_t start_lo, int64_t start_hi, int max_nmis, int min_nmis)
 {
 	// window starts c0 in [start_lo, start_hi)
 	int64_t word_lo = start_lo >> 5, word_hi = (start_hi + 31) >> 5;
@@ -393,7 +448,7 @@ scan_tb_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R, BsgpuReport 
 			if (id >= 0 && w > 32)
 				id = resolve_long_tb(I, S, id, e, 1);
 			if (id >= 0)
-				tb_hit(I, S, R, C, direct, id, e);
+				tb_hit(I, S, R, C, direct, id, e, max_nmis, min_nmis);
 		}
 	}
 }
@@ -746,7 +801,116 @@ finalize_ends_kernel(BsgpuSubjectView S, const int64_t *__restrict__ tail_off, i
 			v = v - __ldg(S.seg_start + seg) + 1 + Tlen + __ldg(S.seg_coord + seg);
 		}
 		ends[t] = (int32_t) v;
-		atomicAdd(counts + key, 1);
+		if (counts != nullptr)
+			atomicAdd(counts + key, 1);
+	}
+}
+
+// ------------------------------------------------------------------------------------
+// Count - scan - write compaction of the hit records into rows (the reference's MatchBuf: one
+// int list per pattern, src/match_pdict_utils.c:87-116, src/match_reporting.c:150-201).
+//   1. count_rows_kernel   counts[key]++ for every record (key << 34 | position)
+//   2. exclusive scan of the counts -> row offsets (the CSR the host receives)
+//   3. write_rows_kernel   every record takes a place in its row (per-row cursor)
+//   4. order_rows_kernel   rows are tiny: one thread puts a row of <= 32 records in ascending
+//      position order (the order the reference appends them in, view by view); the rare
+//      longer rows (repeats) are listed and sorted by bitonic_rows_kernel, one block per row
+//   5. finalize_ends_kernel turns the ordered records into end coordinates
+// No global sort: the work is proportional to the hits and stays inside the rows.
+// ------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+count_rows_kernel(const unsigned long long *__restrict__ rec, unsigned long long n, int32_t *__restrict__ counts)
+{
+	unsigned long long t = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+
+	for (; t < n; t += stride)
+		atomicAdd(counts + (rec[t] >> BSGPU_POS_BITS), 1);
+}
+
+__global__ void __launch_bounds__(256)
+write_rows_kernel(const unsigned long long *__restrict__ rec, unsigned long long n,
+		  const int64_t *__restrict__ row_off, int32_t *__restrict__ cursor,
+		  unsigned long long *__restrict__ rows)
+{
+	unsigned long long t = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+
+	for (; t < n; t += stride) {
+		unsigned long long r = rec[t];
+		unsigned long long key = r >> BSGPU_POS_BITS;
+
+		rows[row_off[key] + atomicAdd(cursor + key, 1)] = r;
+	}
+}
+
+#define BSGPU_SMALL_ROW 32
+
+__global__ void __launch_bounds__(256)
+order_rows_kernel(unsigned long long *__restrict__ rows, const int64_t *__restrict__ row_off,
+		  const int32_t *__restrict__ counts, int32_t M, int32_t *__restrict__ big, int32_t *__restrict__ n_big)
+{
+	int32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+	int32_t stride = gridDim.x * blockDim.x;
+
+	for (; key < M; key += stride) {
+		int n = counts[key];
+
+		if (n < 2)
+			continue;
+		if (n > BSGPU_SMALL_ROW) {
+			big[atomicAdd(n_big, 1)] = key;
+			continue;
+		}
+		unsigned long long *row = rows + row_off[key];
+		for (int i = 1; i < n; i++) {           // insertion sort: rows arrive almost in order
+			unsigned long long v = row[i];
+			int j = i - 1;
+
+			while (j >= 0 && row[j] > v) {
+				row[j + 1] = row[j];
+				j--;
+			}
+			row[j + 1] = v;
+		}
+	}
+}
+
+// one block per long row: bitonic sort in place (the row is padded to a power of two with
+// virtual +infinity elements)
+__global__ void __launch_bounds__(1024)
+bitonic_rows_kernel(unsigned long long *__restrict__ rows, const int64_t *__restrict__ row_off,
+		    const int32_t *__restrict__ counts, const int32_t *__restrict__ big, const int32_t *__restrict__ n_big)
+{
+	for (int b = blockIdx.x; b < *n_big; b += gridDim.x) {
+		int32_t key = big[b];
+		unsigned long long *row = rows + row_off[key];
+		const unsigned int n = (unsigned int) counts[key];
+		unsigned int np2 = 1;
+
+		while (np2 < n)
+			np2 <<= 1;
+		// the network with all comparators ascending (first step of a merge pairs i with its
+		// mirror i ^ (k - 1)): the virtual tail never has to move
+		for (unsigned int k = 2; k <= np2; k <<= 1)
+			for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+				const unsigned int flip = j == (k >> 1) ? k - 1 : j;
+
+				for (unsigned int i = threadIdx.x; i < np2; i += blockDim.x) {
+					unsigned int l = i ^ flip;
+
+					if (l > i && l < n) {
+						unsigned long long a = row[i], c = row[l];
+
+						if (a > c) {
+							row[i] = c;
+							row[l] = a;
+						}
+					}
+				}
+				__syncthreads();
+			}
 	}
 }
 

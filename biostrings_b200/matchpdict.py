@@ -152,19 +152,49 @@ def _as_array(ptr, n, dtype):
     return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
 
 
+class _OwnedResult:
+    """Keeps a bsgpu_result alive while numpy arrays view its (pinned, recycled) blocks: the big
+    vectors of a result -- counts, CSR offsets, ends -- are handed out without a copy (a fresh 8 MB
+    array costs more in page faults than the whole device side of a matchPDict call) and the
+    blocks go back to the library when the last view dies."""
+
+    def __init__(self, res):
+        self.res, self.views = res, 0
+
+    def view(self, ptr, n, dtype):
+        import weakref
+        if n == 0:
+            return np.zeros(0, dtype=dtype)
+        arr = np.ctypeslib.as_array(ptr, shape=(n,))
+        assert arr.dtype == dtype
+        self.views += 1
+        weakref.finalize(arr, self._release).atexit = False
+        return arr
+
+    def _release(self):
+        self.views -= 1
+        if self.views == 0:
+            _lib.lib().bsgpu_result_free(C.byref(self.res))
+
+    def done(self):
+        if self.views == 0:
+            _lib.lib().bsgpu_result_free(C.byref(self.res))
+
+
 def _take_result(res, mode, vmatch_collapse=None, n_subjects=None):
+    own = _OwnedResult(res)
     try:
         if mode == MATCHES_AS_COUNTS:
             if res.dcounts:
                 return _as_array(res.dcounts, res.n_counts, np.float64)
-            return _as_array(res.counts, res.n_counts, np.int32)
+            return own.view(res.counts, res.n_counts, np.int32)
         if mode == MATCHES_AS_WHICH and n_subjects is None:
             return _as_array(res.which, res.n_which, np.int32)
-        offsets = _as_array(res.ends_offsets, res.n_rows + 1, np.int64)
-        ends = _as_array(res.ends, int(offsets[-1]) if res.n_rows else 0, np.int32)
+        offsets = own.view(res.ends_offsets, res.n_rows + 1, np.int64)
+        ends = own.view(res.ends, int(offsets[-1]) if res.n_rows else 0, np.int32)
         return offsets, ends
     finally:
-        _lib.lib().bsgpu_result_free(C.byref(res))
+        own.done()
 
 
 def match_parts(parts, dsubj, max_mismatch, min_mismatch, fixed, mode):
