@@ -150,6 +150,8 @@ extern "C" int bsgpu_device_count(void)
 	return n;
 }
 
+static bool device_state_exists(void);
+
 extern "C" int bsgpu_set_device(int device)
 {
 	int n = bsgpu_device_count();
@@ -158,6 +160,9 @@ extern "C" int bsgpu_set_device(int device)
 		return fail(BSGPU_ENODEVICE, "no CUDA device available: libbsgpu has no CPU fallback");
 	if (device < 0 || device >= n)
 		return fail(BSGPU_EINVAL, "invalid CUDA device %d (have %d)", device, n);
+	if (g_device >= 0 && device != g_device && device_state_exists())
+		return fail(BSGPU_EINVAL, "bsgpu_set_device(%d): the library already holds buffers and indexes on device "
+			    "%d; select the device before the first call (one process per GPU)", device, g_device);
 	CUDA_TRY(cudaSetDevice(device));
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -265,6 +270,8 @@ static void pool_free(void *p, size_t bytes)
 	g_pool_bytes += bytes;
 }
 
+static long g_live_allocs = 0;           // device blocks currently held by DevBuf objects
+
 template <typename T>
 struct DevBuf {
 	T *p = nullptr;
@@ -275,7 +282,15 @@ struct DevBuf {
 	DevBuf(const DevBuf &) = delete;
 	DevBuf &operator=(const DevBuf &) = delete;
 	~DevBuf() { release(); }
-	void release() { pool_free(p, bytes); p = nullptr; n = 0; bytes = 0; }
+	void release()
+	{
+		if (p != nullptr)
+			g_live_allocs--;
+		pool_free(p, bytes);
+		p = nullptr;
+		n = 0;
+		bytes = 0;
+	}
 	void swap(DevBuf &o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(bytes, o.bytes); }
 	int alloc(size_t count)
 	{
@@ -287,6 +302,7 @@ struct DevBuf {
 			bytes = 0;
 			return fail(BSGPU_ENOMEM, "cudaMalloc of %zu bytes failed", count * sizeof(T));
 		}
+		g_live_allocs++;
 		n = count;
 		return BSGPU_OK;
 	}
@@ -1019,7 +1035,7 @@ static int upload_packed_flanks(bsgpu_pdict3parts *p3)
 	return BSGPU_OK;
 }
 
-extern "C" int bsgpu_pdict3parts_build(int algo, int32_t M,
+static int bsgpu_pdict3parts_build_impl(int algo, int32_t M,
 		const uint8_t *tb_concat, const int32_t *tb_widths,
 		const uint8_t *head_concat, const int32_t *head_widths,
 		const uint8_t *tail_concat, const int32_t *tail_widths,
@@ -1186,9 +1202,29 @@ extern "C" int bsgpu_pdict3parts_build(int algo, int32_t M,
 	return BSGPU_OK;
 }
 
+extern "C" int bsgpu_pdict3parts_build(int algo, int32_t M,
+		const uint8_t *tb_concat, const int32_t *tb_widths,
+		const uint8_t *head_concat, const int32_t *head_widths,
+		const uint8_t *tail_concat, const int32_t *tail_widths,
+		const int32_t *pp_exclude, int32_t *high2low_out,
+		bsgpu_pdict3parts **out)
+{
+	int rc;
+
+	try {
+		rc = bsgpu_pdict3parts_build_impl(algo, M, tb_concat, tb_widths, head_concat, head_widths, tail_concat, tail_widths, pp_exclude, high2low_out, out);
+	} catch (const std::bad_alloc &) {
+		rc = fail(BSGPU_ENOMEM, "bsgpu_pdict3parts_build(): out of host memory");
+	} catch (const std::exception &e) {
+		rc = fail(BSGPU_ECUDA, "bsgpu_pdict3parts_build(): %s", e.what());
+	}
+	return rc;
+}
+
+
 // A non-preprocessed dictionary: the handle carries the pattern letters only and is accepted
 // by bsgpu_match() / bsgpu_vmatch() like a PDict3Parts (match_XStringSet_XString & co).
-extern "C" int bsgpu_patterns_build(const uint8_t *concat, const int32_t *widths, int32_t M,
+static int bsgpu_patterns_build_impl(const uint8_t *concat, const int32_t *widths, int32_t M,
 		bsgpu_pdict3parts **out)
 {
 	if (out == nullptr || M < 0 || (M > 0 && widths == nullptr))
@@ -1233,6 +1269,22 @@ extern "C" int bsgpu_patterns_build(const uint8_t *concat, const int32_t *widths
 	*out = p3.release();
 	return BSGPU_OK;
 }
+
+extern "C" int bsgpu_patterns_build(const uint8_t *concat, const int32_t *widths, int32_t M,
+		bsgpu_pdict3parts **out)
+{
+	int rc;
+
+	try {
+		rc = bsgpu_patterns_build_impl(concat, widths, M, out);
+	} catch (const std::bad_alloc &) {
+		rc = fail(BSGPU_ENOMEM, "bsgpu_patterns_build(): out of host memory");
+	} catch (const std::exception &e) {
+		rc = fail(BSGPU_ECUDA, "bsgpu_patterns_build(): %s", e.what());
+	}
+	return rc;
+}
+
 
 extern "C" int bsgpu_pdict3parts_set_flanks(bsgpu_pdict3parts *p3,
 		const uint8_t *head_concat, const int32_t *head_widths,
@@ -1838,6 +1890,11 @@ struct Workspace {
 };
 
 static Workspace *g_ws = nullptr;
+
+static bool device_state_exists(void)
+{
+	return g_ws != nullptr || !g_pool.empty() || g_live_allocs > 0;
+}
 
 static int host_counts(Workspace *ws, size_t n, int32_t **out)
 {
@@ -2615,7 +2672,7 @@ static void which_from_counts(bsgpu_result *res, const int32_t *counts, int32_t 
 			res->which[n++] = i + 1;        // sort(ids)+1, src/match_reporting.c:150-161
 }
 
-extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
+static int bsgpu_match_impl(const bsgpu_pdict3parts *const *parts, int nparts,
 		const bsgpu_subject *subj, int max_nmis, int min_nmis, int fixedP, int fixedS,
 		int matches_as, bsgpu_result *res)
 {
@@ -2776,7 +2833,26 @@ extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
 	return BSGPU_OK;
 }
 
-extern "C" int bsgpu_count_device(const bsgpu_pdict3parts *const *parts, int nparts,
+extern "C" int bsgpu_match(const bsgpu_pdict3parts *const *parts, int nparts,
+		const bsgpu_subject *subj, int max_nmis, int min_nmis, int fixedP, int fixedS,
+		int matches_as, bsgpu_result *res)
+{
+	int rc;
+
+	try {
+		rc = bsgpu_match_impl(parts, nparts, subj, max_nmis, min_nmis, fixedP, fixedS, matches_as, res);
+	} catch (const std::bad_alloc &) {
+		rc = fail(BSGPU_ENOMEM, "bsgpu_match(): out of host memory");
+	} catch (const std::exception &e) {
+		rc = fail(BSGPU_ECUDA, "bsgpu_match(): %s", e.what());
+	}
+	if (rc != BSGPU_OK && res != nullptr)
+		bsgpu_result_free(res);        // nothing of a failed call stays allocated
+	return rc;
+}
+
+
+static int bsgpu_count_device_impl(const bsgpu_pdict3parts *const *parts, int nparts,
 		const bsgpu_subject *subj, int max_nmis, int min_nmis, int fixedP, int fixedS,
 		int32_t *d_counts, void *stream, int *n_launches_out)
 {
@@ -2837,6 +2913,23 @@ extern "C" int bsgpu_count_device(const bsgpu_pdict3parts *const *parts, int npa
 	return BSGPU_OK;
 }
 
+extern "C" int bsgpu_count_device(const bsgpu_pdict3parts *const *parts, int nparts,
+		const bsgpu_subject *subj, int max_nmis, int min_nmis, int fixedP, int fixedS,
+		int32_t *d_counts, void *stream, int *n_launches_out)
+{
+	int rc;
+
+	try {
+		rc = bsgpu_count_device_impl(parts, nparts, subj, max_nmis, min_nmis, fixedP, fixedS, d_counts, stream, n_launches_out);
+	} catch (const std::bad_alloc &) {
+		rc = fail(BSGPU_ENOMEM, "bsgpu_count_device(): out of host memory");
+	} catch (const std::exception &e) {
+		rc = fail(BSGPU_ECUDA, "bsgpu_count_device(): %s", e.what());
+	}
+	return rc;
+}
+
+
 // ---------------------------------------------------------------------------------------
 // countPDict on a subject that lives in HOST memory: the upload is cut into slices and slice
 // k is scanned while slice k + 1 crosses PCIe, so a call costs the copy plus one slice of
@@ -2873,7 +2966,7 @@ static bool counts_directly(const bsgpu_pdict3parts *const *parts, int nparts, c
 	return nparts == 1 || (useq && subj->kind != SUBJ_VIEWS);
 }
 
-extern "C" int bsgpu_count_host(const bsgpu_pdict3parts *const *parts, int nparts,
+static int bsgpu_count_host_impl(const bsgpu_pdict3parts *const *parts, int nparts,
 		const uint8_t *letters, int64_t length, int64_t chunk_start, int64_t subject_len,
 		int64_t report_lo, int64_t report_hi,
 		int max_nmis, int min_nmis, int fixedP, int fixedS,
@@ -3058,11 +3151,30 @@ extern "C" int bsgpu_count_host(const bsgpu_pdict3parts *const *parts, int npart
 	return BSGPU_OK;
 }
 
+extern "C" int bsgpu_count_host(const bsgpu_pdict3parts *const *parts, int nparts,
+		const uint8_t *letters, int64_t length, int64_t chunk_start, int64_t subject_len,
+		int64_t report_lo, int64_t report_hi,
+		int max_nmis, int min_nmis, int fixedP, int fixedS,
+		int32_t *counts_out, int32_t *d_counts, void *stream)
+{
+	int rc;
+
+	try {
+		rc = bsgpu_count_host_impl(parts, nparts, letters, length, chunk_start, subject_len, report_lo, report_hi, max_nmis, min_nmis, fixedP, fixedS, counts_out, d_counts, stream);
+	} catch (const std::bad_alloc &) {
+		rc = fail(BSGPU_ENOMEM, "bsgpu_count_host(): out of host memory");
+	} catch (const std::exception &e) {
+		rc = fail(BSGPU_ECUDA, "bsgpu_count_host(): %s", e.what());
+	}
+	return rc;
+}
+
+
 // ---------------------------------------------------------------------------------------
 // vmatch: vcountPDict / vwhichPDict on a set of subjects (src/match_pdict.c:320-346,386-432)
 // ---------------------------------------------------------------------------------------
 
-extern "C" int bsgpu_vmatch(const bsgpu_pdict3parts *const *parts, int nparts,
+static int bsgpu_vmatch_impl(const bsgpu_pdict3parts *const *parts, int nparts,
 		const bsgpu_subject *subj, int max_nmis, int min_nmis, int fixedP, int fixedS,
 		int collapse, int weight_is_double, const void *weight, int64_t weight_length,
 		int matches_as, bsgpu_result *res)
@@ -3191,6 +3303,26 @@ extern "C" int bsgpu_vmatch(const bsgpu_pdict3parts *const *parts, int nparts,
 	}
 	return BSGPU_OK;
 }
+
+extern "C" int bsgpu_vmatch(const bsgpu_pdict3parts *const *parts, int nparts,
+		const bsgpu_subject *subj, int max_nmis, int min_nmis, int fixedP, int fixedS,
+		int collapse, int weight_is_double, const void *weight, int64_t weight_length,
+		int matches_as, bsgpu_result *res)
+{
+	int rc;
+
+	try {
+		rc = bsgpu_vmatch_impl(parts, nparts, subj, max_nmis, min_nmis, fixedP, fixedS, collapse, weight_is_double, weight, weight_length, matches_as, res);
+	} catch (const std::bad_alloc &) {
+		rc = fail(BSGPU_ENOMEM, "bsgpu_vmatch(): out of host memory");
+	} catch (const std::exception &e) {
+		rc = fail(BSGPU_ECUDA, "bsgpu_vmatch(): %s", e.what());
+	}
+	if (rc != BSGPU_OK && res != nullptr)
+		bsgpu_result_free(res);        // nothing of a failed call stays allocated
+	return rc;
+}
+
 
 // ---------------------------------------------------------------------------------------
 // Host-buffer entry points with the reference's .Call shapes
@@ -3331,7 +3463,7 @@ indels_candidates_kernel(BsgpuSubjectView S, const uint8_t *__restrict__ pat, co
 	}
 }
 
-extern "C" int bsgpu_count_indels(const bsgpu_pdict3parts *plain, const bsgpu_subject *subj, int max_mismatch,
+static int bsgpu_count_indels_impl(const bsgpu_pdict3parts *plain, const bsgpu_subject *subj, int max_mismatch,
 		int fixedP, int fixedS, int per_sequence, int32_t *counts_out)
 {
 	if (plain == nullptr || subj == nullptr || counts_out == nullptr)
@@ -3401,6 +3533,22 @@ extern "C" int bsgpu_count_indels(const bsgpu_pdict3parts *plain, const bsgpu_su
 					    per_sequence != 0, counts_out);
 	return BSGPU_OK;
 }
+
+extern "C" int bsgpu_count_indels(const bsgpu_pdict3parts *plain, const bsgpu_subject *subj, int max_mismatch,
+		int fixedP, int fixedS, int per_sequence, int32_t *counts_out)
+{
+	int rc;
+
+	try {
+		rc = bsgpu_count_indels_impl(plain, subj, max_mismatch, fixedP, fixedS, per_sequence, counts_out);
+	} catch (const std::bad_alloc &) {
+		rc = fail(BSGPU_ENOMEM, "bsgpu_count_indels(): out of host memory");
+	} catch (const std::exception &e) {
+		rc = fail(BSGPU_ECUDA, "bsgpu_count_indels(): %s", e.what());
+	}
+	return rc;
+}
+
 
 // ---------------------------------------------------------------------------------------
 // oligonucleotideFrequency (XString_oligo_frequency / XStringSet_oligo_frequency,

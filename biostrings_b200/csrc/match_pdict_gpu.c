@@ -77,47 +77,56 @@ static int matches_as_code(SEXP matches_as)
 	return -1;
 }
 
-/* ---- device index cache ---------------------------------------------------------------
+/* ---- the device index lives in the PreprocessedTB object ------------------------------------
  * The Trusted Band is preprocessed once (build_Twobit / ACtree2_build) while head and tail
- * arrive with every match call, so the index is created at build time, remembered by the
- * identity of the `tb` object that ends up in the pptb@tb slot, and gets its flanks
- * attached on the first match call.  (A production integration would hang an externalptr
- * with a finalizer on the PreprocessedTB object instead of this small table.) */
+ * arrive with every match call.  The device index is created at build time and hung on an
+ * external pointer the object already owns -- no new slot, the R classes stay as they are:
+ *   ACtree2: pptb@nodebuf_ptr@xp   (IntegerBAB_new makes it with a NULL address, src/BAB_class.c:9-22)
+ *   Twobit : pptb@sign2pos@shared@xp   (the SharedInteger behind the XInteger, NULL address too)
+ * with a C finalizer, so the index is freed when R garbage-collects the PDict, copies of the
+ * object share it, and no table keyed by SEXP addresses can go stale.  An object whose pointer
+ * is NULL (readRDS, or built by the CPU package) is rebuilt from its own slots on first use:
+ * the patterns the build skipped (pp_exclude) are recovered from what the object records --
+ * the leaf nodes / sign2pos entries name the Trusted-Band leaders, pptb@dups the duplicates. */
 
-#define CACHE_SIZE 64
-static struct cache_entry {
-	SEXP tb;			/* identity of the Trusted Band object */
+struct dev_index {
 	bsgpu_pdict3parts *p3;
 	uint64_t flank_sig;		/* which head/tail are attached */
 	int dups_blanked;
-} cache[CACHE_SIZE];
-static int cache_next = 0;
+};
 
-static struct cache_entry *cache_find(SEXP tb)
+static int live_indexes = 0;
+int bsgpu_dispatch_live_indexes(void) { return live_indexes; }
+
+static void dev_index_finalizer(SEXP xp)
 {
-	int i;
+	struct dev_index *d = (struct dev_index *) R_ExternalPtrAddr(xp);
 
-	for (i = 0; i < CACHE_SIZE; i++)
-		if (cache[i].p3 != NULL && cache[i].tb == tb)
-			return &cache[i];
-	return NULL;
+	if (d == NULL)
+		return;
+	bsgpu_pdict3parts_free(d->p3);
+	free(d);
+	R_SetExternalPtrAddr(xp, NULL);
+	live_indexes--;
 }
 
-static void cache_put(SEXP tb, bsgpu_pdict3parts *p3)
+static void dev_index_attach(SEXP xp, bsgpu_pdict3parts *p3)
 {
-	struct cache_entry *e = cache_find(tb);
+	struct dev_index *d = (struct dev_index *) calloc(1, sizeof(*d));
 
-	if (e == NULL) {
-		e = &cache[cache_next];
-		cache_next = (cache_next + 1) % CACHE_SIZE;
+	if (d == NULL) {
+		bsgpu_pdict3parts_free(p3);
+		error("out of memory");
 	}
-	if (e->p3 != NULL)
-		bsgpu_pdict3parts_free(e->p3);
-	e->tb = tb;
-	e->p3 = p3;
-	e->flank_sig = 0;
-	e->dups_blanked = 0;
+	dev_index_finalizer(xp);		/* a rebuilt object: drop what it held */
+	d->p3 = p3;
+	R_SetExternalPtrAddr(xp, d);
+	R_RegisterCFinalizerEx(xp, dev_index_finalizer, TRUE);
+	live_indexes++;
 }
+
+static SEXP bab_xp(SEXP bab) { return GET_SLOT(bab, install("xp")); }
+static SEXP xinteger_xp(SEXP x) { return GET_SLOT(GET_SLOT(x, install("shared")), install("xp")); }
 
 static uint64_t fnv(uint64_t h, const void *p, size_t n)
 {
@@ -143,29 +152,82 @@ static int algo_of(SEXP pptb)
 	return -1;
 }
 
+/* the external pointer of 'pptb' that carries the device index */
+static SEXP pptb_xp(SEXP pptb)
+{
+	if (algo_of(pptb) == BSGPU_ALGO_TWOBIT)
+		return xinteger_xp(GET_SLOT(pptb, install("sign2pos")));
+	return bab_xp(GET_SLOT(pptb, install("nodebuf_ptr")));
+}
+
+#define ISLEAF_BIT (1 << 30)		/* src/match_pdict_ACtree2.c:389-392 */
+#define MAX_P_ID (ISLEAF_BIT - 1)
+
+/* Rebuilds the device index of an object that does not carry one.  pp_exclude[i] = NA for the
+ * patterns the original build indexed: the Trusted-Band leaders (Twobit: the values of sign2pos;
+ * ACtree2: the P_ids of the leaf nodes in the node buffer, two ints per node) and their
+ * duplicates (non-NA in pptb@dups); every other pattern was excluded (or is a duplicate of a
+ * blanked dups slot, which the C level never reports either). */
+static struct dev_index *rebuild_index(SEXP pptb, SEXP xp)
+{
+	SEXP tb = pptb_tb(pptb), h2l = get_H2LGrouping_high2low(pptb_dups(pptb));
+	FlatSet t = flatten(tb);
+	int *excl = (int *) R_alloc((size_t) (t.n ? t.n : 1), sizeof(int)), i, algo = algo_of(pptb);
+	bsgpu_pdict3parts *p3;
+
+	for (i = 0; i < t.n; i++)
+		excl[i] = 1;
+	for (i = 0; i < LENGTH(h2l) && i < t.n; i++)
+		if (INTEGER(h2l)[i] != NA_INTEGER)
+			excl[i] = NA_INTEGER;
+	if (algo == BSGPU_ALGO_TWOBIT) {
+		SEXP tag = R_ExternalPtrTag(xp);
+
+		for (i = 0; i < LENGTH(tag); i++) {
+			int id = INTEGER(tag)[i];
+
+			if (id != NA_INTEGER && id >= 1 && id <= t.n)
+				excl[id - 1] = NA_INTEGER;
+		}
+	} else {
+		SEXP blocks = R_ExternalPtrTag(xp), prot = R_ExternalPtrProtected(xp);
+		int nblock = INTEGER(prot)[0], last_nelt = INTEGER(prot)[1], b, k;
+
+		for (b = 0; b < nblock; b++) {
+			SEXP block = VECTOR_ELT(blocks, b);
+			int nnodes = b == nblock - 1 ? last_nelt : LENGTH(block) / 2;
+
+			for (k = 0; k < nnodes; k++) {
+				int attribs = INTEGER(block)[2 * k];
+
+				if ((attribs & ISLEAF_BIT) && attribs > 0) {
+					int id = attribs & MAX_P_ID;
+
+					if (id >= 1 && id <= t.n)
+						excl[id - 1] = NA_INTEGER;
+				}
+			}
+		}
+	}
+	if (bsgpu_pdict3parts_build(algo, t.n, t.concat, t.widths, NULL, NULL, NULL, NULL,
+				    excl, NULL, &p3) != BSGPU_OK)
+		error("%s", bsgpu_last_error());
+	dev_index_attach(xp, p3);
+	return (struct dev_index *) R_ExternalPtrAddr(xp);
+}
+
 /* The device index of (pptb, head, tail), ready for matching. */
 static bsgpu_pdict3parts *get_p3(SEXP pptb, SEXP pdict_head, SEXP pdict_tail)
 {
-	SEXP tb = pptb_tb(pptb);
-	struct cache_entry *e = cache_find(tb);
+	SEXP xp = pptb_xp(pptb);
+	struct dev_index *e = (struct dev_index *) R_ExternalPtrAddr(xp);
 	FlatSet hd = {NULL, NULL, 0}, tl = {NULL, NULL, 0};
 	uint64_t sig = 0xCBF29CE484222325ull;
 	int i, all_na = 1;
 	SEXP h2l;
 
-	if (e == NULL) {
-		/* not built through this library in this session (e.g. a PDict loaded from disk):
-		   rebuild from the object; excluded patterns are those absent from every group,
-		   which the object does not record, so exclusion is taken from exclude_dups0 = FALSE */
-		FlatSet t = flatten(tb);
-		bsgpu_pdict3parts *p3;
-
-		if (bsgpu_pdict3parts_build(algo_of(pptb), t.n, t.concat, t.widths, NULL, NULL, NULL, NULL,
-					    NULL, NULL, &p3) != BSGPU_OK)
-			error("%s", bsgpu_last_error());
-		cache_put(tb, p3);
-		e = cache_find(tb);
-	}
+	if (e == NULL)
+		e = rebuild_index(pptb, xp);
 	if (pdict_head != R_NilValue) {
 		size_t tot = 0;
 
@@ -206,9 +268,17 @@ static bsgpu_pdict3parts *get_p3(SEXP pptb, SEXP pdict_head, SEXP pdict_tail)
 	return e->p3;
 }
 
+/* test hook: forget the device index of an object, as readRDS() would hand it back */
+SEXP bsgpu_dispatch_detach(SEXP pptb)
+{
+	dev_index_finalizer(pptb_xp(pptb));
+	return R_NilValue;
+}
+
 /* ---- preprocessing entry points -------------------------------------------------------- */
 
-static SEXP build_common(int algo, SEXP tb, SEXP pp_exclude, SEXP first_elt, const char *first_name)
+static SEXP build_common(int algo, SEXP tb, SEXP pp_exclude, SEXP first_elt, const char *first_name,
+			 bsgpu_pdict3parts **p3_out)
 {
 	FlatSet t = flatten(tb);
 	SEXP ans, ans_names, h2l;
@@ -219,7 +289,7 @@ static SEXP build_common(int algo, SEXP tb, SEXP pp_exclude, SEXP first_elt, con
 				    pp_exclude == R_NilValue ? NULL : INTEGER(pp_exclude),
 				    INTEGER(h2l), &p3) != BSGPU_OK)
 		error("%s", bsgpu_last_error());	/* the reference's own message */
-	cache_put(tb, p3);
+	*p3_out = p3;
 	PROTECT(ans = NEW_LIST(2));
 	PROTECT(ans_names = NEW_CHARACTER(2));
 	SET_STRING_ELT(ans_names, 0, mkChar(first_name));
@@ -240,13 +310,14 @@ SEXP build_Twobit(SEXP tb, SEXP pp_exclude, SEXP base_codes)
 	XVectorList_holder h = hold_XVectorList(tb);
 	int n = get_length_from_XVectorList_holder(&h), w = -1, i, d;
 	SEXP sign2pos, xint, ans;
+	bsgpu_pdict3parts *p3 = NULL;
 
 	for (i = 0; i < n && w < 0; i++)
 		if (pp_exclude == R_NilValue || INTEGER(pp_exclude)[i] == NA_INTEGER)
 			w = get_elt_from_XRawList_holder(&h, i).length;
 	/* argument errors (empty TB, w > 14, ragged, non-base) come from the library, with
 	   the reference's text, before any table is allocated */
-	PROTECT(ans = build_common(BSGPU_ALGO_TWOBIT, tb, pp_exclude, R_NilValue, "sign2pos"));
+	PROTECT(ans = build_common(BSGPU_ALGO_TWOBIT, tb, pp_exclude, R_NilValue, "sign2pos", &p3));
 	PROTECT(sign2pos = NEW_INTEGER(w < 0 ? 0 : 1 << (2 * w)));
 	for (i = 0; i < LENGTH(sign2pos); i++)
 		INTEGER(sign2pos)[i] = NA_INTEGER;
@@ -266,6 +337,7 @@ SEXP build_Twobit(SEXP tb, SEXP pp_exclude, SEXP base_codes)
 			INTEGER(sign2pos)[sig] = i + 1;
 	}
 	PROTECT(xint = new_XInteger_from_tag("XInteger", sign2pos));
+	dev_index_attach(xinteger_xp(xint), p3);
 	SET_VECTOR_ELT(ans, 0, xint);
 	UNPROTECT(3);
 	(void) base_codes;
@@ -275,8 +347,41 @@ SEXP build_Twobit(SEXP tb, SEXP pp_exclude, SEXP base_codes)
 /* --- .Call ENTRY POINT --- (src/match_pdict_ACtree2.c:792) */
 SEXP ACtree2_build(SEXP tb, SEXP pp_exclude, SEXP base_codes, SEXP nodebuf_ptr, SEXP nodeextbuf_ptr)
 {
-	(void) base_codes; (void) nodebuf_ptr; (void) nodeextbuf_ptr;
-	return build_common(BSGPU_ALGO_ACTREE2, tb, pp_exclude, R_NilValue, "ACtree");
+	bsgpu_pdict3parts *p3 = NULL;
+	SEXP ans, h2l, xp = bab_xp(nodebuf_ptr), blocks, prot, block;
+	int n, i, nleaves = 0;
+
+	(void) base_codes; (void) nodeextbuf_ptr;
+	PROTECT(ans = build_common(BSGPU_ALGO_ACTREE2, tb, pp_exclude, R_NilValue, "ACtree", &p3));
+	dev_index_attach(xp, p3);
+	/* The trie itself is not built, but its leaf nodes are written to the node buffer the way
+	   the reference writes them (attribs = ISLEAF_BIT | P_id, src/match_pdict_ACtree2.c:389-392,
+	   750-781): they are what names the indexed patterns when the object comes back from disk
+	   without its device index (rebuild_index). */
+	h2l = VECTOR_ELT(ans, 1);
+	n = LENGTH(h2l);
+	for (i = 0; i < n; i++)
+		if (INTEGER(h2l)[i] == NA_INTEGER && (pp_exclude == R_NilValue || INTEGER(pp_exclude)[i] == NA_INTEGER))
+			nleaves++;
+	blocks = R_ExternalPtrTag(xp);
+	prot = R_ExternalPtrProtected(xp);
+	if (nleaves > 0 && LENGTH(blocks) > 0) {
+		int k = 0;
+
+		PROTECT(block = NEW_INTEGER(2 * nleaves));
+		for (i = 0; i < n; i++)
+			if (INTEGER(h2l)[i] == NA_INTEGER && (pp_exclude == R_NilValue || INTEGER(pp_exclude)[i] == NA_INTEGER)) {
+				INTEGER(block)[2 * k] = ISLEAF_BIT | (i + 1);
+				INTEGER(block)[2 * k + 1] = -1;
+				k++;
+			}
+		SET_ELEMENT(blocks, 0, block);
+		UNPROTECT(1);
+		INTEGER(prot)[0] = 1;
+		INTEGER(prot)[1] = nleaves;
+	}
+	UNPROTECT(1);
+	return ans;
 }
 
 /* The node buffers of the CPU tree are not needed: the index lives on the device.  The
@@ -303,7 +408,7 @@ SEXP ACtree2_nnodes(SEXP pptb)
 {
 	/* no CPU tree: report the number of Trusted-Band letters indexed, an upper bound of
 	   the node count of the reference's trie */
-	struct cache_entry *e = cache_find(pptb_tb(pptb));
+	struct dev_index *e = (struct dev_index *) R_ExternalPtrAddr(pptb_xp(pptb));
 
 	return ScalarInteger(e ? bsgpu_pdict3parts_length(e->p3) * bsgpu_pdict3parts_tb_width(e->p3) + 1
 			       : NA_INTEGER);
@@ -471,19 +576,23 @@ SEXP vmatch_PDict3Parts_XStringSet(SEXP pptb, SEXP pdict_head, SEXP pdict_tail,
 
 /* ---- non-preprocessed dictionaries: 'pattern' is a plain XStringSet --------------------------
  * The reference runs one matchPattern() per pattern with the algorithm R selected; all of them
- * report the same matches, so 'algorithm' only needs to be a known name here.  with.indels is
- * the one thing the device path does not do. */
+ * report the same matches, so 'algorithm' only needs to be a known name here.  with.indels
+ * (algorithm "indels", counts / which only, R/matchPDict.R:171-191) goes to bsgpu_count_indels. */
+
+static int wants_indels(SEXP with_indels, SEXP algorithm)
+{
+	return LOGICAL(with_indels)[0] || strcmp(CHAR(STRING_ELT(algorithm, 0)), "indels") == 0;
+}
 
 static bsgpu_pdict3parts *plain_handle(SEXP pattern, SEXP with_indels, SEXP algorithm)
 {
-	static const char *known[] = {"naive-exact", "naive-inexact", "boyer-moore", "shift-or", NULL};
+	static const char *known[] = {"naive-exact", "naive-inexact", "boyer-moore", "shift-or", "indels", NULL};
 	const char *algo = CHAR(STRING_ELT(algorithm, 0));
 	FlatSet p = flatten(pattern);
 	bsgpu_pdict3parts *p3 = NULL;
 	int k;
 
-	if (LOGICAL(with_indels)[0] || strcmp(algo, "indels") == 0)
-		error("with.indels=TRUE is not supported on the GPU path");
+	(void) with_indels;
 	for (k = 0; known[k] != NULL && strcmp(known[k], algo) != 0; k++)
 		;
 	if (known[k] == NULL)
@@ -491,6 +600,52 @@ static bsgpu_pdict3parts *plain_handle(SEXP pattern, SEXP with_indels, SEXP algo
 	if (bsgpu_patterns_build(p.concat, p.widths, p.n, &p3) != BSGPU_OK)
 		error("%s", bsgpu_last_error());
 	return p3;
+}
+
+/* with.indels = TRUE: the counts behind countPDict / whichPDict (src/match_pdict.c:174-199 with
+ * algo "indels" -> _match_pattern_indels, src/match_pattern_indels.c:58-107).  Frees p3 and the
+ * subject handle.  per_sequence: M x N column-major, else M. */
+static int *indels_counts(bsgpu_pdict3parts *p3, bsgpu_subject *subj, int rc_subj, int M, int N,
+			  SEXP max_mismatch, SEXP fixed, int per_sequence, int ms_code)
+{
+	int *counts = (int *) R_alloc((size_t) M * (size_t) (per_sequence ? N : 1) + 1, sizeof(int)), rc = rc_subj;
+
+	if (rc == BSGPU_OK && ms_code != BSGPU_MATCHES_AS_WHICH && ms_code != BSGPU_MATCHES_AS_COUNTS) {
+		bsgpu_subject_free(subj);
+		bsgpu_pdict3parts_free(p3);
+		error("at the moment, within the matchPDict family, only countPDict(), whichPDict(), "
+		      "vcountPDict() and vwhichPDict() support indels");
+	}
+	if (rc == BSGPU_OK)
+		rc = bsgpu_count_indels(p3, subj, INTEGER(max_mismatch)[0], LOGICAL(fixed)[0], LOGICAL(fixed)[1],
+					per_sequence, counts);
+	if (subj != NULL)
+		bsgpu_subject_free(subj);
+	bsgpu_pdict3parts_free(p3);
+	if (rc != BSGPU_OK)
+		error("%s", bsgpu_last_error());
+	return counts;
+}
+
+static SEXP counts_or_which(const int *counts, int M, int ms_code)
+{
+	SEXP ans;
+	int i, n = 0;
+
+	if (ms_code == BSGPU_MATCHES_AS_COUNTS) {
+		PROTECT(ans = NEW_INTEGER(M));
+		memcpy(INTEGER(ans), counts, (size_t) M * sizeof(int));
+		UNPROTECT(1);
+		return ans;
+	}
+	for (i = 0; i < M; i++)
+		n += counts[i] != 0;
+	PROTECT(ans = NEW_INTEGER(n));
+	for (i = 0, n = 0; i < M; i++)
+		if (counts[i] != 0)
+			INTEGER(ans)[n++] = i + 1;	/* sort(ids) + 1, src/match_reporting.c:150-161 */
+	UNPROTECT(1);
+	return ans;
 }
 
 /* --- .Call ENTRY POINT --- (src/match_pdict.c:174) */
@@ -504,6 +659,13 @@ SEXP match_XStringSet_XString(SEXP pattern, SEXP subject,
 	bsgpu_result r;
 
 	(void) envir;
+	if (wants_indels(with_indels, algorithm)) {
+		bsgpu_subject *subj = NULL;
+		int M = get_XVectorList_length(pattern);
+
+		rc = bsgpu_subject_xstring((const uint8_t *) S.ptr, S.length, &subj);
+		return counts_or_which(indels_counts(p3, subj, rc, M, 1, max_mismatch, fixed, 0, ms_code), M, ms_code);
+	}
 	rc = bsgpu_match_PDict3Parts_XString(p3, (const uint8_t *) S.ptr, S.length,
 			INTEGER(max_mismatch)[0], INTEGER(min_mismatch)[0],
 			LOGICAL(fixed)[0], LOGICAL(fixed)[1], ms_code, &r);
@@ -524,6 +686,14 @@ SEXP match_XStringSet_XStringViews(SEXP pattern, SEXP subject, SEXP views_start,
 	bsgpu_result r;
 
 	(void) envir;
+	if (wants_indels(with_indels, algorithm)) {
+		bsgpu_subject *subj = NULL;
+		int M = get_XVectorList_length(pattern);
+
+		rc = bsgpu_subject_views((const uint8_t *) S.ptr, S.length, INTEGER(views_start), INTEGER(views_width),
+					 LENGTH(views_start), &subj);
+		return counts_or_which(indels_counts(p3, subj, rc, M, 1, max_mismatch, fixed, 0, ms_code), M, ms_code);
+	}
 	rc = bsgpu_match_PDict3Parts_XStringViews(p3, (const uint8_t *) S.ptr, S.length,
 			INTEGER(views_start), INTEGER(views_width), LENGTH(views_start),
 			INTEGER(max_mismatch)[0], INTEGER(min_mismatch)[0],
@@ -543,6 +713,46 @@ SEXP vmatch_XStringSet_XStringSet(SEXP pattern, SEXP subject,
 	SEXP ans;
 
 	(void) envir;
+	if (wants_indels(with_indels, algorithm)) {
+		FlatSet s = flatten(subject);
+		bsgpu_subject *subj = NULL;
+		int M = get_XVectorList_length(pattern), N = s.n, ms_code = matches_as_code(matches_as);
+		int coll = ms_code == BSGPU_MATCHES_AS_COUNTS ? INTEGER(collapse)[0] : 0, i, j;
+		int rc = bsgpu_subject_set(s.concat, s.widths, s.n, &subj);
+		const int *mat = indels_counts(p3, subj, rc, M, N, max_mismatch, fixed, 1, ms_code);
+
+		if (ms_code == BSGPU_MATCHES_AS_WHICH) {
+			PROTECT(ans = NEW_LIST(N));
+			for (j = 0; j < N; j++)
+				SET_VECTOR_ELT(ans, j, counts_or_which(mat + (size_t) j * M, M, BSGPU_MATCHES_AS_WHICH));
+		} else if (coll == 0) {
+			PROTECT(ans = allocMatrix(INTSXP, M, N));
+			memcpy(INTEGER(ans), mat, (size_t) M * (size_t) N * sizeof(int));
+		} else if (IS_INTEGER(weight)) {
+			/* src/match_pdict.c:85-127: subjects outer, patterns inner */
+			PROTECT(ans = NEW_INTEGER(coll == 1 ? M : N));
+			memset(INTEGER(ans), 0, (size_t) LENGTH(ans) * sizeof(int));
+			for (j = 0; j < N; j++)
+				for (i = 0; i < M; i++) {
+					if (coll == 1)
+						INTEGER(ans)[i] += mat[(size_t) j * M + i] * INTEGER(weight)[j];
+					else
+						INTEGER(ans)[j] += mat[(size_t) j * M + i] * INTEGER(weight)[i];
+				}
+		} else {
+			PROTECT(ans = NEW_NUMERIC(coll == 1 ? M : N));
+			memset(REAL(ans), 0, (size_t) LENGTH(ans) * sizeof(double));
+			for (j = 0; j < N; j++)
+				for (i = 0; i < M; i++) {
+					if (coll == 1)
+						REAL(ans)[i] += mat[(size_t) j * M + i] * REAL(weight)[j];
+					else
+						REAL(ans)[j] += mat[(size_t) j * M + i] * REAL(weight)[i];
+				}
+		}
+		UNPROTECT(1);
+		return ans;
+	}
 	/* an error() inside vmatch_common() leaks p3 until the process ends (longjmp), as any C
 	 * allocation would in an R entry point that errors */
 	ans = vmatch_common(p3, get_XVectorList_length(pattern), "vmatch_XStringSet_XStringSet",

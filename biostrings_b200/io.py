@@ -68,26 +68,64 @@ def _read_text(filepath):
         return f.read()
 
 
-def _cut(text, nrec, skip, seek_first_rec):
-    """nrec / skip / seek.first.rec of parse_FASTA_file (src/read_fasta_files.c:276-316) applied
-    to the text before it is uploaded: records are delimited by the lines that start with '>'."""
-    if nrec < 0 and skip == 0 and not seek_first_rec:
-        return text
-    arr = text if isinstance(text, np.ndarray) else np.frombuffer(text, dtype=np.uint8)
+def _record_starts(arr):
     gt = np.flatnonzero(arr == ord(">"))
-    starts = gt[(gt == 0) | (arr[np.maximum(gt - 1, 0)] == ord("\n"))]
+    return gt[(gt == 0) | (arr[np.maximum(gt - 1, 0)] == ord("\n"))]
+
+
+def _check_preamble(arr, upto, name):
+    """A line of sequence data in front of the first record is an error in the reference whatever
+    `skip` says (parse_FASTA_file, src/read_fasta_files.c:320-325: dont_load == -1); empty lines
+    and comment lines (';') are ignored."""
+    lineno = 0
+    for line in bytes(arr[:upto]).split(b"\n"):
+        lineno += 1
+        line = line.rstrip(b"\r")
+        if line and not line.startswith(b";"):
+            raise _lib.BsgpuError(-1, f'reading FASTA file {name}: ">" expected at beginning of line {lineno}')
+
+
+def _cut(text, nrec, skip, seek_first_rec, name="<memory>"):
+    """nrec / skip / seek.first.rec of parse_FASTA_file (src/read_fasta_files.c:276-316) applied
+    to the text before it is uploaded: records are delimited by the lines that start with '>'.
+    Returns (text to parse, number of records the text holds up to the cut)."""
+    arr = text if isinstance(text, np.ndarray) else np.frombuffer(text, dtype=np.uint8)
+    if nrec < 0 and skip == 0 and not seek_first_rec:
+        return text, None
+    starts = _record_starts(arr)
     if seek_first_rec:
         if starts.size == 0:
             raise ValueError("no FASTA record found")
         lo = int(starts[0])
     else:
         lo = 0
+        if skip > 0:
+            _check_preamble(arr, int(starts[0]) if starts.size else arr.size, name)
     if skip > 0:
         lo = int(starts[skip]) if skip < starts.size else len(text)
     hi = len(text)
+    seen = int(starts.size)
     if nrec >= 0 and skip + nrec < starts.size:
         hi = int(starts[skip + nrec])
-    return text[lo:hi]
+        seen = skip + nrec
+    return text[lo:hi], seen
+
+
+def _file_windows(records_per_file, nrec, skip):
+    """(nrec, skip) to apply to every file of a list so that, together, they select the records
+    [skip, skip + nrec) of the concatenated files: read_fasta_files() keeps one record counter over
+    the whole list (src/read_fasta_files.c:447-458; parse_FASTA_file stops at `*recno >= skip + nrec`
+    and loads nothing while `*recno < skip`)."""
+    out, recno = [], 0
+    for in_file in records_per_file:
+        if nrec >= 0 and recno >= skip + nrec:
+            f_nrec, f_skip = 0, 0
+        else:
+            f_skip = max(0, skip - recno)
+            f_nrec = -1 if nrec < 0 else skip + nrec - max(recno, skip)
+        out.append((f_nrec, f_skip))
+        recno += in_file if f_nrec < 0 else min(in_file, f_skip + f_nrec)
+    return out
 
 
 def read_fasta_to_device(filepath, nrec=-1, skip=0, seek_first_rec=False, use_names=True, lkup=None):
@@ -98,7 +136,7 @@ def read_fasta_to_device(filepath, nrec=-1, skip=0, seek_first_rec=False, use_na
     if not isinstance(seek_first_rec, (bool, np.bool_)):
         raise ValueError("'seek.first.rec' must be TRUE or FALSE")
     name = filepath if isinstance(filepath, str) else "<memory>"
-    text = _cut(_read_text(filepath), nrec, skip, bool(seek_first_rec))
+    text, _ = _cut(_read_text(filepath), nrec, skip, bool(seek_first_rec), name)
     lk = dna_lkup() if lkup is None else np.ascontiguousarray(lkup, dtype=np.int32)
     buf = text if isinstance(text, np.ndarray) else np.frombuffer(text, dtype=np.uint8)
     h = C.c_void_p()
@@ -172,7 +210,15 @@ def readDNAStringSet(filepath, format="fasta", nrec=-1, skip=0, seek_first_rec=F
     if format != "fasta":
         raise ValueError("only format=\"fasta\" is on this path")
     if isinstance(filepath, (list, tuple)):
-        parts = [readDNAStringSet(f, format, nrec, skip, seek_first_rec, use_names) for f in filepath]
+        # one record counter over the whole list, as read_fasta_files() keeps it
+        # (src/read_fasta_files.c:447-458, parse_FASTA_file: `*recno >= skip + nrec`): nrec and skip
+        # select records of the concatenated files, seek.first.rec applies to every file
+        nrec, skip = _normarg_nrec(nrec), _normarg_skip(skip)
+        texts = [_read_text(f) for f in filepath]
+        counts = [int(_record_starts(t if isinstance(t, np.ndarray) else np.frombuffer(t, dtype=np.uint8)).size)
+                  for t in texts]
+        parts = [readDNAStringSet(t, format, f_nrec, f_skip, seek_first_rec, use_names)
+                 for t, (f_nrec, f_skip) in zip(texts, _file_windows(counts, nrec, skip))]
         names = sum((p.names or [] for p in parts), []) if use_names else None
         return DNAStringSet(concat=np.concatenate([p.concat for p in parts]) if parts else np.zeros(0, np.uint8),
                             widths=np.concatenate([p.widths for p in parts]) if parts else np.zeros(0, np.int32),

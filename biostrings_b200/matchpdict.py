@@ -67,6 +67,39 @@ def normarg_fixed(fixed):
     return "pattern" in fixed, "subject" in fixed
 
 
+def recycle_numeric_arg(arg, argname, length_out):
+    """recycleNumericArg() of S4Vectors as R/matchPDict.R:541-560 uses it for 'weight' (the package
+    is not vendored in the reference tree; texts as in S4Vectors/R/utils.R): a numeric vector
+    without NAs, neither empty nor longer than what it is recycled to; recycling to a length that
+    is not a multiple of its own warns the way R's `ans[] <- x` does."""
+    import warnings
+    a = np.asarray(arg)
+    if isinstance(arg, (bool, np.bool_)) or a.dtype.kind not in "iuf":
+        raise ValueError(f"'{argname}' must be a numeric vector")
+    a = np.atleast_1d(a)
+    if a.dtype.kind != "f":
+        a = a.astype(np.int32)
+    if length_out == 0:
+        if a.size > 1:
+            raise ValueError(f"invalid length for '{argname}'")
+    elif a.size == 0:
+        raise ValueError(f"'{argname}' has no elements")
+    elif a.size > length_out:
+        raise ValueError(f"'{argname}' is longer than the object it applies to")
+    if a.dtype.kind == "f" and np.isnan(a).any():
+        raise ValueError(f"'{argname}' contains NAs")
+    if a.size and length_out % a.size != 0:
+        warnings.warn("number of items to replace is not a multiple of replacement length")
+    return np.resize(a, length_out) if a.size else a
+
+
+def check_weight_without_collapse(weight):
+    """R/matchPDict.R:559-561: `if (!identical(weight, 1L)) warning(...)`."""
+    import warnings
+    if not (isinstance(weight, (int, np.integer)) and not isinstance(weight, bool) and int(weight) == 1):
+        warnings.warn("'weight' is ignored when 'collapse=FALSE'")
+
+
 def normarg_collapse(collapse):
     if collapse is False:
         return 0
@@ -541,11 +574,13 @@ def _vmatch_plain(pset, subject, max_mismatch, min_mismatch, with_indels, fixed,
         fixed = normarg_fixed(fixed)
         if mode == MATCHES_AS_COUNTS:
             collapse = normarg_collapse(collapse)
-            weight = np.atleast_1d(np.asarray(weight))
             if collapse == 1:
-                weight = np.resize(weight, N)
+                weight = recycle_numeric_arg(weight, "weight", N)
             elif collapse == 2:
-                weight = np.resize(weight, M)
+                weight = recycle_numeric_arg(weight, "weight", M)
+            else:
+                check_weight_without_collapse(weight)
+                weight = np.ones(1, dtype=np.int32)
         else:
             collapse = 0
         algo = _check_plain_args(pset, max_mismatch, min_mismatch, with_indels, fixed, algorithm, mode)
@@ -599,11 +634,13 @@ def _vmatch_pdict(pdict, subject, max_mismatch, min_mismatch, fixed, collapse, w
         fixed = normarg_fixed(fixed)
         if mode == MATCHES_AS_COUNTS:
             collapse = normarg_collapse(collapse)
-            weight = np.atleast_1d(np.asarray(weight))
-            if collapse == 1:
-                weight = np.resize(weight, N)
+            if collapse == 0:
+                check_weight_without_collapse(weight)
+                weight = np.ones(1, dtype=np.int32)
+            elif collapse == 1:
+                weight = recycle_numeric_arg(weight, "weight", N)
             elif collapse == 2:
-                weight = np.resize(weight, M).copy()
+                weight = recycle_numeric_arg(weight, "weight", M).copy()
                 if which_pp_excluded is not None and which_pp_excluded.size:
                     # R/matchPDict.R:547-558: duplicates' weights are folded into the
                     # representative's before the C call

@@ -64,6 +64,7 @@ def lib():
                                      C.c_void_p, C.c_void_p]
         L.ref_pptb_blank_dups.argtypes = [C.c_void_p]
         L.ref_pptb_free.argtypes = [C.c_void_p]
+        L.ref_pptb_detach_device.argtypes = [C.c_void_p]
         L.ref_actree2_nnodes.argtypes = [C.c_void_p]
         L.ref_actree2_has_all_flinks.argtypes = [C.c_void_p]
         L.ref_actree2_compute_all_flinks.argtypes = [C.c_void_p]
@@ -355,8 +356,8 @@ def dna_lkup():
 
 
 def read_fasta(text, lkup=None, nrec=-1, skip=0, seek_first_rec=False, use_names=True):
-    """read_fasta_files() on one in-memory file -> (widths int32[n], concat uint8, names or None,
-    warning text).  `text`: bytes."""
+    """read_fasta_files() on one in-memory file, or on a list of them (one record counter over
+    the list) -> (widths int32[n], concat uint8, names or None, warning text).  `text`: bytes."""
     L = lib()
     L.ref_read_fasta.argtypes = [C.c_char_p, C.c_long, C.c_void_p, C.c_int] + [C.c_int] * 4
     L.ref_result_set_widths.restype = C.c_long
@@ -366,9 +367,16 @@ def read_fasta(text, lkup=None, nrec=-1, skip=0, seek_first_rec=False, use_names
     L.ref_result_set_names.argtypes = [C.c_char_p, C.c_long]
     lk = dna_lkup() if lkup is None else _i32(lkup)
     L.ref_clear_warning()
-    text = bytes(text)
-    _check(L.ref_read_fasta(text, len(text), _ptr(lk), len(lk), nrec, skip, int(seek_first_rec),
-                            int(use_names)), L)
+    if isinstance(text, (list, tuple)):
+        sizes = (C.c_long * len(text))(*[len(t) for t in text])
+        text = b"".join(bytes(t) for t in text)
+        L.ref_read_fasta_multi.argtypes = [C.c_char_p, C.POINTER(C.c_long), C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 4
+        _check(L.ref_read_fasta_multi(text, sizes, len(sizes), _ptr(lk), len(lk), nrec, skip,
+                                      int(seek_first_rec), int(use_names)), L)
+    else:
+        text = bytes(text)
+        _check(L.ref_read_fasta(text, len(text), _ptr(lk), len(lk), nrec, skip, int(seek_first_rec),
+                                int(use_names)), L)
     n = L.ref_result_set_length()
     widths = np.empty(n, dtype=np.int32)
     total = L.ref_result_set_widths(_ptr(widths))

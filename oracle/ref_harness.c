@@ -223,6 +223,26 @@ int ref_pptb_blank_dups(void *pptb_)
 	GUARD_END(0, -1)
 }
 
+/* Hooks of the product's dispatch library (absent from the reference library: weak). */
+extern SEXP bsgpu_dispatch_detach(SEXP pptb) __attribute__((weak));
+extern int bsgpu_dispatch_live_indexes(void) __attribute__((weak));
+
+/* Forget the device index an object carries, as readRDS() would hand the object back. */
+int ref_pptb_detach_device(void *pptb)
+{
+	if (bsgpu_dispatch_detach == NULL)
+		return -1;
+	GUARD_BEGIN
+	minir_set_generation(2);
+	bsgpu_dispatch_detach(pptb);
+	GUARD_END(0, -1)
+}
+
+int ref_dispatch_live_indexes(void)
+{
+	return bsgpu_dispatch_live_indexes == NULL ? -1 : bsgpu_dispatch_live_indexes();
+}
+
 void ref_pptb_free(void *pptb)
 {
 	minir_free_object(pptb);
@@ -520,6 +540,32 @@ int ref_read_fasta(const char *text, long nbytes, const int *lkup, int lkup_leng
 	SET_VECTOR_ELT(files, 0, minir_new_filexp(text, nbytes));
 	names = NEW_CHARACTER(1);
 	SET_STRING_ELT(names, 0, Rf_mkChar("<memory>"));
+	SET_NAMES(files, names);
+	result = read_fasta_files(files, Rf_ScalarInteger(nrec), Rf_ScalarInteger(skip),
+			Rf_ScalarLogical(seek_first_rec), Rf_ScalarLogical(use_names),
+			Rf_mkString("DNAString"),
+			lkup != NULL ? new_int(lkup_length, lkup) : R_NilValue);
+	GUARD_END(0, -1)
+}
+
+/* several in-memory files in one call: texts back to back, nbytes[i] each (one record counter over
+   the whole list, src/read_fasta_files.c:447-458) */
+int ref_read_fasta_multi(const char *texts, const long *nbytes, int nfiles, const int *lkup, int lkup_length,
+		int nrec, int skip, int seek_first_rec, int use_names)
+{
+	SEXP files, names;
+	long off = 0;
+	int i;
+
+	GUARD_BEGIN
+	minir_set_generation(2);
+	files = NEW_LIST(nfiles);
+	names = NEW_CHARACTER(nfiles);
+	for (i = 0; i < nfiles; i++) {
+		SET_VECTOR_ELT(files, i, minir_new_filexp(texts + off, nbytes[i]));
+		SET_STRING_ELT(names, i, Rf_mkChar("<memory>"));
+		off += nbytes[i];
+	}
 	SET_NAMES(files, names);
 	result = read_fasta_files(files, Rf_ScalarInteger(nrec), Rf_ScalarInteger(skip),
 			Rf_ScalarLogical(seek_first_rec), Rf_ScalarLogical(use_names),

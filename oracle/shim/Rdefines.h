@@ -45,6 +45,7 @@ struct minir_sexp {
 	struct minir_slot *slots;/* S4 objects */
 	void *xptr;              /* external pointers / shim payload */
 	SEXP tag, prot;          /* external pointers */
+	void (*fin)(struct minir_sexp *);  /* C finalizer of an external pointer (run when it is freed) */
 	struct minir_sexp *prev, *next;
 };
 
@@ -132,6 +133,9 @@ SEXP R_MakeExternalPtr(void *p, SEXP tag, SEXP prot);
 SEXP R_ExternalPtrTag(SEXP x);
 SEXP R_ExternalPtrProtected(SEXP x);
 void *R_ExternalPtrAddr(SEXP x);
+void R_SetExternalPtrAddr(SEXP x, void *p);
+typedef void (*R_CFinalizer_t)(SEXP);
+void R_RegisterCFinalizerEx(SEXP x, R_CFinalizer_t fun, Rboolean onexit);
 SEXP R_lsInternal(SEXP env, Rboolean all);
 
 char *S_alloc(long n, int size);

@@ -170,6 +170,13 @@ static void free_sexp(SEXP x)
 {
 	struct minir_slot *s, *s2;
 
+	if (x->type == EXTPTRSXP && x->fin != NULL) {
+		void (*fin)(SEXP) = x->fin;
+
+		x->fin = NULL;
+		fin(x);
+	}
+
 	if (x->prev != NULL)
 		x->prev->next = x->next;
 	else
@@ -493,6 +500,15 @@ SEXP R_MakeExternalPtr(void *p, SEXP tag, SEXP prot)
 SEXP R_ExternalPtrTag(SEXP x) { return x->tag; }
 SEXP R_ExternalPtrProtected(SEXP x) { return x->prot; }
 void *R_ExternalPtrAddr(SEXP x) { return x->xptr; }
+void R_SetExternalPtrAddr(SEXP x, void *p) { x->xptr = p; }
+
+/* the finalizer runs when the external pointer is freed (minir_release_scratch after
+   minir_free_object: the stand-in for R's garbage collector) */
+void R_RegisterCFinalizerEx(SEXP x, R_CFinalizer_t fun, Rboolean onexit)
+{
+	(void) onexit;
+	x->fin = fun;
+}
 
 SEXP R_lsInternal(SEXP env, Rboolean all)
 {
@@ -892,6 +908,14 @@ SEXP new_XInteger_from_tag(const char *classname, SEXP tag)
 
 	SET_SLOT(x, Rf_install("tag"), tag);
 	x->length = tag->length;
+	{
+		/* XVector: x@shared is a SharedVector whose @xp external pointer carries the data
+		   vector as its tag (XVector/src/SharedVector_class.c) */
+		SEXP shared = NEW_OBJECT(MAKE_CLASS("SharedInteger"));
+
+		SET_SLOT(shared, Rf_install("xp"), R_MakeExternalPtr(NULL, tag, R_NilValue));
+		SET_SLOT(x, Rf_install("shared"), shared);
+	}
 	return x;
 }
 

@@ -183,15 +183,42 @@ def test_nrec_skip_seek_first_rec_cut_equals_reference():
     clean = text[text.index(b">"):]
     for nrec, skip in [(-1, 0), (3, 0), (-1, 2), (2, 4), (0, 0), (5, 7), (-1, 9), (4, 20)]:
         w, c, names, warn = ref.read_fasta(clean, nrec=nrec, skip=skip)
-        got = OF.read_fasta(_cut(clean, nrec, skip, False))
+        got = OF.read_fasta(_cut(clean, nrec, skip, False)[0])
         assert got[0].tolist() == w.tolist() and np.array_equal(got[1], c) and got[2] == names
         w, c, names, warn = ref.read_fasta(text, nrec=nrec, skip=skip, seek_first_rec=True)
-        got = OF.read_fasta(_cut(text, nrec, skip, True))
+        got = OF.read_fasta(_cut(text, nrec, skip, True)[0])
         assert got[0].tolist() == w.tolist() and np.array_equal(got[1], c) and got[2] == names
     with pytest.raises(ref.RefError, match="no FASTA record found"):
         ref.read_fasta(b"junk\nmore junk\n", seek_first_rec=True)
     with pytest.raises(ValueError, match="no FASTA record found"):
         _cut(b"junk\nmore junk\n", -1, 0, True)
+    # sequence data in front of the first record is an error whatever `skip` says
+    with pytest.raises(ref.RefError, match='">" expected at beginning of line 3'):
+        ref.read_fasta(b";c\n\nACGT\n>a\nAC\n>b\nGT\n", skip=1)
+    with pytest.raises(Exception, match='">" expected at beginning of line 3'):
+        _cut(b";c\n\nACGT\n>a\nAC\n>b\nGT\n", -1, 1, False)
+
+
+@needs_ref
+def test_file_list_shares_one_record_counter():
+    """readDNAStringSet(<list of files>, nrec, skip): the per-file (nrec, skip) windows the product
+    derives (biostrings_b200.io._file_windows) applied file by file equal read_fasta_files() of
+    the reference on the whole list."""
+    from biostrings_b200.io import _cut, _file_windows, _record_starts
+    g = rng(5160)
+    files = [rand_fasta(g, n) for n in (4, 1, 6, 3)]
+    files = [f[f.index(b">"):] for f in files]
+    counts = [int(_record_starts(np.frombuffer(f, dtype=np.uint8)).size) for f in files]
+    for nrec, skip in [(-1, 0), (3, 2), (3, 0), (-1, 5), (6, 4), (2, 11), (0, 3), (50, 1), (1, 4)]:
+        w, c, names, warn = ref.read_fasta(files, nrec=nrec, skip=skip)
+        gw, gc, gn = [], [], []
+        for f, (f_nrec, f_skip) in zip(files, _file_windows(counts, nrec, skip)):
+            ww, cc, nn, _ = OF.read_fasta(_cut(f, f_nrec, f_skip, False)[0])
+            gw += ww.tolist()
+            gc.append(cc)
+            gn += nn or []
+        assert gw == w.tolist() and gn == (names or []), (nrec, skip)
+        assert np.array_equal(np.concatenate(gc) if gc else np.zeros(0, np.uint8), c)
 
 
 def test_chunk_walk_lines_longer_than_a_group(hostcheck):

@@ -234,3 +234,79 @@ def test_read_fasta_files_through_the_dot_call_boundary():
             ref.read_fasta(b"junk\n", seek_first_rec=True)
     finally:
         ref.use("ref")
+
+
+def _dispatch_lib():
+    ref.use("dispatch")
+    try:
+        return ref.lib()
+    finally:
+        ref.use("ref")
+
+
+@pytest.mark.parametrize("algo", ["ACtree2", "Twobit"])
+def test_device_index_lives_in_the_object(algo):
+    """The device index hangs on an external pointer of the PreprocessedTB object (finalizer frees
+    it); an object that comes back without it (readRDS) is rebuilt from its own slots, including
+    which patterns the build skipped (pp_exclude), and gives the same answers."""
+    g = rng(310)
+    s = random_dna(g, 20_000)
+    w = 12 if algo == "Twobit" else 20
+    pats = [s[i:i + w + 6].copy() for i in g.integers(0, 19_000, 120)]
+    pats += [pats[3].copy(), pats[3].copy(), np.concatenate([pats[5][:w], random_dna(g, 6)])]   # dups0 + a TB duplicate
+    a, b = pair(pats, algorithm=algo, tb_start=1, tb_end=w)
+    L = _dispatch_lib()
+    live0 = L.ref_dispatch_live_indexes()
+    assert live0 >= 1
+    want = {mm: R.countPDict(a, s, max_mismatch=mm).tolist() for mm in (0, 2)}
+    for mm in (0, 2):
+        assert R.countPDict(b, s, max_mismatch=mm).tolist() == want[mm]
+    # "readRDS": the pointer is gone, the next call rebuilds the index from the object
+    ref.use("dispatch")
+    try:
+        for tp in b.threeparts_list:
+            assert L.ref_pptb_detach_device(tp.pptb._h) == 0
+        assert L.ref_dispatch_live_indexes() == live0 - len(b.threeparts_list)
+        for mm in (0, 2):
+            assert R.countPDict(b, s, max_mismatch=mm).tolist() == want[mm]
+            assert R.whichPDict(b, s, max_mismatch=mm).tolist() == R.whichPDict(a, s, max_mismatch=mm).tolist()
+        assert L.ref_dispatch_live_indexes() == live0
+        # garbage collection of the object frees the device index
+        for tp in b.threeparts_list:
+            tp.pptb.close()
+        assert L.ref_dispatch_live_indexes() == live0 - len(b.threeparts_list)
+    finally:
+        ref.use("ref")
+
+
+def test_indels_through_the_dot_call_boundary():
+    g = rng(311)
+    s = random_dna(g, 5_000)
+    pats = []
+    for _ in range(30):
+        a0 = int(g.integers(0, 4_900))
+        p = s[a0:a0 + int(g.integers(8, 25))].copy()
+        if g.random() < 0.5:
+            p = np.delete(p, int(g.integers(0, len(p))))
+        pats.append(p)
+    pc, pw = np.concatenate(pats), np.array([len(p) for p in pats], dtype=np.int32)
+    reads = [s[i:i + 200].copy() for i in g.integers(0, 4_700, 12)]
+    sc, sw = np.concatenate(reads), np.array([len(r) for r in reads], dtype=np.int32)
+    out = {}
+    for which in ("ref", "dispatch"):
+        ref.use(which)
+        try:
+            out[which] = (
+                ref.match_set_xstring(pc, pw, s, 2, 0, True, (True, True), "indels", ref.MATCHES_AS_COUNTS).tolist(),
+                ref.match_set_xstring(pc, pw, s, 1, 0, True, (True, True), "indels", ref.MATCHES_AS_WHICH).tolist(),
+                ref.match_set_views(pc, pw, s, [1, 2000], [1500, 2500], 2, 0, True, (True, True), "indels",
+                                    ref.MATCHES_AS_COUNTS).tolist(),
+                np.asarray(ref.vmatch_set_set(pc, pw, sc, sw, 2, 0, True, (True, True), "indels", 0,
+                                              np.ones(1, np.int32), ref.MATCHES_AS_COUNTS)).tolist(),
+                np.asarray(ref.vmatch_set_set(pc, pw, sc, sw, 2, 0, True, (True, True), "indels", 1,
+                                              np.arange(1, len(reads) + 1, dtype=np.int32), ref.MATCHES_AS_COUNTS)).tolist(),
+                np.asarray(ref.vmatch_set_set(pc, pw, sc, sw, 2, 0, True, (True, True), "indels", 2,
+                                              np.linspace(0.5, 2.0, len(pats)), ref.MATCHES_AS_COUNTS)).tolist())
+        finally:
+            ref.use("ref")
+    assert out["ref"] == out["dispatch"] and sum(out["ref"][0]) > 10

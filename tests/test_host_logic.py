@@ -206,3 +206,32 @@ def test_plain_dictionary_argument_checks():
     assert R.naive_match_ends(enc("TG"), enc("GTGACGTGCAT"), 0, 0, True, True) == [3, 8]
     assert R.naive_match_ends(enc("---"), enc("ACGTGCA"), 3, 0, True, True) == list(range(1, 10))
     assert R.naive_match_ends(enc("---"), enc("A"), 0, 0, True, True) == []
+
+
+def test_weight_recycling_follows_recycleNumericArg():
+    """R/matchPDict.R:541-561: 'weight' goes through recycleNumericArg (numeric, no NA, not empty,
+    not longer than its target) when collapsing, and is warned about when it is not."""
+    import warnings
+    from biostrings_b200 import matchpdict as mp
+    assert mp.recycle_numeric_arg(2, "weight", 4).tolist() == [2, 2, 2, 2]
+    assert mp.recycle_numeric_arg([1, 2], "weight", 4).tolist() == [1, 2, 1, 2]
+    assert mp.recycle_numeric_arg(np.array([0.5]), "weight", 3).dtype == np.float64
+    with pytest.raises(ValueError, match="'weight' must be a numeric vector"):
+        mp.recycle_numeric_arg("a", "weight", 3)
+    with pytest.raises(ValueError, match="'weight' must be a numeric vector"):
+        mp.recycle_numeric_arg(True, "weight", 3)
+    with pytest.raises(ValueError, match="'weight' has no elements"):
+        mp.recycle_numeric_arg([], "weight", 3)
+    with pytest.raises(ValueError, match="'weight' is longer"):
+        mp.recycle_numeric_arg([1, 2, 3, 4], "weight", 3)
+    with pytest.raises(ValueError, match="'weight' contains NAs"):
+        mp.recycle_numeric_arg([1.0, float("nan")], "weight", 2)
+    with pytest.warns(UserWarning, match="not a multiple"):
+        assert mp.recycle_numeric_arg([1, 2], "weight", 3).tolist() == [1, 2, 1]
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        mp.check_weight_without_collapse(1)
+    with pytest.warns(UserWarning, match="'weight' is ignored when 'collapse=FALSE'"):
+        mp.check_weight_without_collapse(2)
+    with pytest.warns(UserWarning, match="'weight' is ignored when 'collapse=FALSE'"):
+        mp.check_weight_without_collapse(1.0)
