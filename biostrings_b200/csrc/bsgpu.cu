@@ -3487,10 +3487,45 @@ static int bsgpu_count_indels_impl(const bsgpu_pdict3parts *plain, const bsgpu_s
 		return BSGPU_OK;
 	std::vector<int64_t> pat_off((size_t) M + 1);
 	CUDA_TRY(cudaMemcpy(pat_off.data(), plain->d_pat_off.p, ((size_t) M + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
-	for (int32_t i = 0; i < M; i++)
-		if (pat_off[(size_t) i + 1] - pat_off[(size_t) i] <= max_mismatch)
-			return fail(BSGPU_EUNSUPPORTED, "with.indels=TRUE: pattern %d is not longer than max.mismatch "
-				    "(the reference counts such patterns with its mismatch-only loop)", i + 1);
+	// Patterns not longer than max.mismatch are counted by the reference's mismatch-only loop
+	// whatever the algorithm (src/match_pattern.c:95-96): they go through the plain-dictionary
+	// kernel as a dictionary of their own; the indels kernels skip them.
+	{
+		std::vector<int32_t> short_ids, short_w;
+		std::vector<uint8_t> short_letters;
+		for (int32_t i = 0; i < M; i++) {
+			int64_t plen = pat_off[(size_t) i + 1] - pat_off[(size_t) i];
+
+			if (plen <= max_mismatch) {
+				size_t at = short_letters.size();
+
+				short_ids.push_back(i);
+				short_w.push_back((int32_t) plen);
+				short_letters.resize(at + (size_t) plen);
+				CUDA_TRY(cudaMemcpy(short_letters.data() + at, plain->d_pat.p + pat_off[(size_t) i], (size_t) plen,
+						    cudaMemcpyDeviceToHost));
+			}
+		}
+		if (!short_ids.empty()) {
+			bsgpu_pdict3parts *sp = nullptr;
+			bsgpu_result r;
+			const bsgpu_pdict3parts *spc;
+
+			TRY(bsgpu_patterns_build(short_letters.data(), short_w.data(), (int32_t) short_ids.size(), &sp));
+			spc = sp;
+			int rc = per_sequence
+				? bsgpu_vmatch(&spc, 1, subj, max_mismatch, 0, fixedP, fixedS, 0, 0, nullptr, 0,
+					       BSGPU_MATCHES_AS_COUNTS, &r)
+				: bsgpu_match(&spc, 1, subj, max_mismatch, 0, fixedP, fixedS, BSGPU_MATCHES_AS_COUNTS, &r);
+			bsgpu_pdict3parts_free(sp);
+			TRY(rc);
+			const int64_t ns = (int64_t) short_ids.size();
+			for (int64_t j = 0; j < N; j++)
+				for (int64_t k = 0; k < ns; k++)
+					counts_out[j * M + short_ids[(size_t) k]] = r.counts[j * ns + k];
+			bsgpu_result_free(&r);
+		}
+	}
 	cudaStream_t st = 0;
 	DevBuf<int16_t> d_first;
 	DevBuf<unsigned long long> d_keys, d_n;

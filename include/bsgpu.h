@@ -314,8 +314,9 @@ int bsgpu_mindex_combine(const bsgpu_result *const *components, int ncomponents,
  * independent subject.  counts_out: M entries, or M x N column-major when per_sequence != 0.
  * The per-position core (csrc/bsgpu_indels.cuh) equals the reference on the CPU
  * (tests/test_indels_oracle.py), the engine equals it on the device (tests/test_gpu_indels.py).
- * Limits: 1 <= max_mismatch <= 15, every pattern longer than
- * max_mismatch, no subject chunks, min.mismatch = 0 (R/match-utils.R:54-57).
+ * Patterns not longer than max_mismatch are counted without indels, as the reference does
+ * (src/match_pattern.c:95-96).  Limits: 1 <= max_mismatch <= 15, no subject chunks,
+ * min.mismatch = 0 (R/match-utils.R:54-57).
  * ------------------------------------------------------------------------------------ */
 int bsgpu_count_indels(const bsgpu_pdict3parts *plain, const bsgpu_subject *subject, int max_mismatch,
 		int fixedP, int fixedS, int per_sequence, int32_t *counts_out);

@@ -170,3 +170,23 @@ def test_letters_encoded_on_the_device():
         bs.device_subject_from_letters(bytes(bad))
     with pytest.raises(ValueError, match=r"key 90 \(char 'Z'\) not in lookup table"):
         bs.encode_dna(bytes(bad))
+
+
+def test_file_list_nrec_skip_share_one_record_counter(tmp_path):
+    """readDNAStringSet(c(f1, f2, f3), nrec, skip): nrec / skip select records of the concatenated
+    files (src/read_fasta_files.c:447-458), checked against the reference on the same list."""
+    g = rng(8800)
+    texts = []
+    for k, n in enumerate((3, 1, 5)):
+        recs = [f">f{k}r{i} d\n{bs.decode_dna(random_dna(g, int(g.integers(0, 90))))}\n" for i in range(n)]
+        texts.append("".join(recs).encode())
+    paths = []
+    for k, t in enumerate(texts):
+        p = tmp_path / f"f{k}.fa"
+        p.write_bytes(t)
+        paths.append(str(p))
+    for nrec, skip in [(-1, 0), (3, 2), (-1, 4), (2, 3), (5, 1), (0, 0), (1, 8), (9, 9)]:
+        got = bs.readDNAStringSet(paths, nrec=nrec, skip=skip)
+        w, c, names, _ = ref.read_fasta(texts, nrec=nrec, skip=skip)
+        assert got.widths.tolist() == w.tolist() and np.array_equal(got.concat, c), (nrec, skip)
+        assert (got.names or []) == (names or [])

@@ -90,7 +90,15 @@ def test_views_and_sets_are_independent_subjects():
 
 
 def test_limits():
-    with pytest.raises(bs.BsgpuError, match="not longer than max.mismatch"):
-        bs.countPDict(bs.DNAStringSet(["AC", "ACGTACGT"]), "ACGTACGT", max_mismatch=2, with_indels=True)
+    # a pattern not longer than max.mismatch is counted by the mismatch-only loop
+    # (src/match_pattern.c:95-96), out-of-limits matches included
+    S = bs.encode_dna("ACGTACGTTTACGGA")
+    pats = [bs.encode_dna(p) for p in ("AC", "ACGTACGT", "G", "TTT")]
+    got = bs.countPDict(bs.DNAStringSet(pats), S, max_mismatch=2, with_indels=True)
+    assert got.tolist() == want_counts(pats, S, 2)
+    sset = bs.DNAStringSet([S[:7], S[5:], S[:0]])
+    mat = bs.vcountPDict(bs.DNAStringSet(pats), sset, max_mismatch=2, with_indels=True)
+    assert mat.tolist() == np.stack([want_counts(pats, S[:7], 2), want_counts(pats, S[5:], 2),
+                                     want_counts(pats, S[:0], 2)], axis=1).tolist()
     with pytest.raises(ValueError, match="only countPDict"):
         bs.matchPDict(bs.DNAStringSet(["ACGT"]), "ACGT", max_mismatch=1, with_indels=True)

@@ -194,8 +194,12 @@ def test_through_the_dot_call_boundary():
             assert np.array_equal(np.asarray(a), np.asarray(b))
     ref.use("dispatch")
     try:
-        with pytest.raises(ref.RefError, match="not supported on the GPU path"):
-            ref.match_set_xstring(pc, pw, s, 1, 0, 1, (1, 1), "indels", ref.MATCHES_AS_COUNTS)
+        # with.indels: patterns of 1 letter (<= max.mismatch) take the mismatch-only loop
+        got = ref.match_set_xstring(pc, pw, s, 1, 0, 1, (1, 1), "indels", ref.MATCHES_AS_COUNTS)
+        ref.use("ref")
+        want = ref.match_set_xstring(pc, pw, s, 1, 0, 1, (1, 1), "indels", ref.MATCHES_AS_COUNTS)
+        ref.use("dispatch")
+        assert np.array_equal(got, want)
         with pytest.raises(ref.RefError, match="empty patterns"):
             ref.match_set_xstring(pc[:3], [3, 0], s, 0, 0, 0, (1, 1), "naive-exact", ref.MATCHES_AS_COUNTS)
     finally:
