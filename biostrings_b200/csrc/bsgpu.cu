@@ -2780,9 +2780,11 @@ static int bsgpu_match_impl(const bsgpu_pdict3parts *const *parts, int nparts,
 			// row_cursor[M + 1] = number of long rows
 			order_rows_kernel<<<grid_for(M, 256, 16), 256, 0, st>>>(ws->rec2.p, d_off.p, d_counts.p, M,
 					ws->big_rows.p, ws->row_cursor.p + M + 1);
-			bitonic_rows_kernel<<<256, 1024, 0, st>>>(ws->rec2.p, d_off.p, d_counts.p, ws->big_rows.p,
-								   ws->row_cursor.p + M + 1);
-			g_launches += 6;
+			bitonic_rows_kernel<<<g_num_sms * 16, 128, 0, st>>>(ws->rec2.p, d_off.p, d_counts.p, ws->big_rows.p,
+									     ws->row_cursor.p + M + 1, 0u, 8192u);
+			bitonic_rows_kernel<<<g_num_sms, 1024, 0, st>>>(ws->rec2.p, d_off.p, d_counts.p, ws->big_rows.p,
+									 ws->row_cursor.p + M + 1, 8192u, 0xFFFFFFFFu);
+			g_launches += 7;
 			CUDA_TRY(cudaGetLastError());
 			ordered = ws->rec2.p;
 		} else if (!compact) {

@@ -878,16 +878,21 @@ order_rows_kernel(unsigned long long *__restrict__ rows, const int64_t *__restri
 }
 
 // one block per long row: bitonic sort in place (the row is padded to a power of two with
-// virtual +infinity elements)
+// virtual +infinity elements).  Launched twice: small blocks (cheap barriers, many rows in flight)
+// for the rows of n_lo < n <= n_hi records, 1024 threads for the few longer ones.
 __global__ void __launch_bounds__(1024)
 bitonic_rows_kernel(unsigned long long *__restrict__ rows, const int64_t *__restrict__ row_off,
-		    const int32_t *__restrict__ counts, const int32_t *__restrict__ big, const int32_t *__restrict__ n_big)
+		    const int32_t *__restrict__ counts, const int32_t *__restrict__ big, const int32_t *__restrict__ n_big,
+		    unsigned int n_lo, unsigned int n_hi)
 {
 	for (int b = blockIdx.x; b < *n_big; b += gridDim.x) {
 		int32_t key = big[b];
 		unsigned long long *row = rows + row_off[key];
 		const unsigned int n = (unsigned int) counts[key];
 		unsigned int np2 = 1;
+
+		if (n <= n_lo || n > n_hi)
+			continue;               // the other launch's row (uniform over the block)
 
 		while (np2 < n)
 			np2 <<= 1;

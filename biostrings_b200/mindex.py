@@ -37,23 +37,38 @@ class ByPos_MIndex:
         r = self._row(i)
         return self.ends[self.offsets[r]:self.offsets[r + 1]]
 
+    def _as_list(self, values):
+        """values (aligned with self.ends) cut into one array per pattern, None where the reference
+        has NULL; one numpy split over the non-empty rows instead of a Python loop over all M
+        patterns (a 4.5 M-pattern result spends seconds in such a loop; the reference's
+        elementNROWS(endIndex(x)) on it is the 23-31 s of SolexaYi2-benchmark.txt:127-136)."""
+        rows = self._rows()
+        lo, hi = self.offsets[rows], self.offsets[rows + 1]
+        out = [None] * len(self)
+        nz = np.flatnonzero(hi > lo)
+        if nz.size == 0:
+            return out
+        if self.dups0 is None:
+            # rows are the patterns themselves, in CSR order: one split of the whole array
+            pieces = np.split(values, hi[nz][:-1])
+            pieces[0] = pieces[0][lo[nz[0]]:] if lo[nz[0]] else pieces[0]
+            for i, p in zip(nz.tolist(), pieces):
+                out[i] = p
+            return out
+        for i in nz.tolist():
+            out[i] = values[lo[i]:hi[i]].copy()
+        return out
+
     def endIndex(self):
         """list of int arrays, None where the reference has NULL
         (ByPos_MIndex_endIndex(high2low, ends, NULL), src/MIndex_class.c:134-158)."""
-        out = []
-        for i in range(len(self)):
-            e = self._ends_of(i)
-            out.append(e.copy() if e.size else None)
-        return out
+        return self._as_list(self.ends)
 
     def startIndex(self):
-        """ends - width0 + 1 per pattern (src/MIndex_class.c:149-154)."""
-        out = []
-        for i in range(len(self)):
-            r = self._row(i)
-            e = self.ends[self.offsets[r]:self.offsets[r + 1]]
-            out.append(e + (1 - int(self.width0[r])) if e.size else None)
-        return out
+        """ends - width0 + 1 per pattern (src/MIndex_class.c:149-154); a duplicate gets its low
+        element's starts (same width)."""
+        n = np.diff(self.offsets)
+        return self._as_list(self.ends - np.repeat(self.width0, n).astype(np.int32) + 1)
 
     def elementNROWS(self):
         """Number of matches per pattern, from the CSR offsets (no list is built)."""
@@ -109,12 +124,10 @@ class ByPos_MIndex:
         s, e = self.unlist()
         if width is None:
             width = int(e.max()) if e.size else 0
-        d = np.zeros(width + 2, dtype=np.int64)
         lo = np.clip(s.astype(np.int64), 1, width + 1)
         hi = np.clip(e.astype(np.int64) + 1, 1, width + 1)
         keep = hi > lo
-        np.add.at(d, lo[keep], 1)
-        np.add.at(d, hi[keep], -1)
+        d = np.bincount(lo[keep], minlength=width + 2) - np.bincount(hi[keep], minlength=width + 2)
         return np.cumsum(d)[1:width + 1].astype(np.int32)
 
 

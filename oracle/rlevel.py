@@ -372,6 +372,42 @@ class MIndex:
     def elementNROWS(self):
         return np.array([0 if e is None else len(e) for e in self.endIndex()], dtype=np.int32)
 
+    def unlist(self, use_names=True):
+        """unlist(<MIndex>), R/MIndex-class.R:56-79: start / end of every match, pattern-major,
+        built from startIndex() / endIndex() exactly as the R method does; names repeated per
+        match when the dictionary has names.  -> (start, end, names or None)."""
+        si, ei = self.startIndex(), self.endIndex()
+        s = [x for x in si if x is not None]
+        e = [x for x in ei if x is not None]
+        ans_start = np.concatenate(s).astype(np.int32) if s else np.zeros(0, np.int32)
+        ans_end = np.concatenate(e).astype(np.int32) if e else np.zeros(0, np.int32)
+        names = None
+        if use_names and self.names is not None:
+            names = [nm for nm, x in zip(self.names, ei) for _ in range(0 if x is None else len(x))]
+        return ans_start, ans_end, names
+
+    def coverage(self, width=None):
+        """coverage(<MIndex>): the IRanges method on unlist(x) -- for every subject position
+        1..width the number of matches covering it (ranges are clipped to 1..width, as
+        IRanges::coverage does with its default shift=0 / given width); width defaults to the
+        largest end."""
+        s, e, _ = self.unlist(use_names=False)
+        if width is None:
+            width = int(e.max()) if e.size else 0
+        cov = np.zeros(max(width, 0), dtype=np.int32)
+        for a, b in zip(s.tolist(), e.tolist()):        # plain loop: this is the oracle
+            a, b = max(a, 1), min(b, width)
+            if b >= a:
+                cov[a - 1:b] += 1
+        return cov
+
+
+def extractAllMatches(subject, mindex):
+    """R/MIndex-class.R:91-103: views (start, width, names) of all matches on the unmasked subject;
+    unsafe.newXStringViews does not check the limits."""
+    s, e, names = mindex.unlist()
+    return s, e - s + 1, names
+
 
 def mindex_combine(ends_listlist):
     """ByPos_MIndex_combine, src/MIndex_class.c:230-263."""
