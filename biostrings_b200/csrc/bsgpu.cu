@@ -2042,27 +2042,30 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 				int per_sm = 1;
 				const char *env_v = getenv("BSGPU_XSEED_VARIANT");     // experiments (tools/bench_exact.py)
 				int var = env_v ? atoi(env_v) : 0;
-#define PREPARE_XSEED(NP, AL, KB, V) do { \
+				const bool fused = getenv("BSGPU_XSEED_SPLIT_CONFIRM") == nullptr && var == 0;
+#define PREPARE_XSEED(NP, AL, KB, V, FU) do { \
 	static bool attr_set = false; \
 	if (!attr_set) { \
-		CUDA_TRY(cudaFuncSetAttribute(scan_xseed_kernel<NP, AL, KB, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+		CUDA_TRY(cudaFuncSetAttribute(scan_xseed_kernel<NP, AL, KB, V, FU>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
 			BSGPU_XSEED_WARPS * BSGPU_XSEED_STAGES * (int) xseed_stage_bytes(NP, AL ? 16 : 32, AL))); \
 		attr_set = true; \
 	} \
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_xseed_kernel<NP, AL, KB, V>, 256, smem)); \
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_xseed_kernel<NP, AL, KB, V, FU>, 256, smem)); \
 } while (0)
-#define LAUNCH_XSEED(NP, AL, KB, V) \
-	scan_xseed_kernel<NP, AL, KB, V><<<grid, 256, smem, st>>>(S, xi->t, first, nprobes, ws->cand.p, cap, ws->xseed_counts.p)
-#define XSEED_DISPATCH(WHAT) do { \
-	if (var == 16 && aligned && np == 4 && xi->t.kbits == 4) { WHAT(4, true, 4, 16); } \
+#define LAUNCH_XSEED(NP, AL, KB, V, FU) \
+	scan_xseed_kernel<NP, AL, KB, V, FU><<<grid, 256, smem, st>>>(S, xi->t, R, first, nprobes, ws->cand.p, cap, \
+								      ws->xseed_counts.p, end_lo, end_hi)
+#define XSEED_DISPATCH2(WHAT, FU) do { \
+	if (var == 16 && aligned && np == 4 && xi->t.kbits == 4) { WHAT(4, true, 4, 16, false); } \
 	else if (xi->t.kbits == 8) { \
-		if (aligned) { if (np == 4) WHAT(4, true, 8, 0); else WHAT(2, true, 8, 0); } \
-		else { if (np == 4) WHAT(4, false, 8, 0); else WHAT(2, false, 8, 0); } \
+		if (aligned) { if (np == 4) WHAT(4, true, 8, 0, FU); else WHAT(2, true, 8, 0, FU); } \
+		else { if (np == 4) WHAT(4, false, 8, 0, FU); else WHAT(2, false, 8, 0, FU); } \
 	} else { \
-		if (aligned) { if (np == 4) WHAT(4, true, 4, 0); else WHAT(2, true, 4, 0); } \
-		else { if (np == 4) WHAT(4, false, 4, 0); else WHAT(2, false, 4, 0); } \
+		if (aligned) { if (np == 4) WHAT(4, true, 4, 0, FU); else WHAT(2, true, 4, 0, FU); } \
+		else { if (np == 4) WHAT(4, false, 4, 0, FU); else WHAT(2, false, 4, 0, FU); } \
 	} \
 } while (0)
+#define XSEED_DISPATCH(WHAT) do { if (fused) XSEED_DISPATCH2(WHAT, true); else XSEED_DISPATCH2(WHAT, false); } while (0)
 				XSEED_DISPATCH(PREPARE_XSEED);
 				int64_t ntile = (nprobes + (int64_t) np * 32 - 1) / ((int64_t) np * 32);
 				int grid = (int) std::max<int64_t>(1, std::min<int64_t>(
@@ -2081,18 +2084,19 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 				}
 				g_launches++;
 				CUDA_TRY(cudaGetLastError());
-				{
+				if (!fused) {
 					KernelTimer kt("confirm_xseed_kernel", st);
 					const char *env_c = getenv("BSGPU_XSEED_CONFIRM_BLOCKS");
 					int cx = env_c != nullptr && atoi(env_c) > 0 ? atoi(env_c) : 4;
 					confirm_xseed_kernel<<<dim3((unsigned) cx, (unsigned) grid), 256, 0, st>>>(
 						S, xi->t, R, ws->cand.p, cap, ws->xseed_counts.p, end_lo, end_hi);
+					g_launches++;
+					CUDA_TRY(cudaGetLastError());
 				}
 #undef PREPARE_XSEED
 #undef LAUNCH_XSEED
 #undef XSEED_DISPATCH
-				g_launches++;
-				CUDA_TRY(cudaGetLastError());
+#undef XSEED_DISPATCH2
 			}
 			return BSGPU_OK;
 		}

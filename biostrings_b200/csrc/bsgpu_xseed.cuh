@@ -215,6 +215,14 @@ __device__ __forceinline__ void xseed_confirm(const BsgpuSubjectView &S, const B
 	}
 }
 
+// out-of-line copy for the scan kernel (its parameters are __grid_constant__: their address is
+// the constant bank, nothing is copied for the call)
+__device__ __noinline__ void xseed_confirm_call(const BsgpuSubjectView *S, const BsgpuXSeedView *T,
+		const BsgpuReport *R, unsigned long long cand, int64_t own_lo, int64_t own_hi)
+{
+	xseed_confirm(*S, *T, *R, cand, own_lo, own_hi);
+}
+
 #define BSGPU_XSEED_WARPS 8             // all of them scan
 #define BSGPU_XSEED_STAGES 3
 #ifndef BSGPU_XSEED_MIN_BLOCKS
@@ -259,10 +267,16 @@ __host__ __device__ __forceinline__ int64_t xseed_warp_capacity(int64_t nprobes,
 // ALIGNED (S == 16 and first - 8 on a 16-byte boundary): a probe's 32 bytes are two aligned
 // 16-byte shared-memory chunks, consecutive lanes read consecutive chunks (no bank conflicts,
 // no realignment shifts).
-template <int NP, bool ALIGNED, int KB = 4, int VAR = 0, int STAGES = BSGPU_XSEED_STAGES, int MINB = BSGPU_XSEED_MIN_BLOCKS>
+// FUSED: a warp confirms its own candidates as soon as it holds 32 of them (and the rest when it
+// runs out of tiles), one per lane, while the other warps of the SM keep scanning: the DRAM round
+// trips of the confirmations hide under the scan and the second launch disappears.
+template <int NP, bool ALIGNED, int KB = 4, int VAR = 0, bool FUSED = true, int STAGES = BSGPU_XSEED_STAGES,
+	  int MINB = BSGPU_XSEED_MIN_BLOCKS>
 __global__ void __launch_bounds__(256, MINB)
-scan_xseed_kernel(BsgpuSubjectView S, BsgpuXSeedView T, int64_t first, int64_t nprobes,
-		  unsigned long long *__restrict__ cand, int64_t cap, unsigned int *__restrict__ n_cand)
+scan_xseed_kernel(const __grid_constant__ BsgpuSubjectView S, const __grid_constant__ BsgpuXSeedView T,
+		  const __grid_constant__ BsgpuReport R, int64_t first, int64_t nprobes,
+		  unsigned long long *__restrict__ cand, int64_t cap, unsigned int *__restrict__ n_cand,
+		  int64_t own_lo, int64_t own_hi)
 {
 	constexpr int NW = BSGPU_XSEED_WARPS;
 	extern __shared__ __align__(128) uint8_t xseed_smem[];
@@ -279,6 +293,7 @@ scan_xseed_kernel(BsgpuSubjectView S, BsgpuXSeedView T, int64_t first, int64_t n
 	const uint64_t policy = l2_policy_evict_first();
 	unsigned long long *mine = cand + gw * cap;
 	unsigned int n_mine = 0;                // candidates of this warp so far (the same in every lane)
+	unsigned int n_done = 0;                // ... of which confirmed (FUSED)
 
 	// tile tl -> the letters from 8 before its first probe on (16-byte aligned source)
 	auto issue = [&](int64_t tl, int stage) {
@@ -400,9 +415,22 @@ scan_xseed_kernel(BsgpuSubjectView S, BsgpuXSeedView T, int64_t first, int64_t n
 			}
 			n_mine += __popc(who);
 		}
+		if (FUSED && n_mine - n_done >= 32u) {
+			__syncwarp();           // the lanes' writes to the slice
+			do {
+				xseed_confirm_call(&S, &T, &R, mine[n_done + lane], own_lo, own_hi);
+				n_done += 32u;
+			} while (n_mine - n_done >= 32u);
+		}
+	}
+	if (FUSED) {
+		__syncwarp();
+		if ((unsigned int) lane < n_mine - n_done)
+			xseed_confirm_call(&S, &T, &R, mine[n_done + lane], own_lo, own_hi);
+		n_done = n_mine;
 	}
 	if (lane == 0)
-		n_cand[gw] = n_mine;
+		n_cand[gw] = n_mine - n_done;    // what confirm_xseed_kernel still has to do
 }
 
 // One candidate per thread.  blockIdx.y walks the scan blocks, whose 8 warps each left a slice:

@@ -49,7 +49,7 @@ def cut(g, s, w, k):
 
 
 ENGINES = {"xseed": {}, "xseed_np2": {"BSGPU_XSEED_NP": "2"}, "xseed_np4": {"BSGPU_XSEED_NP": "4"},
-           "xseed_kbits8": {"BSGPU_XSEED_KBITS": "8"},
+           "xseed_kbits8": {"BSGPU_XSEED_KBITS": "8"}, "xseed_split": {"BSGPU_XSEED_SPLIT_CONFIRM": "1"},
            "xseed_unaligned": {"BSGPU_XSEED_UNALIGNED": "1"}, "byteseed": {"BSGPU_NO_XSEED": "1"}}
 
 
@@ -65,7 +65,7 @@ def expect_engine(engine, w):
     assert ("xseed" in plan()) == (engine.startswith("xseed") and w >= 25), plan()
 
 
-@pytest.mark.parametrize("variant", ["xseed_np2", "xseed_np4", "xseed_kbits8", "xseed_unaligned"])
+@pytest.mark.parametrize("variant", ["xseed_np2", "xseed_np4", "xseed_kbits8", "xseed_unaligned", "xseed_split"])
 @pytest.mark.parametrize("w", [25, 31])
 def test_xseed_tile_variants(w, variant, monkeypatch):
     for k, v in ENGINES[variant].items():
