@@ -15,7 +15,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import biostrings_b200 as bs                                    # noqa: E402
-from biostrings_b200 import _lib, matchpdict as mp, synth       # noqa: E402
+from biostrings_b200 import _lib, matchpdict as mp, synth, workloads as W       # noqa: E402
 
 L = _lib.lib()
 
@@ -41,8 +41,8 @@ def c3(scale):
     """countPDict of 1M 36-mers, tb.start=1, tb.end=12, max.mismatch=2, 100 Mbp."""
     n = int(100e6 * scale)
     M = int(1e6 * scale) or 1000
-    subj = synth.subject_region(0, n, n, seed=5, with_n=False)
-    pats = synth.dictionary(M, 36, n, 1, seed=4, subject_seed=5, nsub=3, sub_lo=12)
+    subj = W.c3_subject(0, n, n)
+    pats = W.c3_dictionary(M, n)
     t0 = time.perf_counter()
     pd = bs.PDict(dna_set(pats), tb_start=1, tb_end=12)
     t_build = time.perf_counter() - t0
@@ -78,8 +78,8 @@ def c4(scale):
     """vcountPDict of 100k 25-mers against 10M x 150 bp reads, collapse=1 and 2."""
     nreads = int(1e7 * scale)
     M = int(1e5 * scale) or 1000
-    probes = synth.dictionary(M, 25, 10_000_000, 1, seed=6, frac_planted=0.0)
-    reads = synth.reads(nreads, 150, 0, seed=7, frac_planted=0.05, probes=probes)
+    probes = W.c4_probes(M)
+    reads = W.c4_reads(0, nreads, probes)
     t0 = time.perf_counter()
     pd = bs.PDict(dna_set(probes))
     t_build = time.perf_counter() - t0
@@ -102,20 +102,8 @@ def c5(scale):
     (387.5 Mbp) of a 3.1 Gbp genome with isolated IUPAC letters at rate 1e-3."""
     n = int(387.5e6 * scale)
     M = int(2e6 * scale) or 1000
-    g = np.random.Generator(np.random.PCG64(8))
-    subj = synth.subject_region(0, n, n, seed=9, with_n=False)
-    amb_pos = np.flatnonzero(g.random(n) < 1e-3)
-    amb_pos = amb_pos[np.concatenate([[True], np.diff(amb_pos) > 15])]
-    amb = np.array([3, 5, 9, 6, 10, 12, 7, 11, 13, 14, 15], dtype=np.uint8)
-    subj[amb_pos] = amb[g.integers(0, len(amb), amb_pos.size)]
-    widths = g.integers(15, 41, M).astype(np.int32)
-    total = int(widths.sum())
-    concat = synth.BASES[g.integers(0, 4, total, dtype=np.uint8)]
-    offs = np.concatenate([[0], np.cumsum(widths)])
-    clean = synth.subject_region(0, min(n, 8_000_000), n, seed=9, with_n=False)
-    for i in g.choice(M, M // 10, replace=False).tolist():      # 10 % cut from the subject
-        st = int(g.integers(0, clean.size - 40))
-        concat[offs[i]:offs[i + 1]] = clean[st:st + widths[i]]
+    subj = W.c5_genome_region(0, n)
+    concat, widths = W.c5_dictionary(M, max(n, 64 << 20))
     t0 = time.perf_counter()
     pd = bs.PDict(bs.DNAStringSet(concat=concat, widths=widths), tb_start=1, tb_width=15)
     t_build = time.perf_counter() - t0
