@@ -66,8 +66,16 @@ def main(launch_csv, rep, tag):
             if k in hdr:
                 out.append(f"| {k} | {last[hdr.index(k)]} | {units[hdr.index(k)]} |")
         out.append("")
-    with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
-        json.dump(traffic, f, indent=1)
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    merged = {}
+    if os.path.exists(tpath):           # captures of different kernels come from different runs
+        with open(tpath) as f:
+            merged = json.load(f)
+    for k, v in traffic.items():
+        v["capture"] = f"profiles/{tag}_ncu_raw.csv"
+        merged[k] = v
+    with open(tpath, "w") as f:
+        json.dump(merged, f, indent=1)
     with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md"), "w") as f:
         f.write("\n".join(out) + "\n")
     print("\n".join(out))
