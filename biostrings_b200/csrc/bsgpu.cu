@@ -398,6 +398,9 @@ struct QIndex {
 	BsgpuQIndexView v = {};
 	DevBuf<uint2> d_dir;
 	DevBuf<uint32_t> d_entries, d_bitmap;
+	DevBuf<uint2> d_cells2;                 // qscan2_kernel: rank directory
+	DevBuf<unsigned long long> d_entries2;  // ... and its 8-byte slots
+	size_t nent = 0;
 	DevBuf<ulonglong2> d_pat;
 	DevBuf<unsigned long long> d_pat8;
 	DevBuf<uint8_t> d_len;
@@ -606,6 +609,78 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 	for (size_t k2 = 0; k2 < nkeys; k2++)
 		if (cnt[k2] > 254)
 			return done();  // a very repetitive dictionary: keep the Trusted-Band engine
+	v.shift_bits = bits_for((unsigned long long) std::max(v.nshifts - 1, 1));
+	v.id_bits = bits_for((unsigned long long) std::max(M - 1, 1));
+	if (v.shift_bits + v.id_bits > 32)
+		return done();
+	// --- rank directory + inline patterns (qscan2_kernel) --------------------------------------
+	// constant width <= 29 (the pattern, the shift and two flags share 64 bits), the id fits
+	// under the seed shape, the split experiment is off
+	if (v.mode == 1 && v.const_len > 0 && v.const_len <= QS2_MAX_LEN && v.id_bits <= v.key_bits &&
+	    v.key_bits >= 4 && nent < ((size_t) 1 << 31) && getenv("BSGPU_Q_V1") == nullptr &&
+	    getenv("BSGPU_Q_SPLIT") == nullptr) {
+		size_t ncells = nkeys / 16, nmain = 0, nover = 0;
+		std::vector<uint2> cells(ncells, make_uint2(0u, 0u));
+		std::vector<uint32_t> at(nkeys);        // key -> its first slot, then the fill cursor
+
+		for (size_t k2 = 0; k2 < nkeys; k2++) {
+			uint32_t slots = std::min<uint32_t>(cnt[k2], 3u);
+
+			if ((k2 & 15) == 0)
+				cells[k2 >> 4].y = (uint32_t) nmain;
+			cells[k2 >> 4].x |= slots << (2 * (k2 & 15));
+			at[k2] = (uint32_t) nmain;
+			nmain += slots;
+			if (cnt[k2] > 3)
+				nover += cnt[k2] - 2;
+		}
+		std::vector<unsigned long long> slots(nmain + nover + 1, 0ull);
+		std::vector<uint8_t> filled(nkeys, 0);  // entries of the key placed so far (counts are <= 254)
+		size_t over_at = nmain;
+
+		for (int i = 0; i < M; i++) {
+			if (p0->excluded[i])
+				continue;
+			for (int s2 = 0; s2 < v.nshifts; s2++) {
+				int t = v.shift[s2];
+				uint32_t k2 = seed_key(i, t), c = cnt[k2], n = filled[k2]++;
+				unsigned long long e = (pat[i].x & ~(v.mask2 << (2 * t))) | (q2_deposit(v, (uint32_t) i) << (2 * t)) |
+						       ((unsigned long long) t << QS2_T_SHIFT);
+
+				if (c <= 3 || n < 2) {
+					slots[at[k2] + n] = e;
+					continue;
+				}
+				if (n == 2) {           // the third slot points at the chain
+					slots[at[k2] + 2] = QS2_PTR | (unsigned long long) over_at;
+					at[k2] = (uint32_t) over_at - 2;        // chain slot of entry n = at + n
+					over_at += c - 2;
+				}
+				slots[at[k2] + n] = e | (n + 1 < c ? QS2_MORE : 0ull);
+			}
+		}
+		TRY(qi->d_cells2.upload(cells.data(), cells.size()));
+		TRY(qi->d_entries2.upload(slots.data(), slots.size()));
+		TRY(qi->d_pat.upload(pat.data(), pat.size()));
+		{
+			std::vector<unsigned long long> p8(M);
+			for (int i = 0; i < M; i++)
+				p8[i] = pat[i].x;
+			TRY(qi->d_pat8.upload(p8.data(), p8.size()));
+			v.pat8 = qi->d_pat8.p;
+		}
+		TRY(qi->d_len.upload(plen.data(), plen.size()));
+		v.cells2 = qi->d_cells2.p;
+		v.entries2 = qi->d_entries2.p;
+		v.pat = qi->d_pat.p;
+		v.pat_len = qi->d_len.p;
+		v.v2 = 1;
+		v.nfp = 0;
+		qi->nent = nent;
+		qi->max_len = max_w;
+		qi->ok = true;
+		return done();
+	}
 	std::vector<uint2> dir(nkeys / 4);
 	std::vector<uint32_t> start(nkeys), bitmap(nkeys / 32, 0);
 	uint32_t run = 0;
@@ -623,10 +698,6 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 	// entry word = [fingerprint][pattern id][shift index]; the fingerprint is up to 4 pattern
 	// letters from outside the seed (the first positions of the window the shape, placed at
 	// that shift, does not cover): a cheap pre-check before the pattern is loaded
-	v.shift_bits = bits_for((unsigned long long) std::max(v.nshifts - 1, 1));
-	v.id_bits = bits_for((unsigned long long) std::max(M - 1, 1));
-	if (v.shift_bits + v.id_bits > 32)
-		return done();
 	v.nfp = std::min(4, (32 - v.shift_bits - v.id_bits) / 2);
 	if (getenv("BSGPU_Q_NFP") != nullptr)
 		v.nfp = std::min(v.nfp, std::max(0, atoi(getenv("BSGPU_Q_NFP"))));
@@ -672,6 +743,7 @@ static int get_qindex(const bsgpu_pdict3parts *const *parts, int nparts, const Q
 		v.pat8 = qi->d_pat8.p;
 	}
 	TRY(qi->d_len.upload(plen.data(), plen.size()));
+	qi->nent = nent;
 	v.dir = qi->d_dir.p;
 	v.entries = qi->d_entries.p;
 	v.pat = qi->d_pat.p;
@@ -2453,8 +2525,9 @@ static int run_q(const QIndex *qi, const bsgpu_subject *subj, const MatchParams 
 	int64_t nwords = ((probe_hi + 31) >> 5) - (probe_lo >> 5);
 	if (nwords <= 0)
 		return BSGPU_OK;
-	set_plan("qgram_%s q=%d shifts=%d stride=%d window=%d key_bits=%d entries=%zu", Q.mode ? "hamming" : "exact",
-		 Q.q, Q.nshifts, Q.stride, Q.min_w, Q.key_bits, qi->d_entries.n);
+	set_plan("qgram_%s q=%d shifts=%d stride=%d window=%d key_bits=%d entries=%zu %s", Q.mode ? "hamming" : "exact",
+		 Q.q, Q.nshifts, Q.stride, Q.min_w, Q.key_bits, qi->nent,
+		 Q.v2 ? "rank_directory+inline_patterns" : "bitmap+directory+entries");
 	// The split form (emit candidates, verify one per thread) measured slower than the
 	// warp-synchronous fused kernel on B200 (6.4 vs 3.7 ms per 250 Mbp); kept for experiments.
 	const char *env_f = getenv("BSGPU_Q_SPLIT");
@@ -2521,8 +2594,34 @@ static int run_q(const QIndex *qi, const bsgpu_subject *subj, const MatchParams 
 		{
 			const char *env_g = getenv("BSGPU_Q_GRID");     // blocks per SM of the grid-stride launch
 			int qgrid = env_g != nullptr && atoi(env_g) > 0 ? atoi(env_g) : 1024;
-			KernelTimer kt("qscan_kernel", st);
-			if (qi->max_len > 32)
+			KernelTimer kt(Q.v2 ? "qscan2_kernel" : "qscan_kernel", st);
+			if (Q.v2) {
+				// one batch of 32 words per warp
+				long long nbatches = (nwords + 31) / 32;
+#define QS2_LAUNCH(SH) qscan2_kernel<SH><<<grid_for(nbatches * 32, QS2_WARPS * 32, qgrid), QS2_WARPS * 32, 0, st>>>( \
+						subj->view(), Q, R, mp.max_nmis, mp.min_nmis, probe_lo, probe_hi, own_lo, own_hi)
+				// the shapes of csrc/bsgpu_shapes.inc for windows of <= 29 letters have their key
+				// extraction compiled in; any other shape goes through the generic kernel
+				// (BSGPU_Q_GENERIC: tests run the generic kernel on a known shape)
+				switch (getenv("BSGPU_Q_GENERIC") != nullptr ? 0ull : (unsigned long long) Q.shape1) {
+				case 0x1777ull: QS2_LAUNCH(0x1777ull); break;
+				case 0x3777ull: QS2_LAUNCH(0x3777ull); break;
+				case 0x7777ull: QS2_LAUNCH(0x7777ull); break;
+				case 0x1b6dbull: QS2_LAUNCH(0x1b6dbull); break;
+				case 0x36b6bull: QS2_LAUNCH(0x36b6bull); break;
+				case 0x7e3full: QS2_LAUNCH(0x7e3full); break;
+				case 0x1cb17ull: QS2_LAUNCH(0x1cb17ull); break;
+				case 0xe5cbull: QS2_LAUNCH(0xe5cbull); break;
+				case 0x5cb97ull: QS2_LAUNCH(0x5cb97ull); break;
+				case 0x165965ull: QS2_LAUNCH(0x165965ull); break;
+				case 0xfa9full: QS2_LAUNCH(0xfa9full); break;
+				case 0xe4ea7ull: QS2_LAUNCH(0xe4ea7ull); break;
+				case 0x4c8b97ull: QS2_LAUNCH(0x4c8b97ull); break;
+				case 0xFFFull: QS2_LAUNCH(0xFFFull); break;
+				default: QS2_LAUNCH(0ull); break;
+				}
+#undef QS2_LAUNCH
+			} else if (qi->max_len > 32)
 				qscan_kernel<true><<<grid_for(nwords, 256, qgrid), 256, 0, st>>>(subj->view(), Q, R,
 						mp.max_nmis, mp.min_nmis, probe_lo, probe_hi, own_lo, own_hi);
 			else

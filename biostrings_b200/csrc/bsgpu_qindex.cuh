@@ -53,6 +53,10 @@ struct BsgpuQIndexView {
 	int32_t shift_bits, id_bits;
 	int32_t nfp;                 // 0..4 pattern letters outside the seed kept in the entry
 	uint32_t fp_pos[BSGPU_Q_MAX_SHIFTS]; // per shift index: their pattern positions, one byte each
+	// rank directory + inline patterns (qscan2_kernel; constant width <= 29, mode 1): see below
+	int32_t v2;                  // 1: cells2 / entries2 are built
+	const uint2 *cells2;         // [2^key_bits / 16] {16 x 2-bit slot counts, index of the cell's first slot}
+	const unsigned long long *entries2;  // slots grouped by seed key, then the overflow chains
 };
 
 __host__ __device__ __forceinline__ int q_ent_shift(const BsgpuQIndexView &Q, uint32_t ent)
@@ -450,6 +454,314 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 				d_cell = __ldg(Q.dir + (d_key >> 2));
 				d_valid = true;
 			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------
+// qscan2_kernel: the Hamming filter with ONE gather per subject position and ONE per candidate.
+//
+// qscan_kernel sits on the L1 gather rate (one tag lookup per divergent lane): a bitmap word per
+// position, then directory cell -> entry -> pattern for each of the 0.42 candidates per position,
+// ~2.1 random sectors per position.  Here
+//   cells2   : 8 bytes per 16 seed keys = 16 two-bit slot counts + the index of the cell's first
+//              slot.  The position's one gather answers "any entry?" AND "where": the slots of key
+//              b start at  first + sum of the counts below b  (two popcounts).
+//   entries2 : 8-byte slots grouped by key.  A slot holds the WHOLE pattern in place (2 bits per
+//              letter, <= 29 letters) -- except that the 2q bits under the seed shape, which a
+//              candidate shares with the subject window by construction (the key is injective),
+//              carry the pattern id instead; bits 58..62 = the shift t the seed was cut at.
+//              So a candidate is decided by one 8-byte load, an XOR with the subject window (cut
+//              from the warp's shared-memory copy of the batch) under the complement of the
+//              shifted shape, and a popcount; the pattern table is read for real matches only.
+//              Keys with more than 3 entries (0.1 % at 7 M entries over 2^24 keys) keep two in
+//              place and a pointer slot to a chain behind the grouped slots.
+// Lane l of a warp owns the positions l, l + 32, ... of a batch of 1024: the slots a load group
+// found are handed to the warp's ring in shared memory by ballot (no prefix pass), and the ring is
+// drained 32 x QS2_U independent candidate loads at a time, so every lane has the same work
+// whatever the distribution of the entries over the positions.
+// ------------------------------------------------------------------------------------
+
+#define QS2_CAP 512             // ring items per warp (power of two)
+#define QS2_U 4                 // candidate loads in flight per lane
+#define QS2_WARPS 4
+#define QS2_PTR (1ull << 62)    // slot is a pointer: low 32 bits = index of the chain
+#define QS2_MORE (1ull << 63)   // chain slot: the next slot belongs to the same key
+#define QS2_T_SHIFT 58
+#define QS2_MAX_LEN 29
+
+__host__ __device__ __forceinline__ unsigned long long q2_deposit(const BsgpuQIndexView &Q, uint32_t id)
+{
+	unsigned long long out = 0;
+
+	for (int i = 0; i < BSGPU_Q_MAX_RUNS; i++)
+		if (i < Q.nruns)
+			out |= (unsigned long long) ((id / Q.run_mul[i]) & Q.run_mask[i]) << Q.run_shift[i];
+	return out;
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+	uint64_t p;
+
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+
+// index loads that should stay in L2 against the planes streaming through it
+__device__ __forceinline__ uint2 ldg_keep_u2(const uint2 *p, uint64_t policy)
+{
+	uint2 v;
+
+	asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(policy));
+	return v;
+}
+
+__device__ __forceinline__ unsigned long long ldg_keep_u64(const unsigned long long *p, uint64_t policy)
+{
+	unsigned long long v;
+
+	asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));
+	return v;
+}
+
+// A slot that survived the XOR + popcount: its id sits under the shape.  Out of line (real
+// matches only); the kernel's parameters are __grid_constant__, so their address is the constant
+// bank and nothing is copied for the call.
+__device__ __noinline__ void q2_survivor(const BsgpuSubjectView *S, const BsgpuQIndexView *Q, const BsgpuReport *R,
+		unsigned long long e, int64_t p, int max_nmis, int min_nmis, int64_t own_lo, int64_t own_hi)
+{
+	const int t = (int) (e >> QS2_T_SHIFT) & 31;
+	const uint32_t id = q_key(*Q, e >> (2 * t)) & ((1u << Q->id_bits) - 1u);
+	int ti = 0;
+
+	while (ti + 1 < Q->nshifts && Q->shift[ti] != t)
+		ti++;
+	q_verify<false>(*S, *Q, *R, (id << Q->shift_bits) | (uint32_t) ti, p, max_nmis, min_nmis, own_lo, own_hi);
+}
+
+// The seed key with the shape known at compile time: run i of the shape (letters [I, I + n)) goes
+// to the key bits [at, at + 2n) -- one funnel shift and one AND-OR per run, all immediates.  The
+// value equals q_key() of the same window (the host builds the index with that one).
+__host__ __device__ constexpr int q2_run_len(unsigned long long shape, int i)
+{
+	int n = 0;
+
+	while ((shape >> (i + n)) & 1ull)
+		n++;
+	return n;
+}
+
+__host__ __device__ constexpr int q2_letters_below(unsigned long long shape, int i)
+{
+	int n = 0;
+
+	for (int k = 0; k < i; k++)
+		n += (int) ((shape >> k) & 1ull);
+	return n;
+}
+
+template <unsigned long long SHAPE, int I>
+__device__ __forceinline__ uint32_t q2_key_runs(uint32_t lo, uint32_t hi)
+{
+	if constexpr (I >= 32 || (SHAPE >> I) == 0ull) {
+		return 0u;
+	} else if constexpr (((SHAPE >> I) & 1ull) != 0ull) {
+		constexpr int n = q2_run_len(SHAPE, I), at = 2 * q2_letters_below(SHAPE, I), d = 2 * I - at;
+		constexpr uint32_t M = (uint32_t) (((1ull << (2 * n)) - 1ull) << at);
+		const uint32_t piece = d == 0 ? lo : (d < 32 ? __funnelshift_r(lo, hi, d) : hi >> (d - 32));
+
+		return (piece & M) | q2_key_runs<SHAPE, I + n>(lo, hi);
+	} else {
+		return q2_key_runs<SHAPE, I + 1>(lo, hi);
+	}
+}
+
+template <unsigned long long SHAPE>
+__device__ __forceinline__ uint32_t q2_key(const BsgpuQIndexView &Q, uint32_t lo, uint32_t hi)
+{
+	if constexpr (SHAPE == 0ull)
+		return q_key(Q, (uint64_t) lo | ((uint64_t) hi << 32));
+	else
+		return q2_key_runs<SHAPE, 0>(lo, hi);
+}
+
+// 64 bits from bit offset sh (0..63) of the 128-bit little-endian value {c0, c1}
+__device__ __forceinline__ void q2_cut(uint64_t c0, uint64_t c1, int sh, uint32_t &lo, uint32_t &hi)
+{
+	const bool up = sh >= 32;
+	const uint32_t a0 = (uint32_t) c0, a1 = (uint32_t) (c0 >> 32), b0 = (uint32_t) c1, b1 = (uint32_t) (c1 >> 32);
+	const uint32_t w0 = up ? a1 : a0, w1 = up ? b0 : a1, w2 = up ? b1 : b0;
+
+	lo = __funnelshift_r(w0, w1, sh);       // the shift amount wraps at 32
+	hi = __funnelshift_r(w1, w2, sh);
+}
+
+#ifndef QS2_MIN_BLOCKS
+#define QS2_MIN_BLOCKS 8
+#endif
+#define QS2_GROUP 4             // positions per lane and load group: 4 x 96 slots + a round's rest < QS2_CAP
+
+template <unsigned long long SHAPE>
+__global__ void __launch_bounds__(QS2_WARPS * 32, QS2_MIN_BLOCKS)
+qscan2_kernel(const __grid_constant__ BsgpuSubjectView S, const __grid_constant__ BsgpuQIndexView Q,
+	      const __grid_constant__ BsgpuReport R, int max_nmis, int min_nmis,
+	      int64_t probe_lo, int64_t probe_hi, int64_t own_lo, int64_t own_hi)
+{
+	const unsigned FULL = 0xFFFFFFFFu;
+	const uint64_t E = 0x5555555555555555ull;
+	__shared__ uint64_t wc_all[QS2_WARPS][34], wi_all[QS2_WARPS][34];
+	__shared__ uint32_t mw_all[QS2_WARPS][32];
+	__shared__ uint2 ring_all[QS2_WARPS][QS2_CAP];  // {slot index, position in the batch}
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint64_t *wc = wc_all[warp], *wi = wi_all[warp];
+	uint32_t *mw = mw_all[warp];
+	uint2 *ring = ring_all[warp];
+	const int64_t word_lo = probe_lo >> 5, word_hi = (probe_hi + 31) >> 5;
+	const int64_t stride = (int64_t) gridDim.x * QS2_WARPS * 32;
+	const int len = Q.const_len;
+	const uint64_t len2 = (1ull << (2 * len)) - 1, lenE = E & len2;
+	const uint64_t mask2 = Q.mask2;
+	const uint32_t lt = (1u << lane) - 1u;
+	const uint64_t keep = l2_policy_evict_last();
+	uint32_t head = 0, tail = 0;            // ring cursors (the same in every lane)
+
+	for (int64_t jb = word_lo + ((int64_t) blockIdx.x * QS2_WARPS + warp) * 32; jb < word_hi; jb += stride) {
+		const int64_t j = jb + lane, base = j << 5, base0 = jb << 5;
+		const bool ld = j < word_hi + 2;        // the planes have spare words after the end
+		uint32_t m = 0;
+		uint64_t inv = ld ? __ldcs(S.inv2 + j) : ~0ull;
+
+		__syncwarp();
+		wc[lane + 1] = ld ? __ldcs(S.codes + j) : 0ull;
+		wi[lane + 1] = inv;
+		if (lane == 0) {
+			uint64_t i0 = jb > 0 ? __ldcs(S.inv2 + jb - 1) : ~0ull;
+
+			wc[0] = jb > 0 ? __ldcs(S.codes + jb - 1) : 0ull;
+			wi[0] = i0;
+			inv |= i0;
+		}
+		if (lane == 31) {
+			const bool ld2 = j + 1 < word_hi + 2;
+			uint64_t i1 = ld2 ? __ldcs(S.inv2 + j + 1) : ~0ull;
+
+			wc[33] = ld2 ? __ldcs(S.codes + j + 1) : 0ull;
+			wi[33] = i1;
+			inv |= i1;
+		}
+		// no N (or separator) anywhere near the batch: the candidates skip the not-a-base plane
+		const bool any_inv = __any_sync(FULL, inv != 0ull);
+		if (j < word_hi) {
+			uint64_t v = (uint64_t) __ldcs(S.valid + j) | ((uint64_t) __ldcs(S.valid + j + 1) << 32);
+
+			m = q_valid_positions(Q, v);
+			if (base < probe_lo)
+				m &= 0xFFFFFFFFu << (int) (probe_lo - base);
+			if (base + 32 > probe_hi)
+				m &= (probe_hi - base) <= 0 ? 0u : 0xFFFFFFFFu >> (int) (base + 32 - probe_hi);
+		}
+		// every position of the batch is a probe (the usual case): the load groups skip the masks
+		const bool all_on = __all_sync(FULL, m == 0xFFFFFFFFu);
+		mw[lane] = m;
+		__syncwarp();
+#pragma unroll 1
+		for (int g0 = 0; g0 <= 32; g0 += QS2_GROUP) {
+			// Drain: 32 x QS2_U slots per round, one load + XOR + popcount each.  Between the load
+			// groups only full rounds run (what is left stays in the ring).
+			while (tail - head >= (g0 == 32 ? 1u : 32u * QS2_U)) {
+				const uint32_t nround = min(tail - head, 32u * QS2_U);
+				uint2 item[QS2_U];
+				unsigned long long ent[QS2_U];
+#pragma unroll
+				for (int u = 0; u < QS2_U; u++) {
+					const uint32_t k = (uint32_t) (u * 32 + lane);
+
+					item[u] = ring[(head + k) & (QS2_CAP - 1)];
+					ent[u] = k < nround ? ldg_keep_u64(Q.entries2 + item[u].x, keep) : QS2_PTR;
+				}
+				head += nround;
+				__syncwarp();           // the ring items just read may be overwritten below
+#pragma unroll
+				for (int u = 0; u < QS2_U; u++) {
+					const unsigned long long e = ent[u];
+					const int pos = (int) item[u].y;
+
+					if ((e & QS2_PTR) == 0ull) {
+						const int t = (int) (e >> QS2_T_SHIFT) & 31;
+						const int at0 = pos - t + 32;    // window start, in letters from word jb-1
+						const int w = at0 >> 5, sh = 2 * (at0 & 31);
+						uint32_t x_lo, x_hi, i_lo = 0, i_hi = 0;
+
+						q2_cut(wc[w], wc[w + 1], sh, x_lo, x_hi);
+						if (any_inv)
+							q2_cut(wi[w], wi[w + 1], sh, i_lo, i_hi);
+						uint64_t d = (((uint64_t) x_lo | ((uint64_t) x_hi << 32)) ^ e) & len2 & ~(mask2 << (2 * t));
+
+						d = (d | (d >> 1) | ((uint64_t) i_lo | ((uint64_t) i_hi << 32))) & lenE;
+						if (__popcll(d) <= max_nmis)
+							q2_survivor(&S, &Q, &R, e, base0 + pos, max_nmis, min_nmis, own_lo, own_hi);
+					}
+					// the rare key with more than 3 entries: the chain behind a pointer slot, or the
+					// next chain slot (an idle lane's QS2_PTR is masked by the round's length)
+					const bool need = (e & (QS2_PTR | QS2_MORE)) != 0ull && (uint32_t) (u * 32 + lane) < nround;
+					const uint32_t who = __ballot_sync(FULL, need);
+
+					if (who != 0u) {
+						if (need)
+							ring[(tail + __popc(who & lt)) & (QS2_CAP - 1)] =
+								make_uint2((e & QS2_PTR) ? (uint32_t) e : item[u].x + 1u, (uint32_t) pos);
+						tail += __popc(who);
+					}
+				}
+				__syncwarp();
+			}
+			if (g0 == 32)
+				break;
+			// Load group: the positions (g0 + qq) * 32 + lane
+			uint32_t key[QS2_GROUP];
+			uint2 cell[QS2_GROUP];
+			uint64_t c0 = wc[g0 + 1];
+#pragma unroll
+			for (int qq = 0; qq < QS2_GROUP; qq++) {
+				const uint64_t c1 = wc[g0 + qq + 2];
+				uint32_t w_lo, w_hi;
+
+				q2_cut(c0, c1, 2 * lane, w_lo, w_hi);
+				key[qq] = q2_key<SHAPE>(Q, w_lo, w_hi);
+				c0 = c1;
+			}
+			if (all_on) {
+#pragma unroll
+				for (int qq = 0; qq < QS2_GROUP; qq++)
+					cell[qq] = ldg_keep_u2(Q.cells2 + (key[qq] >> 4), keep);
+			} else {
+#pragma unroll
+				for (int qq = 0; qq < QS2_GROUP; qq++)
+					cell[qq] = ((mw[g0 + qq] >> lane) & 1u) ? ldg_keep_u2(Q.cells2 + (key[qq] >> 4), keep)
+										: make_uint2(0u, 0u);
+			}
+#pragma unroll
+			for (int qq = 0; qq < QS2_GROUP; qq++) {
+				const int b2 = 2 * (int) (key[qq] & 15u);
+				const uint32_t c = (cell[qq].x >> b2) & 3u;
+				const uint32_t b_lo = __ballot_sync(FULL, (c & 1u) != 0u), b_hi = __ballot_sync(FULL, (c & 2u) != 0u);
+
+				if (c != 0u) {
+					const uint32_t below = cell[qq].x & ((1u << b2) - 1u);
+					const uint32_t first = cell[qq].y + __popc(below & 0x55555555u) + 2 * __popc(below & 0xAAAAAAAAu);
+					const uint32_t at = tail + __popc(b_lo & lt) + 2 * __popc(b_hi & lt);
+					const uint32_t p = (uint32_t) ((g0 + qq) * 32 + lane);
+
+					ring[at & (QS2_CAP - 1)] = make_uint2(first, p);
+					if (c > 1u)
+						ring[(at + 1u) & (QS2_CAP - 1)] = make_uint2(first + 1u, p);
+					if (c > 2u)
+						ring[(at + 2u) & (QS2_CAP - 1)] = make_uint2(first + 2u, p);
+				}
+				tail += __popc(b_lo) + 2 * __popc(b_hi);
+			}
+			__syncwarp();
 		}
 	}
 }
