@@ -41,7 +41,8 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return SO
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + SOURCES
+    extra = os.environ.get("BSGPU_NVCC_EXTRA", "").split()      # tuning sweeps: -DQS2_GROUP=8 ...
+    cmd = [nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + SOURCES
     subprocess.check_call(cmd)
     return SO
 

@@ -482,9 +482,15 @@ qscan_kernel(BsgpuSubjectView S, BsgpuQIndexView Q, BsgpuReport R, int max_nmis,
 // whatever the distribution of the entries over the positions.
 // ------------------------------------------------------------------------------------
 
-#define QS2_CAP 512             // ring items per warp (power of two)
-#define QS2_U 4                 // candidate loads in flight per lane
-#define QS2_WARPS 4
+#ifndef QS2_CAP
+#define QS2_CAP 256             // ring items per warp (power of two)
+#endif
+#ifndef QS2_U
+#define QS2_U 2                 // candidate loads in flight per lane
+#endif
+#ifndef QS2_WARPS
+#define QS2_WARPS 2             // measured (tools/mm2_sweep.sh, 250 Mbp, ms): 2 warps x 16 blocks 1.39, 4 x 8 1.40, 8 x 4 1.45
+#endif
 #define QS2_PTR (1ull << 62)    // slot is a pointer: low 32 bits = index of the chain
 #define QS2_MORE (1ull << 63)   // chain slot: the next slot belongs to the same key
 #define QS2_T_SHIFT 58
@@ -598,9 +604,14 @@ __device__ __forceinline__ void q2_cut(uint64_t c0, uint64_t c1, int sh, uint32_
 }
 
 #ifndef QS2_MIN_BLOCKS
-#define QS2_MIN_BLOCKS 8
+#define QS2_MIN_BLOCKS 16
 #endif
-#define QS2_GROUP 4             // positions per lane and load group: 4 x 96 slots + a round's rest < QS2_CAP
+#ifndef QS2_GROUP
+#define QS2_GROUP 2             // positions per lane and load group: 2 x 96 slots + a round's rest < QS2_CAP
+                                // (group 2 / ring 256 / rounds of 64: 1.40 ms; 4 / 512 / 128: 1.66; 8 / 1024 / 128: 3.1)
+#endif
+static_assert(QS2_GROUP * 96 + 32 * QS2_U <= QS2_CAP && (QS2_CAP & (QS2_CAP - 1)) == 0 && 32 % QS2_GROUP == 0,
+	      "ring too small for a load group on top of an unfinished round");
 
 template <unsigned long long SHAPE>
 __global__ void __launch_bounds__(QS2_WARPS * 32, QS2_MIN_BLOCKS)

@@ -166,6 +166,42 @@ def test_mtb_pdict(k, width):
         bs.countPDict(prod, s, max_mismatch=k + 1)
 
 
+@pytest.mark.parametrize("variant", ["compiled_shape", "generic_shape", "bitmap_directory"])
+@pytest.mark.parametrize("k,width", [(1, 25), (2, 25), (1, 18), (2, 24), (2, 28), (2, 29)])
+def test_mtb_scan_variants(k, width, variant, monkeypatch, engine):
+    """The three forms of the Hamming scan (qscan2_kernel with the shape compiled in, the same with
+    the shape read from the index, and the older bitmap + directory qscan_kernel) on a dictionary
+    with families of near-duplicates: keys with more than 3 entries go through the chain slots."""
+    if engine != "qgram":
+        pytest.skip("q-gram engine only")
+    if variant == "generic_shape":
+        monkeypatch.setenv("BSGPU_Q_GENERIC", "1")
+    elif variant == "bitmap_directory":
+        monkeypatch.setenv("BSGPU_Q_V1", "1")
+    g = rng(900 + 10 * k + width)
+    s = subject_with_n_runs(g, 30_000)
+    pats = make_dict(g, s, 600, width, nsub=k + 1, frac_dup=0.0)
+    fam = []
+    for p in pats[:60]:                 # 12 relatives each, differing in 1..2 letters
+        for _ in range(12):
+            q = p.copy()
+            for _ in range(int(g.integers(1, 3))):
+                q[int(g.integers(0, width))] = [1, 2, 4, 8][int(g.integers(4))]
+            fam.append(q)
+    pats = pats + fam
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        prod, orac = both(pats, max_mismatch=k)
+    total = check_all(prod, orac, s, s, max_mismatch=k)
+    assert total > 100
+    check_all(prod, orac, s, s, max_mismatch=k, min_mismatch=1)
+    from biostrings_b200 import _lib
+    bs.countPDict(prod, s, max_mismatch=k)
+    plan = _lib.lib().bsgpu_last_plan().decode()
+    assert ("rank_directory" in plan) == (variant != "bitmap_directory"), plan
+
+
 def test_views_subject():
     g = rng(31)
     s = subject_with_n_runs(g, 20_000)
