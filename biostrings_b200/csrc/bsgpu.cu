@@ -23,6 +23,7 @@
 #include "../../include/bsgpu.h"
 #include "bsgpu_qindex.cuh"
 #include "bsgpu_xseed.cuh"
+#include "bsgpu_tbdir.cuh"
 #include "bsgpu_oligo.cuh"
 #include "bsgpu_fasta.cuh"
 #include "bsgpu_indels.cuh"
@@ -334,6 +335,7 @@ struct bsgpu_pdict3parts {
 	mutable std::unique_ptr<struct QIndex> qcache;  // q-gram index built on first use
 	mutable std::unique_ptr<struct ByteSeedIndex> bcache;   // byte-seed index (exact, no planes)
 	mutable std::unique_ptr<struct XSeedIndex> xcache;      // extended-seed index (exact, w >= 25)
+	mutable std::unique_ptr<struct TbDirIndex> tcache;      // band directory (w <= 12, packed flanks)
 	// non-preprocessed dictionary (bsgpu_patterns_build): the letters only, no Trusted Band
 	bool plain = false;
 	DevBuf<uint8_t> d_pat;
@@ -1003,6 +1005,108 @@ static int get_xseed(const bsgpu_pdict3parts *p3, const XSeedIndex **out)
 	return done();
 }
 
+// Band directory for Trusted Bands of <= 12 letters whose keys all have packed flanks
+// (scan_tbdir_kernel, bsgpu_tbdir.cuh): one slot per key, the keys of a band side by side
+// (leader first, then low2high[leader] ascending, src/match_pdict_utils.c:153-181).
+struct TbDirIndex {
+	bool ok = false;
+	BsgpuTbDirView v = {};
+	DevBuf<uint2> d_cells;
+	DevBuf<unsigned long long> d_slots;
+	size_t nslots = 0;
+};
+
+static int get_tbdir(const bsgpu_pdict3parts *p3, const TbDirIndex **out)
+{
+	*out = nullptr;
+	if (p3->tcache) {
+		*out = p3->tcache.get();
+		return BSGPU_OK;
+	}
+	std::unique_ptr<TbDirIndex> ti(new TbDirIndex());
+	auto done = [&]() {
+		p3->tcache = std::move(ti);
+		*out = p3->tcache.get();
+		return BSGPU_OK;
+	};
+	const int M = p3->M, w = p3->w;
+
+	if (getenv("BSGPU_NO_TBDIR") != nullptr || w < 2 || w > TBD_MAX_W || !p3->flanks_all_packed ||
+	    M == 0 || M >= (1 << TBD_ID_BITS) || p3->plain)
+		return done();
+	const size_t nkeys = (size_t) 1 << (2 * w), ncells = nkeys / 16;
+	std::vector<uint32_t> cnt(nkeys, 0);
+	// members of every leader, ascending (the groups bsgpu_pdict3parts_blank_dups() leaves are singletons)
+	std::vector<int32_t> grp_n(M, 0);
+	for (int i = 0; i < M; i++)
+		if (p3->high2low[i] != BSGPU_NA)
+			grp_n[p3->high2low[i] - 1]++;
+	for (int i = 0; i < M; i++)
+		if (!p3->excluded[i] && !p3->is_tb_dup[i])
+			cnt[p3->keys[i]] += 1 + (uint32_t) grp_n[i];
+	std::vector<uint2> cells(ncells, make_uint2(0u, 0u));
+	std::vector<uint32_t> at(nkeys);
+	size_t nmain = 0, nover = 0;
+	for (size_t k = 0; k < nkeys; k++) {
+		uint32_t n3 = std::min<uint32_t>(cnt[k], 3u);
+
+		if ((k & 15) == 0)
+			cells[k >> 4].y = (uint32_t) nmain;
+		cells[k >> 4].x |= n3 << (2 * (k & 15));
+		at[k] = (uint32_t) nmain;
+		nmain += n3;
+		if (cnt[k] > 3)
+			nover += cnt[k] - 2;
+	}
+	if (nmain + nover >= ((size_t) 1 << 31))
+		return done();
+	std::vector<unsigned long long> slots(nmain + nover + 1, 0ull);
+	std::vector<uint32_t> filled(nkeys, 0);
+	size_t over_at = nmain;
+	auto place = [&](int key_id, uint64_t band) {
+		int64_t h0 = p3->has_head ? p3->h_head_off[key_id] : 0, t0 = p3->has_tail ? p3->h_tail_off[key_id] : 0;
+		int hl = p3->has_head ? (int) (p3->h_head_off[key_id + 1] - h0) : 0;
+		int tl = p3->has_tail ? (int) (p3->h_tail_off[key_id + 1] - t0) : 0;
+		int nt = std::min(8, tl), nh = std::min(8 - nt, hl);
+		unsigned long long fp = 0;
+
+		for (int d = 0; d < nt; d++)
+			fp |= (unsigned long long) bsgpu_base_code(p3->h_tail[(size_t) t0 + d]) << (2 * d);
+		for (int d = 0; d < nh; d++)    // the last nh letters of the head, in subject order
+			fp |= (unsigned long long) bsgpu_base_code(p3->h_head[(size_t) h0 + hl - nh + d]) << (2 * (nt + d));
+		unsigned long long e = (unsigned long long) (uint32_t) key_id | (fp << TBD_FP_SHIFT) |
+				       ((unsigned long long) nt << TBD_NT_SHIFT) | ((unsigned long long) nh << TBD_NH_SHIFT);
+		uint32_t c = cnt[band], n = filled[band]++;
+
+		if (c <= 3 || n < 2) {
+			slots[at[band] + n] = e;
+			return;
+		}
+		if (n == 2) {           // the third slot points at the chain
+			slots[at[band] + 2] = QS2_PTR | (unsigned long long) over_at;
+			at[band] = (uint32_t) over_at - 2;      // chain slot of entry n = at + n
+			over_at += c - 2;
+		}
+		slots[at[band] + n] = e | (n + 1 < c ? QS2_MORE : 0ull);
+	};
+	// leaders first (ascending), their members follow in ascending order: two passes keep
+	// "leader first" without sorting, the order inside a band does not change any result
+	for (int i = 0; i < M; i++)
+		if (!p3->excluded[i] && !p3->is_tb_dup[i])
+			place(i, p3->keys[i]);
+	for (int i = 0; i < M; i++)
+		if (p3->high2low[i] != BSGPU_NA)
+			place(i, p3->keys[p3->high2low[i] - 1]);
+	TRY(ti->d_cells.upload(cells.data(), cells.size()));
+	TRY(ti->d_slots.upload(slots.data(), slots.size()));
+	ti->nslots = nmain + nover;
+	ti->v.cells = ti->d_cells.p;
+	ti->v.slots = ti->d_slots.p;
+	ti->v.w = w;
+	ti->ok = true;
+	return done();
+}
+
 static int upload_groups(bsgpu_pdict3parts *p3, bool blank)
 {
 	int M = p3->M;
@@ -1377,6 +1481,7 @@ extern "C" int bsgpu_pdict3parts_set_flanks(bsgpu_pdict3parts *p3,
 	p3->qcache.reset();
 	p3->bcache.reset();
 	p3->xcache.reset();
+	p3->tcache.reset();
 	return BSGPU_OK;
 }
 
@@ -1391,6 +1496,7 @@ extern "C" int bsgpu_pdict3parts_blank_dups(bsgpu_pdict3parts *p3)
 	p3->qcache.reset();
 	p3->bcache.reset();
 	p3->xcache.reset();
+	p3->tcache.reset();
 	return BSGPU_OK;
 }
 
@@ -2250,6 +2356,26 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 				g_launches++;
 				CUDA_TRY(cudaGetLastError());
 			}
+			return BSGPU_OK;
+		}
+	}
+	if (direct == 2 && mp.fixedS) {
+		// short band + packed flanks: the band addresses a directory (bsgpu_tbdir.cuh)
+		const TbDirIndex *ti = nullptr;
+		TRY(get_tbdir(p3, &ti));
+		if (ti != nullptr && ti->ok) {
+			TRY(ensure_packed(subj, st));
+			S = subj->view();
+			set_plan("tb_directory w=%d cells=%zu slots=%zu + flank fingerprint in the slot", p3->w,
+				 ti->d_cells.n, ti->nslots);
+			long long nbatches = (nwords + 31) / 32;
+			{
+				KernelTimer kt("scan_tbdir_kernel", st);
+				scan_tbdir_kernel<<<grid_for(nbatches * 32, TBD_WARPS * 32, 1024), TBD_WARPS * 32, 0, st>>>(
+					S, I, ti->v, R, start_lo, start_hi, mp.max_nmis, mp.min_nmis);
+			}
+			g_launches++;
+			CUDA_TRY(cudaGetLastError());
 			return BSGPU_OK;
 		}
 	}
