@@ -1005,9 +1005,9 @@ static int get_xseed(const bsgpu_pdict3parts *p3, const XSeedIndex **out)
 	return done();
 }
 
-// Band directory for Trusted Bands of <= 12 letters whose keys all have packed flanks
-// (scan_tbdir_kernel, bsgpu_tbdir.cuh): one slot per key, the keys of a band side by side
-// (leader first, then low2high[leader] ascending, src/match_pdict_utils.c:153-181).
+// Band directory for Trusted Bands of <= 32 letters with heads / tails or duplicated bands
+// (scan_tbdir_kernel, bsgpu_tbdir.cuh): one slot per key under the first min(w, 12) letters of its
+// band, the keys of a band side by side (src/match_pdict_utils.c:153-181).
 struct TbDirIndex {
 	bool ok = false;
 	BsgpuTbDirView v = {};
@@ -1029,21 +1029,22 @@ static int get_tbdir(const bsgpu_pdict3parts *p3, const TbDirIndex **out)
 		*out = p3->tcache.get();
 		return BSGPU_OK;
 	};
-	const int M = p3->M, w = p3->w;
+	const int M = p3->M, w = p3->w, prefix = std::min(w, TBD_PREFIX);
 
-	if (getenv("BSGPU_NO_TBDIR") != nullptr || w < 2 || w > TBD_MAX_W || !p3->flanks_all_packed ||
-	    M == 0 || M >= (1 << TBD_ID_BITS) || p3->plain)
+	if (getenv("BSGPU_NO_TBDIR") != nullptr || getenv("BSGPU_NO_PACKED_FLANKS") != nullptr || w < 2 || w > TBD_MAX_W || M == 0 || M >= (1 << TBD_ID_BITS) ||
+	    p3->plain || p3->d_flank_len.n < (size_t) M)
 		return done();
-	const size_t nkeys = (size_t) 1 << (2 * w), ncells = nkeys / 16;
+	const size_t nkeys = (size_t) 1 << (2 * prefix), ncells = nkeys / 16;
+	const uint64_t pmask = ((uint64_t) 1 << (2 * prefix)) - 1;
 	std::vector<uint32_t> cnt(nkeys, 0);
-	// members of every leader, ascending (the groups bsgpu_pdict3parts_blank_dups() leaves are singletons)
+	// members of every leader (the groups bsgpu_pdict3parts_blank_dups() leaves are singletons)
 	std::vector<int32_t> grp_n(M, 0);
 	for (int i = 0; i < M; i++)
 		if (p3->high2low[i] != BSGPU_NA)
 			grp_n[p3->high2low[i] - 1]++;
 	for (int i = 0; i < M; i++)
 		if (!p3->excluded[i] && !p3->is_tb_dup[i])
-			cnt[p3->keys[i]] += 1 + (uint32_t) grp_n[i];
+			cnt[p3->keys[i] & pmask] += 1 + (uint32_t) grp_n[i];
 	std::vector<uint2> cells(ncells, make_uint2(0u, 0u));
 	std::vector<uint32_t> at(nkeys);
 	size_t nmain = 0, nover = 0;
@@ -1063,34 +1064,40 @@ static int get_tbdir(const bsgpu_pdict3parts *p3, const TbDirIndex **out)
 	std::vector<unsigned long long> slots(nmain + nover + 1, 0ull);
 	std::vector<uint32_t> filled(nkeys, 0);
 	size_t over_at = nmain;
+	const int nr = std::min(8, w - prefix);
 	auto place = [&](int key_id, uint64_t band) {
 		int64_t h0 = p3->has_head ? p3->h_head_off[key_id] : 0, t0 = p3->has_tail ? p3->h_tail_off[key_id] : 0;
 		int hl = p3->has_head ? (int) (p3->h_head_off[key_id + 1] - h0) : 0;
 		int tl = p3->has_tail ? (int) (p3->h_tail_off[key_id + 1] - t0) : 0;
-		int nt = std::min(8, tl), nh = std::min(8 - nt, hl);
-		unsigned long long fp = 0;
+		int nt = 0, nh = 0;
+		unsigned long long fp = (band >> (2 * prefix)) & (((unsigned long long) 1 << (2 * nr)) - 1);
 
+		// the leading base letters of the tail, then the trailing base letters of the head
+		while (nt < std::min(8 - nr, tl) && bsgpu_is_base(p3->h_tail[(size_t) t0 + nt]))
+			nt++;
+		while (nh < std::min(8 - nr - nt, hl) && bsgpu_is_base(p3->h_head[(size_t) h0 + hl - 1 - nh]))
+			nh++;
 		for (int d = 0; d < nt; d++)
-			fp |= (unsigned long long) bsgpu_base_code(p3->h_tail[(size_t) t0 + d]) << (2 * d);
+			fp |= (unsigned long long) bsgpu_base_code(p3->h_tail[(size_t) t0 + d]) << (2 * (nr + d));
 		for (int d = 0; d < nh; d++)    // the last nh letters of the head, in subject order
-			fp |= (unsigned long long) bsgpu_base_code(p3->h_head[(size_t) h0 + hl - nh + d]) << (2 * (nt + d));
+			fp |= (unsigned long long) bsgpu_base_code(p3->h_head[(size_t) h0 + hl - nh + d]) << (2 * (nr + nt + d));
 		unsigned long long e = (unsigned long long) (uint32_t) key_id | (fp << TBD_FP_SHIFT) |
-				       ((unsigned long long) nt << TBD_NT_SHIFT) | ((unsigned long long) nh << TBD_NH_SHIFT);
-		uint32_t c = cnt[band], n = filled[band]++;
+				       ((unsigned long long) nt << TBD_NT_SHIFT) | ((unsigned long long) nh << TBD_NH_SHIFT) |
+				       ((unsigned long long) nr << TBD_NR_SHIFT);
+		uint64_t cellkey = band & pmask;
+		uint32_t c = cnt[cellkey], n = filled[cellkey]++;
 
 		if (c <= 3 || n < 2) {
-			slots[at[band] + n] = e;
+			slots[at[cellkey] + n] = e;
 			return;
 		}
 		if (n == 2) {           // the third slot points at the chain
-			slots[at[band] + 2] = QS2_PTR | (unsigned long long) over_at;
-			at[band] = (uint32_t) over_at - 2;      // chain slot of entry n = at + n
+			slots[at[cellkey] + 2] = QS2_PTR | (unsigned long long) over_at;
+			at[cellkey] = (uint32_t) over_at - 2;   // chain slot of entry n = at + n
 			over_at += c - 2;
 		}
-		slots[at[band] + n] = e | (n + 1 < c ? QS2_MORE : 0ull);
+		slots[at[cellkey] + n] = e | (n + 1 < c ? QS2_MORE : 0ull);
 	};
-	// leaders first (ascending), their members follow in ascending order: two passes keep
-	// "leader first" without sorting, the order inside a band does not change any result
 	for (int i = 0; i < M; i++)
 		if (!p3->excluded[i] && !p3->is_tb_dup[i])
 			place(i, p3->keys[i]);
@@ -1103,6 +1110,7 @@ static int get_tbdir(const bsgpu_pdict3parts *p3, const TbDirIndex **out)
 	ti->v.cells = ti->d_cells.p;
 	ti->v.slots = ti->d_slots.p;
 	ti->v.w = w;
+	ti->v.prefix = prefix;
 	ti->ok = true;
 	return done();
 }
@@ -2359,39 +2367,48 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 			return BSGPU_OK;
 		}
 	}
-	if (direct == 2 && mp.fixedS) {
-		// short band + packed flanks: the band addresses a directory (bsgpu_tbdir.cuh)
+	bool base_windows_done = false;
+	if (direct != 1) {
+		// heads / tails or duplicated bands: the band's first letters address a directory and the
+		// scan verifies its own hits (bsgpu_tbdir.cuh); nothing goes through the candidate buffer
 		const TbDirIndex *ti = nullptr;
 		TRY(get_tbdir(p3, &ti));
 		if (ti != nullptr && ti->ok) {
 			TRY(ensure_packed(subj, st));
 			S = subj->view();
-			set_plan("tb_directory w=%d cells=%zu slots=%zu + flank fingerprint in the slot", p3->w,
-				 ti->d_cells.n, ti->nslots);
+			set_plan("tb_directory w=%d prefix=%d cells=%zu slots=%zu + flank fingerprint in the slot%s", p3->w,
+				 ti->v.prefix, ti->d_cells.n, ti->nslots, mp.fixedS ? "" : " + iupac_expansion");
 			long long nbatches = (nwords + 31) / 32;
 			{
 				KernelTimer kt("scan_tbdir_kernel", st);
-				scan_tbdir_kernel<<<grid_for(nbatches * 32, TBD_WARPS * 32, 1024), TBD_WARPS * 32, 0, st>>>(
-					S, I, ti->v, R, start_lo, start_hi, mp.max_nmis, mp.min_nmis);
+				if (mp.fixedS)
+					scan_tbdir_kernel<false><<<grid_for(nbatches * 32, TBD_WARPS * 32, 1024), TBD_WARPS * 32, 0, st>>>(
+						S, I, ti->v, R, start_lo, start_hi, mp.max_nmis, mp.min_nmis, mp.fixedP, mp.fixedS);
+				else
+					scan_tbdir_kernel<true><<<grid_for(nbatches * 32, TBD_WARPS * 32, 1024), TBD_WARPS * 32, 0, st>>>(
+						S, I, ti->v, R, start_lo, start_hi, mp.max_nmis, mp.min_nmis, mp.fixedP, mp.fixedS);
 			}
 			g_launches++;
 			CUDA_TRY(cudaGetLastError());
-			return BSGPU_OK;
+			if (mp.fixedS)
+				return BSGPU_OK;
+			base_windows_done = true;       // the windows with ambiguity letters follow below
 		}
 	}
 	TRY(ensure_packed(subj, st));
 	S = subj->view();
-	set_plan("tb_hash w=%d buckets=%u table_bytes=%llu%s%s", p3->w, p3->nbuckets,
-		 (unsigned long long) p3->nbuckets * 16,
-		 direct == 1 ? "" : (direct == 2 ? " + packed flank check in the scan" : " + verify_flanks"),
-		 mp.fixedS ? "" : " + iupac_expansion");
-	{
+	if (!base_windows_done)
+		set_plan("tb_hash w=%d buckets=%u table_bytes=%llu%s%s", p3->w, p3->nbuckets,
+			 (unsigned long long) p3->nbuckets * 16,
+			 direct == 1 ? "" : (direct == 2 ? " + packed flank check in the scan" : " + verify_flanks"),
+			 mp.fixedS ? "" : " + iupac_expansion");
+	if (!base_windows_done) {
 		KernelTimer kt("scan_tb_kernel", st);
 		scan_tb_kernel<<<grid_for(nwords, 256, tb_grid()), 256, 0, st>>>(S, I, R, C, direct, start_lo, start_hi,
 										  mp.max_nmis, mp.min_nmis);
+		g_launches++;
+		CUDA_TRY(cudaGetLastError());
 	}
-	g_launches++;
-	CUDA_TRY(cudaGetLastError());
 	if (!mp.fixedS) {
 		const size_t OVF_CAP = 1u << 20;
 		unsigned long long n_ovf = 0;
@@ -2529,6 +2546,12 @@ static int run_part(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, cons
 	// every key's flanks are packed and the subject is taken literally: the scan verifies its own
 	// hits (XOR + popcount), no candidate buffer and no host synchronisation
 	bool inline_flanks = !direct && p3->flanks_all_packed && mp.fixedS && getenv("BSGPU_NO_PACKED_FLANKS") == nullptr;
+	if (!direct && mp.fixedS && !inline_flanks) {
+		// the band directory verifies any flanks itself (letter by letter where they are not packed)
+		const TbDirIndex *ti = nullptr;
+		TRY(get_tbdir(p3, &ti));
+		inline_flanks = ti != nullptr && ti->ok;
+	}
 	BsgpuReport C = {};
 	int64_t lo = subj->scan_lo, hi = subj->scan_hi;
 

@@ -15,16 +15,19 @@ pytestmark = pytest.mark.gpu
 BACKEND = "ref" if ref.available() else "port"
 
 
-@pytest.fixture(autouse=True, params=["qgram", "tb_only"])
+@pytest.fixture(autouse=True, params=["qgram", "tb_only", "tb_hash"])
 def engine(request, monkeypatch):
-    """Every case runs twice: with the q-gram seed engine allowed (default) and with the
-    Trusted-Band engine forced (BSGPU_NO_QINDEX=1); both must equal the reference."""
-    if request.param == "tb_only":
+    """Every case runs three times: with the seed engines allowed (default), with the Trusted-Band
+    engines forced (BSGPU_NO_QINDEX=1: band directory where it applies, else the hash scan), and with
+    the hash scan alone (BSGPU_NO_TBDIR=1: scan_tb_kernel + tb_hit / verify_flanks_kernel); all must
+    equal the reference."""
+    for k in ("BSGPU_NO_QINDEX", "BSGPU_NO_BYTESEED", "BSGPU_NO_TBDIR"):
+        monkeypatch.delenv(k, raising=False)
+    if request.param in ("tb_only", "tb_hash"):
         monkeypatch.setenv("BSGPU_NO_QINDEX", "1")
         monkeypatch.setenv("BSGPU_NO_BYTESEED", "1")        # plain one-probe-per-window scan
-    else:
-        monkeypatch.delenv("BSGPU_NO_QINDEX", raising=False)
-        monkeypatch.delenv("BSGPU_NO_BYTESEED", raising=False)
+    if request.param == "tb_hash":
+        monkeypatch.setenv("BSGPU_NO_TBDIR", "1")
     return request.param
 
 
