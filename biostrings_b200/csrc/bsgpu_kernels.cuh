@@ -470,25 +470,51 @@ scan_tb_iupac_kernel(BsgpuSubjectView S, BsgpuIndexView I, BsgpuReport R, BsgpuR
 		     unsigned int max_expansions, long long *ovf_pos, unsigned long long *n_ovf,
 		     unsigned long long ovf_capacity)
 {
+	// A warp takes 32 words (1024 window starts) at a time; the windows holding an ambiguity letter
+	// come in runs of w (one letter spoils w consecutive windows, all in one or two lanes' words), so
+	// they are listed in shared memory first and dealt round-robin to the lanes.
+	__shared__ uint16_t list_all[4][1024];
+	const unsigned FULL = 0xFFFFFFFFu;
+	const int lane = threadIdx.x & 31;
+	uint16_t *list = list_all[threadIdx.x >> 5];
 	int64_t word_lo = start_lo >> 5, word_hi = (start_hi + 31) >> 5;
-	int64_t j = word_lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t jb = word_lo + ((int64_t) blockIdx.x * blockDim.x + (threadIdx.x & ~31));
 	int64_t stride = (int64_t) gridDim.x * blockDim.x;
 	const int w = I.w, sw = I.seed_w;
 
-	for (; j < word_hi; j += stride) {
-		uint64_t u0 = (uint64_t) __ldg(S.iupac + j) | ((uint64_t) __ldg(S.iupac + j + 1) << 32);
-		uint64_t v0 = (uint64_t) __ldg(S.valid + j) | ((uint64_t) __ldg(S.valid + j + 1) << 32);
-		uint32_t m_iu = window_mask(S.iupac, j, u0, w), m_va = window_mask(S.valid, j, v0, w);
-		uint32_t m = m_iu & ~m_va;      // IUPAC-only windows that are not all-base
-		int64_t base = j << 5;
-		if (base < start_lo)
-			m &= 0xFFFFFFFFu << (int) (start_lo - base);
-		if (base + 32 > start_hi)
-			m &= (start_hi - base) <= 0 ? 0u : 0xFFFFFFFFu >> (int) (base + 32 - start_hi);
-		while (m) {
-			int r = __ffs(m) - 1;
-			m &= m - 1;
-			int64_t c0 = base + r, e = c0 + w - 1;
+	for (; jb < word_hi; jb += stride) {
+		const int64_t j = jb + lane;
+		uint32_t m = 0;
+
+		if (j < word_hi) {
+			uint64_t u0 = (uint64_t) __ldg(S.iupac + j) | ((uint64_t) __ldg(S.iupac + j + 1) << 32);
+			uint64_t v0 = (uint64_t) __ldg(S.valid + j) | ((uint64_t) __ldg(S.valid + j + 1) << 32);
+			uint32_t m_iu = window_mask(S.iupac, j, u0, w), m_va = window_mask(S.valid, j, v0, w);
+			int64_t base = j << 5;
+
+			m = m_iu & ~m_va;       // IUPAC-only windows that are not all-base
+			if (base < start_lo)
+				m &= 0xFFFFFFFFu << (int) (start_lo - base);
+			if (base + 32 > start_hi)
+				m &= (start_hi - base) <= 0 ? 0u : 0xFFFFFFFFu >> (int) (base + 32 - start_hi);
+		}
+		if (!__any_sync(FULL, m != 0u))
+			continue;
+		int mine = __popc(m), before = mine;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			int up = __shfl_up_sync(FULL, before, d);
+			if (lane >= d)
+				before += up;
+		}
+		const int nitems = __shfl_sync(FULL, before, 31);
+		before -= mine;
+		__syncwarp();
+		for (uint32_t h = m; h != 0u; h &= h - 1)
+			list[before++] = (uint16_t) (lane * 32 + __ffs(h) - 1);
+		__syncwarp();
+		for (int it = lane; it < nitems; it += 32) {
+			int64_t c0 = (jb << 5) + list[it], e = c0 + w - 1;
 			const uint8_t *s = S.bytes + c0;
 			// ambiguity letters inside the hashed seed (first sw letters)
 			uint64_t key0 = 0;
