@@ -2,7 +2,7 @@
 """bench.py -- countPDict subject Gbp/s (BASELINE.json metric) on N B200s of one box.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mm 0|2]
-                    [--config c2|c3|c4|c5] [--scaling weak|strong] [--collective per-step|once]
+                    [--config c2|c3|c4|c5] [--scaling weak|strong] [--collective peer|overlapped|per-step|once]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Headline workload (config c2, the default; BASELINE.json configs[1]): countPDict of 1M 25-mers (10 %
@@ -17,10 +17,12 @@ width-1.  Other configurations (BASELINE.json configs[2..4], `biostrings_b200/wo
 
 A step = one pass of the hot path over the rank's resident shard of 1-byte letters, treated as a new
 batch (derived planes dropped), counting into the rank's device count vector, followed by the
-all-reduce of the counts a countPDict call on N GPUs needs.  --collective overlapped (default):
-every step has its own all-reduce, issued on a side stream so that it overlaps the scan of the next
-batch (two count vectors); per-step: the same, serialised behind the scan on one stream; once: one
-all-reduce after the last step.  The modes not chosen are reported in `collective_other_modes`.  `value`
+gathering of the counts a countPDict call on N GPUs needs.  --collective peer (default): ONE count
+vector in rank 0's memory (bsgpu_shared_counts_*, CUDA IPC), every rank's scan kernels increment it
+directly with system-scope reductions over NVLink -- the gather is part of the scan launch, no
+collective is launched; overlapped: every step has its own NCCL all-reduce, issued on a side
+stream so that it overlaps the scan of the next batch (two count vectors); per-step: the same,
+serialised behind the scan on one stream; once: one all-reduce after the last step.  The modes not chosen are reported in `collective_other_modes`.  `value`
 times EXACTLY K steps between barrier + synchronize, one CUDA event on each side on the launching
 stream, max over ranks.  No L2 flush inside the bracket: every step streams a subject larger than
 the 126 MB L2 (config.l2 says so).  `e2e` times the public host-buffer call: pinned host letters
@@ -58,7 +60,7 @@ def parse_args():
                     help="max.mismatch of the headline metric (0 = exact, 2 = MTB_PDict); config c2 only")
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--collective", default="overlapped", choices=["overlapped", "per-step", "once"])
+    ap.add_argument("--collective", default="peer", choices=["peer", "overlapped", "per-step", "once"])
     ap.add_argument("--subject-mbp", type=float, default=250.0, help="config c2: letters per GPU (weak) / in total (strong), Mbp")
     ap.add_argument("--patterns", type=int, default=1_000_000)
     ap.add_argument("--scale", type=float, default=1.0, help="configs c3-c5: shrink the workload (smoke runs)")
@@ -240,6 +242,9 @@ def c2_config(args, world):
 
 
 COLLECTIVE_TEXT = {
+    "peer": "none launched: one int32 count vector in rank 0's memory (CUDA IPC, bsgpu_shared_counts_*), every rank's scan "
+            "kernels add their matches to it with system-scope reductions over NVLink peer memory, i.e. the gather of the "
+            "counts is fused into the scan launch; zeroed once before the K steps (K x the per-step counts checked)",
     "overlapped": "all-reduce of the int32 counts of EVERY step (what one countPDict call on N GPUs needs), on a side "
                   "stream: it overlaps the scan of the next batch (two count vectors)",
     "per-step": "all-reduce of the int32 counts after every step, serialised behind the scan on the launching stream",
@@ -280,6 +285,37 @@ class Env:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
+    def shared_counts(self, M):
+        """One int32[M] count vector for all ranks, in rank 0's memory: returns (device pointer valid
+        in this process, torch view of it on rank 0 / None elsewhere).  Cached per M."""
+        from biostrings_b200 import _lib
+        torch = self.torch
+        if not hasattr(self, "_shared"):
+            self._shared = {}
+        if M in self._shared:
+            return self._shared[M]
+        ptr = C.c_void_p()
+        h = torch.zeros(64, dtype=torch.uint8, device=self.dev)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 64)()
+            _lib.check(self.L.bsgpu_shared_counts_create(M, C.byref(ptr), buf))
+            h.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+        if self.world > 1:
+            self.dist.broadcast(h, 0)
+        view = None
+        if self.rank != 0:
+            buf = (C.c_ubyte * 64)(*h.cpu().tolist())
+            _lib.check(self.L.bsgpu_shared_counts_open(buf, C.byref(ptr)))
+        else:
+            view = torch.as_tensor(_DevArray(ptr.value, M), device=self.dev)
+        self._shared[M] = (ptr.value, view)
+        return self._shared[M]
+
+    def broadcast0(self, t):
+        if self.world > 1:
+            self.dist.broadcast(t, 0)
+        return t
+
     def all_reduce(self, t, op=None):
         if self.world > 1:
             self.dist.all_reduce(t, op=op or self.dist.ReduceOp.SUM)
@@ -289,6 +325,13 @@ class Env:
         t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
         self.all_reduce(t, self.dist.ReduceOp.MAX if self.world > 1 else None)
         return t.item()
+
+
+class _DevArray:
+    """A raw device pointer as something torch.as_tensor understands (rank 0's own allocation)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
 
 
 def bind_to_gpu_numa_node(local):
@@ -348,12 +391,14 @@ class Pieces:
             _lib.check(L.bsgpu_subject_repack(it[6].handle, self.env.sptr))
             _lib.check(L.bsgpu_count_device(self.parr, len(self.parts), it[6].handle, self.mm, 0,
                                             int(self.fixed[0]), int(self.fixed[1]),
-                                            C.c_void_p(counts.data_ptr()), self.env.sptr, C.byref(nl)))
+                                            C.c_void_p(counts if isinstance(counts, int) else counts.data_ptr()),
+                                            self.env.sptr, C.byref(nl)))
 
     def e2e_step(self, counts):
         for it in self.items:
             self.mp.count_parts_host(self.parts, it[1], self.mm, 0, self.fixed, chunk_start=it[2],
-                                     subject_len=it[3], report=(it[4], it[5]), d_counts=counts.data_ptr(),
+                                     subject_len=it[3], report=(it[4], it[5]),
+                                     d_counts=counts if isinstance(counts, int) else counts.data_ptr(),
                                      stream=self.env.stream.cuda_stream)
 
 
@@ -366,8 +411,37 @@ def timed_steps(env, pieces, counts, nsteps, collective):
     torch, L = env.torch, env.L
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     one = torch.zeros_like(counts)
-    if env.world == 1 and collective == "overlapped":
+    if env.world == 1 and collective in ("overlapped", "peer"):
         collective = "per-step"
+    if collective == "peer":
+        # every rank counts straight into rank 0's vector: nothing to launch but the scans.  The
+        # vector is zeroed once, before the bracket, and accumulates the K steps (every step does
+        # its whole gather -- each match is one reduction over NVLink -- only the 4 MB memset per
+        # call is left out, which would need a barrier of its own between the steps)
+        M = counts.numel()
+        ptr, view = env.shared_counts(M)
+        if view is not None:
+            view.zero_()
+        L.bsgpu_kernel_timing(1)
+        l0 = L.bsgpu_launch_count()
+        env.barrier()
+        ev0.record(env.stream)
+        for _ in range(nsteps):
+            pieces.device_step(ptr)
+        ev1.record(env.stream)
+        env.barrier()
+        launches = int(L.bsgpu_launch_count() - l0)
+        acc = {}
+        for name, ms in _lib.kernel_times():
+            acc.setdefault(name, []).append(ms)
+        L.bsgpu_kernel_timing(0)
+        total_ms = env.max_over_ranks(ev0.elapsed_time(ev1))
+        if view is not None:
+            one.copy_(view)
+        env.broadcast0(one)
+        tot = one.cpu().numpy().astype(np.int64)
+        assert (tot % nsteps == 0).all(), "every step must find the same matches"
+        return total_ms, {k: sum(v) / len(v) for k, v in acc.items()}, launches, tot // nsteps
     bufs = [counts, torch.zeros_like(counts)]
     comm = torch.cuda.Stream() if collective == "overlapped" else None
     scanned = [torch.cuda.Event() for _ in range(2)]
@@ -419,24 +493,43 @@ def timed_steps(env, pieces, counts, nsteps, collective):
     return total_ms, {k: sum(v) / len(v) for k, v in acc.items()}, launches, per_step
 
 
-def e2e_leg(env, pieces, counts, M, n, total_letters):
+def e2e_leg(env, pieces, counts, M, n, total_letters, collective="overlapped"):
     """The public host-buffer path, n timed calls after one warm-up: pinned letters -> sliced H2D
-    overlapped with the scan -> all-reduce on the device -> ONE D2H of the counts into pinned
-    memory.  Also times the bare pinned H2D copy of the same bytes on all ranks at once (the
-    ceiling this box gives the path)."""
+    overlapped with the scan -> the counts of all ranks in one vector -> ONE D2H of the counts into
+    pinned memory.  collective "peer" (N > 1): every rank's scans add into rank 0's vector over
+    NVLink, a barrier says that all of them are done, rank 0 copies the vector out; otherwise an
+    NCCL all-reduce on the device before the copy.  Also times the bare pinned H2D copy of the same
+    bytes on all ranks at once (the ceiling this box gives the path)."""
     torch = env.torch
     out = torch.empty(M, dtype=torch.int32, pin_memory=True)
+    peer = collective == "peer" and env.world > 1
     times = []
+    if peer:
+        ptr, view = env.shared_counts(M)
     for k in range(n + 1):
+        if peer and view is not None:
+            view.zero_()                # (before the bracket: zeroing inside it would need a barrier of its own)
         env.barrier()
         t0 = time.perf_counter()
-        counts.zero_()
-        pieces.e2e_step(counts)
-        env.all_reduce(counts)
-        out.copy_(counts, non_blocking=True)
+        if peer:
+            pieces.e2e_step(ptr)
+            env.barrier()
+            if view is not None:
+                out.copy_(view, non_blocking=True)
+        else:
+            counts.zero_()
+            pieces.e2e_step(counts)
+            env.all_reduce(counts)
+            out.copy_(counts, non_blocking=True)
         torch.cuda.synchronize()
         if k > 0:
             times.append(time.perf_counter() - t0)
+    if peer:                            # the other ranks get the vector too (they compare it with their steps)
+        if view is not None:
+            counts.copy_(view)
+        env.broadcast0(counts)
+        out.copy_(counts)
+        torch.cuda.synchronize()
     te = env.max_over_ranks(sum(times) / len(times))
     # the H2D ceiling: the same pinned buffers, one plain copy each, all ranks together
     dst = [torch.empty_like(it[0], device=env.dev) for it in pieces.items]
@@ -458,8 +551,9 @@ def e2e_leg(env, pieces, counts, M, n, total_letters):
                             "note": "bare cudaMemcpyAsync of the same pinned bytes, all ranks at once, max over ranks",
                             "e2e_over_ceiling": te / tc},
             "call": "bsgpu_count_host (countPDict on host letters: 16 MB slices copied on a copy stream, slice k "
-                    "scanned while slice k+1 is in flight, persistent staging buffer) -> all-reduce on the device "
-                    "-> one D2H of the int32 counts into pinned memory",
+                    "scanned while slice k+1 is in flight, persistent staging buffer) -> " +
+                    ("counts added to rank 0's vector over NVLink by the scans themselves, barrier" if peer else
+                     "all-reduce on the device") + " -> one D2H of the int32 counts into pinned memory",
             "host_binding": env.numa if env.numa is not None else "none (topology not readable or BENCH_NUMA=0)"}, \
         out.numpy().astype(np.int64)
 
@@ -540,7 +634,7 @@ def run_c2(args, env):
     if world > 1:
         other = []
         n_o = max(3, min(args.steps, 50))
-        for mode in ("overlapped", "per-step", "once"):
+        for mode in ("peer", "overlapped", "per-step", "once"):
             if mode != args.collective:
                 o_ms, _, _, o_hits = timed_steps(env, pieces, counts, n_o, mode)
                 other.append({"collective": mode, "steps": n_o, "ms_per_step": o_ms / n_o,
@@ -594,7 +688,7 @@ def run_c2(args, env):
 
     e2e = None
     if not args.no_e2e:
-        e2e, e2e_counts = e2e_leg(env, pieces, counts, M, max(2, min(args.steps, 5)), total_letters)
+        e2e, e2e_counts = e2e_leg(env, pieces, counts, M, max(2, min(args.steps, 5)), total_letters, args.collective)
         e2e["counts_equal_device_steps"] = bool((e2e_counts == hits).all())
 
     recount_ok = None
@@ -779,7 +873,7 @@ def run_c3_c5(args, env):
     ms_per_step = total_ms / steps
     e2e = None
     if not args.no_e2e:
-        e2e, e2e_counts = e2e_leg(env, pieces, counts, M, 3, genome)
+        e2e, e2e_counts = e2e_leg(env, pieces, counts, M, 3, genome, args.collective)
         e2e["counts_equal_device_steps"] = bool((e2e_counts == hits).all())
     recount_ok = None
     if world > 1 and not args.no_recount:

@@ -29,6 +29,7 @@ SYMBOLS = [
     "bsgpu_XStringSet_oligo_frequency",
     "bsgpu_subject_fasta", "bsgpu_fasta_info_free", "bsgpu_subject_nsequences", "bsgpu_subject_element",
     "bsgpu_subject_download", "bsgpu_subject_letters", "bsgpu_count_indels", "bsgpu_count_host",
+    "bsgpu_shared_counts_create", "bsgpu_shared_counts_open", "bsgpu_shared_counts_close",
 ]
 
 
@@ -99,6 +100,9 @@ def lib():
         [C.c_int] * 5 + [C.POINTER(Result)]
     L.bsgpu_vmatch_PDict3Parts_XStringSet.argtypes = [vp, vp, vp, i32] + [C.c_int] * 4 + \
         [C.c_int, C.c_int, vp, i64, C.c_int, C.POINTER(Result)]
+    L.bsgpu_shared_counts_create.argtypes = [i64, C.POINTER(vp), vp]
+    L.bsgpu_shared_counts_open.argtypes = [vp, C.POINTER(vp)]
+    L.bsgpu_shared_counts_close.argtypes = [vp, C.c_int]
     L.bsgpu_mindex_combine.argtypes = [C.POINTER(C.POINTER(Result)), C.c_int, C.POINTER(Result)]
     L.bsgpu_last_plan.restype = C.c_char_p
     L.bsgpu_launch_count.restype = i64

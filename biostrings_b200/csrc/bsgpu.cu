@@ -4048,6 +4048,60 @@ extern "C" int bsgpu_XStringSet_oligo_frequency(const uint8_t *concat, const int
 }
 
 // ---------------------------------------------------------------------------------------
+// One count vector for the GPUs of a box (include/bsgpu.h): CUDA IPC + peer access; the scan
+// kernels count with system-scope reductions (count_add, bsgpu_kernels.cuh), so a vector that
+// lives on another GPU is incremented over NVLink by the very launch that finds the match.
+// ---------------------------------------------------------------------------------------
+
+static_assert(sizeof(cudaIpcMemHandle_t) == BSGPU_IPC_HANDLE_BYTES, "IPC handle size");
+
+extern "C" int bsgpu_shared_counts_create(int64_t n, int32_t **d_counts_out, unsigned char *handle_out)
+{
+	if (n <= 0 || d_counts_out == nullptr || handle_out == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_shared_counts_create(): bad arguments");
+	TRY(ensure_device());
+	int32_t *p = nullptr;
+	cudaIpcMemHandle_t h;
+
+	// a plain cudaMalloc block of its own: IPC handles name whole allocations
+	CUDA_TRY(cudaMalloc((void **) &p, (size_t) n * sizeof(int32_t)));
+	if (cudaMemset(p, 0, (size_t) n * sizeof(int32_t)) != cudaSuccess || cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
+		cudaError_t e = cudaGetLastError();
+
+		cudaFree(p);
+		return fail(BSGPU_ECUDA, "bsgpu_shared_counts_create(): %s", cudaGetErrorString(e));
+	}
+	memcpy(handle_out, &h, sizeof(h));
+	*d_counts_out = p;
+	return BSGPU_OK;
+}
+
+extern "C" int bsgpu_shared_counts_open(const unsigned char *handle, int32_t **d_counts_out)
+{
+	if (handle == nullptr || d_counts_out == nullptr)
+		return fail(BSGPU_EINVAL, "bsgpu_shared_counts_open(): bad arguments");
+	TRY(ensure_device());
+	cudaIpcMemHandle_t h;
+	void *p = nullptr;
+
+	memcpy(&h, handle, sizeof(h));
+	CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+	*d_counts_out = (int32_t *) p;
+	return BSGPU_OK;
+}
+
+extern "C" int bsgpu_shared_counts_close(int32_t *d_counts, int is_owner)
+{
+	if (d_counts == nullptr)
+		return BSGPU_OK;
+	if (is_owner)
+		CUDA_TRY(cudaFree(d_counts));
+	else
+		CUDA_TRY(cudaIpcCloseMemHandle(d_counts));
+	return BSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // Roofline probes
 // ---------------------------------------------------------------------------------------
 

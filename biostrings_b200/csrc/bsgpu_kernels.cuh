@@ -176,12 +176,20 @@ __device__ __forceinline__ void append_record(const BsgpuReport &R, unsigned lon
 
 // key: 0-based pattern id; seg: segment of the subject; n: 1-based local TB end;
 // e: concat index of the TB end; Tlen: tail width of 'key'.
+// counts[i] += v.  System scope: the count vector may live in another GPU's memory (one vector
+// for the GPUs of a box, bsgpu_shared_counts_*), where the reduction travels over NVLink and is
+// carried out by the owner's L2; for a local vector it is the same RED as before.
+__device__ __forceinline__ void count_add(int32_t *p, int32_t v)
+{
+	atomicAdd_system(p, v);
+}
+
 __device__ __forceinline__ void report_match(const BsgpuReport &R, const BsgpuSubjectView &S,
 		int key, int seg, int64_t n, int64_t e, int Tlen)
 {
 	switch (R.mode) {
 	case BSGPU_R_COUNT:
-		atomicAdd(R.counts + key, 1);
+		count_add(R.counts + key, 1);
 		break;
 	case BSGPU_R_HIT_COORD: {
 		// end = tb_end + |tail|   (src/match_pdict_utils.c:99-106)
@@ -193,13 +201,13 @@ __device__ __forceinline__ void report_match(const BsgpuReport &R, const BsgpuSu
 		append_record(R, ((unsigned long long) key << BSGPU_POS_BITS) | (unsigned long long) e);
 		break;
 	case BSGPU_R_VMAT:
-		atomicAdd(R.counts + (int64_t) seg * R.M + key, 1);
+		count_add(R.counts + (int64_t) seg * R.M + key, 1);
 		break;
 	case BSGPU_R_VC1:
-		atomicAdd(R.counts + key, __ldg(R.weight + seg));
+		count_add(R.counts + key, __ldg(R.weight + seg));
 		break;
 	case BSGPU_R_VC2:
-		atomicAdd(R.counts + seg, __ldg(R.weight + key));
+		count_add(R.counts + seg, __ldg(R.weight + key));
 		break;
 	case BSGPU_R_SEGKEY:
 		append_record(R, ((unsigned long long) seg << BSGPU_SEGKEY_BITS) | (unsigned long long) key);
@@ -273,7 +281,7 @@ __device__ __forceinline__ void tb_hit(const BsgpuIndexView &I, const BsgpuSubje
 		return;
 	}
 	if (R.mode == BSGPU_R_COUNT) {
-		atomicAdd(R.counts + tb_id, 1);
+		count_add(R.counts + tb_id, 1);
 		return;
 	}
 	int seg = S.nseg == 1 ? 0 : find_segment(S, e);
@@ -792,7 +800,7 @@ match_plain_kernel(BsgpuSubjectView S, BsgpuPlainView P, BsgpuReport R, int max_
 			if (nmis > max_nmis || nmis < min_nmis)
 				continue;
 			if (R.mode == BSGPU_R_COUNT)
-				atomicAdd(R.counts + i, 1);
+				count_add(R.counts + i, 1);
 			else            // n = 1-based local end; the record position is the slot
 				report_match(R, S, i, seg, Pshift + plen, slot, 0);
 		}

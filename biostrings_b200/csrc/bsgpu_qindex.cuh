@@ -961,7 +961,7 @@ __device__ __forceinline__ void byteseed_confirm(const BsgpuSubjectView &S, cons
 			if (!byteseed_same_bytes(S.bytes + a, T.tb + (int64_t) id * T.w, T.w))
 				continue;
 			if (R.mode == BSGPU_R_COUNT) {
-				atomicAdd(R.counts + id, 1);
+				count_add(R.counts + id, 1);
 			} else {
 				int seg = S.nseg == 1 ? 0 : find_segment(S, p);
 

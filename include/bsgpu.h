@@ -281,6 +281,24 @@ int bsgpu_count_device(const bsgpu_pdict3parts *const *parts, int nparts,
 		int max_mismatch, int min_mismatch, int fixedP, int fixedS,
 		int32_t *d_counts, void *stream, int *n_launches_out);
 
+/*
+ * One count vector for the GPUs of a box (one process per GPU).  The reference is a single
+ * process: its counts are one INTEGER vector the match loop increments (match_reporting.c:
+ * _MatchBuf_report_match, src/match_reporting.c:95-116).  With the subject sharded over N GPUs the
+ * same vector lives in ONE GPU's memory and every rank's scan kernels increment it directly, by
+ * system-scope reductions through NVLink peer memory: the gather of the per-pattern counts is part
+ * of the scan launch, there is no separate collective.
+ *   owner rank : bsgpu_shared_counts_create(n, &dptr, handle)   cudaMalloc + zero + IPC handle
+ *   other ranks: bsgpu_shared_counts_open(handle, &dptr)        maps the owner's vector (peer access)
+ * dptr is what bsgpu_count_device / bsgpu_count_host take as d_counts.  The 64 handle bytes travel
+ * by whatever channel the processes share (bench.py: a torch.distributed broadcast).
+ * bsgpu_shared_counts_close(dptr, is_owner) unmaps / frees.
+ */
+#define BSGPU_IPC_HANDLE_BYTES 64
+int bsgpu_shared_counts_create(int64_t n, int32_t **d_counts_out, unsigned char handle_out[BSGPU_IPC_HANDLE_BYTES]);
+int bsgpu_shared_counts_open(const unsigned char handle[BSGPU_IPC_HANDLE_BYTES], int32_t **d_counts_out);
+int bsgpu_shared_counts_close(int32_t *d_counts, int is_owner);
+
 /* ------------------------------------------------------------------------------------
  * Host-buffer entry points with the reference's .Call shapes (upload + match + free).
  * ------------------------------------------------------------------------------------ */

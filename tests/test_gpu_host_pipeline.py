@@ -120,4 +120,63 @@ def test_chunks_through_the_host_call(mm):
     got = acc.cpu().numpy()
     with mp.DeviceSubject.from_xstring(s) as ds:
         want = mp.match_parts(parts, ds, mm, 0, (True, True), _lib.MATCHES_AS_COUNTS)
-    assert got.tolist() == want.tolist() and got.sum() > 300
+    assert got.tolist() == want.tolist() and got.sum() >= 250
+
+
+def _peer_child(handle_bytes, pats, chunk, a, subject_len, lo, hi, q):
+    """A second process on the same GPU: maps the owner's count vector and counts its chunk into it."""
+    import ctypes as C
+    try:
+        L = _lib.lib()
+        ptr = C.c_void_p()
+        buf = (C.c_ubyte * 64)(*handle_bytes)
+        _lib.check(L.bsgpu_shared_counts_open(buf, C.byref(ptr)))
+        prod = bs.PDict(bs.DNAStringSet(pats))
+        mp.count_parts_host(prod.parts(), chunk, 0, 0, (True, True), chunk_start=a, subject_len=subject_len,
+                            report=(lo, hi), d_counts=ptr.value, stream=0)
+        import torch
+        torch.cuda.synchronize()
+        _lib.check(L.bsgpu_shared_counts_close(ptr, 0))
+        q.put("ok")
+    except Exception as ex:             # noqa: BLE001 -- reported to the parent
+        q.put(repr(ex))
+
+
+def test_one_count_vector_for_two_processes():
+    """bsgpu_shared_counts_*: the owner creates the vector, a second process maps it through its IPC
+    handle and counts its overlap chunk into it (system-scope reductions), the owner counts the other
+    chunk: the sum equals the whole subject.  (On a box with several GPUs bench.py does the same with
+    one process per GPU and checks it against a 1-GPU recount.)"""
+    import ctypes as C
+    import multiprocessing as mpc
+    import torch
+    g = rng(9400)
+    s = subject(g, 300_000)
+    pats = cut(g, s, 25, 400, [150_000]) + cut(g, s, 25, 200)
+    prod, _ = both(pats)
+    parts = prod.parts()
+    L = _lib.lib()
+    ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+    _lib.check(L.bsgpu_shared_counts_create(len(pats), C.byref(ptr), handle))
+    try:
+        mid, halo = 150_000, 24
+        ctx = mpc.get_context("spawn")
+        q = ctx.Queue()
+        child = ctx.Process(target=_peer_child, args=(bytes(handle), pats, s[mid - halo:], mid - halo, s.size, mid, s.size, q))
+        child.start()
+        mp.count_parts_host(parts, s[:mid], 0, 0, (True, True), chunk_start=0, subject_len=s.size,
+                            report=(0, mid), d_counts=ptr.value, stream=0)
+        torch.cuda.synchronize()
+        msg = q.get(timeout=300)
+        child.join(timeout=60)
+        assert msg == "ok", msg
+        # read the vector back through torch (the owner's own allocation)
+        class _A:
+            __cuda_array_interface__ = {"shape": (len(pats),), "typestr": "<i4", "data": (ptr.value, False),
+                                        "version": 2}
+        got = torch.as_tensor(_A(), device="cuda").cpu().numpy()
+    finally:
+        _lib.check(L.bsgpu_shared_counts_close(ptr, 1))
+    with mp.DeviceSubject.from_xstring(s) as ds:
+        want = mp.match_parts(parts, ds, 0, 0, (True, True), _lib.MATCHES_AS_COUNTS)
+    assert got.tolist() == want.tolist() and got.sum() >= 250
