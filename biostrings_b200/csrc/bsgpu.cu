@@ -2264,40 +2264,14 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 					TRY(ws->cand.alloc((size_t) cap * nslices));
 				if (nslices > ws->xseed_counts.n)
 					TRY(ws->xseed_counts.alloc(nslices));
-				// keep the filter in L2 against the subject streaming through it: a persisting
-				// access-policy window on the launching stream (the per-load evict_last / evict_first
-				// hints alone still let ~a filter's worth of DRAM traffic through per launch)
-				static int persist_ok = -1;
-				if (persist_ok < 0) {
-					int max_persist = 0, max_window = 0;
-					cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, g_device);
-					cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, g_device);
-					persist_ok = getenv("BSGPU_NO_L2_WINDOW") == nullptr && max_persist > 0 && max_window > 0 &&
-						     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize,
-									std::min<size_t>((size_t) max_persist, (size_t) 64 << 20)) == cudaSuccess;
-					cudaGetLastError();
-				}
-				if (persist_ok > 0) {
-					cudaStreamAttrValue attr = {};
-					int max_window = 0;
-					cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, g_device);
-					attr.accessPolicyWindow.base_ptr = (void *) xi->t.filter;
-					attr.accessPolicyWindow.num_bytes = std::min<size_t>((size_t) xi->nfilter * 32, (size_t) max_window);
-					attr.accessPolicyWindow.hitRatio = 1.0f;
-					attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-					attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-					cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
-					cudaGetLastError();
-				}
+				// (A persisting access-policy window on the filter was tried on top of the per-load
+				// evict_last / evict_first hints: no gain for this kernel, and the 64 MB set aside by
+				// cudaLimitPersistingL2CacheSize halved the bandwidth of every streaming kernel that ran
+				// afterwards in the process -- pack_subject_kernel 0.082 -> 0.135 ms, the copy probe
+				// 6.2 -> 2.9 TB/s -- so it is gone.)
 				{
 					KernelTimer kt("scan_xseed_kernel", st);
 					XSEED_DISPATCH(LAUNCH_XSEED);
-				}
-				if (persist_ok > 0) {
-					cudaStreamAttrValue attr = {};
-					attr.accessPolicyWindow.num_bytes = 0;          // window off for whatever the caller launches next
-					cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
-					cudaGetLastError();
 				}
 				g_launches++;
 				CUDA_TRY(cudaGetLastError());

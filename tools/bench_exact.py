@@ -25,7 +25,6 @@ SETTINGS = {
     "xseed_kbits8_np2": {"BSGPU_XSEED_KBITS": "8", "BSGPU_XSEED_NP": "2"},
     "xseed_unaligned": {"BSGPU_XSEED_UNALIGNED": "1"},
     "xseed_split_confirm": {"BSGPU_XSEED_SPLIT_CONFIRM": "1"},
-    "xseed_no_l2_window": {"BSGPU_NO_L2_WINDOW": "1"},
     # candidates dropped (results wrong by construction): what the scan alone costs
     "xseed_var16_no_candidates": {"BSGPU_XSEED_VARIANT": "16"},
 }
