@@ -338,6 +338,13 @@ struct bsgpu_pdict3parts {
 	mutable std::unique_ptr<struct TbDirIndex> tcache;      // band directory (w <= 12, packed flanks)
 	// non-preprocessed dictionary (bsgpu_patterns_build): the letters only, no Trusted Band
 	bool plain = false;
+	std::vector<uint8_t> h_pat;             // host copy of the letters (for the automatic index below)
+	std::vector<int64_t> h_pat_off;
+	// a large base-only non-preprocessed dictionary matched exactly gets a Trusted-Band index of its
+	// own on first use (plain_auto_index): same results as one matchPattern() per pattern
+	mutable bsgpu_pdict3parts *auto_idx = nullptr;
+	mutable int auto_state = 0;             // 0 = not tried, 1 = built, -1 = not eligible
+	~bsgpu_pdict3parts();
 	DevBuf<uint8_t> d_pat;
 	DevBuf<int64_t> d_pat_off;
 	DevBuf<uint4> d_pat_head;
@@ -1430,6 +1437,8 @@ static int bsgpu_patterns_build_impl(const uint8_t *concat, const int32_t *width
 	TRY(ensure_device());
 	std::unique_ptr<bsgpu_pdict3parts> p3(new bsgpu_pdict3parts());
 	p3->plain = true;
+	p3->h_pat.assign(concat, concat + off[M]);
+	p3->h_pat_off = off;
 	p3->max_plen = max_plen;
 	p3->M = M;
 	p3->w = 0;
@@ -1508,6 +1517,7 @@ extern "C" int bsgpu_pdict3parts_blank_dups(bsgpu_pdict3parts *p3)
 	return BSGPU_OK;
 }
 
+bsgpu_pdict3parts::~bsgpu_pdict3parts() { delete auto_idx; }
 extern "C" void bsgpu_pdict3parts_free(bsgpu_pdict3parts *p3) { delete p3; }
 extern "C" int32_t bsgpu_pdict3parts_length(const bsgpu_pdict3parts *p3) { return p3 ? p3->M : 0; }
 extern "C" int32_t bsgpu_pdict3parts_tb_width(const bsgpu_pdict3parts *p3) { return p3 ? p3->w : 0; }
@@ -2416,6 +2426,69 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 	return BSGPU_OK;
 }
 
+// The automatic index of a non-preprocessed dictionary (the reference runs one
+// matchPattern() per pattern, src/match_pdict.c:174-199,267-293,519-550 -- fine for 1000 patterns,
+// hopeless for 10^6).  Exact matching of base-only patterns against a literally taken subject is
+// what a Trusted-Band dictionary computes: band = the first min(width) letters (at most 32; the
+// whole pattern when all widths agree), the rest is the tail, whole-pattern duplicates share a band
+// and are reported through its group like any other keys (src/match_pdict_utils.c:153-181) -- so
+// the call is handed to the preprocessed engines (extended seeds / band directory) and returns
+// the same counts, which-indices and ends.  Not for chunked subjects with open ends (the two paths
+// own boundary matches differently), not below BSGPU_PLAIN_INDEX_MIN patterns (default 256: the
+// brute force wins), switched off by BSGPU_PLAIN_INDEX=0.
+static int plain_auto_index(const bsgpu_pdict3parts *p3, int max_nmis, int min_nmis, int fixedP, int fixedS,
+			    bool open_ends, const bsgpu_pdict3parts **out)
+{
+	*out = nullptr;
+	if (!p3->plain || max_nmis != 0 || min_nmis != 0 || !fixedS || open_ends || p3->auto_state < 0)
+		return BSGPU_OK;
+	(void) fixedP;          // base-only patterns: fixedP does not matter
+	if (p3->auto_state > 0) {
+		*out = p3->auto_idx;
+		return BSGPU_OK;
+	}
+	p3->auto_state = -1;
+	const char *env = getenv("BSGPU_PLAIN_INDEX"), *env_min = getenv("BSGPU_PLAIN_INDEX_MIN");
+	const int M = p3->M, min_m = env_min != nullptr ? atoi(env_min) : 256;
+	if ((env != nullptr && env[0] == '0') || M < min_m || M >= (1 << 24) || p3->h_pat_off.size() != (size_t) M + 1)
+		return BSGPU_OK;
+	int64_t min_w = INT64_MAX, max_w = 0;
+	for (int i = 0; i < M; i++) {
+		int64_t wd = p3->h_pat_off[i + 1] - p3->h_pat_off[i];
+		min_w = std::min(min_w, wd);
+		max_w = std::max(max_w, wd);
+	}
+	if (min_w < 8)
+		return BSGPU_OK;
+	for (uint8_t b : p3->h_pat)
+		if (!bsgpu_is_base(b))
+			return BSGPU_OK;
+	const int tbw = (int) (min_w == max_w ? min_w : std::min<int64_t>(min_w, 32));
+	std::vector<uint8_t> tb((size_t) M * tbw), tail;
+	std::vector<int32_t> tbwid((size_t) M, tbw), tailwid((size_t) M, 0);
+	for (int i = 0; i < M; i++) {
+		const uint8_t *src = p3->h_pat.data() + p3->h_pat_off[i];
+		int64_t wd = p3->h_pat_off[i + 1] - p3->h_pat_off[i];
+
+		memcpy(tb.data() + (size_t) i * tbw, src, (size_t) tbw);
+		tailwid[i] = (int32_t) (wd - tbw);
+		tail.insert(tail.end(), src + tbw, src + wd);
+	}
+	bsgpu_pdict3parts *idx = nullptr;
+	const bool has_tail = max_w > tbw;
+	int rc = bsgpu_pdict3parts_build_impl(BSGPU_ALGO_ACTREE2, M, tb.data(), tbwid.data(), nullptr, nullptr,
+					      has_tail ? tail.data() : nullptr, has_tail ? tailwid.data() : nullptr,
+					      nullptr, nullptr, &idx);
+	if (rc != BSGPU_OK || idx == nullptr) {
+		g_err[0] = 0;           // not an error of the call: the brute force answers it
+		return BSGPU_OK;
+	}
+	p3->auto_idx = idx;
+	p3->auto_state = 1;
+	*out = idx;
+	return BSGPU_OK;
+}
+
 // A non-preprocessed dictionary against the subject: every (segment, shift) slot x every
 // pattern, brute force as in the reference (which runs one matchPattern per pattern).
 static int run_plain(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, const MatchParams &mp,
@@ -2936,6 +3009,16 @@ static int bsgpu_match_impl(const bsgpu_pdict3parts *const *parts, int nparts,
 	TRY(check_args(parts, nparts, subj, max_nmis, min_nmis));
 	if (res == nullptr)
 		return fail(BSGPU_EINVAL, "bsgpu_match(): NULL result");
+	const bsgpu_pdict3parts *auto_part[1];
+	if (nparts == 1 && parts[0]->plain) {
+		const bsgpu_pdict3parts *ai = nullptr;
+		TRY(plain_auto_index(parts[0], max_nmis, min_nmis, fixedP, fixedS,
+				     subj->kind == SUBJ_CHUNK && (subj->open_left || subj->open_right), &ai));
+		if (ai != nullptr) {
+			auto_part[0] = ai;
+			parts = auto_part;
+		}
+	}
 	memset(res, 0, sizeof(*res));
 	if (subj->kind == SUBJ_SET)
 		return fail(BSGPU_EINVAL, "please use vmatchPDict() when 'subject' is an XStringSet "
@@ -3118,6 +3201,16 @@ static int bsgpu_count_device_impl(const bsgpu_pdict3parts *const *parts, int np
 	TRY(check_args(parts, nparts, subj, max_nmis, min_nmis));
 	if (d_counts == nullptr)
 		return fail(BSGPU_EINVAL, "bsgpu_count_device(): NULL d_counts");
+	const bsgpu_pdict3parts *auto_part[1];
+	if (nparts == 1 && parts[0]->plain) {
+		const bsgpu_pdict3parts *ai = nullptr;
+		TRY(plain_auto_index(parts[0], max_nmis, min_nmis, fixedP, fixedS,
+				     subj->kind == SUBJ_CHUNK && (subj->open_left || subj->open_right), &ai));
+		if (ai != nullptr) {
+			auto_part[0] = ai;
+			parts = auto_part;
+		}
+	}
 	TRY(ensure_device());
 	Workspace *ws;
 	TRY(workspace(&ws));
@@ -3240,6 +3333,16 @@ static int bsgpu_count_host_impl(const bsgpu_pdict3parts *const *parts, int npar
 		if (parts[p] == nullptr || parts[p]->M != parts[0]->M)
 			return fail(BSGPU_EINVAL, "cannot combine MIndex objects of different lengths");
 	TRY(ensure_device());
+	const bsgpu_pdict3parts *auto_part[1];
+	if (nparts == 1 && parts[0]->plain) {
+		const bsgpu_pdict3parts *ai = nullptr;
+		TRY(plain_auto_index(parts[0], max_nmis, min_nmis, fixedP, fixedS,
+				     chunk_start > 0 || chunk_start + length < subject_len, &ai));
+		if (ai != nullptr) {
+			auto_part[0] = ai;
+			parts = auto_part;
+		}
+	}
 	Workspace *ws;
 	TRY(workspace(&ws));
 	cudaStream_t st = (cudaStream_t) stream;
@@ -3441,6 +3544,16 @@ static int bsgpu_vmatch_impl(const bsgpu_pdict3parts *const *parts, int nparts,
 	TRY(check_args(parts, nparts, subj, max_nmis, min_nmis));
 	if (res == nullptr)
 		return fail(BSGPU_EINVAL, "bsgpu_vmatch(): NULL result");
+	const bsgpu_pdict3parts *auto_part[1];
+	if (nparts == 1 && parts[0]->plain) {
+		const bsgpu_pdict3parts *ai = nullptr;
+		TRY(plain_auto_index(parts[0], max_nmis, min_nmis, fixedP, fixedS,
+				     subj->kind == SUBJ_CHUNK && (subj->open_left || subj->open_right), &ai));
+		if (ai != nullptr) {
+			auto_part[0] = ai;
+			parts = auto_part;
+		}
+	}
 	memset(res, 0, sizeof(*res));
 	if (subj->kind != SUBJ_SET)
 		return fail(BSGPU_EINVAL, "please use matchPDict() when 'subject' is an XString or "

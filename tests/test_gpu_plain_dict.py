@@ -240,3 +240,53 @@ def test_chunked_subject_equals_whole():
                 mp.match_parts([pat], ch, 0, 0, (True, True), _lib.MATCHES_AS_COUNTS)
     finally:
         pat.close()
+
+
+@pytest.mark.parametrize("widths", [(12, 40), (25, 25), (40, 64)])
+def test_large_base_only_dictionary_gets_its_own_index(widths, monkeypatch):
+    """>= 256 base-only patterns matched exactly: the library builds a Trusted-Band index behind the
+    non-preprocessed dictionary (plain_auto_index) -- counts, which and ends must equal the
+    reference's one-matchPattern-per-pattern loop, whole-pattern duplicates included, on a
+    sequence, on views, on a set, and equal the brute force the same call runs with
+    BSGPU_PLAIN_INDEX=0.  Anything the index does not cover (mismatches, IUPAC subject) stays brute force."""
+    g = rng(9700 + widths[0])
+    s = random_dna(g, 60_000)
+    s[1000:1010] = 15
+    pats = []
+    for i in g.integers(0, 59_000, 500):
+        w = int(g.integers(widths[0], widths[1] + 1))
+        p = s[i:i + w].copy()
+        if not np.isin(p, [1, 2, 4, 8]).all():
+            p = random_dna(g, w)
+        pats.append(p)
+    pats += [random_dna(g, int(g.integers(widths[0], widths[1] + 1))) for _ in range(100)]
+    pats += [pats[int(k)].copy() for k in g.integers(0, 500, 40)]          # whole-pattern duplicates
+    pats += [pats[int(k)][:widths[0]].copy() for k in g.integers(0, 500, 20)]  # prefixes of other patterns
+    pset, oset = bs.DNAStringSet(pats), R.SeqSet(pats)
+    L = _lib.lib()
+    subjects = [(s, s), (bs.XStringViews(s, [1, 500, 30_000], [20_000, 3000, 30_000]),
+                         R.Views(s, [1, 500, 30_000], [20_000, 3000, 30_000]))]
+    for sp, so in subjects:
+        want = R.countPDict(oset, so, backend=BACKEND)
+        got = bs.countPDict(pset, sp)
+        assert not L.bsgpu_last_plan().decode().startswith("plain_bruteforce")
+        assert got.tolist() == want.tolist() and got.sum() > 300
+        assert bs.whichPDict(pset, sp).tolist() == R.whichPDict(oset, so, backend=BACKEND).tolist()
+        mp_, mo = bs.matchPDict(pset, sp), R.matchPDict(oset, so, backend=BACKEND)
+        assert_same_ends(mp_.endIndex(), mo.endIndex())
+        assert_same_ends(mp_.startIndex(), mo.startIndex())
+    # a set of reads
+    reads = [s[i:i + int(g.integers(0, 200))].copy() for i in g.integers(0, 59_000, 200)]
+    rp, ro = bs.DNAStringSet(reads), R.SeqSet(reads)
+    a, b = bs.vcountPDict(pset, rp), R.vcountPDict(oset, ro, backend=BACKEND)
+    assert not L.bsgpu_last_plan().decode().startswith("plain_bruteforce")
+    assert a.shape == b.shape and (a == b).all()
+    # what the index does not cover keeps the brute force
+    assert bs.countPDict(pset, s, max_mismatch=1).tolist() == R.countPDict(oset, s, max_mismatch=1, backend=BACKEND).tolist()
+    assert L.bsgpu_last_plan().decode().startswith("plain_bruteforce")
+    # and the brute force agrees when the index is switched off (a fresh dictionary object)
+    monkeypatch.setenv("BSGPU_PLAIN_INDEX", "0")
+    pset2 = bs.DNAStringSet(pats)
+    got2 = bs.countPDict(pset2, s)
+    assert L.bsgpu_last_plan().decode().startswith("plain_bruteforce")
+    assert got2.tolist() == R.countPDict(oset, s, backend=BACKEND).tolist()
