@@ -232,7 +232,7 @@ def c2_config(args, world):
             "patterns": args.patterns, "pattern_width": WIDTH, "max_mismatch": args.mm,
             "subject_letters_per_gpu": int(per * 1e6),
             "sharding": f"{world} overlap chunk(s) by Trusted-Band end, halo = width-1",
-            "collective": COLLECTIVE_TEXT[args.collective] if world > 1 else "none",
+            "collective": COLLECTIVE_TEXT[COLLECTIVE_USED.get("mode") or args.collective] if world > 1 else "none",
             "l2": "inputs larger than L2: every step streams the subject chunk through the 126 MB L2 "
                   "(no flush inside the bracket)" if per * 1e6 > 126e6 else
                   "the rank's chunk is smaller than the 126 MB L2: consecutive steps may find it there (strong scaling)",
@@ -240,6 +240,8 @@ def c2_config(args, world):
                     "(max.mismatch 0: the extended-seed scan reads the letters directly + candidate confirmation; "
                     "otherwise pack to 2-bit planes first)"}
 
+
+COLLECTIVE_USED = {}        # "mode": what timed_steps fell back to when the peer mapping is not available
 
 COLLECTIVE_TEXT = {
     "peer": "none launched: one int32 count vector in rank 0's memory (CUDA IPC, bsgpu_shared_counts_*), every rank's scan "
@@ -296,18 +298,29 @@ class Env:
             return self._shared[M]
         ptr = C.c_void_p()
         h = torch.zeros(64, dtype=torch.uint8, device=self.dev)
+        ok = 1
         if self.rank == 0:
             buf = (C.c_ubyte * 64)()
-            _lib.check(self.L.bsgpu_shared_counts_create(M, C.byref(ptr), buf))
-            h.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+            if self.L.bsgpu_shared_counts_create(M, C.byref(ptr), buf) == 0:
+                h.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+            else:
+                ok = 0
         if self.world > 1:
             self.dist.broadcast(h, 0)
         view = None
         if self.rank != 0:
             buf = (C.c_ubyte * 64)(*h.cpu().tolist())
-            _lib.check(self.L.bsgpu_shared_counts_open(buf, C.byref(ptr)))
-        else:
+            if self.L.bsgpu_shared_counts_open(buf, C.byref(ptr)) != 0:
+                ok = 0
+        elif ok:
             view = torch.as_tensor(_DevArray(ptr.value, M), device=self.dev)
+        # every rank must have the vector (CUDA IPC + peer access), or nobody uses it
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            self._shared[M] = None
+            return None
         self._shared[M] = (ptr.value, view)
         return self._shared[M]
 
@@ -419,7 +432,11 @@ def timed_steps(env, pieces, counts, nsteps, collective):
         # its whole gather -- each match is one reduction over NVLink -- only the 4 MB memset per
         # call is left out, which would need a barrier of its own between the steps)
         M = counts.numel()
-        ptr, view = env.shared_counts(M)
+        shared = env.shared_counts(M)
+        if shared is None:              # no peer mapping on this box: the NCCL path
+            COLLECTIVE_USED["mode"] = "overlapped"
+            return timed_steps(env, pieces, counts, nsteps, "overlapped")
+        ptr, view = shared
         if view is not None:
             view.zero_()
         L.bsgpu_kernel_timing(1)
@@ -502,7 +519,7 @@ def e2e_leg(env, pieces, counts, M, n, total_letters, collective="overlapped"):
     bytes on all ranks at once (the ceiling this box gives the path)."""
     torch = env.torch
     out = torch.empty(M, dtype=torch.int32, pin_memory=True)
-    peer = collective == "peer" and env.world > 1
+    peer = collective == "peer" and env.world > 1 and env.shared_counts(M) is not None
     times = []
     if peer:
         ptr, view = env.shared_counts(M)
@@ -923,7 +940,7 @@ def run_c3_c5(args, env):
             "config": {"workload": label, "patterns": M, "subject_letters_total": genome,
                        "sharding": f"{world} rank(s), overlap chunks by Trusted-Band end inside every chromosome "
                                    f"(halo {halo[0]} before, {halo[1]} after), {len(pieces.items)} piece(s) on rank 0",
-                       "collective": COLLECTIVE_TEXT[args.collective] if world > 1 else "none",
+                       "collective": COLLECTIVE_TEXT[COLLECTIVE_USED.get("mode") or args.collective] if world > 1 else "none",
                        "l2": "the rank's chunks are streamed once per step"},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roof,
             "cpu_baseline": cpu, "parity_with_gpu_on_sample": parity,

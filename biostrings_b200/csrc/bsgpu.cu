@@ -2246,10 +2246,10 @@ static int launch_scans(const bsgpu_pdict3parts *p3, const bsgpu_subject *subj, 
 			BSGPU_XSEED_WARPS * BSGPU_XSEED_STAGES * (int) xseed_stage_bytes(NP, AL ? 16 : 32, AL))); \
 		attr_set = true; \
 	} \
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_xseed_kernel<NP, AL, KB, V, FU>, 256, smem)); \
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_xseed_kernel<NP, AL, KB, V, FU>, BSGPU_XSEED_WARPS * 32, smem)); \
 } while (0)
 #define LAUNCH_XSEED(NP, AL, KB, V, FU) \
-	scan_xseed_kernel<NP, AL, KB, V, FU><<<grid, 256, smem, st>>>(S, xi->t, R, first, nprobes, ws->cand.p, cap, \
+	scan_xseed_kernel<NP, AL, KB, V, FU><<<grid, BSGPU_XSEED_WARPS * 32, smem, st>>>(S, xi->t, R, first, nprobes, ws->cand.p, cap, \
 								      ws->xseed_counts.p, end_lo, end_hi)
 #define XSEED_DISPATCH2(WHAT, FU) do { \
 	if (var == 16 && aligned && np == 4 && xi->t.kbits == 4) { WHAT(4, true, 4, 16, false); } \

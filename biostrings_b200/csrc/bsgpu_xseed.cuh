@@ -223,8 +223,12 @@ __device__ __noinline__ void xseed_confirm_call(const BsgpuSubjectView *S, const
 	xseed_confirm(*S, *T, *R, cand, own_lo, own_hi);
 }
 
+#ifndef BSGPU_XSEED_WARPS
 #define BSGPU_XSEED_WARPS 8             // all of them scan
-#define BSGPU_XSEED_STAGES 3
+#endif
+#ifndef BSGPU_XSEED_STAGES
+#define BSGPU_XSEED_STAGES 2            // 2 stages 0.0955 ms, 3 stages 0.0983, 6 stages 0.18: shared memory taken from L1 costs the gathers more than a deeper ring gains
+#endif
 #ifndef BSGPU_XSEED_MIN_BLOCKS
 #define BSGPU_XSEED_MIN_BLOCKS 3        // resident blocks per SM the register budget is cut for
 #endif
@@ -272,7 +276,7 @@ __host__ __device__ __forceinline__ int64_t xseed_warp_capacity(int64_t nprobes,
 // trips of the confirmations hide under the scan and the second launch disappears.
 template <int NP, bool ALIGNED, int KB = 4, int VAR = 0, bool FUSED = true, int STAGES = BSGPU_XSEED_STAGES,
 	  int MINB = BSGPU_XSEED_MIN_BLOCKS>
-__global__ void __launch_bounds__(256, MINB)
+__global__ void __launch_bounds__(BSGPU_XSEED_WARPS * 32, MINB)
 scan_xseed_kernel(const __grid_constant__ BsgpuSubjectView S, const __grid_constant__ BsgpuXSeedView T,
 		  const __grid_constant__ BsgpuReport R, int64_t first, int64_t nprobes,
 		  unsigned long long *__restrict__ cand, int64_t cap, unsigned int *__restrict__ n_cand,
