@@ -236,9 +236,10 @@ def c2_config(args, world):
             "l2": "inputs larger than L2: every step streams the subject chunk through the 126 MB L2 "
                   "(no flush inside the bracket)" if per * 1e6 > 126e6 else
                   "the rank's chunk is smaller than the 126 MB L2: consecutive steps may find it there (strong scaling)",
-            "step": "new batch of 1-byte letters resident in HBM -> scan into the rank's device count vector "
-                    "(max.mismatch 0: the extended-seed scan reads the letters directly + candidate confirmation; "
-                    "otherwise pack to 2-bit planes first)"}
+            "step": "new batch of 1-byte letters resident in HBM -> scan into the count vector (max.mismatch 0: the "
+                    "extended-seed scan reads the letters directly and confirms its candidates; otherwise pack to 2-bit "
+                    "planes first); --collective peer (default): the vector is zeroed once before the K steps and must "
+                    "hold K x the counts of one step afterwards (checked), the other modes zero it every step"}
 
 
 COLLECTIVE_USED = {}        # "mode": what timed_steps fell back to when the peer mapping is not available
@@ -424,7 +425,7 @@ def timed_steps(env, pieces, counts, nsteps, collective):
     torch, L = env.torch, env.L
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     one = torch.zeros_like(counts)
-    if env.world == 1 and collective in ("overlapped", "peer"):
+    if env.world == 1 and collective == "overlapped":
         collective = "per-step"
     if collective == "peer":
         # every rank counts straight into rank 0's vector: nothing to launch but the scans.  The
@@ -432,7 +433,7 @@ def timed_steps(env, pieces, counts, nsteps, collective):
         # its whole gather -- each match is one reduction over NVLink -- only the 4 MB memset per
         # call is left out, which would need a barrier of its own between the steps)
         M = counts.numel()
-        shared = env.shared_counts(M)
+        shared = (counts.data_ptr(), counts) if env.world == 1 else env.shared_counts(M)    # N = 1: the same protocol, local vector
         if shared is None:              # no peer mapping on this box: the NCCL path
             COLLECTIVE_USED["mode"] = "overlapped"
             return timed_steps(env, pieces, counts, nsteps, "overlapped")
@@ -457,6 +458,8 @@ def timed_steps(env, pieces, counts, nsteps, collective):
             one.copy_(view)
         env.broadcast0(one)
         tot = one.cpu().numpy().astype(np.int64)
+        if env.world == 1:
+            counts.zero_()
         assert (tot % nsteps == 0).all(), "every step must find the same matches"
         return total_ms, {k: sum(v) / len(v) for k, v in acc.items()}, launches, tot // nsteps
     bufs = [counts, torch.zeros_like(counts)]
