@@ -3141,8 +3141,9 @@ static int bsgpu_match_impl(const bsgpu_pdict3parts *const *parts, int nparts,
 			g_launches++;
 			CUDA_TRY(cudaGetLastError());
 		}
-		CUDA_TRY(cudaMemcpyAsync(counts, d_counts.p, (size_t) M * sizeof(int32_t),
-					 cudaMemcpyDeviceToHost, st));
+		if (matches_as != BSGPU_MATCHES_AS_ENDS)        // (the CSR below says everything the counts would)
+			CUDA_TRY(cudaMemcpyAsync(counts, d_counts.p, (size_t) M * sizeof(int32_t),
+						 cudaMemcpyDeviceToHost, st));
 		if (matches_as == BSGPU_MATCHES_AS_ENDS) {
 			res->ends = (int32_t *) malloc((size_t) std::max<unsigned long long>(nrec, 1) * sizeof(int32_t));
 			if (res->ends == nullptr)
