@@ -2693,7 +2693,6 @@ static int run_q(const QIndex *qi, const bsgpu_subject *subj, const MatchParams 
 	const BsgpuQIndexView &Q = qi->v;
 	int64_t own_lo = 0, own_hi = INT64_MAX;
 
-	TRY(ensure_packed(subj, st));
 	if (subj->kind == SUBJ_CHUNK) {
 		int64_t need_l = (int64_t) Q.min_w - 1, need_r = (int64_t) qi->max_len - Q.min_w;
 
@@ -2721,6 +2720,41 @@ static int run_q(const QIndex *qi, const bsgpu_subject *subj, const MatchParams 
 	int64_t nwords = ((probe_hi + 31) >> 5) - (probe_lo >> 5);
 	if (nwords <= 0)
 		return BSGPU_OK;
+	// one launch of qscan2_kernel over the probe positions [lo, hi) on stream `sx`
+	auto launch_v2 = [&](int64_t lo, int64_t hi, cudaStream_t sx) {
+		const char *env_g = getenv("BSGPU_Q_GRID");     // blocks per SM of the grid-stride launch
+		int qgrid = env_g != nullptr && atoi(env_g) > 0 ? atoi(env_g) : 1024;
+		long long nbatches = ((((hi + 31) >> 5) - (lo >> 5)) + 31) / 32;       // one batch of 32 words per warp
+		KernelTimer kt("qscan2_kernel", sx);
+#define QS2_LAUNCH(SH) qscan2_kernel<SH><<<grid_for(nbatches * 32, QS2_WARPS * 32, qgrid), QS2_WARPS * 32, 0, sx>>>( \
+				subj->view(), Q, R, mp.max_nmis, mp.min_nmis, lo, hi, own_lo, own_hi)
+		// the shapes of csrc/bsgpu_shapes.inc for windows of <= 29 letters have their key
+		// extraction compiled in; any other shape goes through the generic kernel
+		// (BSGPU_Q_GENERIC: tests run the generic kernel on a known shape)
+		switch (getenv("BSGPU_Q_GENERIC") != nullptr ? 0ull : (unsigned long long) Q.shape1) {
+		case 0x1777ull: QS2_LAUNCH(0x1777ull); break;
+		case 0x3777ull: QS2_LAUNCH(0x3777ull); break;
+		case 0x7777ull: QS2_LAUNCH(0x7777ull); break;
+		case 0x1b6dbull: QS2_LAUNCH(0x1b6dbull); break;
+		case 0x36b6bull: QS2_LAUNCH(0x36b6bull); break;
+		case 0x7e3full: QS2_LAUNCH(0x7e3full); break;
+		case 0x1cb17ull: QS2_LAUNCH(0x1cb17ull); break;
+		case 0xe5cbull: QS2_LAUNCH(0xe5cbull); break;
+		case 0x5cb97ull: QS2_LAUNCH(0x5cb97ull); break;
+		case 0x165965ull: QS2_LAUNCH(0x165965ull); break;
+		case 0xfa9full: QS2_LAUNCH(0xfa9full); break;
+		case 0xe4ea7ull: QS2_LAUNCH(0xe4ea7ull); break;
+		case 0x4c8b97ull: QS2_LAUNCH(0x4c8b97ull); break;
+		case 0xFFFull: QS2_LAUNCH(0xFFFull); break;
+		default: QS2_LAUNCH(0ull); break;
+		}
+#undef QS2_LAUNCH
+		g_launches++;
+	};
+	// (Packing the planes in slices on a second stream while the slice before is scanned was tried:
+	// pack_subject_kernel takes issue slots and L1 from the gather-bound scan, 4 x 0.375 ms of scans
+	// instead of 1.377 ms -- the step went from 1.46 to 1.54 ms.)
+	TRY(ensure_packed(subj, st));
 	set_plan("qgram_%s q=%d shifts=%d stride=%d window=%d key_bits=%d entries=%zu %s", Q.mode ? "hamming" : "exact",
 		 Q.q, Q.nshifts, Q.stride, Q.min_w, Q.key_bits, qi->nent,
 		 Q.v2 ? "rank_directory+inline_patterns" : "bitmap+directory+entries");
@@ -2790,39 +2824,18 @@ static int run_q(const QIndex *qi, const bsgpu_subject *subj, const MatchParams 
 		{
 			const char *env_g = getenv("BSGPU_Q_GRID");     // blocks per SM of the grid-stride launch
 			int qgrid = env_g != nullptr && atoi(env_g) > 0 ? atoi(env_g) : 1024;
-			KernelTimer kt(Q.v2 ? "qscan2_kernel" : "qscan_kernel", st);
 			if (Q.v2) {
-				// one batch of 32 words per warp
-				long long nbatches = (nwords + 31) / 32;
-#define QS2_LAUNCH(SH) qscan2_kernel<SH><<<grid_for(nbatches * 32, QS2_WARPS * 32, qgrid), QS2_WARPS * 32, 0, st>>>( \
-						subj->view(), Q, R, mp.max_nmis, mp.min_nmis, probe_lo, probe_hi, own_lo, own_hi)
-				// the shapes of csrc/bsgpu_shapes.inc for windows of <= 29 letters have their key
-				// extraction compiled in; any other shape goes through the generic kernel
-				// (BSGPU_Q_GENERIC: tests run the generic kernel on a known shape)
-				switch (getenv("BSGPU_Q_GENERIC") != nullptr ? 0ull : (unsigned long long) Q.shape1) {
-				case 0x1777ull: QS2_LAUNCH(0x1777ull); break;
-				case 0x3777ull: QS2_LAUNCH(0x3777ull); break;
-				case 0x7777ull: QS2_LAUNCH(0x7777ull); break;
-				case 0x1b6dbull: QS2_LAUNCH(0x1b6dbull); break;
-				case 0x36b6bull: QS2_LAUNCH(0x36b6bull); break;
-				case 0x7e3full: QS2_LAUNCH(0x7e3full); break;
-				case 0x1cb17ull: QS2_LAUNCH(0x1cb17ull); break;
-				case 0xe5cbull: QS2_LAUNCH(0xe5cbull); break;
-				case 0x5cb97ull: QS2_LAUNCH(0x5cb97ull); break;
-				case 0x165965ull: QS2_LAUNCH(0x165965ull); break;
-				case 0xfa9full: QS2_LAUNCH(0xfa9full); break;
-				case 0xe4ea7ull: QS2_LAUNCH(0xe4ea7ull); break;
-				case 0x4c8b97ull: QS2_LAUNCH(0x4c8b97ull); break;
-				case 0xFFFull: QS2_LAUNCH(0xFFFull); break;
-				default: QS2_LAUNCH(0ull); break;
-				}
-#undef QS2_LAUNCH
-			} else if (qi->max_len > 32)
+				launch_v2(probe_lo, probe_hi, st);
+				g_launches--;           // (counted below)
+			} else if (qi->max_len > 32) {
+				KernelTimer kt("qscan_kernel", st);
 				qscan_kernel<true><<<grid_for(nwords, 256, qgrid), 256, 0, st>>>(subj->view(), Q, R,
 						mp.max_nmis, mp.min_nmis, probe_lo, probe_hi, own_lo, own_hi);
-			else
+			} else {
+				KernelTimer kt("qscan_kernel", st);
 				qscan_kernel<false><<<grid_for(nwords, 256, qgrid), 256, 0, st>>>(subj->view(), Q, R,
 						mp.max_nmis, mp.min_nmis, probe_lo, probe_hi, own_lo, own_hi);
+			}
 		}
 		g_launches++;
 		CUDA_TRY(cudaGetLastError());

@@ -360,6 +360,20 @@ class PlainPatterns:
             pass
 
 
+def _plain_patterns_of(pset):
+    """The device handle of a non-preprocessed dictionary, kept on the DNAStringSet object (immutable,
+    like its R counterpart): the index the library builds behind a large base-only dictionary on first
+    use (plain_auto_index, csrc/bsgpu.cu) then serves every later call on the same object."""
+    pat = getattr(pset, "_bsgpu_plain", None)
+    if pat is None or not getattr(pat, "_h", None):
+        pat = PlainPatterns(pset)
+        try:
+            pset._bsgpu_plain = pat
+        except AttributeError:          # an object without a __dict__: one handle per call
+            pass
+    return pat
+
+
 def _as_plain_set(pdict):
     if isinstance(pdict, DNAStringSet):
         return pdict
@@ -448,7 +462,7 @@ def _match_plain(pset, subject, max_mismatch, min_mismatch, with_indels, fixed, 
         min_mismatch = normarg_min_mismatch(min_mismatch, max_mismatch)
         fixed = normarg_fixed(fixed)
         algo = _check_plain_args(pset, max_mismatch, min_mismatch, with_indels, fixed, algorithm, mode)
-        pat = PlainPatterns(pset)
+        pat = _plain_patterns_of(pset)
         if algo == "indels":
             ans = _count_indels(pat, dsubj, max_mismatch, fixed, False)
             if mode == MATCHES_AS_WHICH:
@@ -456,7 +470,7 @@ def _match_plain(pset, subject, max_mismatch, min_mismatch, with_indels, fixed, 
         else:
             ans = match_parts([pat], dsubj, max_mismatch, min_mismatch, fixed, mode)
     finally:
-        if pat is not None:
+        if pat is not None and getattr(pset, "_bsgpu_plain", None) is not pat:
             pat.close()
         if owned:
             dsubj.close()
@@ -584,7 +598,7 @@ def _vmatch_plain(pset, subject, max_mismatch, min_mismatch, with_indels, fixed,
         else:
             collapse = 0
         algo = _check_plain_args(pset, max_mismatch, min_mismatch, with_indels, fixed, algorithm, mode)
-        pat = PlainPatterns(pset)
+        pat = _plain_patterns_of(pset)
         if algo == "indels":
             mat = _count_indels(pat, dsubj, max_mismatch, fixed, True)
             if mode == MATCHES_AS_WHICH:
@@ -601,7 +615,7 @@ def _vmatch_plain(pset, subject, max_mismatch, min_mismatch, with_indels, fixed,
             return ans
         ans = vmatch_parts([pat], dsubj, max_mismatch, min_mismatch, fixed, collapse, weight, mode)
     finally:
-        if pat is not None:
+        if pat is not None and getattr(pset, "_bsgpu_plain", None) is not pat:
             pat.close()
         if owned:
             dsubj.close()
