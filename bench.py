@@ -726,11 +726,13 @@ def run_c2(args, env):
     dom_ms = kms[dominant]
     alg_bytes = float(pieces.letters)              # 1.0 B per subject letter
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(dominant, {}).get("dram_bytes_per_launch")
+            ent = json.load(f).get(dominant, {})
+        traffic = ent.get("dram_bytes_per_launch")
+        traffic_note = {k: ent[k] for k in ("capture", "note", "dram_bytes_per_launch_cold") if k in ent} or None
     cg, gg = C.c_double(), C.c_double()
     in_run = None
     if L.bsgpu_probe_peaks(C.byref(cg), C.byref(gg), 32 << 20) == 0:
@@ -742,7 +744,7 @@ def run_c2(args, env):
         if tok.startswith("S="):
             stride_s = int(tok[2:])
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic, "kernel": dominant,
+            "frac": achieved / peak, "traffic": traffic, "traffic_capture": traffic_note, "kernel": dominant,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
             "kernel_ms": kms,
             "kernel_ms_source": "CUDA events recorded by the library around each of its launches, on the "
