@@ -87,7 +87,12 @@ int bsgpu_pdict3parts_build(int algo, int32_t M,
  * match_XStringSet_XStringViews and vmatch_XStringSet_XStringSet (src/match_pdict.c:174,267,519),
  * which run one matchPattern() per pattern; all of the reference's algorithms report what its
  * naive inexact one does (src/match_pattern.c:53-76), and so does this.  The handle is passed to
- * bsgpu_match() / bsgpu_vmatch() (nparts = 1) like a PDict3Parts; with.indels is not supported.
+ * bsgpu_match() / bsgpu_vmatch() (nparts = 1) like a PDict3Parts; with.indels goes through
+ * bsgpu_count_indels().  A dictionary of >= 256 base-only patterns of >= 8 letters that is matched
+ * exactly (max.mismatch 0, subject taken literally, no open-ended chunk) gets a Trusted-Band
+ * index of its own on first use and is answered by the preprocessed engines -- same counts,
+ * which-indices and ends as the matchPattern() loop, without its M x L cost (BSGPU_PLAIN_INDEX=0
+ * switches this off, BSGPU_PLAIN_INDEX_MIN moves the threshold).
  * Errors: "empty patterns are not supported", "patterns with more than 20000 letters are not
  * supported" (R/match-utils.R:47-52). */
 int bsgpu_patterns_build(const uint8_t *concat, const int32_t *widths, int32_t M,
