@@ -12,7 +12,9 @@
 //                         (replaces the matchPattern loop of match_XStringSet_XString & co,
 //                          src/match_pdict.c:174-199, src/match_pattern.c:53-110)
 //   finalize_ends_kernel  sorted records -> end coordinates
-// The exact whole-pattern scan and the q-gram (MTB) scan are in bsgpu_qindex.cuh.
+// The exact whole-pattern scans are in bsgpu_xseed.cuh (w >= 25) and bsgpu_qindex.cuh (17 <= w < 25),
+// the q-gram (MTB) scans in bsgpu_qindex.cuh, the band directory (Trusted Bands with heads / tails
+// or duplicated bands) in bsgpu_tbdir.cuh.
 #pragma once
 #include <cooperative_groups.h>
 #include "bsgpu_common.cuh"

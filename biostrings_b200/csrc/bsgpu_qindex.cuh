@@ -7,7 +7,9 @@
 //       met exactly once, at the probe position p = a + ((-a) mod S).  The seeds are hashed from
 //       the raw encoded bytes (TMA-staged tiles), filtered by a blocked Bloom filter and
 //       confirmed byte for byte by dedicated warps -- no packed planes.
-//   qscan_kernel  an MTB_PDict (max.mismatch = k >= 1): the union over its k+1 Trusted Bands
+//   qscan2_kernel / qscan_kernel  an MTB_PDict (max.mismatch = k >= 1; qscan2_kernel for one
+//       pattern width <= 29: rank directory + patterns inline in the slots, see below; qscan_kernel
+//       for variable widths and up to 64 letters): the union over its k+1 Trusted Bands
 //       (R/matchPDict.R:335-377, src/MIndex_class.c:230-263) is exactly the set of alignments
 //       with min <= #mismatches <= max (pigeonhole), so any complete filter for Hamming
 //       distance <= k gives the same result.  One gapped shape of weight q applied at a small
