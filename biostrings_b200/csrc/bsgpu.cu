@@ -3979,14 +3979,22 @@ extern "C" int bsgpu_count_indels(const bsgpu_pdict3parts *plain, const bsgpu_su
 template <typename CT>
 static int launch_oligo(const bsgpu_subject *subj, const BsgpuOligoParams &P, CT *d_out, cudaStream_t st)
 {
-	size_t shmem = P.replicas > 0 ? ((size_t) P.replicas << (2 * P.w)) * sizeof(uint32_t) : 0;
+	size_t shmem = P.slice_bits > 0 ? ((size_t) 1 << P.slice_bits) * sizeof(uint32_t)
+					: (P.replicas > 0 ? ((size_t) P.replicas << (2 * P.w)) * sizeof(uint32_t) : 0);
 
 	if (shmem > 48 * 1024)
 		CUDA_TRY(cudaFuncSetAttribute(oligo_freq_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 					      (int) shmem));
 	{
 		KernelTimer kt("oligo_freq_kernel", st);
-		oligo_freq_kernel<CT><<<grid_for(P.nwords, 256, 8), 256, shmem, st>>>(subj->view(), P, d_out);
+		if (P.slice_bits > 0) {
+			// width 8: 2 slices of 2^15 counters (128 KB, one block of 1024 threads per SM);
+			// every slice reads the planes again, which is cheap next to one L2 atomic per window
+			dim3 grid((unsigned) grid_for(P.nwords, 1024, 1), 1u << (2 * P.w - P.slice_bits));
+			oligo_freq_kernel<CT><<<grid, 1024, shmem, st>>>(subj->view(), P, d_out);
+		} else {
+			oligo_freq_kernel<CT><<<grid_for(P.nwords, 256, 8), 256, shmem, st>>>(subj->view(), P, d_out);
+		}
 	}
 	g_launches++;
 	CUDA_TRY(cudaGetLastError());
@@ -4028,7 +4036,13 @@ static BsgpuOligoParams oligo_params(const bsgpu_subject *subj, int width, int s
 
 		P.replicas = std::max(1, std::min(32, r));
 	}
+	// one row of 4^8 counters: too big for one block's shared memory, small enough to be counted in
+	// two slices
 	P.fast = !per_segment && step == 1 && getenv("BSGPU_OLIGO_GENERIC") == nullptr;
+	// width 8: 0.48 ms per 250 Mbp against 1.64 ms through L2 atomics; width 9 would need 8 slices:
+	// 1.87 ms against 1.33 ms, so it stays with the atomics (tools/oligo_w9_probe.py)
+	if (P.fast && width == 8 && getenv("BSGPU_OLIGO_NO_SLICES") == nullptr)
+		P.slice_bits = 15;      // (the unrolled path only: it counts through oligo_bump)
 	P.scan_lo = subj->scan_lo;
 	P.scan_hi = subj->scan_hi;
 	P.nwords = subj->total / 32;
@@ -4066,7 +4080,8 @@ extern "C" int bsgpu_oligo_frequency(const bsgpu_subject *subj, int width, int s
 	cudaStream_t st = 0;
 	TRY(ensure_packed(subj, st));
 	BsgpuOligoParams P = oligo_params(subj, width, step, invert_twobit_order, !collapsed);
-	set_plan("oligo_freq w=%d step=%d rows=%zu table=%s", width, step, nrow, P.replicas ? "shared" : "global");
+	set_plan("oligo_freq w=%d step=%d rows=%zu table=%s", width, step, nrow,
+		 P.slice_bits ? "shared_slices" : (P.replicas ? "shared" : "global"));
 	if (collapsed) {
 		// 64-bit counters: a collapsed set may hold more than 2^31 windows of one kind
 		DevBuf<unsigned long long> d_out;

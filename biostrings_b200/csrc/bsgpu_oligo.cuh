@@ -32,6 +32,8 @@ struct BsgpuOligoParams {
 	int32_t per_segment;    // 1: out[segment * 4^w + code], 0: one row
 	int32_t coord_step;     // chunk subjects: starts are judged in subject coordinates
 	int32_t replicas;       // copies of the table in shared memory (0 = global atomics)
+	int32_t slice_bits;     // > 0 (width 8): blockIdx.y owns the codes with code >> slice_bits == blockIdx.y,
+				// 2^slice_bits counters in shared memory; every slice scans the whole subject
 	int32_t fast;           // step == 1 and one row: the unrolled path
 	int64_t scan_lo, scan_hi;       // only windows whose last letter is in [scan_lo, scan_hi)
 	int64_t nwords;
@@ -60,14 +62,18 @@ template <typename CT>
 __device__ __forceinline__ void oligo_bump(uint32_t code, const BsgpuOligoParams &P, uint32_t *sh_hist,
 					   CT *__restrict__ out, int tid)
 {
-	if (P.replicas > 0)
+	if (P.slice_bits > 0) {
+		if ((code >> P.slice_bits) == blockIdx.y)
+			atomicAdd(&sh_hist[code & ((1u << P.slice_bits) - 1u)], 1u);
+	} else if (P.replicas > 0) {
 		atomicAdd(&sh_hist[code * P.replicas + (tid & (P.replicas - 1))], 1u);
-	else
+	} else {
 		atomicAdd(out + code, (CT) 1);
+	}
 }
 
 template <typename CT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 oligo_freq_kernel(BsgpuSubjectView S, BsgpuOligoParams P, CT *__restrict__ out)
 {
 	extern __shared__ uint32_t sh_hist[];
@@ -75,8 +81,9 @@ oligo_freq_kernel(BsgpuSubjectView S, BsgpuOligoParams P, CT *__restrict__ out)
 	const uint32_t cmask = ncol - 1;
 	const int tid = threadIdx.x;
 
-	if (P.replicas > 0) {
-		for (uint32_t k = tid; k < ncol * P.replicas; k += blockDim.x)
+	const uint32_t nsh = P.slice_bits > 0 ? 1u << P.slice_bits : ncol * (uint32_t) P.replicas;   // counters in shared memory
+	if (nsh > 0) {
+		for (uint32_t k = tid; k < nsh; k += blockDim.x)
 			sh_hist[k] = 0;
 		__syncthreads();
 	}
@@ -167,7 +174,12 @@ oligo_freq_kernel(BsgpuSubjectView S, BsgpuOligoParams P, CT *__restrict__ out)
 				atomicAdd(out + (P.per_segment ? (size_t) seg * ncol : (size_t) 0) + code, (CT) 1);
 		}
 	}
-	if (P.replicas > 0) {
+	if (P.slice_bits > 0) {
+		__syncthreads();
+		for (uint32_t c = tid; c < nsh; c += blockDim.x)
+			if (sh_hist[c] != 0)
+				atomicAdd(out + ((size_t) blockIdx.y << P.slice_bits) + c, (CT) sh_hist[c]);
+	} else if (P.replicas > 0) {
 		__syncthreads();
 		for (uint32_t c = tid; c < ncol; c += blockDim.x) {
 			uint32_t sum = 0;

@@ -30,7 +30,7 @@ def want_xstring(x, width, step=1, as_prob=False, invert=False):
 
 
 @pytest.mark.parametrize("width,step", [(1, 1), (1, 4), (2, 1), (2, 2), (3, 1), (3, 2), (3, 3), (4, 9),
-                                        (5, 1), (6, 1), (6, 5), (7, 1), (7, 3), (8, 1), (10, 7),
+                                        (5, 1), (6, 1), (6, 5), (7, 1), (7, 3), (8, 1), (9, 1), (8, 3), (10, 7),
                                         (12, 1), (13, 2)])
 @pytest.mark.parametrize("invert", [False, True])
 def test_xstring_counts_and_probabilities(width, step, invert):

@@ -53,7 +53,7 @@ def bench_oligo(x, sample):
     L = x.size
     lines = []
     with bs.DeviceSubject.from_xstring(x) as d:
-        for w in (3, 6, 8, 12):
+        for w in (3, 6, 8, 9, 12):
             def run():
                 _lib.lib().bsgpu_subject_repack(d.handle, None)         # pack inside the measurement
                 return oligo_frequency_device(d, w, 1, False, True, False)
