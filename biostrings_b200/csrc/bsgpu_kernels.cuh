@@ -838,7 +838,7 @@ finalize_ends_kernel(BsgpuSubjectView S, const int64_t *__restrict__ tail_off, i
 		}
 		ends[t] = (int32_t) v;
 		if (counts != nullptr)
-			atomicAdd(counts + key, 1);
+			count_add(counts + key, 1);     // (may be the caller's vector on another GPU)
 	}
 }
 
