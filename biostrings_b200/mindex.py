@@ -108,10 +108,17 @@ class ByPos_MIndex:
         if total == 0:
             z = np.zeros(0, dtype=np.int32)
             return (z, z, None) if use_names else (z, z)
-        # gather the CSR rows in pattern order
-        first = np.repeat(self.offsets[rows] - np.concatenate([[0], np.cumsum(n)[:-1]]), n)
-        e = self.ends[first + np.arange(total, dtype=np.int64)]
-        s = e - np.repeat(self.width0.astype(np.int32), n) + 1
+        if self.dups0 is None:
+            e = self.ends                   # the CSR is already pattern-major
+        else:
+            # gather the CSR rows in pattern order
+            first = np.repeat(self.offsets[rows] - np.concatenate([[0], np.cumsum(n)[:-1]]), n)
+            e = self.ends[first + np.arange(total, dtype=np.int64)]
+        w0 = self.width0.astype(np.int32)
+        if w0.size and (w0 == w0[0]).all():
+            s = e - (int(w0[0]) - 1)        # one width: no per-match width vector
+        else:
+            s = e - np.repeat(w0, n) + 1
         if not use_names:
             return s, e
         names = None if self.NAMES is None else np.repeat(np.asarray(self.NAMES, dtype=object), n)
@@ -124,11 +131,19 @@ class ByPos_MIndex:
         s, e = self.unlist()
         if width is None:
             width = int(e.max()) if e.size else 0
-        lo = np.clip(s.astype(np.int64), 1, width + 1)
-        hi = np.clip(e.astype(np.int64) + 1, 1, width + 1)
-        keep = hi > lo
-        d = np.bincount(lo[keep], minlength=width + 2) - np.bincount(hi[keep], minlength=width + 2)
-        return np.cumsum(d)[1:width + 1].astype(np.int32)
+        if e.size == 0 or width <= 0:
+            return np.zeros(max(width, 0), dtype=np.int32)
+        if int(s.min()) >= 1 and int(e.max()) <= width:
+            lo, hi = s, e + 1               # everything inside 1..width (the usual case): no clipping, no mask
+        else:
+            lo = np.clip(s.astype(np.int64), 1, width + 1)
+            hi = np.clip(e.astype(np.int64) + 1, 1, width + 1)
+            keep = hi > lo
+            lo, hi = lo[keep], hi[keep]
+        # +1 at every start, -1 behind every end, running sum; the difference array in int32
+        d = np.bincount(lo, minlength=width + 2).astype(np.int32)
+        d -= np.bincount(hi, minlength=width + 2).astype(np.int32)
+        return np.cumsum(d[1:width + 1], dtype=np.int32)
 
 
 def extractAllMatches(subject, mindex):
